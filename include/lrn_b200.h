@@ -1,0 +1,141 @@
+/*
+ * lrn_b200.h -- C ABI of the B200-native (sm_100a) LineRefineNet forward hot path.
+ *
+ * The reference (1pathplanningzzj/pointnet_refine) has no native code on this
+ * path: its "FFI" is whatever PyTorch dispatches for the ops in
+ * src/model.py.  Each entry point below therefore cites the reference
+ * *Python* interface it replaces (file:line in the reference tree).  The
+ * reference-side binding (a ctypes stub) is shown in INTEGRATION.md; the
+ * in-tree host mirror is pointnet_refine_b200/model.py.
+ *
+ * Conventions
+ *   - All pointers are raw CUDA *device* pointers unless the name ends in
+ *     "_host".  The caller owns every buffer, including the workspace (size
+ *     via lrn_*_workspace_bytes); the library never allocates or frees device
+ *     memory and never synchronises the device.
+ *   - Every call is enqueued on the passed stream (cudaStream_t) and is
+ *     stream-ordered and re-entrant; one host thread per process per GPU.
+ *   - Return value: lrn_status (0 = ok).  No C++ exceptions cross the ABI.
+ *     lrn_last_error() returns a thread-local detail string.
+ *   - sm_100a only.  On any other device every compute call returns
+ *     LRN_ERR_UNSUPPORTED_ARCH; there is no fallback path.
+ */
+#ifndef LRN_B200_H
+#define LRN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRN_ABI_VERSION 1
+
+typedef struct CUstream_st* lrn_stream_t; /* == cudaStream_t */
+
+enum lrn_status {
+  LRN_OK = 0,
+  LRN_ERR_BAD_SHAPE = 1,        /* B/N/rows out of range                                  */
+  LRN_ERR_MISALIGNED = 2,       /* a pointer is not 16-byte aligned                       */
+  LRN_ERR_UNSUPPORTED_ARCH = 3, /* current device is not compute capability 10.0          */
+  LRN_ERR_CUDA = 4,             /* a CUDA runtime/driver call failed (see lrn_last_error) */
+  LRN_ERR_WORKSPACE = 5,        /* workspace/packed buffer too small                      */
+  LRN_ERR_BAD_ARG = 6,          /* null required pointer, bad enum or flag combination    */
+};
+
+/* Arithmetic tier of the tensor-core layers (conv2..conv5, fusion, gate layer 2,
+ * context_proj).  conv1 and gate layer 1 always run in fp32 FMA on raw fp32 xyz/intensity.
+ *   BF16: operands rounded to bfloat16, fp32 accumulate  (tolerance 1e-2 of range)
+ *   TF32: operands fp32 read as TF32, fp32 accumulate    (tolerance 1e-3 max-abs) */
+enum lrn_precision { LRN_PREC_BF16 = 0, LRN_PREC_TF32 = 1 };
+
+/* Output selection for lrn_encoder_forward (bitwise or). */
+enum lrn_encoder_flags {
+  LRN_OUT_POOL = 1,   /* global_feat (B,2048) = [max_n | mean_n]      src/model.py:58-60 */
+  LRN_OUT_ARGMAX = 2, /* argmax (B,1024) int64, first index on ties   src/model.py:58 (torch.max indices) */
+  LRN_OUT_FUSED = 4,  /* fused fp32 in the reference layout (B,1024,N) src/model.py:55,62 */
+  LRN_OUT_MEMORY = 8, /* memory fp32 (B,N,256) = context_proj(fused^T) src/model.py:194   */
+};
+
+/* Raw fp32 parameters of the reference module, exactly as they sit in its state_dict
+ * (SURVEY.md appendix B).  Conv1d weights are (C_out, C_in, 1) contiguous == (C_out, C_in).
+ * Replaces: MultiScalePointNetEncoder.__init__ parameter tree, src/model.py:7-37, and
+ * LineRefineNet.context_proj, src/model.py:147. */
+typedef struct lrn_encoder_params {
+  const float* conv_w[5];   /* context_encoder.conv{1..5}.weight  (64,4) (128,64) (256,128) (512,256) (1024,512) */
+  const float* conv_b[5];   /* context_encoder.conv{1..5}.bias                                   */
+  const float* bn_w[5];     /* context_encoder.bn{1..5}.weight                                   */
+  const float* bn_b[5];     /* context_encoder.bn{1..5}.bias                                     */
+  const float* bn_mean[5];  /* context_encoder.bn{1..5}.running_mean                             */
+  const float* bn_var[5];   /* context_encoder.bn{1..5}.running_var                              */
+  const float* fusion_w;    /* context_encoder.fusion.0.weight (1024,1984)                       */
+  const float* fusion_b;    /* context_encoder.fusion.0.bias                                     */
+  const float* fusion_bn_w; /* context_encoder.fusion.1.{weight,bias,running_mean,running_var}   */
+  const float* fusion_bn_b;
+  const float* fusion_bn_mean;
+  const float* fusion_bn_var;
+  const float* gate0_w;     /* context_encoder.intensity_gate.0.weight (64,1)                    */
+  const float* gate0_b;
+  const float* gate2_w;     /* context_encoder.intensity_gate.2.weight (1024,64)                 */
+  const float* gate2_b;
+  const float* proj_w;      /* context_proj.weight (256,1024); may be NULL if LRN_OUT_MEMORY is never used */
+  const float* proj_b;
+  float bn_eps;             /* 1e-5 (torch.nn.BatchNorm1d default)                               */
+} lrn_encoder_params;
+
+/* ---- library / device ---- */
+int lrn_abi_version(void);
+const char* lrn_status_string(int status);
+const char* lrn_last_error(void);
+/* LRN_OK iff the current CUDA device can run this library (compute capability 10.0). */
+int lrn_device_check(void);
+
+/* ---- weight folding (eval-mode BatchNorm folded into the preceding 1x1 conv) ----
+ * Replaces: the bn_k(conv_k(x)) pairs of MultiScalePointNetEncoder.forward in eval mode,
+ * src/model.py:43-47,51 (W' = W*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta), and
+ * packs all matrices K-major in the tier's operand type.  Must be re-run whenever a
+ * parameter or running statistic changes. */
+size_t lrn_encoder_packed_bytes(int precision);
+int lrn_encoder_fold(const lrn_encoder_params* params, int precision, void* packed, size_t packed_bytes,
+                     lrn_stream_t stream);
+
+/* ---- the hot path ----
+ * Replaces: MultiScalePointNetEncoder.forward (src/model.py:39-62) in eval mode plus, with
+ * LRN_OUT_MEMORY, the projection in LineRefineNet.forward (src/model.py:192-194).
+ *   context      : (B, N, 4) fp32 contiguous [x,y,z,intensity] (the (B,4,N) view the module is
+ *                  called with at src/model.py:192-193 is a transpose of this buffer)
+ *   global_feat  : (B, 2048) fp32               required iff LRN_OUT_POOL or LRN_OUT_ARGMAX
+ *   fused        : (B, 1024, N) fp32            required iff LRN_OUT_FUSED
+ *   argmax       : (B, 1024) int64              required iff LRN_OUT_ARGMAX
+ *   memory       : (B, N, 256) fp32             required iff LRN_OUT_MEMORY
+ *   chunk_rows   : points processed per wave (0 = library default); a tuning knob only.
+ * B >= 1, N >= 1, B*N < 2^31.  Empty input (B == 0 or N == 0) returns LRN_ERR_BAD_SHAPE, like
+ * the reference, whose torch.max over an empty dimension raises. */
+size_t lrn_encoder_workspace_bytes(int64_t B, int64_t N, int precision, int flags, int64_t chunk_rows);
+int lrn_encoder_forward(const void* packed, int precision, const float* context, int64_t B, int64_t N, int flags,
+                        float* global_feat, float* fused, int64_t* argmax, float* memory, int64_t chunk_rows,
+                        void* workspace, size_t workspace_bytes, lrn_stream_t stream);
+
+/* ---- regression head + cumulative-offset bookkeeping ----
+ * Replaces: reg_branches[i](tgt) and the coordinate update of LineRefineNet.forward,
+ * src/model.py:172-179,220,227-231:
+ *   delta = W2 relu(W1 tgt + b1) + b2;  current += delta;  cum_out = current - noisy
+ *   w1 (128,256) b1 (128) w2 (3,128) b2 (3)  fp32 (reg_branches.{i}.{0,2}.{weight,bias})
+ *   tgt (rows,256), current (rows,3) in/out, noisy (rows,3), cum_out (rows,3); rows = B*M. */
+int lrn_head_forward(const float* w1, const float* b1, const float* w2, const float* b2, const float* tgt,
+                     int64_t rows, float* current, const float* noisy, float* cum_out, lrn_stream_t stream);
+
+/* ---- building block, exported for unit tests and profiling ----
+ * out[M,N] = act(A[M,K] * W[N,K]^T + bias) on the tcgen05 tensor-core path.
+ *   precision BF16: A, W bfloat16, out bfloat16 (out_f32 = 0) or fp32 (out_f32 = 1)
+ *   precision TF32: A, W fp32,     out fp32
+ * lda/ldw/ldo in elements; K % 64 == 0 (bf16) or K % 32 == 0 (tf32); N % 128 == 0. */
+int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                      void* out, int64_t ldo, int out_f32, int relu, int64_t M, int64_t N, int64_t K,
+                      lrn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRN_B200_H */

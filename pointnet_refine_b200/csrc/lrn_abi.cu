@@ -1,0 +1,479 @@
+// C ABI of the B200-native LineRefineNet forward hot path (see include/lrn_b200.h).
+// Host side only orchestrates: it builds TMA tensor maps, carves the caller's workspace and
+// enqueues kernels on the caller's stream.  It never allocates device memory and never syncs.
+#include "../../include/lrn_b200.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "gemm_sm100.cuh"
+#include "pointwise.cuh"
+
+namespace {
+
+using namespace lrn;
+
+thread_local char g_err[512] = "";
+
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+#define LRN_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) return fail(LRN_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+constexpr int kCat = 2048;          // operand row: feat1..feat5 (1984) + gate hidden (64)
+constexpr int kFusionK = 1984;
+constexpr int kGateK = 64;
+constexpr int64_t kDefaultChunkRows = 148 * 128 * 4;  // 75,776 points per wave
+const int kChan[6] = {4, 64, 128, 256, 512, 1024};
+const int kCatOff[6] = {0, 0, 64, 192, 448, 960};  // column of feat_k inside the operand row
+
+size_t elem_size(int precision) { return precision == LRN_PREC_TF32 ? 4 : 2; }
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ packed weight blob
+struct PackedLayout {
+  size_t w1, b1, wg1, bg1;  // fp32: (64,4) (64) (64) (64)
+  size_t w[6];              // operand type: w[2..5] = conv2..conv5 (Cout, Cin)
+  size_t wfg;               // (1024, 2048): [fusion folded | gate layer 2]
+  size_t wp;                // (256, 1024) context_proj
+  size_t b[6];              // fp32 biases conv2..conv5
+  size_t bf, bg, bp;        // fp32 (1024) (1024) (256)
+  size_t total;
+};
+
+PackedLayout packed_layout(int precision) {
+  PackedLayout L{};
+  const size_t es = elem_size(precision);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  L.w1 = take(64 * 4 * 4);
+  L.b1 = take(64 * 4);
+  L.wg1 = take(64 * 4);
+  L.bg1 = take(64 * 4);
+  for (int k = 2; k <= 5; ++k) L.w[k] = take(size_t(kChan[k]) * kChan[k - 1] * es);
+  L.wfg = take(size_t(1024) * kCat * es);
+  L.wp = take(size_t(256) * 1024 * es);
+  for (int k = 2; k <= 5; ++k) L.b[k] = take(size_t(kChan[k]) * 4);
+  L.bf = take(1024 * 4);
+  L.bg = take(1024 * 4);
+  L.bp = take(256 * 4);
+  L.total = off;
+  return L;
+}
+
+// ------------------------------------------------------------------ device / driver helpers
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    LRN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) return fail(LRN_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return LRN_OK;
+}
+
+// K-major 2-D operand: `rows` x `cols` elements, row pitch `ld` elements; box = 128 bytes x box_rows, 128B swizzle.
+int make_tmap(CUtensorMap* m, int precision, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc;
+  int st = get_encode_fn(&enc);
+  if (st) return st;
+  const size_t es = elem_size(precision);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * es) % 16) return fail(LRN_ERR_MISALIGNED, "tensor map base/pitch");
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld * es)};
+  cuuint32_t box[2] = {cuuint32_t(128 / es), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, precision == LRN_PREC_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LRN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  return LRN_OK;
+}
+
+struct DeviceInfo {
+  int device = -1;
+  int sms = 0;
+  int cc = 0;
+};
+
+int device_info(DeviceInfo* out) {
+  static thread_local DeviceInfo cache;
+  int dev = 0;
+  LRN_CUDA(cudaGetDevice(&dev));
+  if (cache.device != dev) {
+    int major = 0, minor = 0, sms = 0;
+    LRN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    LRN_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    LRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cache.device = dev;
+    cache.sms = sms;
+    cache.cc = major * 10 + minor;
+  }
+  *out = cache;
+  if (cache.cc != 100)
+    return fail(LRN_ERR_UNSUPPORTED_ARCH, "device compute capability %d.%d is not 10.0 (sm_100a only, no fallback)",
+                cache.cc / 10, cache.cc % 10);
+  return LRN_OK;
+}
+
+// ------------------------------------------------------------------ GEMM launch
+template <int BN, bool TF32, int EPI, int STAGES>
+int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sms, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  auto kern = gemm_kernel<BN, TF32, EPI, STAGES>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  if (tiles <= 0) return LRN_OK;
+  const int grid = std::min(tiles, sms);
+  kern<<<grid, kGemmThreads, L::kDynamic, stream>>>(ta, tb, p);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int launch_gemm(int precision, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                int sms, cudaStream_t stream) {
+  const bool tf32 = precision == LRN_PREC_TF32;
+  if (epi == EPI_FUSION) {
+    return tf32 ? launch_gemm_t<128, true, EPI_FUSION, 6>(ta, tb, p, sms, stream)
+                : launch_gemm_t<128, false, EPI_FUSION, 6>(ta, tb, p, sms, stream);
+  }
+  if (bn == 128)
+    return tf32 ? launch_gemm_t<128, true, EPI_ACT, 6>(ta, tb, p, sms, stream)
+                : launch_gemm_t<128, false, EPI_ACT, 6>(ta, tb, p, sms, stream);
+  return tf32 ? launch_gemm_t<256, true, EPI_ACT, 4>(ta, tb, p, sms, stream)
+              : launch_gemm_t<256, false, EPI_ACT, 4>(ta, tb, p, sms, stream);
+}
+
+int fold_one(int precision, const float* w, const float* b, const float* g, const float* beta, const float* mean,
+             const float* var, float eps, int cout, int cin, void* out_w, int64_t ld, int col0, float* out_b,
+             cudaStream_t stream) {
+  const long long total = static_cast<long long>(cout) * cin;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
+  if (precision == LRN_PREC_TF32)
+    fold_linear_kernel<float><<<grid, 256, 0, stream>>>(w, b, g, beta, mean, var, eps, cout, cin,
+                                                        static_cast<float*>(out_w), ld, col0, out_b);
+  else
+    fold_linear_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, b, g, beta, mean, var, eps, cout, cin,
+                                                                static_cast<__nv_bfloat16*>(out_w), ld, col0, out_b);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+bool bad_precision(int p) { return p != LRN_PREC_BF16 && p != LRN_PREC_TF32; }
+
+struct WorkspaceLayout {
+  int64_t chunk;
+  size_t cat, fused_pm, keys, total;
+};
+
+WorkspaceLayout workspace_layout(int64_t B, int64_t N, int precision, int flags, int64_t chunk_rows) {
+  WorkspaceLayout W{};
+  const size_t es = elem_size(precision);
+  const int64_t P = B * N;
+  int64_t chunk = chunk_rows > 0 ? chunk_rows : kDefaultChunkRows;
+  chunk = std::min<int64_t>(align_up(size_t(std::max<int64_t>(chunk, 128)), 128), align_up(size_t(P), 128));
+  W.chunk = chunk;
+  size_t off = 0;
+  W.cat = off;
+  off = align_up(off + size_t(chunk) * kCat * es, 1024);
+  W.fused_pm = off;
+  if (flags & LRN_OUT_MEMORY) off = align_up(off + size_t(chunk) * 1024 * es, 1024);
+  W.keys = off;
+  if (flags & LRN_OUT_ARGMAX) off = align_up(off + size_t(B) * 1024 * 8, 1024);
+  W.total = off;
+  return W;
+}
+
+}  // namespace
+
+// ======================================================================== exported C ABI
+extern "C" {
+
+int lrn_abi_version(void) { return LRN_ABI_VERSION; }
+
+const char* lrn_status_string(int status) {
+  switch (status) {
+    case LRN_OK: return "ok";
+    case LRN_ERR_BAD_SHAPE: return "bad shape";
+    case LRN_ERR_MISALIGNED: return "misaligned pointer";
+    case LRN_ERR_UNSUPPORTED_ARCH: return "unsupported architecture (sm_100a only)";
+    case LRN_ERR_CUDA: return "CUDA error";
+    case LRN_ERR_WORKSPACE: return "workspace too small";
+    case LRN_ERR_BAD_ARG: return "bad argument";
+  }
+  return "unknown status";
+}
+
+const char* lrn_last_error(void) { return g_err; }
+
+int lrn_device_check(void) {
+  DeviceInfo d;
+  return device_info(&d);
+}
+
+size_t lrn_encoder_packed_bytes(int precision) {
+  if (bad_precision(precision)) return 0;
+  return packed_layout(precision).total;
+}
+
+int lrn_encoder_fold(const lrn_encoder_params* pr, int precision, void* packed, size_t packed_bytes,
+                     lrn_stream_t stream) {
+  if (!pr || !packed || bad_precision(precision)) return fail(LRN_ERR_BAD_ARG, "null params/packed or bad precision");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const PackedLayout L = packed_layout(precision);
+  if (packed_bytes < L.total) return fail(LRN_ERR_WORKSPACE, "packed buffer %zu < %zu", packed_bytes, L.total);
+  if (reinterpret_cast<uintptr_t>(packed) & 1023) return fail(LRN_ERR_MISALIGNED, "packed buffer must be 1024-byte aligned");
+  for (int k = 0; k < 5; ++k)
+    if (!pr->conv_w[k] || !pr->conv_b[k] || !pr->bn_w[k] || !pr->bn_b[k] || !pr->bn_mean[k] || !pr->bn_var[k])
+      return fail(LRN_ERR_BAD_ARG, "null conv/bn parameter %d", k + 1);
+  if (!pr->fusion_w || !pr->fusion_b || !pr->fusion_bn_w || !pr->fusion_bn_b || !pr->fusion_bn_mean ||
+      !pr->fusion_bn_var || !pr->gate0_w || !pr->gate0_b || !pr->gate2_w || !pr->gate2_b)
+    return fail(LRN_ERR_BAD_ARG, "null fusion/gate parameter");
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // conv1 stays fp32 (FMA kernel); gate layer 1 is copied as is
+  st = fold_one(LRN_PREC_TF32, pr->conv_w[0], pr->conv_b[0], pr->bn_w[0], pr->bn_b[0], pr->bn_mean[0], pr->bn_var[0],
+                pr->bn_eps, 64, 4, base + L.w1, 4, 0, reinterpret_cast<float*>(base + L.b1), s);
+  if (st) return st;
+  LRN_CUDA(cudaMemcpyAsync(base + L.wg1, pr->gate0_w, 64 * 4, cudaMemcpyDeviceToDevice, s));
+  LRN_CUDA(cudaMemcpyAsync(base + L.bg1, pr->gate0_b, 64 * 4, cudaMemcpyDeviceToDevice, s));
+  for (int k = 2; k <= 5; ++k) {
+    st = fold_one(precision, pr->conv_w[k - 1], pr->conv_b[k - 1], pr->bn_w[k - 1], pr->bn_b[k - 1], pr->bn_mean[k - 1],
+                  pr->bn_var[k - 1], pr->bn_eps, kChan[k], kChan[k - 1], base + L.w[k], kChan[k - 1], 0,
+                  reinterpret_cast<float*>(base + L.b[k]), s);
+    if (st) return st;
+  }
+  st = fold_one(precision, pr->fusion_w, pr->fusion_b, pr->fusion_bn_w, pr->fusion_bn_b, pr->fusion_bn_mean,
+                pr->fusion_bn_var, pr->bn_eps, 1024, kFusionK, base + L.wfg, kCat, 0,
+                reinterpret_cast<float*>(base + L.bf), s);
+  if (st) return st;
+  st = fold_one(precision, pr->gate2_w, pr->gate2_b, nullptr, nullptr, nullptr, nullptr, 0.f, 1024, kGateK,
+                base + L.wfg, kCat, kFusionK, reinterpret_cast<float*>(base + L.bg), s);
+  if (st) return st;
+  if (pr->proj_w && pr->proj_b) {
+    st = fold_one(precision, pr->proj_w, pr->proj_b, nullptr, nullptr, nullptr, nullptr, 0.f, 256, 1024, base + L.wp,
+                  1024, 0, reinterpret_cast<float*>(base + L.bp), s);
+    if (st) return st;
+  }
+  return LRN_OK;
+}
+
+size_t lrn_encoder_workspace_bytes(int64_t B, int64_t N, int precision, int flags, int64_t chunk_rows) {
+  if (B <= 0 || N <= 0 || bad_precision(precision)) return 0;
+  return workspace_layout(B, N, precision, flags, chunk_rows).total;
+}
+
+int lrn_encoder_forward(const void* packed, int precision, const float* context, int64_t B, int64_t N, int flags,
+                        float* global_feat, float* fused, int64_t* argmax, float* memory, int64_t chunk_rows,
+                        void* workspace, size_t workspace_bytes, lrn_stream_t stream) {
+  if (bad_precision(precision)) return fail(LRN_ERR_BAD_ARG, "bad precision %d", precision);
+  if (B <= 0 || N <= 0) return fail(LRN_ERR_BAD_SHAPE, "empty input B=%lld N=%lld", (long long)B, (long long)N);
+  if (B * N >= (int64_t(1) << 31) - 128) return fail(LRN_ERR_BAD_SHAPE, "B*N = %lld must be < 2^31", (long long)(B * N));
+  if (!packed || !context || !workspace) return fail(LRN_ERR_BAD_ARG, "null packed/context/workspace");
+  if (!(flags & (LRN_OUT_POOL | LRN_OUT_ARGMAX | LRN_OUT_FUSED | LRN_OUT_MEMORY)))
+    return fail(LRN_ERR_BAD_ARG, "no output requested");
+  if ((flags & (LRN_OUT_POOL | LRN_OUT_ARGMAX)) && !global_feat) return fail(LRN_ERR_BAD_ARG, "global_feat is null");
+  if ((flags & LRN_OUT_ARGMAX) && !argmax) return fail(LRN_ERR_BAD_ARG, "argmax is null");
+  if ((flags & LRN_OUT_FUSED) && !fused) return fail(LRN_ERR_BAD_ARG, "fused is null");
+  if ((flags & LRN_OUT_MEMORY) && !memory) return fail(LRN_ERR_BAD_ARG, "memory is null");
+  if ((reinterpret_cast<uintptr_t>(context) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 1023) ||
+      (reinterpret_cast<uintptr_t>(packed) & 1023) || (reinterpret_cast<uintptr_t>(memory) & 15) ||
+      (reinterpret_cast<uintptr_t>(global_feat) & 15))
+    return fail(LRN_ERR_MISALIGNED, "context/memory/global_feat need 16-byte, packed/workspace 1024-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+
+  const bool tf32 = precision == LRN_PREC_TF32;
+  const size_t es = elem_size(precision);
+  const int bk = int(128 / es);
+  const PackedLayout L = packed_layout(precision);
+  const WorkspaceLayout W = workspace_layout(B, N, precision, flags, chunk_rows);
+  if (workspace_bytes < W.total) return fail(LRN_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, W.total);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  void* cat = ws + W.cat;
+  void* fused_pm = ws + W.fused_pm;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + W.keys);
+  const int64_t P = B * N;
+
+  if (flags & (LRN_OUT_POOL | LRN_OUT_ARGMAX)) LRN_CUDA(cudaMemsetAsync(global_feat, 0, size_t(B) * 2048 * 4, s));
+  if (flags & LRN_OUT_ARGMAX) LRN_CUDA(cudaMemsetAsync(keys, 0, size_t(B) * 1024 * 8, s));
+
+  // weight tensor maps (B operands)
+  CUtensorMap tw[6], twfg, twp;
+  for (int k = 2; k <= 5; ++k) {
+    st = make_tmap(&tw[k], precision, pk + L.w[k], kChan[k], kChan[k - 1], kChan[k - 1], k == 2 ? 128 : 256);
+    if (st) return st;
+  }
+  st = make_tmap(&twfg, precision, pk + L.wfg, 1024, kCat, kCat, 128);
+  if (st) return st;
+  if (flags & LRN_OUT_MEMORY) {
+    st = make_tmap(&twp, precision, pk + L.wp, 256, 1024, 1024, 256);
+    if (st) return st;
+  }
+
+  EmbedWeights ew{reinterpret_cast<const float*>(pk + L.w1), reinterpret_cast<const float*>(pk + L.b1),
+                  reinterpret_cast<const float*>(pk + L.wg1), reinterpret_cast<const float*>(pk + L.bg1)};
+
+  for (int64_t r0 = 0; r0 < P; r0 += W.chunk) {
+    const int64_t rows = std::min<int64_t>(W.chunk, P - r0);
+    const int m_tiles = int((rows + BM - 1) / BM);
+    CUtensorMap ta, tpm;
+    st = make_tmap(&ta, precision, cat, rows, kCat, kCat, BM);
+    if (st) return st;
+
+    {  // layer 1 (+ gate layer 1): raw points -> operand columns
+      const int grid = int(std::min<int64_t>((rows + 15) / 16, int64_t(dev.sms) * 16));
+      if (tf32)
+        point_embed_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context) + r0, rows, ew, cat, kCat);
+      else
+        point_embed_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context) + r0, rows, ew, cat, kCat);
+      LRN_CUDA(cudaGetLastError());
+    }
+    for (int k = 2; k <= 5; ++k) {  // conv2..conv5, each writes its own column block of the operand row
+      GemmParams p{};
+      const int bn = k == 2 ? 128 : 256;
+      p.M = int(rows);
+      p.m_tiles = m_tiles;
+      p.n_tiles = kChan[k] / bn;
+      p.kb_main = kChan[k - 1] / bk;
+      p.kb_gate = 0;
+      p.a_col0 = kCatOff[k - 1];
+      p.bias = reinterpret_cast<const float*>(pk + L.b[k]);
+      p.out = static_cast<uint8_t*>(cat) + size_t(kCatOff[k]) * es;
+      p.ldo = kCat;
+      p.out_f32 = tf32 ? 1 : 0;
+      p.relu = 1;
+      st = launch_gemm(precision, bn, EPI_ACT, ta, tw[k], p, dev.sms, s);
+      if (st) return st;
+    }
+    {  // fusion + gate + pooling
+      GemmParams p{};
+      p.M = int(rows);
+      p.m_tiles = m_tiles;
+      p.n_tiles = 1024 / 128;
+      p.kb_main = kFusionK / bk;
+      p.kb_gate = kGateK / bk;
+      p.a_col0 = 0;
+      p.bias_f = reinterpret_cast<const float*>(pk + L.bf);
+      p.bias_g = reinterpret_cast<const float*>(pk + L.bg);
+      p.row0 = r0;
+      p.npts = int(N);
+      p.inv_npts = 1.0f / float(N);
+      p.flags = ((flags & LRN_OUT_ARGMAX) ? (FUSE_ARGMAX | FUSE_POOL) : (flags & LRN_OUT_POOL) ? FUSE_POOL : 0) |
+                ((flags & LRN_OUT_FUSED) ? FUSE_STORE_CN : 0) | ((flags & LRN_OUT_MEMORY) ? FUSE_STORE_PM : 0);
+      p.global_feat = global_feat;
+      p.pool_key = keys;
+      p.fused_cn = fused;
+      p.fused_pm = fused_pm;
+      st = launch_gemm(precision, 128, EPI_FUSION, ta, twfg, p, dev.sms, s);
+      if (st) return st;
+    }
+    if (flags & LRN_OUT_MEMORY) {  // memory = fused * Wp^T + bp
+      st = make_tmap(&tpm, precision, fused_pm, rows, 1024, 1024, BM);
+      if (st) return st;
+      GemmParams p{};
+      p.M = int(rows);
+      p.m_tiles = m_tiles;
+      p.n_tiles = 1;
+      p.kb_main = 1024 / bk;
+      p.a_col0 = 0;
+      p.bias = reinterpret_cast<const float*>(pk + L.bp);
+      p.out = memory + r0 * 256;
+      p.ldo = 256;
+      p.out_f32 = 1;
+      p.relu = 0;
+      st = launch_gemm(precision, 256, EPI_ACT, tpm, twp, p, dev.sms, s);
+      if (st) return st;
+    }
+  }
+  if (flags & LRN_OUT_ARGMAX) {
+    const int grid = int(std::min<int64_t>((B * 1024 + 255) / 256, 2048));
+    argmax_finalize_kernel<<<grid, 256, 0, s>>>(keys, B, global_feat, reinterpret_cast<long long*>(argmax));
+    LRN_CUDA(cudaGetLastError());
+  }
+  return LRN_OK;
+}
+
+int lrn_head_forward(const float* w1, const float* b1, const float* w2, const float* b2, const float* tgt,
+                     int64_t rows, float* current, const float* noisy, float* cum_out, lrn_stream_t stream) {
+  if (!w1 || !b1 || !w2 || !b2 || !tgt || !current || !noisy || !cum_out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (rows <= 0 || rows > (int64_t(1) << 31)) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld", (long long)rows);
+  if ((reinterpret_cast<uintptr_t>(tgt) & 15) || (reinterpret_cast<uintptr_t>(w1) & 15))
+    return fail(LRN_ERR_MISALIGNED, "tgt/w1 need 16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const int grid = int((rows + kHeadRows - 1) / kHeadRows);
+  head_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w1, b1, w2, b2, tgt, rows, current, noisy,
+                                                                         cum_out);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias,
+                      void* out, int64_t ldo, int out_f32, int relu, int64_t M, int64_t N, int64_t K,
+                      lrn_stream_t stream) {
+  if (bad_precision(precision) || !A || !Wt || !out) return fail(LRN_ERR_BAD_ARG, "null pointer or bad precision");
+  const size_t es = elem_size(precision);
+  const int bk = int(128 / es);
+  if (M <= 0 || N <= 0 || K <= 0 || K % bk || N % 128 || M >= (int64_t(1) << 31))
+    return fail(LRN_ERR_BAD_SHAPE, "M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  if (precision == LRN_PREC_TF32 && !out_f32) return fail(LRN_ERR_BAD_ARG, "tf32 tier writes fp32");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb;
+  st = make_tmap(&ta, precision, A, M, K, lda, BM);
+  if (st) return st;
+  st = make_tmap(&tb, precision, Wt, N, K, ldw, bn);
+  if (st) return st;
+  GemmParams p{};
+  p.M = int(M);
+  p.m_tiles = int((M + BM - 1) / BM);
+  p.n_tiles = int(N / bn);
+  p.kb_main = int(K / bk);
+  p.bias = bias;
+  p.out = out;
+  p.ldo = ldo;
+  p.out_f32 = out_f32;
+  p.relu = relu;
+  return launch_gemm(precision, bn, EPI_ACT, ta, tb, p, dev.sms, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""Host-side mirror of the reference's module interface (reference: src/model.py).
+
+Same class names, constructor arguments, parameter/buffer tree (205 state_dict keys, SURVEY.md
+appendix B) and forward signatures as the reference, so ``load_state_dict(strict=True)`` of a
+reference checkpoint works and ``train.py`` / ``inference*.py`` run unchanged with
+``from src.model import LineRefineNet`` resolved to this file (see compat/src/model.py).
+
+What runs where
+  * eval mode, CUDA tensors: the context encoder (+ pooling, + context_proj) and the regression
+    heads run in the hand-written sm_100a library through the C ABI (ops.py).  The DETR decoder,
+    point_mlp and pos_emb (SURVEY.md section 8f "next" rows) use stock PyTorch CUDA ops.
+  * train mode (batch-statistic BatchNorm, autograd): stock PyTorch ops on the same parameters;
+    the native backward is not part of this round (DESIGN.md "out of scope").
+  * CPU tensors: not supported -- there is no CPU path in the product (the oracle lives in oracle/).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+_DEFAULT_PRECISION = os.environ.get("LRN_PRECISION", "bf16")
+
+
+_warned_autograd = False
+
+
+def _use_native(module: nn.Module, *inputs) -> bool:
+    """The sm_100a kernels implement the eval-mode forward without autograd.  Train mode, or an
+    eval-mode call that autograd is recording, runs the stock-PyTorch formulation instead (and says
+    so once): inference scripts call ``model.eval()`` under ``torch.no_grad()`` (reference
+    inference_whole_scene.py:134-137) and always take the native path."""
+    global _warned_autograd
+    if module.training:
+        return False
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in inputs)
+                                    or any(p.requires_grad for p in module.parameters())):
+        if not _warned_autograd:
+            import warnings
+            warnings.warn("pointnet_refine_b200: eval-mode forward is being recorded by autograd; using the "
+                          "stock PyTorch formulation. Wrap inference in torch.no_grad() for the sm_100a path.")
+            _warned_autograd = True
+        return False
+    return True
+
+
+def _require_cuda(t: torch.Tensor, who: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{who}: the B200-native path has no CPU implementation; move the module and "
+                           f"its inputs to a CUDA device (sm_100a).")
+
+
+class MultiScalePointNetEncoder(nn.Module):
+    """Per-point shared MLP 4->64->128->256->512->1024, multi-scale fusion 1984->1024, intensity
+    gate, max+avg pooling.  Interface of reference src/model.py:5-62:
+    ``forward(x: (B,4,N)) -> (global_feat (B,2048), fused (B,1024,N))``."""
+
+    def __init__(self, in_channel=4, out_dim=1024):
+        super().__init__()
+        if in_channel != 4 or out_dim != 1024:
+            raise ValueError("the sm_100a kernels are specialised for in_channel=4, out_dim=1024 "
+                             "(the only configuration the reference instantiates, src/model.py:146)")
+        widths = (in_channel, 64, 128, 256, 512, out_dim)
+        for k in range(1, 6):
+            setattr(self, f"conv{k}", nn.Conv1d(widths[k - 1], widths[k], 1))
+        for k in range(1, 6):
+            setattr(self, f"bn{k}", nn.BatchNorm1d(widths[k]))
+        self.fusion = nn.Sequential(nn.Conv1d(sum(widths[1:]), out_dim, 1), nn.BatchNorm1d(out_dim), nn.ReLU())
+        self.intensity_gate = nn.Sequential(nn.Conv1d(1, 64, 1), nn.ReLU(), nn.Conv1d(64, out_dim, 1), nn.Sigmoid())
+        self.precision = _DEFAULT_PRECISION     # "bf16" | "tf32" (tensor-core operand tier)
+        self.chunk_rows = 0                     # 0 = library default
+        self._folded = None                     # (fingerprint, FoldedEncoder); never in the state_dict
+        self._proj = None                       # optional nn.Linear(1024,256) folded alongside (set by LineRefineNet)
+
+    # -- folded-weight cache -------------------------------------------------------------------
+    def _fingerprint(self):
+        ts = list(self.parameters()) + list(self.buffers())
+        if self._proj is not None:
+            ts += list(self._proj[0].parameters())
+        return (self.precision,) + tuple((t.data_ptr(), t._version) for t in ts)
+
+    def folded(self) -> ops.FoldedEncoder:
+        """BN-folded operand blob for the current parameters; re-folded whenever a parameter or
+        running statistic changes (optimizer step, load_state_dict, .to())."""
+        fp = self._fingerprint()
+        if self._folded is None or self._folded[0] != fp:
+            tensors = {k: v for k, v in self.state_dict().items() if v.is_floating_point()}
+            if self._proj is not None:
+                tensors["context_proj.weight"] = self._proj[0].weight
+                tensors["context_proj.bias"] = self._proj[0].bias
+            self._folded = (fp, ops.FoldedEncoder(tensors, self.precision, bn_eps=self.bn1.eps))
+        return self._folded[1]
+
+    # -- forward ---------------------------------------------------------------------------------
+    def run_native(self, context, **outputs):
+        """context (B,N,4) -> dict of requested outputs (see ops.encoder_forward)."""
+        _require_cuda(context, "MultiScalePointNetEncoder")
+        return ops.encoder_forward(self.folded(), context, chunk_rows=self.chunk_rows, **outputs)
+
+    def _forward_torch(self, x):
+        """Autograd-capable forward with stock PyTorch ops (batch-statistic BN in train mode)."""
+        feats, h = [], x
+        for k in range(1, 6):
+            h = F.relu(getattr(self, f"bn{k}")(getattr(self, f"conv{k}")(h)))
+            feats.append(h)
+        fused = self.fusion(torch.cat(feats, dim=1)) * (0.5 + 0.5 * self.intensity_gate(x[:, 3:4, :]))
+        return torch.cat([fused.max(dim=2)[0], fused.mean(dim=2)], dim=1), fused
+
+    def forward(self, x):
+        _require_cuda(x, "MultiScalePointNetEncoder")
+        if not _use_native(self, x):
+            return self._forward_torch(x)
+        out = self.run_native(x.transpose(2, 1), pool=True, fused=True)
+        return out["global_feat"], out["fused"]
+
+
+class PositionalEncoding(nn.Module):
+    """MLP positional encoding 3->256->256 (reference src/model.py:64-75)."""
+
+    def __init__(self, in_dim=3, out_dim=256):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(in_dim, out_dim), nn.ReLU(), nn.Linear(out_dim, out_dim))
+
+    def forward(self, xyz):
+        return self.mlp(xyz)
+
+
+class DetrTransformerDecoderLayer(nn.Module):
+    """Post-norm DETR decoder layer (reference src/model.py:77-135): self-attention over the line
+    queries, cross-attention into the context memory, FFN.  Stock PyTorch ops (section 8f row 1-2)."""
+
+    def __init__(self, d_model=256, nhead=8, dim_feedforward=1024, dropout=0.1):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout, batch_first=True)
+        self.cross_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout, batch_first=True)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1, self.norm2, self.norm3 = (nn.LayerNorm(d_model) for _ in range(3))
+        self.dropout1, self.dropout2, self.dropout3 = (nn.Dropout(dropout) for _ in range(3))
+        self.activation = F.relu
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos
+
+    def forward(self, tgt, memory, query_pos=None, pos=None):
+        q = self.with_pos_embed(tgt, query_pos)
+        tgt = self.norm1(tgt + self.dropout1(self.self_attn(q, q, value=tgt, need_weights=False)[0]))
+        attn = self.cross_attn(self.with_pos_embed(tgt, query_pos), self.with_pos_embed(memory, pos), value=memory,
+                               need_weights=False)[0]
+        tgt = self.norm2(tgt + self.dropout2(attn))
+        ffn = self.linear2(self.dropout(self.activation(self.linear1(tgt))))
+        return self.norm3(tgt + self.dropout3(ffn))
+
+
+class LineRefineNet(nn.Module):
+    """Reference src/model.py:137-234.  forward(context (B,N,4), noisy_line (B,M,3)) -> (6,B,M,3)
+    cumulative offsets per decoder layer."""
+
+    def __init__(self, num_line_points=32, feature_dim=1024):
+        super().__init__()
+        self.d_model = 256
+        self.num_decoder_layers = 6
+        self.context_encoder = MultiScalePointNetEncoder(in_channel=4, out_dim=feature_dim)
+        self.context_proj = nn.Linear(feature_dim, self.d_model)
+        self.point_mlp = nn.Sequential(
+            nn.Conv1d(3, 64, 1), nn.BatchNorm1d(64), nn.ReLU(),
+            nn.Conv1d(64, 128, 1), nn.BatchNorm1d(128), nn.ReLU(),
+            nn.Conv1d(128, self.d_model, 1), nn.BatchNorm1d(self.d_model))
+        self.pos_emb = PositionalEncoding(in_dim=3, out_dim=self.d_model)
+        self.decoder_layers = nn.ModuleList(
+            [DetrTransformerDecoderLayer(self.d_model, 8, 1024) for _ in range(self.num_decoder_layers)])
+        self.reg_branches = nn.ModuleList(
+            [nn.Sequential(nn.Linear(self.d_model, 128), nn.ReLU(), nn.Linear(128, 3))
+             for _ in range(self.num_decoder_layers)])
+        # context_proj is folded into the encoder's operand blob (tuple hides it from the module tree)
+        self.context_encoder._proj = (self.context_proj,)
+        self.segment_chunk = 256   # segments per decoder pass in eval mode (bounds the (B,N,256) temporaries)
+
+    @property
+    def precision(self):
+        return self.context_encoder.precision
+
+    @precision.setter
+    def precision(self, value):
+        self.context_encoder.precision = value
+
+    def _refine(self, context, noisy_line, memory, native_heads):
+        pos_mem = self.pos_emb(context[:, :, :3])
+        tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
+        current = noisy_line.clone()
+        outs = []
+        for layer, head in zip(self.decoder_layers, self.reg_branches):
+            tgt = layer(tgt, memory, query_pos=self.pos_emb(current), pos=pos_mem)
+            if native_heads:
+                outs.append(ops.head_forward(head[0].weight, head[0].bias, head[2].weight, head[2].bias,
+                                             tgt, current, noisy_line))
+            else:
+                current = current + head(tgt)
+                outs.append(current - noisy_line)
+        return torch.stack(outs)
+
+    def forward(self, context, noisy_line):
+        _require_cuda(context, "LineRefineNet")
+        if not _use_native(self, context, noisy_line):
+            _, fused = self.context_encoder._forward_torch(context.transpose(2, 1))
+            memory = self.context_proj(fused.transpose(2, 1))
+            return self._refine(context, noisy_line, memory, native_heads=False)
+        outs = []
+        for s in range(0, context.shape[0], self.segment_chunk):
+            ctx = context[s:s + self.segment_chunk].contiguous()
+            line = noisy_line[s:s + self.segment_chunk].contiguous()
+            memory = self.context_encoder.run_native(ctx, pool=False, memory=True)["memory"]
+            outs.append(self._refine(ctx, line, memory, native_heads=True))
+        return torch.cat(outs, dim=1)

@@ -1,0 +1,165 @@
+"""Host-side operator wrappers: torch tensors in, C-ABI calls (raw device pointers + the current
+CUDA stream) out.  PyTorch is only the allocator / stream provider here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import OUT_ARGMAX, OUT_FUSED, OUT_MEMORY, OUT_POOL, PRECISIONS, lib
+
+DEFAULT_CHUNK_ROWS = 148 * 128 * 4   # keep in sync with kDefaultChunkRows (csrc/lrn_abi.cu)
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _aligned_bytes(nbytes: int, device, align: int = 1024):
+    """uint8 buffer whose data pointer is `align`-byte aligned."""
+    raw = torch.empty(nbytes + align, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % align
+    return raw[off:off + nbytes]
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError("expected a float32 CUDA tensor")
+    return t.contiguous()
+
+
+class FoldedEncoder:
+    """Device blob with the BN-folded, K-major operand matrices of one precision tier
+    (lrn_encoder_fold).  Keeps references to nothing: it is a snapshot of the parameters."""
+
+    def __init__(self, tensors: dict, precision: str, bn_eps: float = 1e-5):
+        """tensors: the reference state_dict entries of `context_encoder.*` (prefix stripped) and,
+        optionally, `context_proj.weight` / `context_proj.bias`; float32 CUDA tensors."""
+        self.precision = precision
+        self.prec_id = PRECISIONS[precision]
+        dev = tensors["conv1.weight"].device
+        self.device = dev
+        keep = []
+
+        def ptr(name):
+            t = _f32c(tensors[name].detach())
+            keep.append(t)
+            return t.data_ptr()
+
+        p = _lib.EncoderParams()
+        for k in range(5):
+            p.conv_w[k] = ptr(f"conv{k + 1}.weight")
+            p.conv_b[k] = ptr(f"conv{k + 1}.bias")
+            p.bn_w[k] = ptr(f"bn{k + 1}.weight")
+            p.bn_b[k] = ptr(f"bn{k + 1}.bias")
+            p.bn_mean[k] = ptr(f"bn{k + 1}.running_mean")
+            p.bn_var[k] = ptr(f"bn{k + 1}.running_var")
+        p.fusion_w, p.fusion_b = ptr("fusion.0.weight"), ptr("fusion.0.bias")
+        p.fusion_bn_w, p.fusion_bn_b = ptr("fusion.1.weight"), ptr("fusion.1.bias")
+        p.fusion_bn_mean, p.fusion_bn_var = ptr("fusion.1.running_mean"), ptr("fusion.1.running_var")
+        p.gate0_w, p.gate0_b = ptr("intensity_gate.0.weight"), ptr("intensity_gate.0.bias")
+        p.gate2_w, p.gate2_b = ptr("intensity_gate.2.weight"), ptr("intensity_gate.2.bias")
+        self.has_proj = "context_proj.weight" in tensors
+        if self.has_proj:
+            p.proj_w, p.proj_b = ptr("context_proj.weight"), ptr("context_proj.bias")
+        p.bn_eps = bn_eps
+        nbytes = lib.lrn_encoder_packed_bytes(self.prec_id)
+        self.blob = _aligned_bytes(nbytes, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.lrn_encoder_fold(C.byref(p), self.prec_id, self.blob.data_ptr(), nbytes, _stream_ptr(dev)),
+                       "lrn_encoder_fold")
+        _lib.launch_counter += 7 if self.has_proj else 6
+        del keep
+
+
+_workspaces: dict = {}
+
+
+def _workspace(nbytes: int, device):
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces[key] = ws = _aligned_bytes(nbytes, device)
+    return ws
+
+
+def encoder_forward(folded: FoldedEncoder, context: torch.Tensor, *, pool=True, argmax=False, fused=False,
+                    memory=False, chunk_rows: int = 0):
+    """Run the fused encoder on context (B, N, 4) float32 CUDA.  Returns a dict with the requested
+    outputs: global_feat (B,2048), argmax (B,1024) int64, fused (B,1024,N), memory (B,N,256)."""
+    if context.dim() != 3 or context.shape[-1] != 4:
+        raise ValueError(f"context must be (B, N, 4), got {tuple(context.shape)}")
+    context = _f32c(context)
+    B, N, _ = context.shape
+    if B == 0 or N == 0:
+        raise ValueError("empty context (the reference's torch.max over an empty dimension raises too)")
+    dev = context.device
+    flags = (OUT_POOL if pool else 0) | (OUT_ARGMAX if argmax else 0) | (OUT_FUSED if fused else 0) | \
+            (OUT_MEMORY if memory else 0)
+    if memory and not folded.has_proj:
+        raise ValueError("memory output needs context_proj weights in the folded blob")
+    out = {}
+    gf = fz = am = mem = None
+    if pool or argmax:
+        out["global_feat"] = gf = torch.empty(B, 2048, dtype=torch.float32, device=dev)
+    if argmax:
+        out["argmax"] = am = torch.empty(B, 1024, dtype=torch.int64, device=dev)
+    if fused:
+        out["fused"] = fz = torch.empty(B, 1024, N, dtype=torch.float32, device=dev)
+    if memory:
+        out["memory"] = mem = torch.empty(B, N, 256, dtype=torch.float32, device=dev)
+    nbytes = lib.lrn_encoder_workspace_bytes(B, N, folded.prec_id, flags, chunk_rows)
+    ws = _workspace(nbytes, dev)
+    dp = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.lrn_encoder_forward(folded.blob.data_ptr(), folded.prec_id, context.data_ptr(), B, N, flags,
+                                           dp(gf), dp(fz), dp(am), dp(mem), chunk_rows, ws.data_ptr(), ws.numel(),
+                                           _stream_ptr(dev)), "lrn_encoder_forward")
+    _lib.launch_counter += encoder_launches(B * N, flags, chunk_rows)
+    return out
+
+
+def encoder_launches(P: int, flags: int, chunk_rows: int = 0) -> int:
+    """Kernels lrn_encoder_forward enqueues for P points (mirrors the chunk loop in csrc/lrn_abi.cu)."""
+    al = lambda v: (v + 127) // 128 * 128
+    chunk = min(al(max(chunk_rows or DEFAULT_CHUNK_ROWS, 128)), al(P))
+    chunks = (P + chunk - 1) // chunk
+    per_chunk = 1 + 4 + 1 + (1 if flags & OUT_MEMORY else 0)
+    return chunks * per_chunk + (1 if flags & OUT_ARGMAX else 0)
+
+
+def head_forward(w1, b1, w2, b2, tgt, current, noisy):
+    """reg_branches[i] + cumulative-offset update (lrn_head_forward).  `current` (B,M,3) is updated
+    in place; returns the cumulative offset (B,M,3)."""
+    tgt = _f32c(tgt)
+    rows = tgt.numel() // 256
+    cum = torch.empty_like(current)
+    dev = tgt.device
+    with torch.cuda.device(dev):
+        _lib.check(lib.lrn_head_forward(_f32c(w1).data_ptr(), _f32c(b1).data_ptr(), _f32c(w2).data_ptr(),
+                                        _f32c(b2).data_ptr(), tgt.data_ptr(), rows, current.data_ptr(),
+                                        _f32c(noisy).data_ptr(), cum.data_ptr(), _stream_ptr(dev)),
+                   "lrn_head_forward")
+    _lib.launch_counter += 1
+    return cum
+
+
+def gemm_bias_act(a: torch.Tensor, w: torch.Tensor, bias, *, relu=False, out_dtype=None):
+    """out = act(a @ w.T + bias) on the tcgen05 path.  a (M,K), w (N,K): both bfloat16 (bf16 tier) or
+    both float32 (tf32 tier)."""
+    if a.dtype != w.dtype or a.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("a and w must both be bfloat16 or float32")
+    prec = _lib.PREC_BF16 if a.dtype == torch.bfloat16 else _lib.PREC_TF32
+    a, w = a.contiguous(), w.contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    out_dtype = out_dtype or (torch.float32 if prec == _lib.PREC_TF32 else torch.bfloat16)
+    out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    b = bias.contiguous().float() if bias is not None else None
+    with torch.cuda.device(a.device):
+        _lib.check(lib.lrn_gemm_bias_act(prec, a.data_ptr(), K, w.data_ptr(), K, b.data_ptr() if b is not None else None,
+                                         out.data_ptr(), N, int(out_dtype == torch.float32), int(relu), M, N, K,
+                                         _stream_ptr(a.device)), "lrn_gemm_bias_act")
+    _lib.launch_counter += 1
+    return out
