@@ -126,6 +126,24 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
 int lrn_head_forward(const float* w1, const float* b1, const float* w2, const float* b2, const float* tgt,
                      int64_t rows, float* current, const float* noisy, float* cum_out, lrn_stream_t stream);
 
+/* ---- optional per-stage device timing (bench.py's roofline line) ----
+ * New; nothing in the reference corresponds.  While enabled, lrn_encoder_forward brackets every
+ * kernel it enqueues with cudaEvents on the caller's stream (events are owned by the library).
+ * lrn_profile_read waits for the recorded events, returns the summed milliseconds and launch
+ * counts per stage since the previous read, and resets.  Not thread-safe; off by default. */
+enum lrn_stage {
+  LRN_STAGE_EMBED = 0, /* conv1 + gate layer 1 (fp32 FMA, HBM-bound)  src/model.py:43,33-34 */
+  LRN_STAGE_CONV2 = 1, /* src/model.py:44 */
+  LRN_STAGE_CONV3 = 2, /* src/model.py:45 */
+  LRN_STAGE_CONV4 = 3, /* src/model.py:46 */
+  LRN_STAGE_CONV5 = 4, /* src/model.py:47 */
+  LRN_STAGE_FUSION = 5,/* fusion conv + gate layer 2 + gating + pooling  src/model.py:50-60 */
+  LRN_STAGE_PROJ = 6,  /* context_proj  src/model.py:194 */
+  LRN_STAGE_COUNT = 7
+};
+int lrn_profile_enable(int on);
+int lrn_profile_read(float* ms_per_stage /*[LRN_STAGE_COUNT]*/, int64_t* launches_per_stage /*[LRN_STAGE_COUNT]*/);
+
 /* ---- building block, exported for unit tests and profiling ----
  * out[M,N] = act(A[M,K] * W[N,K]^T + bias) on the tcgen05 tensor-core path.
  *   precision BF16: A, W bfloat16, out bfloat16 (out_f32 = 0) or fp32 (out_f32 = 1)

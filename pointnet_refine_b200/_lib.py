@@ -1,22 +1,18 @@
 """ctypes binding of the C ABI in include/lrn_b200.h (in-tree liblrn_b200.so).
 
 There is no fallback: importing this module raises if the library has not been built
-(``python -c "import __graft_entry__ as g; g.build()"``), and every compute call raises
+(``python pointnet_refine_b200/build.py``), and every compute call raises
 ``RuntimeError`` on a non-zero status (e.g. LRN_ERR_UNSUPPORTED_ARCH off sm_100).
 """
 from __future__ import annotations
 
 import ctypes as C
 import os
-import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblrn_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "lrn_b200.h")
-
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
 
 # enums of include/lrn_b200.h
 LRN_OK = 0
@@ -27,8 +23,9 @@ PRECISIONS = {"bf16": PREC_BF16, "tf32": PREC_TF32}
 EXPORTS = [
     "lrn_abi_version", "lrn_status_string", "lrn_last_error", "lrn_device_check",
     "lrn_encoder_packed_bytes", "lrn_encoder_fold", "lrn_encoder_workspace_bytes", "lrn_encoder_forward",
-    "lrn_head_forward", "lrn_gemm_bias_act",
+    "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read",
 ]
+STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
 
 
 class EncoderParams(C.Structure):
@@ -41,24 +38,11 @@ class EncoderParams(C.Structure):
     )
 
 
-def build(verbose: bool = False) -> str:
-    """Compile csrc/lrn_abi.cu for sm_100a into the in-tree shared library (nvcc cross-compiles
-    without a GPU).  Rebuilds only when a source is newer than the library."""
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [HEADER]
-    if os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs):
-        return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "lrn_abi.cu")]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
-    return LIB_PATH
-
-
 def _load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"{LIB_PATH} is missing: the CUDA library must be built first "
-            "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU or PyTorch fallback.")
+            "(python pointnet_refine_b200/build.py).  There is no CPU or PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
     vp, i64, sz, ci = C.c_void_p, C.c_int64, C.c_size_t, C.c_int
     lib.lrn_abi_version.restype = ci
@@ -78,6 +62,10 @@ def _load():
     lib.lrn_head_forward.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]
     lib.lrn_gemm_bias_act.restype = ci
     lib.lrn_gemm_bias_act.argtypes = [ci, vp, i64, vp, i64, vp, vp, i64, ci, ci, i64, i64, i64, vp]
+    lib.lrn_profile_enable.restype = ci
+    lib.lrn_profile_enable.argtypes = [ci]
+    lib.lrn_profile_read.restype = ci
+    lib.lrn_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     if lib.lrn_abi_version() != 1:
         raise RuntimeError("liblrn_b200.so ABI version mismatch; rebuild it")
     return lib

@@ -44,6 +44,7 @@ struct GemmParams {
   long long ldo;  // elements
   int out_f32;
   int relu;
+  int round_tf32;  // fp32 output is a TF32 operand of the next layer: round to nearest instead of truncating later
   // EPI_FUSION
   const float* bias_f;
   const float* bias_g;
@@ -124,11 +125,19 @@ __device__ __forceinline__ void pool_chunk(const float (&v)[32], bool mask, long
 }
 
 template <bool TF32>
-__device__ __forceinline__ void store_row_chunk(void* out, long long elem_off, const float (&v)[32], bool as_f32) {
+__device__ __forceinline__ void store_row_chunk(void* out, long long elem_off, const float (&v)[32], bool as_f32,
+                                                bool rna_tf32) {
   if (TF32 || as_f32) {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + elem_off);
+    if (rna_tf32) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      for (int q = 0; q < 8; ++q)
+        dst[q] = make_float4(ptx::round_tf32(v[4 * q]), ptx::round_tf32(v[4 * q + 1]), ptx::round_tf32(v[4 * q + 2]),
+                             ptx::round_tf32(v[4 * q + 3]));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
   } else {
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + elem_off);
 #pragma unroll
@@ -273,7 +282,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             v[j] = p.relu ? fmaxf(x, 0.f) : x;
           }
           if (valid)
-            store_row_chunk<TF32>(p.out, static_cast<long long>(row) * p.ldo + n_blk * BN + c0, v, p.out_f32 != 0);
+            store_row_chunk<TF32>(p.out, static_cast<long long>(row) * p.ldo + n_blk * BN + c0, v, p.out_f32 != 0,
+                                  p.round_tf32 != 0);
         }
       } else {
         const long long grow = p.row0 + row;
@@ -309,7 +319,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.npts] = v[j];
           }
           if ((p.flags & FUSE_STORE_PM) && valid)
-            store_row_chunk<TF32>(p.fused_pm, static_cast<long long>(row) * 1024 + ch0, v, false);
+            store_row_chunk<TF32>(p.fused_pm, static_cast<long long>(row) * 1024 + ch0, v, false, TF32);
           if (p.flags & (FUSE_POOL | FUSE_ARGMAX)) {
             if (uniform) {
               pool_chunk(v, true, seg_lo, n_in_seg, ch0, lane, p);

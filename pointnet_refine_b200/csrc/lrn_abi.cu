@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "gemm_sm100.cuh"
 #include "pointwise.cuh"
@@ -176,18 +177,46 @@ int launch_gemm(int precision, int bn, int epi, const CUtensorMap& ta, const CUt
 
 int fold_one(int precision, const float* w, const float* b, const float* g, const float* beta, const float* mean,
              const float* var, float eps, int cout, int cin, void* out_w, int64_t ld, int col0, float* out_b,
-             cudaStream_t stream) {
+             cudaStream_t stream, bool operand = true) {
   const long long total = static_cast<long long>(cout) * cin;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
   if (precision == LRN_PREC_TF32)
     fold_linear_kernel<float><<<grid, 256, 0, stream>>>(w, b, g, beta, mean, var, eps, cout, cin,
-                                                        static_cast<float*>(out_w), ld, col0, out_b);
+                                                        static_cast<float*>(out_w), ld, col0, out_b, operand ? 1 : 0);
   else
     fold_linear_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, b, g, beta, mean, var, eps, cout, cin,
-                                                                static_cast<__nv_bfloat16*>(out_w), ld, col0, out_b);
+                                                                static_cast<__nv_bfloat16*>(out_w), ld, col0, out_b, 0);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
+
+// ------------------------------------------------------------------ optional per-stage timing
+struct StageProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // begin/end pairs
+  std::vector<int> stage;        // stage id of each pair
+  std::vector<cudaEvent_t> pool; // recycled events
+};
+StageProfile g_prof;
+
+struct StageTimer {  // RAII: brackets the kernels of one stage with events when profiling is on
+  cudaStream_t s;
+  cudaEvent_t e1 = nullptr;
+  StageTimer(int stage, cudaStream_t stream) : s(stream) {
+    if (!g_prof.on) return;
+    cudaEvent_t e[2];
+    for (auto& x : e) {
+      if (!g_prof.pool.empty()) { x = g_prof.pool.back(); g_prof.pool.pop_back(); }
+      else if (cudaEventCreate(&x) != cudaSuccess) return;
+    }
+    cudaEventRecord(e[0], s);
+    g_prof.ev.push_back(e[0]);
+    g_prof.ev.push_back(e[1]);
+    g_prof.stage.push_back(stage);
+    e1 = e[1];
+  }
+  ~StageTimer() { if (e1) cudaEventRecord(e1, s); }
+};
 
 bool bad_precision(int p) { return p != LRN_PREC_BF16 && p != LRN_PREC_TF32; }
 
@@ -265,7 +294,7 @@ int lrn_encoder_fold(const lrn_encoder_params* pr, int precision, void* packed, 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // conv1 stays fp32 (FMA kernel); gate layer 1 is copied as is
   st = fold_one(LRN_PREC_TF32, pr->conv_w[0], pr->conv_b[0], pr->bn_w[0], pr->bn_b[0], pr->bn_mean[0], pr->bn_var[0],
-                pr->bn_eps, 64, 4, base + L.w1, 4, 0, reinterpret_cast<float*>(base + L.b1), s);
+                pr->bn_eps, 64, 4, base + L.w1, 4, 0, reinterpret_cast<float*>(base + L.b1), s, /*operand=*/false);
   if (st) return st;
   LRN_CUDA(cudaMemcpyAsync(base + L.wg1, pr->gate0_w, 64 * 4, cudaMemcpyDeviceToDevice, s));
   LRN_CUDA(cudaMemcpyAsync(base + L.bg1, pr->gate0_b, 64 * 4, cudaMemcpyDeviceToDevice, s));
@@ -357,6 +386,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     if (st) return st;
 
     {  // layer 1 (+ gate layer 1): raw points -> operand columns
+      StageTimer timer(LRN_STAGE_EMBED, s);
       const int grid = int(std::min<int64_t>((rows + 15) / 16, int64_t(dev.sms) * 16));
       if (tf32)
         point_embed_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context) + r0, rows, ew, cat, kCat);
@@ -378,6 +408,8 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.ldo = kCat;
       p.out_f32 = tf32 ? 1 : 0;
       p.relu = 1;
+      p.round_tf32 = tf32 ? 1 : 0;
+      StageTimer timer(LRN_STAGE_CONV2 + (k - 2), s);
       st = launch_gemm(precision, bn, EPI_ACT, ta, tw[k], p, dev.sms, s);
       if (st) return st;
     }
@@ -400,6 +432,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.pool_key = keys;
       p.fused_cn = fused;
       p.fused_pm = fused_pm;
+      StageTimer timer(LRN_STAGE_FUSION, s);
       st = launch_gemm(precision, 128, EPI_FUSION, ta, twfg, p, dev.sms, s);
       if (st) return st;
     }
@@ -417,6 +450,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.ldo = 256;
       p.out_f32 = 1;
       p.relu = 0;
+      StageTimer timer(LRN_STAGE_PROJ, s);
       st = launch_gemm(precision, 256, EPI_ACT, tpm, twp, p, dev.sms, s);
       if (st) return st;
     }
@@ -426,6 +460,29 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     argmax_finalize_kernel<<<grid, 256, 0, s>>>(keys, B, global_feat, reinterpret_cast<long long*>(argmax));
     LRN_CUDA(cudaGetLastError());
   }
+  return LRN_OK;
+}
+
+int lrn_profile_enable(int on) {
+  g_prof.on = on != 0;
+  return LRN_OK;
+}
+
+int lrn_profile_read(float* ms_per_stage, int64_t* launches_per_stage) {
+  if (!ms_per_stage || !launches_per_stage) return fail(LRN_ERR_BAD_ARG, "null output");
+  for (int i = 0; i < LRN_STAGE_COUNT; ++i) { ms_per_stage[i] = 0.f; launches_per_stage[i] = 0; }
+  for (size_t i = 0; i < g_prof.stage.size(); ++i) {
+    cudaEvent_t a = g_prof.ev[2 * i], b = g_prof.ev[2 * i + 1];
+    LRN_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    LRN_CUDA(cudaEventElapsedTime(&ms, a, b));
+    ms_per_stage[g_prof.stage[i]] += ms;
+    launches_per_stage[g_prof.stage[i]] += 1;
+    g_prof.pool.push_back(a);
+    g_prof.pool.push_back(b);
+  }
+  g_prof.ev.clear();
+  g_prof.stage.clear();
   return LRN_OK;
 }
 

@@ -16,7 +16,7 @@ __global__ void fold_linear_kernel(const float* __restrict__ w, const float* __r
                                    const float* __restrict__ g, const float* __restrict__ beta,
                                    const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout,
                                    int cin, OutT* __restrict__ out_w, long long ld, int col0,
-                                   float* __restrict__ out_b) {
+                                   float* __restrict__ out_b, int rna_tf32) {
   const long long total = static_cast<long long>(cout) * cin;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -27,7 +27,7 @@ __global__ void fold_linear_kernel(const float* __restrict__ w, const float* __r
     if constexpr (sizeof(OutT) == 2) {
       out_w[co * ld + col0 + ci] = __float2bfloat16_rn(v);
     } else {
-      out_w[co * ld + col0 + ci] = v;
+      out_w[co * ld + col0 + ci] = rna_tf32 ? ptx::round_tf32(v) : v;
     }
     if (ci == 0 && out_b) {
       out_b[co] = g ? (b[co] - mean[co]) * s + beta[co] : b[co];
@@ -73,8 +73,10 @@ __global__ void __launch_bounds__(256) point_embed_kernel(const float4* __restri
     }
     if constexpr (TF32) {
       float* row = reinterpret_cast<float*>(cat) + pt * ld;
-      *reinterpret_cast<float4*>(row + 4 * sub) = make_float4(f[0], f[1], f[2], f[3]);
-      *reinterpret_cast<float4*>(row + 1984 + 4 * sub) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(row + 4 * sub) =
+          make_float4(ptx::round_tf32(f[0]), ptx::round_tf32(f[1]), ptx::round_tf32(f[2]), ptx::round_tf32(f[3]));
+      *reinterpret_cast<float4*>(row + 1984 + 4 * sub) =
+          make_float4(ptx::round_tf32(h[0]), ptx::round_tf32(h[1]), ptx::round_tf32(h[2]), ptx::round_tf32(h[3]));
     } else {
       uint16_t* row = reinterpret_cast<uint16_t*>(cat) + pt * ld;
       *reinterpret_cast<uint2*>(row + 4 * sub) = make_uint2(ptx::pack_bf16x2(f[0], f[1]), ptx::pack_bf16x2(f[2], f[3]));

@@ -162,5 +162,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// fp32 -> TF32 with round-to-nearest (the tensor core itself just drops the low 13 mantissa bits).
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 }  // namespace ptx
 }  // namespace lrn

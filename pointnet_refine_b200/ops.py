@@ -163,3 +163,15 @@ def gemm_bias_act(a: torch.Tensor, w: torch.Tensor, bias, *, relu=False, out_dty
                                          _stream_ptr(a.device)), "lrn_gemm_bias_act")
     _lib.launch_counter += 1
     return out
+
+
+def profile_enable(on: bool) -> None:
+    _lib.check(lib.lrn_profile_enable(int(on)), "lrn_profile_enable")
+
+
+def profile_read() -> dict:
+    """{stage: (milliseconds, launches)} accumulated since the previous read (syncs on the events)."""
+    ms = (C.c_float * len(_lib.STAGES))()
+    n = (C.c_int64 * len(_lib.STAGES))()
+    _lib.check(lib.lrn_profile_read(ms, n), "lrn_profile_read")
+    return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(_lib.STAGES)}

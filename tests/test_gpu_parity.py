@@ -1,0 +1,227 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI
+(pointnet_refine_b200.ops -> liblrn_b200.so); the numpy oracle and the committed golden fixtures
+(generated from the unmodified reference, oracle/make_golden.py) are the checkers.
+
+Tolerances (north_star): TF32 tier max-abs 1e-3; bf16 tier 1e-2 relative to the output range.
+argmax is compared where the reference's top-2 gap exceeds the tier's value tolerance (bit-exact
+argmax is not attainable with reduced-precision operands)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import lrn_oracle as orc  # noqa: E402
+from oracle import synth  # noqa: E402
+from tests.golden_util import EVAL_CASES, load_case  # noqa: E402
+
+TIERS = {"bf16": 1e-2, "tf32": 1e-3}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cudnn.allow_tf32 = False       # keep the stock-PyTorch decoder in true fp32 for parity
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _model(sd, dev, prec):
+    import pointnet_refine_b200 as prb
+    m = prb.LineRefineNet().to(dev).eval()
+    m.load_state_dict(synth.to_torch(sd), strict=True)
+    m.precision = prec
+    return m
+
+
+# ------------------------------------------------------------------ building block
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 128, 128), (1000, 256, 512), (5000, 1024, 512), (129, 512, 256)])
+def test_gemm_bf16_matches_fp64(dev, M, N, K):
+    from pointnet_refine_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device=dev, generator=g)
+    out = ops.gemm_bias_act(a, w, b, relu=True, out_dtype=torch.float32)
+    ref = (a.double() @ w.double().T + b.double()).clamp_min(0)
+    assert (out.double() - ref).abs().max().item() <= 2e-5          # exact products, fp32 accumulation order only
+    out16 = ops.gemm_bias_act(a, w, b, relu=False, out_dtype=torch.bfloat16)
+    ref16 = a.double() @ w.double().T + b.double()
+    assert (out16.double() - ref16).abs().max().item() <= 2.0 ** -8 * ref16.abs().max().item() + 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (1000, 256, 512), (4097, 1024, 96)])
+def test_gemm_tf32_matches_fp64(dev, M, N, K):
+    from pointnet_refine_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = torch.from_numpy(orc.round_tf32(torch.randn(M, K, generator=torch.Generator().manual_seed(1)).numpy())).to(dev)
+    w = torch.from_numpy(orc.round_tf32((torch.randn(N, K, generator=torch.Generator().manual_seed(2)) / K ** 0.5).numpy())).to(dev)
+    b = torch.randn(N, device=dev, generator=g)
+    out = ops.gemm_bias_act(a, w, b, relu=False)
+    ref = a.double() @ w.double().T + b.double()
+    assert (out.double() - ref).abs().max().item() <= 2e-5          # operands already TF32-exact
+
+
+# ------------------------------------------------------------------ encoder vs reference fixtures
+@pytest.mark.parametrize("prec", list(TIERS))
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_encoder_matches_reference_golden(dev, name, prec):
+    g, sd, ctx, line, (sc, sn) = load_case(name)
+    m = _model(sd, dev, prec)
+    with torch.no_grad():
+        out = m.context_encoder.run_native(torch.from_numpy(ctx).to(dev), pool=True, argmax=True, fused=True, memory=True)
+    gf, fused = out["global_feat"].cpu().numpy(), out["fused"].cpu().numpy()
+    arg, mem = out["argmax"].cpu().numpy(), out["memory"].cpu().numpy()
+    rng = max(1.0, float(np.abs(g["global_feat"]).max()))
+    tol = TIERS[prec] * rng
+    assert np.abs(gf - g["global_feat"]).max() <= tol
+    assert np.abs(fused[:, ::sc, ::sn] - g["fused_sub"]).max() <= tol
+    B, N = ctx.shape[:2]
+    assert np.abs(fused.astype(np.float64).sum(2) - g["fused_csum"]).max() <= tol * N
+    assert np.abs(fused.astype(np.float64).sum(1) - g["fused_psum"]).max() <= tol * 1024
+    mrng = max(1.0, float(np.abs(g["memory_sub"]).max()))
+    assert np.abs(mem[:, ::sn, ::sc] - g["memory_sub"]).max() <= TIERS[prec] * mrng
+    # pooled outputs are consistent with the stored per-point map, exactly for max (same values reduced)
+    assert np.array_equal(gf[:, :1024], fused.max(axis=2))
+    np.testing.assert_allclose(gf[:, 1024:], fused.mean(axis=2, dtype=np.float64), rtol=0, atol=2e-6 * rng)
+    assert np.array_equal(arg, fused.argmax(axis=2))                 # first index on ties, like torch.max
+    safe = g["gap"] > 2 * tol                                        # reference argmax where it is unambiguous
+    if safe.any():
+        assert np.array_equal(arg[safe], g["argmax"][safe])
+
+
+@pytest.mark.parametrize("prec", list(TIERS))
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_full_forward_matches_reference_golden(dev, name, prec):
+    g, sd, ctx, line, _ = load_case(name)
+    m = _model(sd, dev, prec)
+    with torch.no_grad():
+        out = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev)).cpu().numpy()
+    assert out.shape == g["out"].shape == (6, ctx.shape[0], 32, 3)
+    rng = max(1.0, float(np.abs(g["out"]).max()))
+    assert np.abs(out - g["out"]).max() <= (5e-2 if prec == "bf16" else 5e-3) * rng
+
+
+def test_module_encoder_interface(dev):
+    """forward(x (B,4,N)) -> (global_feat, fused (B,1024,N)) like reference src/model.py:39-62."""
+    g, sd, ctx, _, _ = load_case("b3_n1000_ragged")
+    m = _model(sd, dev, "tf32")
+    with torch.no_grad():
+        gf, fused = m.context_encoder(torch.from_numpy(ctx).to(dev).transpose(2, 1))
+    assert gf.shape == (3, 2048) and fused.shape == (3, 1024, 1000)
+    assert (gf.cpu().numpy() - g["global_feat"]).__abs__().max() <= 1e-3 * max(1.0, np.abs(g["global_feat"]).max())
+
+
+def test_heads_match_oracle(dev):
+    from pointnet_refine_b200 import ops
+    sd = synth.make_state_dict(3)
+    rs = np.random.default_rng(5)
+    for rows in (1, 31, 64, 1000):
+        tgt = rs.standard_normal((rows, 256)).astype(np.float32)
+        cur = rs.standard_normal((rows, 3)).astype(np.float32)
+        noisy = rs.standard_normal((rows, 3)).astype(np.float32)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in sd.items() if k.startswith("reg_branches.2.")}
+        cur_d = torch.from_numpy(cur).to(dev)
+        cum = ops.head_forward(t["reg_branches.2.0.weight"], t["reg_branches.2.0.bias"], t["reg_branches.2.2.weight"],
+                               t["reg_branches.2.2.bias"], torch.from_numpy(tgt).to(dev), cur_d,
+                               torch.from_numpy(noisy).to(dev))
+        delta = orc.head_forward(sd, 2, tgt, np.float64)
+        np.testing.assert_allclose(cur_d.cpu().numpy(), cur + delta, rtol=0, atol=2e-5)
+        np.testing.assert_allclose(cum.cpu().numpy(), cur + delta - noisy, rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------------ live oracle, odd shapes
+@pytest.mark.parametrize("B,N", [(1, 127), (1, 129), (7, 300), (4, 4096), (300, 3)])
+def test_encoder_vs_live_oracle(dev, B, N):
+    sd = synth.make_state_dict(11)
+    ctx, _ = synth.make_inputs(B, N, seed=77)
+    gf_o, fused_o, _ = orc.encoder_forward(sd, ctx)
+    rng = max(1.0, float(np.abs(gf_o).max()))
+    for prec, t in TIERS.items():
+        m = _model(sd, dev, prec)
+        with torch.no_grad():
+            out = m.context_encoder.run_native(torch.from_numpy(ctx).to(dev), pool=True, fused=True)
+        assert np.abs(out["global_feat"].cpu().numpy() - gf_o).max() <= t * rng
+        assert np.abs(out["fused"].cpu().numpy() - fused_o.transpose(0, 2, 1)).max() <= t * rng
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def test_properties_at_scale(dev):
+    """Chunk invariance, permutation invariance within a segment, segment independence and
+    determinism of the max-pool at a size the oracle cannot run (1024 x 4096 points)."""
+    sd = synth.make_state_dict(0)
+    m = _model(sd, dev, "bf16")
+    B, N = 1024, 4096
+    ctx = torch.randn(B, N, 4, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    enc = m.context_encoder
+    with torch.no_grad():
+        base = enc.run_native(ctx, pool=True, argmax=True)
+        enc.chunk_rows = 128 * 37 * 5                                  # waves that cut through segments
+        chunked = enc.run_native(ctx, pool=True, argmax=True)
+        enc.chunk_rows = 0
+        perm = torch.randperm(N, device=dev)
+        permuted = enc.run_native(ctx[:, perm].contiguous(), pool=True)
+        rev = enc.run_native(ctx.flip(0).contiguous(), pool=True)
+    gf = base["global_feat"]
+    assert torch.isfinite(gf).all() and (gf >= 0).all()
+    assert torch.equal(gf[:, :1024], chunked["global_feat"][:, :1024])           # max is order independent
+    assert torch.equal(base["argmax"], chunked["argmax"])
+    assert (gf[:, 1024:] - chunked["global_feat"][:, 1024:]).abs().max() <= 1e-5
+    assert torch.equal(gf[:, :1024], permuted["global_feat"][:, :1024])
+    assert (gf[:, 1024:] - permuted["global_feat"][:, 1024:]).abs().max() <= 1e-5
+    assert torch.equal(gf[:, :1024], rev["global_feat"].flip(0)[:, :1024])       # segments are independent
+    assert (gf[:, :1024] >= gf[:, 1024:]).all()                                  # max >= mean
+    # spot-check 2 segments against the oracle
+    o = orc.encoder_forward(sd, ctx[:2].cpu().numpy())[0]
+    assert np.abs(gf[:2].cpu().numpy() - o).max() <= 1e-2 * max(1.0, np.abs(o).max())
+
+
+def test_large_context_stress(dev):
+    """BASELINE.json configs[4] shape class: very long segments reduce across many tiles and waves."""
+    sd = synth.make_state_dict(0)
+    m = _model(sd, dev, "bf16")
+    B, N = 4, 65536
+    ctx = torch.randn(B, N, 4, device=dev, generator=torch.Generator(device=dev).manual_seed(6))
+    with torch.no_grad():
+        a = m.context_encoder.run_native(ctx, pool=True, argmax=True)
+        dup = m.context_encoder.run_native(torch.cat([ctx, ctx], dim=1), pool=True, argmax=True)
+    # duplicating every point leaves max, mean and (first-index) argmax unchanged
+    assert torch.equal(a["global_feat"][:, :1024], dup["global_feat"][:, :1024])
+    assert torch.equal(a["argmax"], dup["argmax"])
+    assert (a["global_feat"][:, 1024:] - dup["global_feat"][:, 1024:]).abs().max() <= 1e-5
+    o = orc.encoder_forward(sd, ctx[:1, :].cpu().numpy())[0]
+    assert np.abs(a["global_feat"][:1].cpu().numpy() - o).max() <= 1e-2 * max(1.0, np.abs(o).max())
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors_are_loud(dev):
+    from pointnet_refine_b200 import _lib, ops
+    sd = synth.make_state_dict(0)
+    m = _model(sd, dev, "bf16")
+    with pytest.raises(ValueError):
+        m.context_encoder.run_native(torch.zeros(0, 16, 4, device=dev))
+    with pytest.raises(ValueError):
+        m.context_encoder.run_native(torch.zeros(2, 16, 3, device=dev))
+    folded = m.context_encoder.folded()
+    st = _lib.lib.lrn_encoder_forward(folded.blob.data_ptr(), 0, None, 1, 16, 1, None, None, None, None, 0, None, 0, None)
+    assert st == 6 and b"null" in _lib.lib.lrn_last_error()
+    st = _lib.lib.lrn_encoder_forward(folded.blob.data_ptr(), 0, folded.blob.data_ptr(), 0, 16, 1, None, None, None, None,
+                                      0, folded.blob.data_ptr(), 0, None)
+    assert st == 1                                                   # empty input -> LRN_ERR_BAD_SHAPE
+    with pytest.raises(TypeError):
+        ops.gemm_bias_act(torch.zeros(8, 64, device=dev), torch.zeros(128, 64, device=dev).bfloat16(), None)
+
+
+def test_refold_after_parameter_update(dev):
+    sd = synth.make_state_dict(0)
+    m = _model(sd, dev, "tf32")
+    ctx = torch.from_numpy(synth.make_inputs(2, 256, seed=3)[0]).to(dev)
+    with torch.no_grad():
+        a = m.context_encoder.run_native(ctx, pool=True)["global_feat"].clone()
+        m.context_encoder.bn5.running_mean.add_(0.05)                # e.g. a training step / checkpoint load
+        b = m.context_encoder.run_native(ctx, pool=True)["global_feat"]
+    sd2 = dict(sd)
+    sd2["context_encoder.bn5.running_mean"] = sd["context_encoder.bn5.running_mean"] + np.float32(0.05)
+    o = orc.encoder_forward(sd2, ctx.cpu().numpy())[0]
+    assert not torch.equal(a, b)
+    assert np.abs(b.cpu().numpy() - o).max() <= 1e-3 * max(1.0, np.abs(o).max())

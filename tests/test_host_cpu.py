@@ -1,0 +1,100 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol the header
+declares, the host mirror is state_dict-compatible with the reference interface, argument errors
+are raised loudly, and the segment sharding used for N > 1 ranks is exact (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import pointnet_refine_b200 as prb
+from oracle import synth
+from pointnet_refine_b200 import _lib, ops, shard
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "lrn_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t|const char\*) (lrn_[a-z0-9_]+)\(", header, re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.lrn_abi_version() == 1
+    assert _lib.lib.lrn_status_string(3).decode().startswith("unsupported")
+    assert _lib.lib.lrn_encoder_packed_bytes(0) > 2 * 2_803_000 - 700      # bf16 blob holds all matrices
+    assert _lib.lib.lrn_encoder_packed_bytes(1) > _lib.lib.lrn_encoder_packed_bytes(0)
+    assert _lib.lib.lrn_encoder_packed_bytes(7) == 0
+    assert _lib.lib.lrn_encoder_workspace_bytes(0, 10, 0, 1, 0) == 0        # empty input has no workspace
+
+
+def test_state_dict_is_the_reference_tree():
+    m = prb.LineRefineNet()
+    sd = synth.make_state_dict(0)
+    msd = m.state_dict()
+    assert list(msd.keys()) == list(sd.keys()) and len(msd) == 205
+    for k, v in msd.items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+        assert (v.dtype == torch.int64) == (sd[k].dtype == np.int64), k
+    m.load_state_dict(synth.to_torch(sd), strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 9_695_954
+    # folded operands / workspaces are caches, never persistent state
+    assert not any("fold" in k or "blob" in k for k in msd)
+
+
+def test_cpu_tensors_fail_loudly():
+    m = prb.LineRefineNet().eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU implementation"):
+        m(torch.zeros(1, 8, 4), torch.zeros(1, 32, 3))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU implementation"):
+        m.context_encoder(torch.zeros(1, 4, 8))
+
+
+def test_launch_accounting_matches_chunk_loop():
+    P = 4096 * 4096
+    assert ops.encoder_launches(P, _lib.OUT_POOL) == -(-P // ops.DEFAULT_CHUNK_ROWS) * 6
+    assert ops.encoder_launches(1000, _lib.OUT_POOL | _lib.OUT_ARGMAX | _lib.OUT_MEMORY) == 7 + 1
+    assert ops.encoder_launches(300, _lib.OUT_POOL, chunk_rows=128) == 3 * 6
+
+
+def test_segment_shard_partitions_exactly():
+    for B in (1, 7, 8, 1000, 4096):
+        for world in (1, 2, 3, 8):
+            got = [i for r in range(world) for i in shard.segment_shard(B, r, world)]
+            assert got == list(range(B))
+    with pytest.raises(ValueError):
+        shard.segment_shard(4, 2, 2)
+
+
+def _worker(rank, world, port, B, q):
+    import torch.distributed as dist
+    from oracle import lrn_oracle as orc
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    sd = synth.make_state_dict(0)
+    ctx, _ = synth.make_inputs(B, 64, seed=99)
+    mine = shard.segment_shard(B, rank, world)
+    # the oracle stands in for the device compute here (CPU test of the host-side sharding only)
+    gf = orc.encoder_forward(sd, ctx[mine.start:mine.stop])[0] if len(mine) else np.zeros((0, 2048), np.float32)
+    full = shard.gather_segments(torch.from_numpy(gf), B)
+    if rank == 0:
+        q.put(full.numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_run_equals_unsharded_gloo_world2():
+    import torch.multiprocessing as mp
+    from oracle import lrn_oracle as orc
+    B, world, port = 5, 2, 29541
+    ctx_mp = mp.get_context("spawn")
+    q = ctx_mp.Queue()
+    procs = [ctx_mp.Process(target=_worker, args=(r, world, port, B, q)) for r in range(world)]
+    [p.start() for p in procs]
+    got = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    ctx, _ = synth.make_inputs(B, 64, seed=99)
+    want = orc.encoder_forward(synth.make_state_dict(0), ctx)[0]
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)

@@ -58,3 +58,18 @@ def test_known_answer_head_and_rounding_helpers():
     assert np.array_equal(orc.round_bf16(x).view(np.uint32) & 0xFFFF, np.zeros(4, np.uint32))
     assert np.abs(orc.round_bf16(x) - x).max() <= np.abs(x).max() * 2.0 ** -8
     assert np.abs(orc.round_tf32(x) - x).max() <= np.abs(x).max() * 2.0 ** -10
+
+
+@pytest.mark.parametrize("name", ["b2_n1024", "b3_n1000_ragged", "b2_n2048_realistic"])
+def test_torch_port_matches_reference(name):
+    """The torch-CPU port used as bench.py's cpu_baseline issues the reference's ops: same numbers."""
+    import torch
+    from oracle import synth, torch_port
+    g, sd, ctx, line, (sc, sn) = load_case(name)
+    tsd = synth.to_torch(sd)
+    with torch.no_grad():
+        gf, fused = torch_port.encoder_forward(tsd, torch.from_numpy(ctx).transpose(2, 1))
+        out = torch_port.line_refine_forward(tsd, torch.from_numpy(ctx), torch.from_numpy(line))
+    assert np.abs(gf.numpy() - g["global_feat"]).max() <= 1e-6 * max(1.0, float(np.abs(g["global_feat"]).max()))
+    assert np.abs(fused.numpy()[:, ::sc, ::sn] - g["fused_sub"]).max() <= 1e-6
+    assert np.abs(out.numpy() - g["out"]).max() <= 1e-5
