@@ -29,7 +29,8 @@ constexpr int kGemmThreads = 192;   // 6 warps
 constexpr int kTileRowBytes = 128;  // one swizzle row: 64 bf16 or 32 tf32 along K
 
 enum { EPI_ACT = 0, EPI_FUSION = 1 };
-enum { FUSE_POOL = 1, FUSE_ARGMAX = 2, FUSE_STORE_CN = 4, FUSE_STORE_PM = 8 };
+enum { FUSE_POOL = 1, FUSE_ARGMAX = 2, FUSE_STORE_CN = 4, FUSE_STORE_PM = 8,
+       FUSE_DBG_SKIP_A = 16, FUSE_DBG_SKIP_B = 32, FUSE_DBG_NO_TMA = 64, FUSE_DBG_NO_MMA = 128 };  // tuning experiments only (env LRN_DBG_SKIP, wrong results)
 
 struct GemmParams {
   int M;        // rows (points) covered by this launch
@@ -56,6 +57,7 @@ struct GemmParams {
   unsigned long long* pool_key;  // (B, 1024) packed (value bits << 32 | ~index) for argmax
   float* fused_cn;               // (B, 1024, N) fp32
   void* fused_pm;                // (M, 1024) operand type, rows local to this launch
+  long long* dbg;                // optional: clock64() stamps of cluster 0 (tools/timeline.py), normally null
 };
 
 template <int BN, int STAGES>
@@ -159,7 +161,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr uint32_t kIdesc = ptx::make_idesc(TF32, BM, BN);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the shared address space: LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* bar_empty = bar_full + STAGES;
   uint64_t* bar_tfull = bar_empty + STAGES;

@@ -8,12 +8,14 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <vector>
 
 #include "gemm_sm100.cuh"
+#include "gemm_pair_sm100.cuh"
 #include "pointwise.cuh"
 
 namespace {
@@ -161,14 +163,72 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   return LRN_OK;
 }
 
-int launch_gemm(int precision, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                int sms, cudaStream_t stream) {
+template <int BN, bool TF32, int EPI, int STAGES, bool GENERAL = true>
+int launch_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sms, cudaStream_t stream) {
+  using L = PairSmem<BN, STAGES, EPI == EPI_FUSION>;
+  auto kern = gemm_pair_kernel<BN, TF32, EPI, STAGES, GENERAL>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  if (tiles <= 0) return LRN_OK;
+  const int grid = 2 * std::min(tiles, sms / 2);  // one CTA pair (cluster of 2) per tile slot
+  kern<<<grid, kPairThreads, L::kDynamic, stream>>>(ta, tb, p);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+// How one GEMM is tiled: CTA pairs (cta_group::2, 256-row tiles) by default; LRN_GEMM_V1=1 in the
+// environment selects the single-CTA kernels (kept for A/B measurements).
+struct GemmPlan {
+  bool pair;
+  int bn;          // output channels per tile
+  int b_box_rows;  // weight rows per TMA box (= rows one CTA stages)
+  int m_rows;      // points per tile
+};
+
+GemmPlan plan_gemm(int64_t N, int epi) {
+  static const bool v1 = [] { const char* e = getenv("LRN_GEMM_V1"); return e && e[0] == '1'; }();
+  GemmPlan g{};
+  g.pair = !v1;
+  if (g.pair) {
+    g.bn = (epi == EPI_FUSION || N % 256 == 0) ? 256 : 128;
+    g.b_box_rows = g.bn / 2;
+    g.m_rows = 2 * BM;
+  } else {
+    g.bn = (epi == EPI_FUSION) ? 128 : (N % 256 == 0 ? 256 : 128);
+    g.b_box_rows = g.bn;
+    g.m_rows = BM;
+  }
+  return g;
+}
+
+int launch_gemm(int precision, const GemmPlan& g, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                const GemmParams& p, int sms, cudaStream_t stream) {
   const bool tf32 = precision == LRN_PREC_TF32;
+  if (g.pair) {
+    if (epi == EPI_FUSION) {
+      // fast variant: no argmax and every warp's 32 points are valid and inside one segment
+      const bool fast = !(p.flags & FUSE_ARGMAX) && p.npts % 32 == 0 && p.M % 32 == 0 && p.row0 % 32 == 0;
+      if (fast)
+        return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, false>(ta, tb, p, sms, stream)
+                    : launch_pair_t<256, false, EPI_FUSION, 5, false>(ta, tb, p, sms, stream);
+      return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, true>(ta, tb, p, sms, stream)
+                  : launch_pair_t<256, false, EPI_FUSION, 5, true>(ta, tb, p, sms, stream);
+    }
+    if (g.bn == 128)
+      return tf32 ? launch_pair_t<128, true, EPI_ACT, 8>(ta, tb, p, sms, stream)
+                  : launch_pair_t<128, false, EPI_ACT, 8>(ta, tb, p, sms, stream);
+    return tf32 ? launch_pair_t<256, true, EPI_ACT, 6>(ta, tb, p, sms, stream)
+                : launch_pair_t<256, false, EPI_ACT, 6>(ta, tb, p, sms, stream);
+  }
   if (epi == EPI_FUSION) {
     return tf32 ? launch_gemm_t<128, true, EPI_FUSION, 6>(ta, tb, p, sms, stream)
                 : launch_gemm_t<128, false, EPI_FUSION, 6>(ta, tb, p, sms, stream);
   }
-  if (bn == 128)
+  if (g.bn == 128)
     return tf32 ? launch_gemm_t<128, true, EPI_ACT, 6>(ta, tb, p, sms, stream)
                 : launch_gemm_t<128, false, EPI_ACT, 6>(ta, tb, p, sms, stream);
   return tf32 ? launch_gemm_t<256, true, EPI_ACT, 4>(ta, tb, p, sms, stream)
@@ -217,6 +277,8 @@ struct StageTimer {  // RAII: brackets the kernels of one stage with events when
   }
   ~StageTimer() { if (e1) cudaEventRecord(e1, s); }
 };
+
+long long* g_dbg = nullptr;  // lrn_debug_timeline: device buffer for clock64() stamps of the fusion kernel
 
 bool bad_precision(int p) { return p != LRN_PREC_BF16 && p != LRN_PREC_TF32; }
 
@@ -364,14 +426,17 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
 
   // weight tensor maps (B operands)
   CUtensorMap tw[6], twfg, twp;
+  GemmPlan plan[6];
   for (int k = 2; k <= 5; ++k) {
-    st = make_tmap(&tw[k], precision, pk + L.w[k], kChan[k], kChan[k - 1], kChan[k - 1], k == 2 ? 128 : 256);
+    plan[k] = plan_gemm(kChan[k], EPI_ACT);
+    st = make_tmap(&tw[k], precision, pk + L.w[k], kChan[k], kChan[k - 1], kChan[k - 1], plan[k].b_box_rows);
     if (st) return st;
   }
-  st = make_tmap(&twfg, precision, pk + L.wfg, 1024, kCat, kCat, 128);
+  const GemmPlan plan_f = plan_gemm(1024, EPI_FUSION), plan_p = plan_gemm(256, EPI_ACT);
+  st = make_tmap(&twfg, precision, pk + L.wfg, 1024, kCat, kCat, plan_f.b_box_rows);
   if (st) return st;
   if (flags & LRN_OUT_MEMORY) {
-    st = make_tmap(&twp, precision, pk + L.wp, 256, 1024, 1024, 256);
+    st = make_tmap(&twp, precision, pk + L.wp, 256, 1024, 1024, plan_p.b_box_rows);
     if (st) return st;
   }
 
@@ -380,7 +445,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
 
   for (int64_t r0 = 0; r0 < P; r0 += W.chunk) {
     const int64_t rows = std::min<int64_t>(W.chunk, P - r0);
-    const int m_tiles = int((rows + BM - 1) / BM);
+    auto m_tiles_of = [&](const GemmPlan& g) { return int((rows + g.m_rows - 1) / g.m_rows); };
     CUtensorMap ta, tpm;
     st = make_tmap(&ta, precision, cat, rows, kCat, kCat, BM);
     if (st) return st;
@@ -396,10 +461,9 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     }
     for (int k = 2; k <= 5; ++k) {  // conv2..conv5, each writes its own column block of the operand row
       GemmParams p{};
-      const int bn = k == 2 ? 128 : 256;
       p.M = int(rows);
-      p.m_tiles = m_tiles;
-      p.n_tiles = kChan[k] / bn;
+      p.m_tiles = m_tiles_of(plan[k]);
+      p.n_tiles = kChan[k] / plan[k].bn;
       p.kb_main = kChan[k - 1] / bk;
       p.kb_gate = 0;
       p.a_col0 = kCatOff[k - 1];
@@ -410,14 +474,14 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.relu = 1;
       p.round_tf32 = tf32 ? 1 : 0;
       StageTimer timer(LRN_STAGE_CONV2 + (k - 2), s);
-      st = launch_gemm(precision, bn, EPI_ACT, ta, tw[k], p, dev.sms, s);
+      st = launch_gemm(precision, plan[k], EPI_ACT, ta, tw[k], p, dev.sms, s);
       if (st) return st;
     }
     {  // fusion + gate + pooling
       GemmParams p{};
       p.M = int(rows);
-      p.m_tiles = m_tiles;
-      p.n_tiles = 1024 / 128;
+      p.m_tiles = m_tiles_of(plan_f);
+      p.n_tiles = 1024 / plan_f.bn;
       p.kb_main = kFusionK / bk;
       p.kb_gate = kGateK / bk;
       p.a_col0 = 0;
@@ -428,12 +492,15 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.inv_npts = 1.0f / float(N);
       p.flags = ((flags & LRN_OUT_ARGMAX) ? (FUSE_ARGMAX | FUSE_POOL) : (flags & LRN_OUT_POOL) ? FUSE_POOL : 0) |
                 ((flags & LRN_OUT_FUSED) ? FUSE_STORE_CN : 0) | ((flags & LRN_OUT_MEMORY) ? FUSE_STORE_PM : 0);
+      static const int dbg_skip = [] { const char* e = getenv("LRN_DBG_SKIP"); return e ? atoi(e) : 0; }();
+      p.flags |= (dbg_skip & 15) * FUSE_DBG_SKIP_A;  // tuning experiments only
       p.global_feat = global_feat;
       p.pool_key = keys;
       p.fused_cn = fused;
       p.fused_pm = fused_pm;
+      p.dbg = g_dbg;
       StageTimer timer(LRN_STAGE_FUSION, s);
-      st = launch_gemm(precision, 128, EPI_FUSION, ta, twfg, p, dev.sms, s);
+      st = launch_gemm(precision, plan_f, EPI_FUSION, ta, twfg, p, dev.sms, s);
       if (st) return st;
     }
     if (flags & LRN_OUT_MEMORY) {  // memory = fused * Wp^T + bp
@@ -441,8 +508,8 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       if (st) return st;
       GemmParams p{};
       p.M = int(rows);
-      p.m_tiles = m_tiles;
-      p.n_tiles = 1;
+      p.m_tiles = m_tiles_of(plan_p);
+      p.n_tiles = 256 / plan_p.bn;
       p.kb_main = 1024 / bk;
       p.a_col0 = 0;
       p.bias = reinterpret_cast<const float*>(pk + L.bp);
@@ -451,7 +518,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.out_f32 = 1;
       p.relu = 0;
       StageTimer timer(LRN_STAGE_PROJ, s);
-      st = launch_gemm(precision, 256, EPI_ACT, tpm, twp, p, dev.sms, s);
+      st = launch_gemm(precision, plan_p, EPI_ACT, tpm, twp, p, dev.sms, s);
       if (st) return st;
     }
   }
@@ -460,6 +527,11 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     argmax_finalize_kernel<<<grid, 256, 0, s>>>(keys, B, global_feat, reinterpret_cast<long long*>(argmax));
     LRN_CUDA(cudaGetLastError());
   }
+  return LRN_OK;
+}
+
+int lrn_debug_timeline(long long* device_buffer) {
+  g_dbg = device_buffer;
   return LRN_OK;
 }
 
@@ -514,23 +586,23 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt,
   DeviceInfo dev;
   int st = device_info(&dev);
   if (st) return st;
-  const int bn = (N % 256 == 0) ? 256 : 128;
+  const GemmPlan g = plan_gemm(N, EPI_ACT);
   CUtensorMap ta, tb;
   st = make_tmap(&ta, precision, A, M, K, lda, BM);
   if (st) return st;
-  st = make_tmap(&tb, precision, Wt, N, K, ldw, bn);
+  st = make_tmap(&tb, precision, Wt, N, K, ldw, g.b_box_rows);
   if (st) return st;
   GemmParams p{};
   p.M = int(M);
-  p.m_tiles = int((M + BM - 1) / BM);
-  p.n_tiles = int(N / bn);
+  p.m_tiles = int((M + g.m_rows - 1) / g.m_rows);
+  p.n_tiles = int(N / g.bn);
   p.kb_main = int(K / bk);
   p.bias = bias;
   p.out = out;
   p.ldo = ldo;
   p.out_f32 = out_f32;
   p.relu = relu;
-  return launch_gemm(precision, bn, EPI_ACT, ta, tb, p, dev.sms, reinterpret_cast<cudaStream_t>(stream));
+  return launch_gemm(precision, g, EPI_ACT, ta, tb, p, dev.sms, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,9 +1,10 @@
-set -x
+# usage: bash tools/prof_cmd.sh <tag> <skip> <count>   (ncu launch list + full capture of gemm kernels)
+TAG=${1:-r1b}; SKIP=${2:-33}; CNT=${3:-2}
 CMD="python bench.py --segments 74 --points 4096 --steps 2 --warmup 1 --no-cpu-baseline"
-$CMD > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
+$CMD > gpurun_out/plain_$TAG.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu1_$TAG.log 2>&1
 echo launches_exit=$?
-$CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 33 -c 2 -f -o gpurun_out/prof_r1 $CMD > gpurun_out/ncu2.log 2>&1
+$CMD > gpurun_out/plain2_$TAG.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:gemm -s $SKIP -c $CNT -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu2_$TAG.log 2>&1
 echo full_exit=$?
-tail -3 gpurun_out/plain.log; tail -5 gpurun_out/ncu2.log
+tail -2 gpurun_out/plain_$TAG.log | cut -c1-600

@@ -1,0 +1,25 @@
+"""clock64() timeline of the fusion kernel's first tiles on cluster 0 (tuning aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import pointnet_refine_b200 as prb
+from pointnet_refine_b200 import _lib
+from oracle import synth
+dev = torch.device("cuda:0")
+m = prb.LineRefineNet().to(dev).eval()
+m.load_state_dict(synth.to_torch(synth.make_state_dict(0)))
+m.precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+ctx = torch.randn(148, 4096, 4, device=dev)
+with torch.no_grad():
+    for _ in range(3): m.context_encoder.run_native(ctx, pool=True)
+    buf = torch.zeros(128, dtype=torch.int64, device=dev)
+    _lib.lib.lrn_debug_timeline(buf.data_ptr())
+    m.context_encoder.run_native(ctx, pool=True)
+    torch.cuda.synchronize()
+    _lib.lib.lrn_debug_timeline(None)
+t = buf.cpu().view(16, 8)
+t0 = int(t[0, 0])
+print("tile  acc_free  lastMMAissued | G_ready  gamma_done  F_ready  phaseB_done   (cycles since first tile start; last wave's stamps)")
+for i in range(16):
+    r = [int(x) - t0 for x in t[i, :6]]
+    print(f"{i:3d} {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} {r[5]:9d}   main={r[4]-r[2]:6d} phaseA={r[3]-r[2]:6d} phaseB={r[5]-r[4]:6d} tile={r[5]-r[0]:6d}")
