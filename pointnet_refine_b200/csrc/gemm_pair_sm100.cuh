@@ -28,7 +28,9 @@ constexpr int kPairEpiWarps = 8;
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;  // 320
 constexpr int kPoolRowStride = 36;                      // floats; 16-byte aligned rows, conflict-free both ways
 
-template <int BN, int STAGES, bool POOL>
+// STAGED: bf16 outputs leave through shared memory ([128 x 64] blocks in the 128-byte-swizzled layout TMA
+// and UMMA share) and one TMA store per block, instead of 16-byte pieces of 32 different rows per instruction.
+template <int BN, int STAGES, bool POOL, bool STAGED = false>
 struct PairSmem {
   static constexpr int kA = BM * kTileRowBytes;        // this CTA's 128 rows
   static constexpr int kB = (BN / 2) * kTileRowBytes;  // this CTA's half of the weight tile
@@ -38,7 +40,9 @@ struct PairSmem {
   static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 4) * 8;
   static constexpr int kBiasOff = kTmemPtrOff + 16;                                // float sbias[2][2 * BN]
   static constexpr int kPoolOff = (kBiasOff + 2 * 2 * BN * 4 + 15) / 16 * 16;      // per-warp 32 x 36 float scratch
-  static constexpr int kTotal = kPoolOff + (POOL ? kPairEpiWarps * 32 * kPoolRowStride * 4 : 0);
+  static constexpr int kStagingOff = (kPoolOff + (POOL ? kPairEpiWarps * 32 * kPoolRowStride * 4 : 0) + 1023) / 1024 * 1024;
+  static constexpr int kStagingBlock = BM * 128;  // 128 rows x 64 bf16
+  static constexpr int kTotal = kStagingOff + (STAGED ? (BN / 64) * kStagingBlock : 0);
   static constexpr int kDynamic = kTotal + 1024;
 };
 
@@ -85,10 +89,12 @@ __device__ __forceinline__ float gamma_hi(uint32_t q) { return __uint_as_float(0
 
 // GENERAL = false is the common fusion case (no argmax, every warp's 32 points valid and inside one
 // segment: N % 32 == 0); it drops the masked / 64-bit-key pooling paths and their registers.
-template <int BN, bool TF32, int EPI, int STAGES, bool GENERAL = true>
+template <int BN, bool TF32, int EPI, int STAGES, bool GENERAL = true, bool STAGED = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using L = PairSmem<BN, STAGES, EPI == EPI_FUSION>;
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
+  static_assert(!STAGED || (EPI == EPI_ACT && !TF32), "staged TMA stores are implemented for bf16 EPI_ACT outputs");
+  using L = PairSmem<BN, STAGES, EPI == EPI_FUSION, STAGED>;
   constexpr int BK = TF32 ? 32 : 64;
   constexpr int kMmaPerKb = 4;
   constexpr uint32_t kTmemCols = 2 * BN;
@@ -243,8 +249,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       if (EPI == EPI_ACT) {
         const int as = it & 1;
+        uint8_t* staging = smem + L::kStagingOff;
+        const bool issuer = (ew & 3) == 0 && lane == 0;  // one thread per column half issues the TMA stores
+        const bool stamp = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it < 16;
+        if (stamp) p.dbg[it * 8 + 2] = clock64();  // epilogue of this tile starts
+        if (STAGED) {
+          if (issuer) ptx::bulk_wait_read_all();  // the previous tile's stores have drained the staging blocks
+          ptx::named_bar_sync(2 + half, 128);
+        }
+        if (stamp) p.dbg[it * 8 + 3] = clock64();  // staging free
         ptx::mbar_wait(&bar_tfull[as], (it >> 1) & 1);
         ptx::tc_fence_after();
+        if (stamp) p.dbg[it * 8 + 4] = clock64();  // accumulator ready
         // software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
         uint32_t r[2][32];
         ptx::tmem_ld_32x32b_x32(t_lane + as * BN + col_lo, r[0]);
@@ -259,13 +275,38 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float x = __uint_as_float(r[i & 1][j]) + sb[c0 + j];
             v[j] = p.relu ? fmaxf(x, 0.f) : x;
           }
-          if (valid)
+          if (STAGED) {
+            // row r of block b: 128 bytes, 16-byte piece c lives at ((c ^ (r & 7)) << 4)  (128B swizzle)
+            const int rr = q * 32 + lane;
+            const uint32_t blk = ptx::smem_u32(staging) + (c0 >> 6) * L::kStagingBlock + rr * 128;
+            const int cbase = (c0 & 63) >> 3;  // first 16-byte piece of this 32-column chunk inside the 64-column block
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              ptx::st_shared_v4(blk + (((cbase + t) ^ (rr & 7)) << 4), ptx::pack_bf16x2(v[8 * t], v[8 * t + 1]),
+                                ptx::pack_bf16x2(v[8 * t + 2], v[8 * t + 3]), ptx::pack_bf16x2(v[8 * t + 4], v[8 * t + 5]),
+                                ptx::pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+          } else if (valid) {
             store_row_chunk<TF32>(p.out, static_cast<long long>(row) * p.ldo + n_blk * BN + c0, v, p.out_f32 != 0,
                                   p.round_tf32 != 0);
+          }
         }
         ptx::tc_fence_before();
+        if (STAGED) ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
         __syncwarp();
+        if (stamp) p.dbg[it * 8 + 5] = clock64();  // accumulator drained
         if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[as]), 0));
+        if (STAGED) {
+          ptx::named_bar_sync(2 + half, 128);
+          if (issuer) {
+#pragma unroll
+            for (int b = 0; b < kHalfCols / 64; ++b) {
+              const int blk = half * (kHalfCols / 64) + b;
+              ptx::tma_store_2d(&tmOut, staging + blk * L::kStagingBlock, p.out_col0 + n_blk * BN + blk * 64,
+                                m_blk * 2 * BM + static_cast<int>(rank) * BM);
+            }
+            ptx::bulk_commit();
+          }
+        }
       } else {
         const int rf = it & 1;  // region of F_t; G_t is in the other one
         const long long grow = p.row0 + row;
@@ -358,6 +399,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
+  if (STAGED && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) ptx::bulk_wait_all();
   // Both CTAs stay resident until every MMA that reads the peer's shared memory / signals its
   // barriers has retired (the epilogue above waited for the last commit), then free TMEM.
   ptx::tc_fence_before();

@@ -46,6 +46,7 @@ struct GemmParams {
   int out_f32;
   int relu;
   int round_tf32;  // fp32 output is a TF32 operand of the next layer: round to nearest instead of truncating later
+  int out_col0;    // pair kernels with staged TMA stores: first output column inside the output tensor map
   // EPI_FUSION
   const float* bias_f;
   const float* bias_g;

@@ -163,10 +163,11 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   return LRN_OK;
 }
 
-template <int BN, bool TF32, int EPI, int STAGES, bool GENERAL = true>
-int launch_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sms, cudaStream_t stream) {
-  using L = PairSmem<BN, STAGES, EPI == EPI_FUSION>;
-  auto kern = gemm_pair_kernel<BN, TF32, EPI, STAGES, GENERAL>;
+template <int BN, bool TF32, int EPI, int STAGES, bool GENERAL = true, bool STAGED = false>
+int launch_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p, int sms,
+                  cudaStream_t stream) {
+  using L = PairSmem<BN, STAGES, EPI == EPI_FUSION, STAGED>;
+  auto kern = gemm_pair_kernel<BN, TF32, EPI, STAGES, GENERAL, STAGED>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
@@ -175,7 +176,7 @@ int launch_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   const int tiles = p.m_tiles * p.n_tiles;
   if (tiles <= 0) return LRN_OK;
   const int grid = 2 * std::min(tiles, sms / 2);  // one CTA pair (cluster of 2) per tile slot
-  kern<<<grid, kPairThreads, L::kDynamic, stream>>>(ta, tb, p);
+  kern<<<grid, kPairThreads, L::kDynamic, stream>>>(ta, tb, tout, p);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
@@ -205,24 +206,30 @@ GemmPlan plan_gemm(int64_t N, int epi) {
   return g;
 }
 
+// `tout`: tensor map of the bf16 output (box 64 x 128, 128B swizzle) or nullptr -> direct stores.
 int launch_gemm(int precision, const GemmPlan& g, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
-                const GemmParams& p, int sms, cudaStream_t stream) {
+                const GemmParams& p, int sms, cudaStream_t stream, const CUtensorMap* tout = nullptr) {
   const bool tf32 = precision == LRN_PREC_TF32;
+  static const bool no_staged = [] { const char* e = getenv("LRN_NO_STAGED"); return e && e[0] == '1'; }();
+  if (g.pair && epi == EPI_ACT && !tf32 && !p.out_f32 && tout && !no_staged) {
+    return g.bn == 128 ? launch_pair_t<128, false, EPI_ACT, 6, true, true>(ta, tb, *tout, p, sms, stream)
+                       : launch_pair_t<256, false, EPI_ACT, 4, true, true>(ta, tb, *tout, p, sms, stream);
+  }
   if (g.pair) {
     if (epi == EPI_FUSION) {
       // fast variant: no argmax and every warp's 32 points are valid and inside one segment
       const bool fast = !(p.flags & FUSE_ARGMAX) && p.npts % 32 == 0 && p.M % 32 == 0 && p.row0 % 32 == 0;
       if (fast)
-        return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, false>(ta, tb, p, sms, stream)
-                    : launch_pair_t<256, false, EPI_FUSION, 5, false>(ta, tb, p, sms, stream);
-      return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, true>(ta, tb, p, sms, stream)
-                  : launch_pair_t<256, false, EPI_FUSION, 5, true>(ta, tb, p, sms, stream);
+        return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, false>(ta, tb, ta, p, sms, stream)
+                    : launch_pair_t<256, false, EPI_FUSION, 5, false>(ta, tb, ta, p, sms, stream);
+      return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, true>(ta, tb, ta, p, sms, stream)
+                  : launch_pair_t<256, false, EPI_FUSION, 5, true>(ta, tb, ta, p, sms, stream);
     }
     if (g.bn == 128)
-      return tf32 ? launch_pair_t<128, true, EPI_ACT, 8>(ta, tb, p, sms, stream)
-                  : launch_pair_t<128, false, EPI_ACT, 8>(ta, tb, p, sms, stream);
-    return tf32 ? launch_pair_t<256, true, EPI_ACT, 6>(ta, tb, p, sms, stream)
-                : launch_pair_t<256, false, EPI_ACT, 6>(ta, tb, p, sms, stream);
+      return tf32 ? launch_pair_t<128, true, EPI_ACT, 8>(ta, tb, ta, p, sms, stream)
+                  : launch_pair_t<128, false, EPI_ACT, 8>(ta, tb, ta, p, sms, stream);
+    return tf32 ? launch_pair_t<256, true, EPI_ACT, 6>(ta, tb, ta, p, sms, stream)
+                : launch_pair_t<256, false, EPI_ACT, 6>(ta, tb, ta, p, sms, stream);
   }
   if (epi == EPI_FUSION) {
     return tf32 ? launch_gemm_t<128, true, EPI_FUSION, 6>(ta, tb, p, sms, stream)
@@ -473,8 +480,11 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.out_f32 = tf32 ? 1 : 0;
       p.relu = 1;
       p.round_tf32 = tf32 ? 1 : 0;
+      p.out_col0 = kCatOff[k];  // staged TMA stores go through the operand-row tensor map itself
+      static const int dbg_layer = [] { const char* e = getenv("LRN_DBG_LAYER"); return e ? atoi(e) : 0; }();
+      p.dbg = (k == dbg_layer) ? g_dbg : nullptr;
       StageTimer timer(LRN_STAGE_CONV2 + (k - 2), s);
-      st = launch_gemm(precision, plan[k], EPI_ACT, ta, tw[k], p, dev.sms, s);
+      st = launch_gemm(precision, plan[k], EPI_ACT, ta, tw[k], p, dev.sms, s, &ta);
       if (st) return st;
     }
     {  // fusion + gate + pooling
@@ -498,7 +508,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.pool_key = keys;
       p.fused_cn = fused;
       p.fused_pm = fused_pm;
-      p.dbg = g_dbg;
+      p.dbg = getenv("LRN_DBG_LAYER") ? nullptr : g_dbg;
       StageTimer timer(LRN_STAGE_FUSION, s);
       st = launch_gemm(precision, plan_f, EPI_FUSION, ta, twfg, p, dev.sms, s);
       if (st) return st;
@@ -602,7 +612,15 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt,
   p.ldo = ldo;
   p.out_f32 = out_f32;
   p.relu = relu;
-  return launch_gemm(precision, g, EPI_ACT, ta, tb, p, dev.sms, reinterpret_cast<cudaStream_t>(stream));
+  CUtensorMap tout;
+  const bool staged_ok = precision == LRN_PREC_BF16 && !out_f32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                         (ldo * 2) % 16 == 0;
+  if (staged_ok) {
+    st = make_tmap(&tout, precision, out, M, N, ldo, BM);
+    if (st) return st;
+  }
+  return launch_gemm(precision, g, EPI_ACT, ta, tb, p, dev.sms, reinterpret_cast<cudaStream_t>(stream),
+                     staged_ok ? &tout : nullptr);
 }
 
 }  // extern "C"

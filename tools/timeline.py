@@ -19,7 +19,8 @@ with torch.no_grad():
     _lib.lib.lrn_debug_timeline(None)
 t = buf.cpu().view(16, 8)
 t0 = int(t[0, 0])
-print("tile  acc_free  lastMMAissued | G_ready  gamma_done  F_ready  phaseB_done   (cycles since first tile start; last wave's stamps)")
+print("stamps per tile (cycles since first tile start): fusion = [tile start, last MMA issued | G ready, phase A done, F ready, phase B done]; "
+      "LRN_DBG_LAYER=k (conv k) = [tile start, last MMA issued | epilogue start, staging free, acc ready, acc drained]")
 for i in range(16):
     r = [int(x) - t0 for x in t[i, :6]]
     print(f"{i:3d} {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} {r[5]:9d}   main={r[4]-r[2]:6d} phaseA={r[3]-r[2]:6d} phaseB={r[5]-r[4]:6d} tile={r[5]-r[0]:6d}")
