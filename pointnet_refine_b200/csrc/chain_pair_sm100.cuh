@@ -1,0 +1,374 @@
+// Fused front of the shared-MLP chain (bf16 tier): one persistent kernel computes, per 256-point tile
+// of a CTA pair,
+//     conv1 (fp32 FMA) -> conv2 -> conv3 -> conv4        (src/model.py:43-46, BatchNorm folded, ReLU)
+//     gate layer 1 (fp32 FMA)                            (src/model.py:33-34)
+// with every intermediate activation kept in shared memory in the 128-byte-swizzled K-major layout that
+// both UMMA (as the next layer's A operand) and TMA (as the source of the store into the operand row)
+// understand.  Only the folded weights stream through TMA; every output (feat1..feat4, gate hidden block)
+// leaves through TMA stores of [128 x 64] blocks (feat4 is staged in blocks that are idle at that point:
+// 16-byte pieces of 32 different rows per store instruction cost 19k cycles per tile).  Compared with one GEMM
+// launch per layer this removes the HBM round trip of feat1..feat3 as inputs and four launches per wave.
+//
+//   warp 0      : TMA producer for the weight k-blocks (both CTAs; bytes counted on the leader's barrier)
+//   warp 1      : TMEM allocator (both CTAs) + tcgen05.mma.cta_group::2 issuer (leader)
+//   warps 2..9  : compute warps: conv1 / gate layer 1 in fp32, and every layer's epilogue
+//                 (TMEM -> bias + ReLU -> bf16 -> swizzled smem block).  Warp w owns TMEM lane quarter
+//                 (w & 3) and column half ((w - 2) >> 2).
+//
+// TMEM: two 256-column accumulator buffers.  conv2 -> buf0[0:128), conv3 -> buf1, conv4 chunk 0 -> buf0,
+// conv4 chunk 1 -> buf1, so conv4's second chunk runs while the first one is drained, and the next
+// tile's conv1 is computed while conv4's first chunk runs.
+#pragma once
+#include "gemm_pair_sm100.cuh"
+
+namespace lrn {
+
+struct ChainParams {
+  int M;              // points covered by this launch
+  int num_tiles;      // ceil(M / 256)
+  const float4* ctx;  // (M) raw points [x, y, z, intensity]
+  const float* w1;    // (64, 4) folded conv1, fp32
+  const float* b1;    // (64)
+  const float* wg1;   // (64) gate layer 1
+  const float* bg1;   // (64)
+  const float* b2;    // (128) folded biases of conv2..conv4
+  const float* b3;    // (256)
+  const float* b4;    // (512)
+  void* cat;          // operand rows (M, 2048) bf16: feat4 is stored directly
+  long long* dbg;
+};
+
+constexpr int kChainStages = 3;
+constexpr int kChainBlock = BM * 128;  // one [128 x 64] bf16 activation block / one weight stage: 16 KB
+
+struct ChainSmem {
+  static constexpr int kF1 = 0;                          // 1 block
+  static constexpr int kF2 = kF1 + 1 * kChainBlock;      // 2 blocks; F2 + Z = 4 contiguous blocks = staging of feat4[0:256)
+  static constexpr int kZ = kF2 + 2 * kChainBlock;       // 2 blocks
+  static constexpr int kF3 = kZ + 2 * kChainBlock;       // 4 blocks; also staging of feat4[256:512) once conv4 has read it
+  static constexpr int kGH = kF3 + 4 * kChainBlock;      // 1 block (gate hidden, staging for its TMA store only)
+  static constexpr int kStages = kGH + 1 * kChainBlock;  // kChainStages weight stages of 16 KB
+  static constexpr int kConst = kStages + kChainStages * kChainBlock;
+  // fp32 constants: w1 (256) b1 (64) wg1 (64) bg1 (64) b2 (128) b3 (256) b4 (512)
+  static constexpr int kW1 = 0, kB1 = 256, kWg1 = 320, kBg1 = 384, kB2 = 448, kB3 = 576, kB4 = 832, kNumConst = 1344;
+  static constexpr int kBarOff = kConst + kNumConst * 4;  // w_full[S] w_empty[S] act_ready[3] acc_full[2] acc_free[2]
+  static constexpr int kTmemPtrOff = kBarOff + (2 * kChainStages + 7) * 8;
+  static constexpr int kTotal = kTmemPtrOff + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+};
+
+// Write 32 consecutive bf16 channels [c0, c0 + 32) of row `rr` into 64-column block(s) starting at `blocks`
+// (block index c0 / 64), 128-byte swizzle: 16-byte piece c of a row sits at ((c ^ (row & 7)) << 4).
+__device__ __forceinline__ void stage_row_chunk(uint32_t blocks, int rr, int c0, const float (&v)[32]) {
+  const uint32_t blk = blocks + (c0 >> 6) * kChainBlock + rr * 128;
+  const int cbase = (c0 & 63) >> 3;
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+    ptx::st_shared_v4(blk + (((cbase + t) ^ (rr & 7)) << 4), ptx::pack_bf16x2(v[8 * t], v[8 * t + 1]),
+                      ptx::pack_bf16x2(v[8 * t + 2], v[8 * t + 3]), ptx::pack_bf16x2(v[8 * t + 4], v[8 * t + 5]),
+                      ptx::pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+}
+
+// Drain NCHUNKS x 32 accumulator columns starting at TMEM address `t_addr` (layer column `col_lo`) of this
+// thread's row: bias + ReLU -> bf16 -> either swizzled smem blocks (the next layer's A operand and the
+// TMA-store source) or direct global stores.  TMEM loads are double-buffered.
+template <int NCHUNKS, bool TO_SMEM>
+__device__ __forceinline__ void chain_drain(uint32_t t_addr, int col_lo, const float* bias, uint32_t sblocks, int rr,
+                                            void* cat, long long grow, int M, int gcol0) {
+  uint32_t r[2][32];
+  ptx::tmem_ld_32x32b_x32(t_addr, r[0]);
+#pragma unroll
+  for (int i = 0; i < NCHUNKS; ++i) {
+    const int c0 = col_lo + 32 * i;
+    ptx::tmem_ld_wait();
+    if (i + 1 < NCHUNKS) ptx::tmem_ld_32x32b_x32(t_addr + 32 * (i + 1), r[(i + 1) & 1]);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[i & 1][j]) + bias[c0 + j], 0.f);
+    if (TO_SMEM) {
+      stage_row_chunk(sblocks, rr, c0, v);
+    } else if (grow < M) {
+      store_row_chunk<false>(cat, grow * 2048 + gcol0 + c0, v, false, false);
+    }
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3,
+                  const __grid_constant__ CUtensorMap tmW4, const __grid_constant__ CUtensorMap tmCat,
+                  const ChainParams p) {
+  using L = ChainSmem;
+  constexpr int S = kChainStages;
+  constexpr uint32_t kIdesc128 = ptx::make_idesc(false, 2 * BM, 128);
+  constexpr uint32_t kIdesc256 = ptx::make_idesc(false, 2 * BM, 256);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* sconst = reinterpret_cast<float*>(smem + L::kConst);
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* w_empty = w_full + S;
+  uint64_t* act_ready = w_empty + S;  // [3]: F1 / F2 / F3 of BOTH CTAs written (leader's copy is used)
+  uint64_t* acc_full = act_ready + 3;  // [2]: accumulator buffer written by the MMAs
+  uint64_t* acc_free = acc_full + 2;   // [2]: accumulator buffer drained by both CTAs (leader's copy is used)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmW2);
+    ptx::prefetch_tmap(&tmW3);
+    ptx::prefetch_tmap(&tmW4);
+    ptx::prefetch_tmap(&tmCat);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(&w_full[s], 1);
+      ptx::mbar_init(&w_empty[s], 1);
+    }
+    for (int i = 0; i < 3; ++i) ptx::mbar_init(&act_ready[i], 2 * kPairEpiWarps);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_free[i], 2 * kPairEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_pair<512>(tmem_ptr);
+  if (warp >= 2) {  // layer constants -> shared memory, once
+    const int t = threadIdx.x - 64;
+    for (int i = t; i < L::kNumConst; i += 32 * kPairEpiWarps) {
+      float v;
+      if (i < L::kB1) v = p.w1[i];
+      else if (i < L::kWg1) v = p.b1[i - L::kB1];
+      else if (i < L::kBg1) v = p.wg1[i - L::kWg1];
+      else if (i < L::kB2) v = p.bg1[i - L::kBg1];
+      else if (i < L::kB3) v = p.b2[i - L::kB2];
+      else if (i < L::kB4) v = p.b3[i - L::kB3];
+      else v = p.b4[i - L::kB4];
+      sconst[i] = v;
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weight producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load = [&](const CUtensorMap* tm, int kcol, int nrow, uint32_t bytes) {
+        ptx::mbar_wait(&w_empty[stage], phase ^ 1);
+        const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&w_full[stage]), 0);
+        if (leader) ptx::mbar_arrive_expect_tx(&w_full[stage], 2 * bytes);
+        ptx::tma_load_2d_pair(smem + L::kStages + stage * kChainBlock, tm, full_leader, kcol, nrow);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      };
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        load(&tmW2, 0, static_cast<int>(rank) * 64, 64 * 128);                                    // conv2: N = 128
+        for (int kb = 0; kb < 2; ++kb) load(&tmW3, kb * 64, static_cast<int>(rank) * 128, 128 * 128);  // conv3: N = 256
+        for (int c = 0; c < 2; ++c)                                                              // conv4: 2 x (N = 256)
+          for (int kb = 0; kb < 4; ++kb) load(&tmW4, kb * 64, c * 256 + static_cast<int>(rank) * 128, 128 * 128);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      // one weight k-block: A = activation block `a_off` of this CTA (and the peer's at the same offset)
+      auto kblock = [&](uint32_t a_off, uint32_t d_tmem, uint32_t idesc, bool first) {
+        ptx::mbar_wait(&w_full[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + a_off));
+          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + L::kStages + stage * kChainBlock));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::tc_mma_ss_pair<false>(d_tmem, da + 2 * k, db + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+          ptx::tc_commit_pair(&w_empty[stage], 3);
+        }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      };
+      auto commit_acc = [&](int buf) {
+        if (lane == 0) ptx::tc_commit_pair(&acc_full[buf], 3);
+        __syncwarp();
+      };
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+        const uint32_t par = it & 1;
+        const bool stamp = p.dbg && cluster_id == 0 && lane == 0 && it < 16;
+        if (stamp) p.dbg[it * 8 + 0] = clock64();
+        // conv2: F1 (K = 64) -> buf0[0:128)
+        ptx::mbar_wait(&act_ready[0], par);
+        ptx::mbar_wait(&acc_free[0], 1);  // previous tile's conv4 chunk 0 drained
+        ptx::tc_fence_after();
+        kblock(L::kF1, tmem_base, kIdesc128, true);
+        commit_acc(0);
+        // conv3: F2 (K = 128) -> buf1
+        ptx::mbar_wait(&act_ready[1], par);
+        ptx::mbar_wait(&acc_free[1], 1);  // previous tile's conv4 chunk 1 drained
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < 2; ++kb) kblock(L::kF2 + kb * kChainBlock, tmem_base + 256, kIdesc256, kb == 0);
+        commit_acc(1);
+        // conv4: F3 (K = 256) -> buf0 (channels 0..255), buf1 (channels 256..511)
+        ptx::mbar_wait(&act_ready[2], par);
+        for (int c = 0; c < 2; ++c) {
+          ptx::mbar_wait(&acc_free[c], 0);  // this tile's conv2 / conv3 accumulator drained
+          ptx::tc_fence_after();
+          for (int kb = 0; kb < 4; ++kb) kblock(L::kF3 + kb * kChainBlock, tmem_base + c * 256, kIdesc256, kb == 0);
+          commit_acc(c);
+        }
+        if (stamp) p.dbg[it * 8 + 1] = clock64();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ compute / epilogue warps (both CTAs)
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int sub = ew >> 2;
+    const int rr = q * 32 + lane;  // row (point) of this thread inside the CTA's 128
+    const bool issuer = ew == 0 && lane == 0;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t sF1 = ptx::smem_u32(smem + L::kF1), sF2 = ptx::smem_u32(smem + L::kF2);
+    const uint32_t sF3 = ptx::smem_u32(smem + L::kF3), sGH = ptx::smem_u32(smem + L::kGH);
+    const uint32_t ready_leader0 = ptx::mapa(ptx::smem_u32(&act_ready[0]), 0);
+    const uint32_t free_leader0 = ptx::mapa(ptx::smem_u32(&acc_free[0]), 0);
+
+    // Before a block is rewritten, the TMA store that last read it must have finished reading shared memory.
+    // Store groups are committed in program order  F2(t) F3(t) F1GH(t+1) f4c0(t) f4c1(t) F2(t+1) ...; `keep` =
+    // number of groups committed AFTER the one that must be complete (they may stay in flight).
+    auto staging_free = [&](int keep) {
+      if (issuer) {
+        if (keep >= 4) ptx::bulk_wait_read_keep<4>();
+        else if (keep == 2) ptx::bulk_wait_read_keep<2>();
+        else if (keep == 1) ptx::bulk_wait_read_keep<1>();
+        else ptx::bulk_wait_read_all();
+      }
+      ptx::named_bar_sync(1, 32 * kPairEpiWarps);
+    };
+    // conv1 (sub 0) / gate layer 1 (sub 1) for one tile: raw point -> 64 bf16 channels of block F1 / GH
+    auto embed = [&](int tile) {
+      const int row0 = tile * 2 * BM + static_cast<int>(rank) * BM;
+      staging_free(4);  // F1GH(t) was followed by f4c0(t-1) f4c1(t-1) F2(t) F3(t)
+      const int grow = row0 + rr;
+      const float4 x = grow < p.M ? __ldg(p.ctx + grow) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+        if (sub == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 w = reinterpret_cast<const float4*>(sconst + L::kW1)[32 * h + j];
+            v[j] = fmaxf(fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, sconst[L::kB1 + 32 * h + j])))), 0.f);
+          }
+          stage_row_chunk(sF1, rr, 32 * h, v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = fmaxf(fmaf(sconst[L::kWg1 + 32 * h + j], x.w, sconst[L::kBg1 + 32 * h + j]), 0.f);
+          stage_row_chunk(sGH, rr, 32 * h, v);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ready_leader0);
+      ptx::named_bar_sync(1, 32 * kPairEpiWarps);
+      if (issuer) {
+        ptx::tma_store_2d(&tmCat, smem + L::kF1, 0, row0);
+        ptx::tma_store_2d(&tmCat, smem + L::kGH, 1984, row0);
+        ptx::bulk_commit();
+      }
+    };
+
+    int it = 0;
+    if (cluster_id < p.num_tiles) embed(cluster_id);
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+      const int row0 = tile * 2 * BM + static_cast<int>(rank) * BM;
+      const long long grow = row0 + rr;
+      // ---- conv2 epilogue: buf0[0:128) -> F2 (2 blocks); this warp: columns [64 sub, 64 sub + 64)
+      const bool stamp = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it < 16;
+      staging_free(1);  // F2 doubled as feat4 staging of the previous tile: f4c0(t-1), then only f4c1(t-1)
+      ptx::mbar_wait(&acc_full[0], 0);
+      ptx::tc_fence_after();
+      if (stamp) p.dbg[it * 8 + 2] = clock64();  // conv2 accumulator ready
+      chain_drain<2, true>(t_lane + 64 * sub, 64 * sub, sconst + L::kB2, sF2, rr, p.cat, grow, p.M, 0);
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive_cluster(free_leader0);       // buf0 drained
+        ptx::mbar_arrive_cluster(ready_leader0 + 8);  // F2 written
+      }
+      ptx::named_bar_sync(1, 32 * kPairEpiWarps);
+      if (issuer) {
+        ptx::tma_store_2d(&tmCat, smem + L::kF2, 64, row0);
+        ptx::tma_store_2d(&tmCat, smem + L::kF2 + kChainBlock, 128, row0);
+        ptx::bulk_commit();
+      }
+      if (stamp) p.dbg[it * 8 + 3] = clock64();  // conv2 drained, F2 stores issued
+      // ---- conv3 epilogue: buf1 -> F3 (4 blocks); this warp: columns [128 sub, 128 sub + 128)
+      staging_free(1);  // F3 doubled as feat4 staging of the previous tile: f4c1(t-1), then only F2(t)
+      ptx::mbar_wait(&acc_full[1], 0);
+      ptx::tc_fence_after();
+      if (stamp) p.dbg[it * 8 + 4] = clock64();  // conv3 accumulator ready
+      chain_drain<4, true>(t_lane + 256 + 128 * sub, 128 * sub, sconst + L::kB3, sF3, rr, p.cat, grow, p.M, 0);
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive_cluster(free_leader0 + 8);    // buf1 drained
+        ptx::mbar_arrive_cluster(ready_leader0 + 16);  // F3 written
+      }
+      ptx::named_bar_sync(1, 32 * kPairEpiWarps);
+      if (issuer) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) ptx::tma_store_2d(&tmCat, smem + L::kF3 + b * kChainBlock, 192 + 64 * b, row0);
+        ptx::bulk_commit();
+      }
+      if (stamp) p.dbg[it * 8 + 5] = clock64();  // conv3 drained, F3 stores issued
+      // ---- next tile's conv1 while conv4 chunk 0 runs (F1 / GH are free: conv2 of this tile has completed)
+      const bool has_next = tile + num_clusters < p.num_tiles;
+      if (has_next) embed(tile + num_clusters);
+      if (stamp) p.dbg[it * 8 + 6] = clock64();  // next tile's conv1 done
+      // ---- conv4 epilogues: feat4 channels [256 c + 128 sub, +128) -> staging blocks -> operand row columns 448 + ...
+      //      chunk 0 is staged in F2 + Z (conv3 of this tile is done with F2), chunk 1 in F3 (all of conv4 has
+      //      completed once its accumulator is ready).
+      for (int c = 0; c < 2; ++c) {
+        // c = 0 needs F2(t) drained (later groups: F3(t) [F1GH(t+1)]); c = 1 needs F3(t) ([F1GH(t+1)] f4c0(t))
+        staging_free(has_next ? 2 : 1);
+        ptx::mbar_wait(&acc_full[c], 1);
+        ptx::tc_fence_after();
+        chain_drain<4, true>(t_lane + 256 * c + 128 * sub, 128 * sub, sconst + L::kB4 + 256 * c, c == 0 ? sF2 : sF3, rr,
+                             p.cat, grow, p.M, 0);
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(free_leader0 + 8 * c);
+        ptx::named_bar_sync(1, 32 * kPairEpiWarps);
+        if (issuer) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            ptx::tma_store_2d(&tmCat, smem + (c == 0 ? L::kF2 : L::kF3) + b * kChainBlock, 448 + 256 * c + 64 * b, row0);
+          ptx::bulk_commit();
+        }
+      }
+      if (stamp) p.dbg[it * 8 + 7] = clock64();  // conv4 drained
+    }
+    if (issuer) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+}  // namespace lrn

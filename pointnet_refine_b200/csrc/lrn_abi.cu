@@ -16,6 +16,7 @@
 
 #include "gemm_sm100.cuh"
 #include "gemm_pair_sm100.cuh"
+#include "chain_pair_sm100.cuh"
 #include "pointwise.cuh"
 
 namespace {
@@ -440,6 +441,13 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     if (st) return st;
   }
   const GemmPlan plan_f = plan_gemm(1024, EPI_FUSION), plan_p = plan_gemm(256, EPI_ACT);
+  CUtensorMap tw_chain[3];
+  if (!tf32) {
+    for (int k = 2; k <= 4; ++k) {
+      st = make_tmap(&tw_chain[k - 2], precision, pk + L.w[k], kChan[k], kChan[k - 1], kChan[k - 1], k == 2 ? 64 : 128);
+      if (st) return st;
+    }
+  }
   st = make_tmap(&twfg, precision, pk + L.wfg, 1024, kCat, kCat, plan_f.b_box_rows);
   if (st) return st;
   if (flags & LRN_OUT_MEMORY) {
@@ -457,7 +465,32 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     st = make_tmap(&ta, precision, cat, rows, kCat, kCat, BM);
     if (st) return st;
 
-    {  // layer 1 (+ gate layer 1): raw points -> operand columns
+    // bf16 tier: conv1..conv4 + gate layer 1 as ONE fused kernel (activations stay in shared memory);
+    // LRN_NO_CHAIN=1 or the tf32 tier run one kernel per layer.
+    static const bool no_chain = [] { const char* e = getenv("LRN_NO_CHAIN"); return e && e[0] == '1'; }();
+    const bool fused_chain = !tf32 && plan_f.pair && !no_chain;
+    if (fused_chain) {
+      static bool configured = false;
+      if (!configured) {
+        LRN_CUDA(cudaFuncSetAttribute(chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kDynamic));
+        configured = true;
+      }
+      ChainParams cp{};
+      cp.M = int(rows);
+      cp.num_tiles = int((rows + 2 * BM - 1) / (2 * BM));
+      cp.ctx = reinterpret_cast<const float4*>(context) + r0;
+      cp.w1 = ew.w1; cp.b1 = ew.b1; cp.wg1 = ew.wg1; cp.bg1 = ew.bg1;
+      cp.b2 = reinterpret_cast<const float*>(pk + L.b[2]);
+      cp.b3 = reinterpret_cast<const float*>(pk + L.b[3]);
+      cp.b4 = reinterpret_cast<const float*>(pk + L.b[4]);
+      cp.cat = cat;
+      static const int dbg_layer = [] { const char* e = getenv("LRN_DBG_LAYER"); return e ? atoi(e) : 0; }();
+      cp.dbg = dbg_layer == 4 ? g_dbg : nullptr;
+      StageTimer timer(LRN_STAGE_CONV4, s);  // reported as "conv4" (embed/conv2/conv3 read 0)
+      const int grid = 2 * std::min(cp.num_tiles, dev.sms / 2);
+      chain_pair_kernel<<<grid, kPairThreads, ChainSmem::kDynamic, s>>>(tw_chain[0], tw_chain[1], tw_chain[2], ta, cp);
+      LRN_CUDA(cudaGetLastError());
+    } else {  // layer 1 (+ gate layer 1): raw points -> operand columns
       StageTimer timer(LRN_STAGE_EMBED, s);
       const int grid = int(std::min<int64_t>((rows + 15) / 16, int64_t(dev.sms) * 16));
       if (tf32)
@@ -466,7 +499,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
         point_embed_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context) + r0, rows, ew, cat, kCat);
       LRN_CUDA(cudaGetLastError());
     }
-    for (int k = 2; k <= 5; ++k) {  // conv2..conv5, each writes its own column block of the operand row
+    for (int k = fused_chain ? 5 : 2; k <= 5; ++k) {  // conv2..conv5, each writes its own column block of the operand row
       GemmParams p{};
       p.M = int(rows);
       p.m_tiles = m_tiles_of(plan[k]);

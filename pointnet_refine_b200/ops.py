@@ -116,16 +116,19 @@ def encoder_forward(folded: FoldedEncoder, context: torch.Tensor, *, pool=True, 
         _lib.check(lib.lrn_encoder_forward(folded.blob.data_ptr(), folded.prec_id, context.data_ptr(), B, N, flags,
                                            dp(gf), dp(fz), dp(am), dp(mem), chunk_rows, ws.data_ptr(), ws.numel(),
                                            _stream_ptr(dev)), "lrn_encoder_forward")
-    _lib.launch_counter += encoder_launches(B * N, flags, chunk_rows)
+    _lib.launch_counter += encoder_launches(B * N, flags, chunk_rows, folded.precision)
     return out
 
 
-def encoder_launches(P: int, flags: int, chunk_rows: int = 0) -> int:
-    """Kernels lrn_encoder_forward enqueues for P points (mirrors the chunk loop in csrc/lrn_abi.cu)."""
+def encoder_launches(P: int, flags: int, chunk_rows: int = 0, precision: str = "bf16") -> int:
+    """Kernels lrn_encoder_forward enqueues for P points (mirrors the chunk loop in csrc/lrn_abi.cu):
+    bf16 tier = fused conv1..conv4 kernel + conv5 + fusion; tf32 tier = one kernel per layer."""
+    import os
     al = lambda v: (v + 127) // 128 * 128
     chunk = min(al(max(chunk_rows or DEFAULT_CHUNK_ROWS, 128)), al(P))
     chunks = (P + chunk - 1) // chunk
-    per_chunk = 1 + 4 + 1 + (1 if flags & OUT_MEMORY else 0)
+    fused_chain = precision == "bf16" and os.environ.get("LRN_NO_CHAIN") != "1" and os.environ.get("LRN_GEMM_V1") != "1"
+    per_chunk = (3 if fused_chain else 6) + (1 if flags & OUT_MEMORY else 0)
     return chunks * per_chunk + (1 if flags & OUT_ARGMAX else 0)
 
 

@@ -21,6 +21,12 @@ t = buf.cpu().view(16, 8)
 t0 = int(t[0, 0])
 print("stamps per tile (cycles since first tile start): fusion = [tile start, last MMA issued | G ready, phase A done, F ready, phase B done]; "
       "LRN_DBG_LAYER=k (conv k) = [tile start, last MMA issued | epilogue start, staging free, acc ready, acc drained]")
+if os.environ.get("LRN_DBG_LAYER") == "4":
+    print("chain kernel: [MMA tile start, conv4 issued | conv2 acc ready, conv2 drained, conv3 acc ready, conv3 drained, next conv1 done, conv4 drained]")
+    for i in range(16):
+        r = [int(x) - t0 for x in t[i, :8]]
+        print(f"{i:3d} " + " ".join(f"{x:8d}" for x in r) + f"   E1={r[3]-r[2]} wait3={r[4]-r[3]} E2={r[5]-r[4]} embed={r[6]-r[5]} E3={r[7]-r[6]} tile={r[7]-r[2]}")
+    sys.exit(0)
 for i in range(16):
     r = [int(x) - t0 for x in t[i, :6]]
     print(f"{i:3d} {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} {r[5]:9d}   main={r[4]-r[2]:6d} phaseA={r[3]-r[2]:6d} phaseB={r[5]-r[4]:6d} tile={r[5]-r[0]:6d}")
