@@ -18,6 +18,15 @@
 // TMEM: two 256-column accumulator buffers.  conv2 -> buf0[0:128), conv3 -> buf1, conv4 chunk 0 -> buf0,
 // conv4 chunk 1 -> buf1, so conv4's second chunk runs while the first one is drained, and the next
 // tile's conv1 is computed while conv4's first chunk runs.
+//
+// C5 = true appends conv5 (512 -> 1024, src/model.py:47; 75 % of the chain's FLOPs) with its A operand in
+// TENSOR MEMORY: the conv4 epilogue writes feat4 as packed bf16 into TMEM columns [0, 256) (row = lane,
+// two channels per column) besides staging it for the TMA store, and conv5 runs as
+// tcgen05.mma.cta_group::2 [D], [A_tmem], B_desc ("TS" form) over four 256-channel chunks accumulated in
+// columns [256, 512).  Only the weights touch shared memory.  Measured: the TMEM A read costs ~128 cycles
+// per MMA whatever N is, so N = 256 (128-cycle math) is the shape that runs at the tensor-pipe floor
+// (N = 128 chunks with double-buffered accumulators took 125 cycles per MMA, i.e. half rate); the
+// shared-memory-operand form of the same MMA takes ~194 cycles.
 #pragma once
 #include "gemm_pair_sm100.cuh"
 
@@ -34,7 +43,8 @@ struct ChainParams {
   const float* b2;    // (128) folded biases of conv2..conv4
   const float* b3;    // (256)
   const float* b4;    // (512)
-  void* cat;          // operand rows (M, 2048) bf16: feat4 is stored directly
+  const float* b5;    // (1024), C5 only
+  void* cat;          // operand rows (M, 2048) bf16
   long long* dbg;
 };
 
@@ -49,29 +59,54 @@ struct ChainSmem {
   static constexpr int kGH = kF3 + 4 * kChainBlock;      // 1 block (gate hidden, staging for its TMA store only)
   static constexpr int kStages = kGH + 1 * kChainBlock;  // kChainStages weight stages of 16 KB
   static constexpr int kConst = kStages + kChainStages * kChainBlock;
-  // fp32 constants: w1 (256) b1 (64) wg1 (64) bg1 (64) b2 (128) b3 (256) b4 (512)
-  static constexpr int kW1 = 0, kB1 = 256, kWg1 = 320, kBg1 = 384, kB2 = 448, kB3 = 576, kB4 = 832, kNumConst = 1344;
-  static constexpr int kBarOff = kConst + kNumConst * 4;  // w_full[S] w_empty[S] act_ready[3] acc_full[2] acc_free[2]
-  static constexpr int kTmemPtrOff = kBarOff + (2 * kChainStages + 7) * 8;
+  // fp32 constants: w1 (256) b1 (64) wg1 (64) bg1 (64) b2 (128) b3 (256) b4 (512) b5 (1024)
+  static constexpr int kW1 = 0, kB1 = 256, kWg1 = 320, kBg1 = 384, kB2 = 448, kB3 = 576, kB4 = 832, kB5 = 1344,
+                       kNumConst = 2368;
+  // w_full[S] w_empty[S] act_ready[3] acc_full[2] acc_free[2] a4_ready acc5_full[2] acc5_free[2]
+  static constexpr int kBarOff = kConst + kNumConst * 4;
+  static constexpr int kTmemPtrOff = kBarOff + (2 * kChainStages + 12) * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
   static constexpr int kDynamic = kTotal + 1024;
 };
 
 // Write 32 consecutive bf16 channels [c0, c0 + 32) of row `rr` into 64-column block(s) starting at `blocks`
 // (block index c0 / 64), 128-byte swizzle: 16-byte piece c of a row sits at ((c ^ (row & 7)) << 4).
-__device__ __forceinline__ void stage_row_chunk(uint32_t blocks, int rr, int c0, const float (&v)[32]) {
+__device__ __forceinline__ void stage_packed_chunk(uint32_t blocks, int rr, int c0, const uint32_t* pk /* 16 */) {
   const uint32_t blk = blocks + (c0 >> 6) * kChainBlock + rr * 128;
   const int cbase = (c0 & 63) >> 3;
 #pragma unroll
   for (int t = 0; t < 4; ++t)
-    ptx::st_shared_v4(blk + (((cbase + t) ^ (rr & 7)) << 4), ptx::pack_bf16x2(v[8 * t], v[8 * t + 1]),
-                      ptx::pack_bf16x2(v[8 * t + 2], v[8 * t + 3]), ptx::pack_bf16x2(v[8 * t + 4], v[8 * t + 5]),
-                      ptx::pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+    ptx::st_shared_v4(blk + (((cbase + t) ^ (rr & 7)) << 4), pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+}
+__device__ __forceinline__ void stage_row_chunk(uint32_t blocks, int rr, int c0, const float (&v)[32]) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  stage_packed_chunk(blocks, rr, c0, pk);
 }
 
 // Drain NCHUNKS x 32 accumulator columns starting at TMEM address `t_addr` (layer column `col_lo`) of this
 // thread's row: bias + ReLU -> bf16 -> either swizzled smem blocks (the next layer's A operand and the
 // TMA-store source) or direct global stores.  TMEM loads are double-buffered.
+// Same, but the packed bf16 pairs are also kept in registers (they become a TMEM-resident A operand).
+template <int NCHUNKS>
+__device__ __forceinline__ void chain_drain_keep(uint32_t t_addr, int col_lo, const float* bias, uint32_t sblocks, int rr,
+                                                 uint32_t (&keep)[NCHUNKS * 16]) {
+  uint32_t r[2][32];
+  ptx::tmem_ld_32x32b_x32(t_addr, r[0]);
+#pragma unroll
+  for (int i = 0; i < NCHUNKS; ++i) {
+    const int c0 = col_lo + 32 * i;
+    ptx::tmem_ld_wait();
+    if (i + 1 < NCHUNKS) ptx::tmem_ld_32x32b_x32(t_addr + 32 * (i + 1), r[(i + 1) & 1]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      keep[16 * i + j] = ptx::pack_bf16x2(fmaxf(__uint_as_float(r[i & 1][2 * j]) + bias[c0 + 2 * j], 0.f),
+                                          fmaxf(__uint_as_float(r[i & 1][2 * j + 1]) + bias[c0 + 2 * j + 1], 0.f));
+    stage_packed_chunk(sblocks, rr, c0, &keep[16 * i]);
+  }
+}
+
 template <int NCHUNKS, bool TO_SMEM>
 __device__ __forceinline__ void chain_drain(uint32_t t_addr, int col_lo, const float* bias, uint32_t sblocks, int rr,
                                             void* cat, long long grow, int M, int gcol0) {
@@ -93,10 +128,22 @@ __device__ __forceinline__ void chain_drain(uint32_t t_addr, int col_lo, const f
   }
 }
 
+// 256 x N x 16 MMA over a CTA pair with the A operand in tensor memory (each CTA: its own 128 rows).
+__device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <bool C5>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3,
-                  const __grid_constant__ CUtensorMap tmW4, const __grid_constant__ CUtensorMap tmCat,
-                  const ChainParams p) {
+                  const __grid_constant__ CUtensorMap tmW4, const __grid_constant__ CUtensorMap tmW5,
+                  const __grid_constant__ CUtensorMap tmCat, const ChainParams p) {
   using L = ChainSmem;
   constexpr int S = kChainStages;
   constexpr uint32_t kIdesc128 = ptx::make_idesc(false, 2 * BM, 128);
@@ -110,6 +157,9 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
   uint64_t* act_ready = w_empty + S;  // [3]: F1 / F2 / F3 of BOTH CTAs written (leader's copy is used)
   uint64_t* acc_full = act_ready + 3;  // [2]: accumulator buffer written by the MMAs
   uint64_t* acc_free = acc_full + 2;   // [2]: accumulator buffer drained by both CTAs (leader's copy is used)
+  uint64_t* a4_ready = acc_free + 2;   // feat4 of BOTH CTAs is in tensor memory (leader's copy is used)
+  uint64_t* acc5_full = a4_ready + 1;  // [2]: conv5 accumulator chunk written
+  uint64_t* acc5_free = acc5_full + 2; // [2]: conv5 accumulator chunk drained by both CTAs (leader's copy is used)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
 
   const int warp = threadIdx.x >> 5;
@@ -123,6 +173,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     ptx::prefetch_tmap(&tmW2);
     ptx::prefetch_tmap(&tmW3);
     ptx::prefetch_tmap(&tmW4);
+    if (C5) ptx::prefetch_tmap(&tmW5);
     ptx::prefetch_tmap(&tmCat);
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&w_full[s], 1);
@@ -132,13 +183,16 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
       ptx::mbar_init(&acc_free[i], 2 * kPairEpiWarps);
+      ptx::mbar_init(&acc5_full[i], 1);
+      ptx::mbar_init(&acc5_free[i], 2 * kPairEpiWarps);
     }
+    ptx::mbar_init(a4_ready, 2 * kPairEpiWarps);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc_pair<512>(tmem_ptr);
   if (warp >= 2) {  // layer constants -> shared memory, once
     const int t = threadIdx.x - 64;
-    for (int i = t; i < L::kNumConst; i += 32 * kPairEpiWarps) {
+    for (int i = t; i < (C5 ? L::kNumConst : L::kB5); i += 32 * kPairEpiWarps) {
       float v;
       if (i < L::kB1) v = p.w1[i];
       else if (i < L::kWg1) v = p.b1[i - L::kB1];
@@ -146,7 +200,8 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       else if (i < L::kB2) v = p.bg1[i - L::kBg1];
       else if (i < L::kB3) v = p.b2[i - L::kB2];
       else if (i < L::kB4) v = p.b3[i - L::kB3];
-      else v = p.b4[i - L::kB4];
+      else if (i < L::kB5) v = p.b4[i - L::kB4];
+      else v = p.b5[i - L::kB5];
       sconst[i] = v;
     }
   }
@@ -160,11 +215,13 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      auto load = [&](const CUtensorMap* tm, int kcol, int nrow, uint32_t bytes) {
+      // one stage = `nbox` boxes of `bytes` each (conv5 packs two 8 KB k-blocks into a 16 KB stage)
+      auto load = [&](const CUtensorMap* tm, int kcol, int nrow, uint32_t bytes, int nbox = 1) {
         ptx::mbar_wait(&w_empty[stage], phase ^ 1);
         const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&w_full[stage]), 0);
-        if (leader) ptx::mbar_arrive_expect_tx(&w_full[stage], 2 * bytes);
-        ptx::tma_load_2d_pair(smem + L::kStages + stage * kChainBlock, tm, full_leader, kcol, nrow);
+        if (leader) ptx::mbar_arrive_expect_tx(&w_full[stage], 2 * bytes * nbox);
+        for (int b = 0; b < nbox; ++b)
+          ptx::tma_load_2d_pair(smem + L::kStages + stage * kChainBlock + b * bytes, tm, full_leader, kcol + 64 * b, nrow);
         if (++stage == S) { stage = 0; phase ^= 1; }
       };
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
@@ -172,6 +229,9 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         for (int kb = 0; kb < 2; ++kb) load(&tmW3, kb * 64, static_cast<int>(rank) * 128, 128 * 128);  // conv3: N = 256
         for (int c = 0; c < 2; ++c)                                                              // conv4: 2 x (N = 256)
           for (int kb = 0; kb < 4; ++kb) load(&tmW4, kb * 64, c * 256 + static_cast<int>(rank) * 128, 128 * 128);
+        if (C5)                                                                                  // conv5: 4 x (N = 256)
+          for (int n = 0; n < 4; ++n)
+            for (int kb = 0; kb < 8; ++kb) load(&tmW5, kb * 64, n * 256 + static_cast<int>(rank) * 128, 128 * 128);
       }
     }
     __syncwarp();
@@ -204,25 +264,61 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         const uint32_t par = it & 1;
         const bool stamp = p.dbg && cluster_id == 0 && lane == 0 && it < 16;
         if (stamp) p.dbg[it * 8 + 0] = clock64();
+        // Barrier bookkeeping.  Without conv5 each accumulator buffer is drained twice per tile (conv2|conv3 and a
+        // conv4 chunk): waits alternate parity 1 (previous tile's conv4 chunk) / 0.  With conv5 the conv4 chunks are
+        // not handed back (buf0 becomes conv5's A operand, buf1 its accumulators): acc_free completes once per
+        // tile, and the buffers are reusable once the tensor pipe (in order) is past conv5 and acc5_free says
+        // the last conv5 chunks have been drained.
         // conv2: F1 (K = 64) -> buf0[0:128)
         ptx::mbar_wait(&act_ready[0], par);
-        ptx::mbar_wait(&acc_free[0], 1);  // previous tile's conv4 chunk 0 drained
+        if (!C5) ptx::mbar_wait(&acc_free[0], 1);
         ptx::tc_fence_after();
         kblock(L::kF1, tmem_base, kIdesc128, true);
         commit_acc(0);
         // conv3: F2 (K = 128) -> buf1
         ptx::mbar_wait(&act_ready[1], par);
-        ptx::mbar_wait(&acc_free[1], 1);  // previous tile's conv4 chunk 1 drained
+        if (C5) {
+          ptx::mbar_wait(&acc5_free[0], 1);  // previous tile's last conv5 chunk drained
+        } else {
+          ptx::mbar_wait(&acc_free[1], 1);
+        }
         ptx::tc_fence_after();
         for (int kb = 0; kb < 2; ++kb) kblock(L::kF2 + kb * kChainBlock, tmem_base + 256, kIdesc256, kb == 0);
         commit_acc(1);
         // conv4: F3 (K = 256) -> buf0 (channels 0..255), buf1 (channels 256..511)
         ptx::mbar_wait(&act_ready[2], par);
         for (int c = 0; c < 2; ++c) {
-          ptx::mbar_wait(&acc_free[c], 0);  // this tile's conv2 / conv3 accumulator drained
+          ptx::mbar_wait(&acc_free[c], C5 ? par : 0);  // this tile's conv2 / conv3 accumulator drained
           ptx::tc_fence_after();
           for (int kb = 0; kb < 4; ++kb) kblock(L::kF3 + kb * kChainBlock, tmem_base + c * 256, kIdesc256, kb == 0);
           commit_acc(c);
+        }
+        if (C5) {
+          // conv5: A = feat4 in TMEM columns [0, 256) (K = 512), four 256-channel chunks -> columns [256, 512)
+          ptx::mbar_wait(a4_ready, par);
+          ptx::tc_fence_after();
+          const bool stamp5 = p.dbg && cluster_id == 0 && lane == 0 && it == 1;
+          if (stamp5) p.dbg[64 + 8] = clock64();  // feat4 in TMEM
+          for (int n = 0; n < 4; ++n) {
+            ptx::mbar_wait(&acc5_free[0], (n & 1) ^ 1);  // chunk n - 1 (or the previous tile's chunk 3) drained
+            ptx::tc_fence_after();
+            if (stamp5) p.dbg[64 + 16 + n] = clock64();  // accumulator free
+            for (int kb = 0; kb < 8; ++kb) {
+              ptx::mbar_wait(&w_full[stage], phase);
+              ptx::tc_fence_after();
+              if (lane == 0) {
+                const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + L::kStages + stage * kChainBlock));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc_mma_ts_pair(tmem_base + 256, tmem_base + kb * 32 + k * 8, db + 2 * k, kIdesc256, (kb > 0 || k > 0) ? 1u : 0u);
+                ptx::tc_commit_pair(&w_empty[stage], 3);
+                if (kb == 7) ptx::tc_commit_pair(&acc5_full[0], 3);
+                if (kb == 7 && stamp5) p.dbg[64 + n] = clock64();  // chunk n issued
+              }
+              __syncwarp();
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+          }
         }
         if (stamp) p.dbg[it * 8 + 1] = clock64();
       }
@@ -246,6 +342,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     auto staging_free = [&](int keep) {
       if (issuer) {
         if (keep >= 4) ptx::bulk_wait_read_keep<4>();
+        else if (keep == 3) ptx::bulk_wait_read_keep<3>();
         else if (keep == 2) ptx::bulk_wait_read_keep<2>();
         else if (keep == 1) ptx::bulk_wait_read_keep<1>();
         else ptx::bulk_wait_read_all();
@@ -293,7 +390,8 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       const long long grow = row0 + rr;
       // ---- conv2 epilogue: buf0[0:128) -> F2 (2 blocks); this warp: columns [64 sub, 64 sub + 64)
       const bool stamp = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it < 16;
-      staging_free(1);  // F2 doubled as feat4 staging of the previous tile: f4c0(t-1), then only f4c1(t-1)
+      // F2 doubled as staging in the previous tile: feat4 chunk 0 (then only f4c1), or conv5 chunk 2 (then only chunk 3)
+      staging_free(1);
       ptx::mbar_wait(&acc_full[0], 0);
       ptx::tc_fence_after();
       if (stamp) p.dbg[it * 8 + 2] = clock64();  // conv2 accumulator ready
@@ -344,18 +442,64 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         staging_free(has_next ? 2 : 1);
         ptx::mbar_wait(&acc_full[c], 1);
         ptx::tc_fence_after();
-        chain_drain<4, true>(t_lane + 256 * c + 128 * sub, 128 * sub, sconst + L::kB4 + 256 * c, c == 0 ? sF2 : sF3, rr,
-                             p.cat, grow, p.M, 0);
+        uint32_t keep[C5 ? 64 : 1];
+        if (C5) {
+          chain_drain_keep<4>(t_lane + 256 * c + 128 * sub, 128 * sub, sconst + L::kB4 + 256 * c, c == 0 ? sF2 : sF3, rr,
+                              reinterpret_cast<uint32_t(&)[64]>(keep));
+        } else {
+          chain_drain<4, true>(t_lane + 256 * c + 128 * sub, 128 * sub, sconst + L::kB4 + 256 * c, c == 0 ? sF2 : sF3, rr,
+                               p.cat, grow, p.M, 0);
+        }
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(free_leader0 + 8 * c);
-        ptx::named_bar_sync(1, 32 * kPairEpiWarps);
+        if (!C5 && lane == 0) ptx::mbar_arrive_cluster(free_leader0 + 8 * c);
+        ptx::named_bar_sync(1, 32 * kPairEpiWarps);  // every warp is done reading this accumulator buffer
         if (issuer) {
 #pragma unroll
           for (int b = 0; b < 4; ++b)
             ptx::tma_store_2d(&tmCat, smem + (c == 0 ? L::kF2 : L::kF3) + b * kChainBlock, 448 + 256 * c + 64 * b, row0);
           ptx::bulk_commit();
+        }
+        if (C5) {
+          // feat4 channels [256 c + 128 sub, +128) as conv5's A operand: packed columns [128 c + 64 sub, +64) of buf0
+          // (all reads of buf0 by chunk 0 finished at the barrier above / one iteration earlier)
+          ptx::tc_fence_after();
+          ptx::tmem_st_32x32b_x32(t_lane + 128 * c + 64 * sub, reinterpret_cast<const uint32_t(&)[32]>(keep[0]));
+          ptx::tmem_st_32x32b_x32(t_lane + 128 * c + 64 * sub + 32, reinterpret_cast<const uint32_t(&)[32]>(keep[C5 ? 32 : 0]));
+          ptx::tmem_st_wait();
+          if (c == 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(a4_ready), 0));
+          }
+        }
+      }
+      if (C5) {
+        // ---- conv5 epilogues: chunk n = channels [256 n, +256); this warp: columns [128 sub, +128) -> staging blocks
+        //      F2 + Z (n even) / F3 (n odd) -> operand row columns 960 + 256 n + 64 b
+        const uint32_t free5_leader0 = ptx::mapa(ptx::smem_u32(&acc5_free[0]), 0);
+        for (int n = 0; n < 4; ++n) {
+          staging_free(1);  // last read by the store of chunk n - 2 (or feat4 chunk n): one younger group may be in flight
+          const bool stamp5 = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it == 1;
+          if (stamp5) p.dbg[64 + 24 + n] = clock64();  // staging free
+          ptx::mbar_wait(&acc5_full[0], n & 1);
+          ptx::tc_fence_after();
+          if (stamp5) p.dbg[64 + 32 + n] = clock64();  // accumulator ready
+          chain_drain<4, true>(t_lane + 256 + 128 * sub, 128 * sub, sconst + L::kB5 + 256 * n, (n & 1) ? sF3 : sF2, rr, p.cat,
+                               grow, p.M, 0);
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(free5_leader0);
+          ptx::named_bar_sync(1, 32 * kPairEpiWarps);
+          if (issuer) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              ptx::tma_store_2d(&tmCat, smem + ((n & 1) ? L::kF3 : L::kF2) + b * kChainBlock, 960 + 256 * n + 64 * b, row0);
+            ptx::bulk_commit();
+          }
+          if (stamp5) p.dbg[64 + 40 + n] = clock64();  // drained, stores issued
         }
       }
       if (stamp) p.dbg[it * 8 + 7] = clock64();  // conv4 drained

@@ -17,6 +17,7 @@
 #include "gemm_sm100.cuh"
 #include "gemm_pair_sm100.cuh"
 #include "chain_pair_sm100.cuh"
+#include "ts_probe.cuh"
 #include "pointwise.cuh"
 
 namespace {
@@ -441,10 +442,11 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     if (st) return st;
   }
   const GemmPlan plan_f = plan_gemm(1024, EPI_FUSION), plan_p = plan_gemm(256, EPI_ACT);
-  CUtensorMap tw_chain[3];
+  CUtensorMap tw_chain[4];
   if (!tf32) {
-    for (int k = 2; k <= 4; ++k) {
-      st = make_tmap(&tw_chain[k - 2], precision, pk + L.w[k], kChan[k], kChan[k - 1], kChan[k - 1], k == 2 ? 64 : 128);
+    for (int k = 2; k <= 5; ++k) {
+      st = make_tmap(&tw_chain[k - 2], precision, pk + L.w[k], kChan[k], kChan[k - 1], kChan[k - 1],
+                     k == 2 ? 64 : 128);
       if (st) return st;
     }
   }
@@ -468,11 +470,13 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     // bf16 tier: conv1..conv4 + gate layer 1 as ONE fused kernel (activations stay in shared memory);
     // LRN_NO_CHAIN=1 or the tf32 tier run one kernel per layer.
     static const bool no_chain = [] { const char* e = getenv("LRN_NO_CHAIN"); return e && e[0] == '1'; }();
+    static const bool chain5 = [] { const char* e = getenv("LRN_CHAIN5"); return !(e && e[0] == '0'); }();
     const bool fused_chain = !tf32 && plan_f.pair && !no_chain;
     if (fused_chain) {
       static bool configured = false;
       if (!configured) {
-        LRN_CUDA(cudaFuncSetAttribute(chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kDynamic));
+        LRN_CUDA(cudaFuncSetAttribute(chain_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kDynamic));
+        LRN_CUDA(cudaFuncSetAttribute(chain_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kDynamic));
         configured = true;
       }
       ChainParams cp{};
@@ -483,12 +487,19 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       cp.b2 = reinterpret_cast<const float*>(pk + L.b[2]);
       cp.b3 = reinterpret_cast<const float*>(pk + L.b[3]);
       cp.b4 = reinterpret_cast<const float*>(pk + L.b[4]);
+      cp.b5 = reinterpret_cast<const float*>(pk + L.b[5]);
       cp.cat = cat;
       static const int dbg_layer = [] { const char* e = getenv("LRN_DBG_LAYER"); return e ? atoi(e) : 0; }();
       cp.dbg = dbg_layer == 4 ? g_dbg : nullptr;
-      StageTimer timer(LRN_STAGE_CONV4, s);  // reported as "conv4" (embed/conv2/conv3 read 0)
+      // reported as stage "conv5" (with conv5 fused) or "conv4"; the other chain stages then read 0
+      StageTimer timer(chain5 ? LRN_STAGE_CONV5 : LRN_STAGE_CONV4, s);
       const int grid = 2 * std::min(cp.num_tiles, dev.sms / 2);
-      chain_pair_kernel<<<grid, kPairThreads, ChainSmem::kDynamic, s>>>(tw_chain[0], tw_chain[1], tw_chain[2], ta, cp);
+      if (chain5)
+        chain_pair_kernel<true><<<grid, kPairThreads, ChainSmem::kDynamic, s>>>(tw_chain[0], tw_chain[1], tw_chain[2],
+                                                                                tw_chain[3], ta, cp);
+      else
+        chain_pair_kernel<false><<<grid, kPairThreads, ChainSmem::kDynamic, s>>>(tw_chain[0], tw_chain[1], tw_chain[2],
+                                                                                 tw_chain[3], ta, cp);
       LRN_CUDA(cudaGetLastError());
     } else {  // layer 1 (+ gate layer 1): raw points -> operand columns
       StageTimer timer(LRN_STAGE_EMBED, s);
@@ -499,7 +510,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
         point_embed_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context) + r0, rows, ew, cat, kCat);
       LRN_CUDA(cudaGetLastError());
     }
-    for (int k = fused_chain ? 5 : 2; k <= 5; ++k) {  // conv2..conv5, each writes its own column block of the operand row
+    for (int k = fused_chain ? (chain5 ? 6 : 5) : 2; k <= 5; ++k) {  // conv2..conv5, each writes its own column block of the operand row
       GemmParams p{};
       p.M = int(rows);
       p.m_tiles = m_tiles_of(plan[k]);
@@ -570,6 +581,19 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     argmax_finalize_kernel<<<grid, 256, 0, s>>>(keys, B, global_feat, reinterpret_cast<long long*>(argmax));
     LRN_CUDA(cudaGetLastError());
   }
+  return LRN_OK;
+}
+
+int lrn_debug_ts_probe(const void* a_bf16 /* (128,64) */, const void* w_bf16 /* (64,64) */, float* out /* (128,64) */,
+                       lrn_stream_t stream) {
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  CUtensorMap tw;
+  st = make_tmap(&tw, LRN_PREC_BF16, w_bf16, 64, 64, 64, 64);
+  if (st) return st;
+  ts_probe_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tw, static_cast<const uint32_t*>(a_bf16), out);
+  LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
 

@@ -56,7 +56,7 @@ def test_cpu_tensors_fail_loudly():
 def test_launch_accounting_matches_chunk_loop():
     P = 4096 * 4096
     assert ops.encoder_launches(P, _lib.OUT_POOL, precision="tf32") == -(-P // ops.DEFAULT_CHUNK_ROWS) * 6
-    assert ops.encoder_launches(P, _lib.OUT_POOL, precision="bf16") == -(-P // ops.DEFAULT_CHUNK_ROWS) * 3
+    assert ops.encoder_launches(P, _lib.OUT_POOL, precision="bf16") == -(-P // ops.DEFAULT_CHUNK_ROWS) * 2
     assert ops.encoder_launches(1000, _lib.OUT_POOL | _lib.OUT_ARGMAX | _lib.OUT_MEMORY, precision="tf32") == 7 + 1
     assert ops.encoder_launches(300, _lib.OUT_POOL, chunk_rows=128, precision="tf32") == 3 * 6
 

@@ -26,6 +26,12 @@ if os.environ.get("LRN_DBG_LAYER") == "4":
     for i in range(16):
         r = [int(x) - t0 for x in t[i, :8]]
         print(f"{i:3d} " + " ".join(f"{x:8d}" for x in r) + f"   E1={r[3]-r[2]} wait3={r[4]-r[3]} E2={r[5]-r[4]} embed={r[6]-r[5]} E3={r[7]-r[6]} tile={r[7]-r[2]}")
+    f = buf.cpu()
+    if int(f[64 + 8]) != 0:
+        z = int(f[64 + 8])
+        print("conv5 of tile 1 (cycles since feat4-in-TMEM): per chunk n: [acc free (MMA), chunk issued (MMA) | staging free, acc ready, drained (epilogue)]")
+        for n in range(4):
+            print(f"  n={n}: {int(f[64+16+n])-z:7d} {int(f[64+n])-z:7d} | {int(f[64+24+n])-z:7d} {int(f[64+32+n])-z:7d} {int(f[64+40+n])-z:7d}")
     sys.exit(0)
 for i in range(16):
     r = [int(x) - t0 for x in t[i, :6]]
