@@ -244,7 +244,7 @@ def main():
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     if args.precision == "tf32":
         peak *= 0.5    # no TF32 peak is measured; half the bf16 figure
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel<128,EPI_FUSION> (fusion conv + gate + pooling)",
+    roofline = {"bound": "tensor", "kernel": "gemm_pair_kernel<256,EPI_FUSION> (fusion conv + gate + pooling, cta_group::2)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{peak_kind} bf16_tflops_sustained" + (" x 0.5 (tf32)" if args.precision == "tf32" else ""),
                 "traffic": None,

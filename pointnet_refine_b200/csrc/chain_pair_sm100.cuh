@@ -26,7 +26,9 @@
 // columns [256, 512).  Only the weights touch shared memory.  Measured: the TMEM A read costs ~128 cycles
 // per MMA whatever N is, so N = 256 (128-cycle math) is the shape that runs at the tensor-pipe floor
 // (N = 128 chunks with double-buffered accumulators took 125 cycles per MMA, i.e. half rate); the
-// shared-memory-operand form of the same MMA takes ~194 cycles.
+// shared-memory-operand form of the same MMA takes ~194 cycles.  conv5 streams 512 KB of weights per CTA and
+// tile; with a TMA latency of ~2.8k cycles the three 16 KB stages are latency-bound (17 B/clk), so while
+// conv5 runs the four F2 / Z blocks (idle then) serve as four more weight stages (7 x 16 KB in flight).
 #pragma once
 #include "gemm_pair_sm100.cuh"
 
@@ -62,9 +64,10 @@ struct ChainSmem {
   // fp32 constants: w1 (256) b1 (64) wg1 (64) bg1 (64) b2 (128) b3 (256) b4 (512) b5 (1024)
   static constexpr int kW1 = 0, kB1 = 256, kWg1 = 320, kBg1 = 384, kB2 = 448, kB3 = 576, kB4 = 832, kB5 = 1344,
                        kNumConst = 2368;
-  // w_full[S] w_empty[S] act_ready[3] acc_full[2] acc_free[2] a4_ready acc5_full[2] acc5_free[2]
+  // w_full[W] w_empty[W] act_ready[3] acc_full[2] acc_free[2] a4_ready acc5_full[2] acc5_free[2] fz_free
+  static constexpr int kW = kChainStages + 4;  // + the four F2 / Z blocks borrowed as weight stages while conv5 runs
   static constexpr int kBarOff = kConst + kNumConst * 4;
-  static constexpr int kTmemPtrOff = kBarOff + (2 * kChainStages + 12) * 8;
+  static constexpr int kTmemPtrOff = kBarOff + (2 * kW + 13) * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
   static constexpr int kDynamic = kTotal + 1024;
 };
@@ -152,14 +155,18 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sconst = reinterpret_cast<float*>(smem + L::kConst);
+  constexpr int W = L::kW;
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* w_empty = w_full + S;
-  uint64_t* act_ready = w_empty + S;  // [3]: F1 / F2 / F3 of BOTH CTAs written (leader's copy is used)
+  uint64_t* w_empty = w_full + W;
+  uint64_t* act_ready = w_empty + W;  // [3]: F1 / F2 / F3 of BOTH CTAs written (leader's copy is used)
   uint64_t* acc_full = act_ready + 3;  // [2]: accumulator buffer written by the MMAs
   uint64_t* acc_free = acc_full + 2;   // [2]: accumulator buffer drained by both CTAs (leader's copy is used)
   uint64_t* a4_ready = acc_free + 2;   // feat4 of BOTH CTAs is in tensor memory (leader's copy is used)
   uint64_t* acc5_full = a4_ready + 1;  // [2]: conv5 accumulator chunk written
   uint64_t* acc5_free = acc5_full + 2; // [2]: conv5 accumulator chunk drained by both CTAs (leader's copy is used)
+  uint64_t* fz_free = acc5_free + 2;   // this CTA's F2 / Z blocks may be overwritten by conv5 weights (local)
+  // weight stage s: 0..S-1 = dedicated stages, S..S+3 = blocks F2[0], F2[1], Z[0], Z[1]
+  auto stage_ptr = [&](int st) { return smem + (st < S ? L::kStages + st * kChainBlock : L::kF2 + (st - S) * kChainBlock); };
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
 
   const int warp = threadIdx.x >> 5;
@@ -175,10 +182,11 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     ptx::prefetch_tmap(&tmW4);
     if (C5) ptx::prefetch_tmap(&tmW5);
     ptx::prefetch_tmap(&tmCat);
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < W; ++s) {
       ptx::mbar_init(&w_full[s], 1);
       ptx::mbar_init(&w_empty[s], 1);
     }
+    ptx::mbar_init(fz_free, 1);
     for (int i = 0; i < 3; ++i) ptx::mbar_init(&act_ready[i], 2 * kPairEpiWarps);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
@@ -213,48 +221,61 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer (both CTAs)
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      // one stage = `nbox` boxes of `bytes` each (conv5 packs two 8 KB k-blocks into a 16 KB stage)
-      auto load = [&](const CUtensorMap* tm, int kcol, int nrow, uint32_t bytes, int nbox = 1) {
-        ptx::mbar_wait(&w_empty[stage], phase ^ 1);
-        const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&w_full[stage]), 0);
-        if (leader) ptx::mbar_arrive_expect_tx(&w_full[stage], 2 * bytes * nbox);
-        for (int b = 0; b < nbox; ++b)
-          ptx::tma_load_2d_pair(smem + L::kStages + stage * kChainBlock + b * bytes, tm, full_leader, kcol + 64 * b, nrow);
-        if (++stage == S) { stage = 0; phase ^= 1; }
+      // Two stage sequences share the per-stage barriers: conv2..conv4 cycle over the S dedicated stages (pointer
+      // pa), conv5 over all W stages (pointer pb).  Parities are tracked per stage (bit s of `par`); the MMA warp
+      // walks the identical sequence.
+      int pa = 0, pb = 0, it = 0;
+      uint32_t par = 0;
+      auto load = [&](int st, const CUtensorMap* tm, int kcol, int nrow, uint32_t bytes) {
+        ptx::mbar_wait(&w_empty[st], ((par >> st) & 1) ^ 1);
+        par ^= 1u << st;
+        const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&w_full[st]), 0);
+        if (leader) ptx::mbar_arrive_expect_tx(&w_full[st], 2 * bytes);
+        ptx::tma_load_2d_pair(stage_ptr(st), tm, full_leader, kcol, nrow);
       };
-      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
-        load(&tmW2, 0, static_cast<int>(rank) * 64, 64 * 128);                                    // conv2: N = 128
-        for (int kb = 0; kb < 2; ++kb) load(&tmW3, kb * 64, static_cast<int>(rank) * 128, 128 * 128);  // conv3: N = 256
-        for (int c = 0; c < 2; ++c)                                                              // conv4: 2 x (N = 256)
-          for (int kb = 0; kb < 4; ++kb) load(&tmW4, kb * 64, c * 256 + static_cast<int>(rank) * 128, 128 * 128);
-        if (C5)                                                                                  // conv5: 4 x (N = 256)
+      auto next_a = [&]() { const int st = pa; pa = pa + 1 == S ? 0 : pa + 1; return st; };
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+        load(next_a(), &tmW2, 0, static_cast<int>(rank) * 64, 64 * 128);                                    // conv2: N = 128
+        for (int kb = 0; kb < 2; ++kb) load(next_a(), &tmW3, kb * 64, static_cast<int>(rank) * 128, 128 * 128);  // conv3: N = 256
+        for (int c = 0; c < 2; ++c)                                                                        // conv4: 2 x (N = 256)
+          for (int kb = 0; kb < 4; ++kb) load(next_a(), &tmW4, kb * 64, c * 256 + static_cast<int>(rank) * 128, 128 * 128);
+        if (C5) {                                                                                          // conv5: 4 x (N = 256)
+          bool fz_ok = false;
           for (int n = 0; n < 4; ++n)
-            for (int kb = 0; kb < 8; ++kb) load(&tmW5, kb * 64, n * 256 + static_cast<int>(rank) * 128, 128 * 128);
+            for (int kb = 0; kb < 8; ++kb) {
+              const int st = pb;
+              pb = pb + 1 == W ? 0 : pb + 1;
+              if (st >= S && !fz_ok) {  // borrowed block: the feat4 store that staged through it must have drained it
+                ptx::mbar_wait(fz_free, it & 1);
+                fz_ok = true;
+              }
+              load(st, &tmW5, kb * 64, n * 256 + static_cast<int>(rank) * 128, 128 * 128);
+            }
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA)
     if (leader) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
+      int pa = 0, pb = 0, it = 0;
+      uint32_t wpar = 0;  // per-stage parity of w_full (same stage sequence as the producer)
       // one weight k-block: A = activation block `a_off` of this CTA (and the peer's at the same offset)
       auto kblock = [&](uint32_t a_off, uint32_t d_tmem, uint32_t idesc, bool first) {
-        ptx::mbar_wait(&w_full[stage], phase);
+        const int st = pa;
+        pa = pa + 1 == S ? 0 : pa + 1;
+        ptx::mbar_wait(&w_full[st], (wpar >> st) & 1);
+        wpar ^= 1u << st;
         ptx::tc_fence_after();
         if (lane == 0) {
           const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + a_off));
-          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + L::kStages + stage * kChainBlock));
+          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(stage_ptr(st)));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::tc_mma_ss_pair<false>(d_tmem, da + 2 * k, db + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
-          ptx::tc_commit_pair(&w_empty[stage], 3);
+          ptx::tc_commit_pair(&w_empty[st], 3);
         }
         __syncwarp();
-        if (++stage == S) { stage = 0; phase ^= 1; }
       };
       auto commit_acc = [&](int buf) {
         if (lane == 0) ptx::tc_commit_pair(&acc_full[buf], 3);
@@ -304,19 +325,21 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
             ptx::tc_fence_after();
             if (stamp5) p.dbg[64 + 16 + n] = clock64();  // accumulator free
             for (int kb = 0; kb < 8; ++kb) {
-              ptx::mbar_wait(&w_full[stage], phase);
+              const int st = pb;
+              pb = pb + 1 == W ? 0 : pb + 1;
+              ptx::mbar_wait(&w_full[st], (wpar >> st) & 1);
+              wpar ^= 1u << st;
               ptx::tc_fence_after();
               if (lane == 0) {
-                const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + L::kStages + stage * kChainBlock));
+                const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(stage_ptr(st)));
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   tc_mma_ts_pair(tmem_base + 256, tmem_base + kb * 32 + k * 8, db + 2 * k, kIdesc256, (kb > 0 || k > 0) ? 1u : 0u);
-                ptx::tc_commit_pair(&w_empty[stage], 3);
+                ptx::tc_commit_pair(&w_empty[st], 3);
                 if (kb == 7) ptx::tc_commit_pair(&acc5_full[0], 3);
                 if (kb == 7 && stamp5) p.dbg[64 + n] = clock64();  // chunk n issued
               }
               __syncwarp();
-              if (++stage == S) { stage = 0; phase ^= 1; }
             }
           }
         }
@@ -472,22 +495,25 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(a4_ready), 0));
+            if (issuer) {  // feat4 chunk 0's store (staged in F2 + Z) has been read: the blocks may take conv5 weights
+              ptx::bulk_wait_read_keep<1>();
+              ptx::mbar_arrive(fz_free);
+            }
           }
         }
       }
       if (C5) {
         // ---- conv5 epilogues: chunk n = channels [256 n, +256); this warp: columns [128 sub, +128) -> staging blocks
-        //      F2 + Z (n even) / F3 (n odd) -> operand row columns 960 + 256 n + 64 b
+        //      F3 (F2 / Z hold conv5 weights now) -> operand row columns 960 + 256 n + 64 b
         const uint32_t free5_leader0 = ptx::mapa(ptx::smem_u32(&acc5_free[0]), 0);
         for (int n = 0; n < 4; ++n) {
-          staging_free(1);  // last read by the store of chunk n - 2 (or feat4 chunk n): one younger group may be in flight
+          staging_free(0);  // F3 was last read by the previous store group (feat4 chunk 1 / conv5 chunk n - 1)
           const bool stamp5 = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it == 1;
           if (stamp5) p.dbg[64 + 24 + n] = clock64();  // staging free
           ptx::mbar_wait(&acc5_full[0], n & 1);
           ptx::tc_fence_after();
           if (stamp5) p.dbg[64 + 32 + n] = clock64();  // accumulator ready
-          chain_drain<4, true>(t_lane + 256 + 128 * sub, 128 * sub, sconst + L::kB5 + 256 * n, (n & 1) ? sF3 : sF2, rr, p.cat,
-                               grow, p.M, 0);
+          chain_drain<4, true>(t_lane + 256 + 128 * sub, 128 * sub, sconst + L::kB5 + 256 * n, sF3, rr, p.cat, grow, p.M, 0);
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -496,7 +522,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
           if (issuer) {
 #pragma unroll
             for (int b = 0; b < 4; ++b)
-              ptx::tma_store_2d(&tmCat, smem + ((n & 1) ? L::kF3 : L::kF2) + b * kChainBlock, 960 + 256 * n + 64 * b, row0);
+              ptx::tma_store_2d(&tmCat, smem + L::kF3 + b * kChainBlock, 960 + 256 * n + 64 * b, row0);
             ptx::bulk_commit();
           }
           if (stamp5) p.dbg[64 + 40 + n] = clock64();  // drained, stores issued
