@@ -149,6 +149,43 @@ int lrn_debug_timeline(long long* device_buffer);
 int lrn_debug_ts_probe(const void* a_bf16, const void* w_bf16, float* out, lrn_stream_t stream);
 int lrn_profile_read(float* ms_per_stage /*[LRN_STAGE_COUNT]*/, int64_t* launches_per_stage /*[LRN_STAGE_COUNT]*/);
 
+/* ---- train mode: batch-statistic BatchNorm forward + hand-written backward of the context encoder ----
+ * Replaces: MultiScalePointNetEncoder.forward under model.train() (src/model.py:39-55 with nn.BatchNorm1d in
+ * training mode) and its autograd backward, as driven by train.py:56-72 / train_dist.py:168-189.  bf16
+ * tensor-core operands, fp32 parameters and gradients.  The pooling (src/model.py:58-60) and context_proj
+ * stay with the caller (they are differentiable functions of `fused`).
+ *   running     : running_mean / running_var of bn1..bn5 and fusion.1, updated in place like PyTorch
+ *                 (momentum, unbiased variance); may be NULL.  num_batches_tracked is the caller's counter.
+ *   fused       : (B,1024,N) fp32 output;  d_fused: its gradient.
+ *   grads       : fp32 gradient of every encoder parameter (same shapes as lrn_encoder_params).
+ *   workspace   : lrn_train_workspace_bytes(B, N); the forward leaves the saved activations there and the
+ *                 matching backward call must receive the same, untouched buffer. */
+typedef struct lrn_bn_running {
+  float* mean[6]; /* bn1..bn5, fusion.1 */
+  float* var[6];
+} lrn_bn_running;
+typedef struct lrn_encoder_grads {
+  float* conv_w[5];
+  float* conv_b[5];
+  float* bn_w[5];
+  float* bn_b[5];
+  float* fusion_w;
+  float* fusion_b;
+  float* fusion_bn_w;
+  float* fusion_bn_b;
+  float* gate0_w;
+  float* gate0_b;
+  float* gate2_w;
+  float* gate2_b;
+} lrn_encoder_grads;
+size_t lrn_train_workspace_bytes(int64_t B, int64_t N);
+int lrn_encoder_train_forward(const lrn_encoder_params* params, const lrn_bn_running* running, float momentum,
+                              const float* context, int64_t B, int64_t N, float* fused, void* workspace,
+                              size_t workspace_bytes, lrn_stream_t stream);
+int lrn_encoder_train_backward(const lrn_encoder_params* params, const float* context, int64_t B, int64_t N,
+                               const float* d_fused, const lrn_encoder_grads* grads, void* workspace,
+                               size_t workspace_bytes, lrn_stream_t stream);
+
 /* ---- building block, exported for unit tests and profiling ----
  * out[M,N] = act(A[M,K] * W[N,K]^T + bias) on the tcgen05 tensor-core path.
  *   precision BF16: A, W bfloat16, out bfloat16 (out_f32 = 0) or fp32 (out_f32 = 1)

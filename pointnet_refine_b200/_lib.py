@@ -23,7 +23,8 @@ PRECISIONS = {"bf16": PREC_BF16, "tf32": PREC_TF32}
 EXPORTS = [
     "lrn_abi_version", "lrn_status_string", "lrn_last_error", "lrn_device_check",
     "lrn_encoder_packed_bytes", "lrn_encoder_fold", "lrn_encoder_workspace_bytes", "lrn_encoder_forward",
-    "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe",
+    "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe", "lrn_train_workspace_bytes",
+    "lrn_encoder_train_forward", "lrn_encoder_train_backward",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
 

@@ -681,3 +681,275 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt,
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Train-mode path: batch-statistic BatchNorm forward + hand-written backward of the context encoder
+// (reference: MultiScalePointNetEncoder.forward in model.train(), src/model.py:39-55, driven by the training
+// loops train.py:56-72 / train_dist.py:168-189).  bf16 tensor-core operands, fp32 master weights and gradients.
+// Every GEMM (forward, dgrad, wgrad) is the tcgen05 pair kernel; csrc/train_kernels.cuh holds the glue.
+// =====================================================================================================
+#include "train_kernels.cuh"
+
+namespace {
+
+const int kUOff[6] = {0, 64, 192, 448, 960, 1984};  // column of U_k (pre-BN) inside the (P, 3008) buffer; [5] = fusion
+const int kUW[6] = {64, 128, 256, 512, 1024, 1024};
+constexpr int kULd = 3008;
+constexpr int kStatLd = 3008;
+
+struct TrainWs {
+  int64_t P, Pp;
+  // activations saved by the forward
+  size_t X, U, Z;
+  // statistics (fp32, kStatLd each): sum, sumsq, mean, rstd, scale, shift, S1, S2; Sz (1024)
+  size_t stats;
+  // bf16 weights: W2..W5, Wf (1024 x 2048), Wg2 (1024 x 64), and transposed copies for the dgrads
+  size_t w[6], wf, wg2, wt[6], wft, wg2t, wpack_end;
+  // backward temporaries
+  size_t XT, dA, dB, dU, dUT, dZ, dZT, dHp, gW;
+  size_t total;
+};
+
+TrainWs train_layout(int64_t B, int64_t N) {
+  TrainWs W{};
+  W.P = B * N;
+  W.Pp = (W.P + 255) / 256 * 256;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  W.X = take(size_t(W.Pp) * kCat * 2);
+  W.U = take(size_t(W.Pp) * kULd * 2);
+  W.Z = take(size_t(W.Pp) * 1024 * 2);
+  W.stats = take(size_t(8 * kStatLd + 1024) * 4);
+  const size_t wstart = off;
+  for (int k = 2; k <= 5; ++k) W.w[k] = take(size_t(kChan[k]) * kChan[k - 1] * 2);
+  W.wf = take(size_t(1024) * kCat * 2);
+  W.wg2 = take(size_t(1024) * 64 * 2);
+  for (int k = 2; k <= 5; ++k) W.wt[k] = take(size_t(std::max(kChan[k - 1], 128)) * kChan[k] * 2);
+  W.wft = take(size_t(kCat) * 1024 * 2);
+  W.wg2t = take(size_t(128) * 1024 * 2);
+  W.wpack_end = off;
+  (void)wstart;
+  W.XT = take(size_t(kCat) * W.Pp * 2);
+  W.dA = take(size_t(W.Pp) * kCat * 2);
+  W.dB = take(size_t(W.Pp) * 512 * 2);
+  W.dU = take(size_t(W.Pp) * 1024 * 2);
+  W.dUT = take(size_t(1024) * W.Pp * 2);
+  W.dZ = take(size_t(W.Pp) * 1024 * 2);
+  W.dZT = take(size_t(1024) * W.Pp * 2);
+  W.dHp = take(size_t(W.Pp) * 128 * 2);
+  W.gW = take(size_t(1024) * kCat * 4);
+  W.total = off;
+  return W;
+}
+
+// out (M x N) = [relu](A (M x K) * Wt (N x K)^T + bias), bf16 operands, bf16 or fp32 output
+int run_gemm_bf16(const void* A, int64_t lda, int64_t M, int64_t K, const void* Wt, int64_t ldw, int64_t N,
+                  const float* bias, void* out, int64_t ldo, int out_f32, int relu, cudaStream_t s) {
+  return lrn_gemm_bias_act(LRN_PREC_BF16, A, lda, Wt, ldw, bias, out, ldo, out_f32, relu, M, N, K,
+                           reinterpret_cast<lrn_stream_t>(s));
+}
+
+int pack_w(const float* src, int rows, int cols, void* dst, int64_t ld, bool transpose, cudaStream_t s) {
+  const long long total = static_cast<long long>(rows) * cols;
+  pack_bf16_kernel<<<int(std::min<long long>((total + 255) / 256, 2048)), 256, 0, s>>>(
+      src, rows, cols, static_cast<__nv_bfloat16*>(dst), ld, transpose ? 1 : 0);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+dim3 stats_grid(int C, int64_t rows) { return dim3(C / 64, unsigned(std::min<int64_t>((rows + 511) / 512, 512))); }
+
+int transpose_bf16(const void* src, int64_t ld_src, int64_t rows, int C, void* dst, int64_t ld_dst, cudaStream_t s) {
+  dim3 grid(unsigned((ld_dst + 31) / 32), unsigned(C / 32));
+  transpose_bf16_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), ld_src, rows, C,
+                                             static_cast<__nv_bfloat16*>(dst), ld_dst);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int elem_grid(long long total) { return int(std::min<long long>((total + 255) / 256, 148 * 32)); }
+
+}  // namespace
+
+extern "C" {
+
+size_t lrn_train_workspace_bytes(int64_t B, int64_t N) {
+  if (B <= 0 || N <= 0) return 0;
+  return train_layout(B, N).total;
+}
+
+int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running* running, float momentum,
+                              const float* context, int64_t B, int64_t N, float* fused, void* workspace,
+                              size_t workspace_bytes, lrn_stream_t stream) {
+  if (!pr || !context || !fused || !workspace) return fail(LRN_ERR_BAD_ARG, "null argument");
+  if (B <= 0 || N <= 0 || B * N >= (int64_t(1) << 31) - 256) return fail(LRN_ERR_BAD_SHAPE, "B=%lld N=%lld", (long long)B, (long long)N);
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const TrainWs W = train_layout(B, N);
+  if (workspace_bytes < W.total) return fail(LRN_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, W.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LRN_ERR_MISALIGNED, "workspace must be 1024-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto* X = reinterpret_cast<__nv_bfloat16*>(ws + W.X);
+  auto* U = reinterpret_cast<__nv_bfloat16*>(ws + W.U);
+  auto* Z = reinterpret_cast<__nv_bfloat16*>(ws + W.Z);
+  float* stats = reinterpret_cast<float*>(ws + W.stats);
+  float *sum = stats, *sumsq = stats + kStatLd, *mean = stats + 2 * kStatLd, *rstd = stats + 3 * kStatLd,
+        *scale = stats + 4 * kStatLd, *shift = stats + 5 * kStatLd;
+  const int64_t P = W.P;
+
+  LRN_CUDA(cudaMemsetAsync(stats, 0, size_t(2 * kStatLd) * 4, s));
+  LRN_CUDA(cudaMemsetAsync(ws + W.w[2], 0, W.wpack_end - W.w[2], s));
+  for (int k = 2; k <= 5; ++k) {  // bf16 copies of the (unfolded) weights, and transposed for the dgrads
+    if ((st = pack_w(pr->conv_w[k - 1], kChan[k], kChan[k - 1], ws + W.w[k], kChan[k - 1], false, s))) return st;
+    if ((st = pack_w(pr->conv_w[k - 1], kChan[k], kChan[k - 1], ws + W.wt[k], kChan[k], true, s))) return st;
+  }
+  if ((st = pack_w(pr->fusion_w, 1024, kFusionK, ws + W.wf, kCat, false, s))) return st;
+  if ((st = pack_w(pr->fusion_w, 1024, kFusionK, ws + W.wft, 1024, true, s))) return st;
+  if ((st = pack_w(pr->gate2_w, 1024, 64, ws + W.wg2, 64, false, s))) return st;
+  if ((st = pack_w(pr->gate2_w, 1024, 64, ws + W.wg2t, 1024, true, s))) return st;
+
+  train_embed_kernel<<<int(std::min<int64_t>((P + 15) / 16, int64_t(dev.sms) * 16)), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(context), P, pr->conv_w[0], pr->conv_b[0], pr->gate0_w, pr->gate0_b, U, kULd, X, kCat);
+  LRN_CUDA(cudaGetLastError());
+
+  for (int i = 0; i < 6; ++i) {  // i = 0..4: conv1..conv5, i = 5: fusion
+    const int C = kUW[i], uo = kUOff[i];
+    const float* gamma = i < 5 ? pr->bn_w[i] : pr->fusion_bn_w;
+    const float* beta = i < 5 ? pr->bn_b[i] : pr->fusion_bn_b;
+    col_stats_kernel<<<stats_grid(C, P), 256, 0, s>>>(U + uo, kULd, P, sum + uo, sumsq + uo);
+    LRN_CUDA(cudaGetLastError());
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum + uo, sumsq + uo, P, C, gamma, beta, pr->bn_eps, momentum,
+                                                       running ? running->mean[i] : nullptr,
+                                                       running ? running->var[i] : nullptr, mean + uo, rstd + uo,
+                                                       scale + uo, shift + uo);
+    LRN_CUDA(cudaGetLastError());
+    if (i == 5) break;
+    bn_relu_apply_kernel<<<elem_grid(P * C / 8), 256, 0, s>>>(U + uo, kULd, P, C, scale + uo, shift + uo, X + kCatOff[i + 1], kCat);
+    LRN_CUDA(cudaGetLastError());
+    if (i < 4) {  // next layer's pre-activation: U_{k+1} = X_k W_{k+1}^T + b_{k+1}
+      const int k = i + 2;
+      st = run_gemm_bf16(X + kCatOff[i + 1], kCat, P, kChan[k - 1], ws + W.w[k], kChan[k - 1], kChan[k], pr->conv_b[k - 1],
+                         U + kUOff[i + 1], kULd, 0, 0, s);
+      if (st) return st;
+    } else {  // fusion conv over the whole operand row, and gate layer 2 over the gate hidden block
+      st = run_gemm_bf16(X, kCat, P, kFusionK, ws + W.wf, kCat, 1024, pr->fusion_b, U + kUOff[5], kULd, 0, 0, s);
+      if (st) return st;
+      st = run_gemm_bf16(X + kFusionK, kCat, P, kGateK, ws + W.wg2, kGateK, 1024, pr->gate2_b, Z, 1024, 0, 0, s);
+      if (st) return st;
+    }
+  }
+  dim3 grid(unsigned((P + 31) / 32), 32);
+  fusion_gate_fwd_kernel<<<grid, 256, 0, s>>>(U + kUOff[5], kULd, Z, 1024, P, int(N), scale + kUOff[5], shift + kUOff[5], fused);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* context, int64_t B, int64_t N,
+                               const float* d_fused, const lrn_encoder_grads* g, void* workspace,
+                               size_t workspace_bytes, lrn_stream_t stream) {
+  if (!pr || !context || !d_fused || !g || !workspace) return fail(LRN_ERR_BAD_ARG, "null argument");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const TrainWs W = train_layout(B, N);
+  if (workspace_bytes < W.total) return fail(LRN_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, W.total);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto* X = reinterpret_cast<__nv_bfloat16*>(ws + W.X);
+  auto* U = reinterpret_cast<__nv_bfloat16*>(ws + W.U);
+  auto* Z = reinterpret_cast<__nv_bfloat16*>(ws + W.Z);
+  auto* XT = reinterpret_cast<__nv_bfloat16*>(ws + W.XT);
+  auto* dA = reinterpret_cast<__nv_bfloat16*>(ws + W.dA);
+  auto* dB = reinterpret_cast<__nv_bfloat16*>(ws + W.dB);
+  auto* dU = reinterpret_cast<__nv_bfloat16*>(ws + W.dU);
+  auto* dUT = reinterpret_cast<__nv_bfloat16*>(ws + W.dUT);
+  auto* dZ = reinterpret_cast<__nv_bfloat16*>(ws + W.dZ);
+  auto* dZT = reinterpret_cast<__nv_bfloat16*>(ws + W.dZT);
+  auto* dHp = reinterpret_cast<__nv_bfloat16*>(ws + W.dHp);
+  float* gW = reinterpret_cast<float*>(ws + W.gW);
+  float* stats = reinterpret_cast<float*>(ws + W.stats);
+  float *mean = stats + 2 * kStatLd, *rstd = stats + 3 * kStatLd, *scale = stats + 4 * kStatLd, *shift = stats + 5 * kStatLd,
+        *S1 = stats + 6 * kStatLd, *S2 = stats + 7 * kStatLd, *Sz = stats + 8 * kStatLd;
+  const int64_t P = W.P, Pp = W.Pp;
+  auto d2d = [&](float* dst, const float* src, int n) { return cudaMemcpyAsync(dst, src, size_t(n) * 4, cudaMemcpyDeviceToDevice, s); };
+  auto copy_sub = [&](const float* src, int64_t ld, int c0, int rows, int cols, float* dst) {
+    copy_submatrix_kernel<<<elem_grid(static_cast<long long>(rows) * cols), 256, 0, s>>>(src, ld, c0, rows, cols, dst);
+    return cudaGetLastError();
+  };
+
+  LRN_CUDA(cudaMemsetAsync(S1, 0, size_t(2 * kStatLd + 1024) * 4, s));
+  LRN_CUDA(cudaMemsetAsync(g->conv_w[0], 0, 64 * 4 * 4, s));
+  LRN_CUDA(cudaMemsetAsync(g->conv_b[0], 0, 64 * 4, s));
+  LRN_CUDA(cudaMemsetAsync(g->gate0_w, 0, 64 * 4, s));
+  LRN_CUDA(cudaMemsetAsync(g->gate0_b, 0, 64 * 4, s));
+  for (int k = 1; k < 5; ++k) LRN_CUDA(cudaMemsetAsync(g->conv_b[k], 0, size_t(kChan[k + 1]) * 4, s));
+  LRN_CUDA(cudaMemsetAsync(g->fusion_b, 0, 1024 * 4, s));
+  // operand rows, channel-major, for the weight gradients (K = points)
+  if ((st = transpose_bf16(X, kCat, P, kCat, XT, Pp, s))) return st;
+
+  // ---- fused output: gate, ReLU, fusion BatchNorm
+  {
+    dim3 grid(unsigned((P + 31) / 32), 32);
+    fusion_gate_bwd_kernel<<<grid, 256, 0, s>>>(d_fused, U + kUOff[5], kULd, Z, 1024, P, int(N), scale + kUOff[5],
+                                                shift + kUOff[5], dU, dZ, 1024);
+    LRN_CUDA(cudaGetLastError());
+    col_stats_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dZ, 1024, P, Sz, nullptr);  // d(gate layer 2 bias)
+    LRN_CUDA(cudaGetLastError());
+    LRN_CUDA(d2d(g->gate2_b, Sz, 1024));
+    const int uo = kUOff[5];
+    bn_bwd_reduce_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, 0, U + uo, kULd, P, mean + uo,
+                                                             rstd + uo, S1 + uo, S2 + uo);
+    LRN_CUDA(cudaGetLastError());
+    LRN_CUDA(d2d(g->fusion_bn_b, S1 + uo, 1024));
+    LRN_CUDA(d2d(g->fusion_bn_w, S2 + uo, 1024));
+    bn_bwd_apply_kernel<<<elem_grid(P * 1024), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, 0, U + uo, kULd, P, 1024, mean + uo,
+                                                            rstd + uo, pr->fusion_bn_w, S1 + uo, S2 + uo, dU, 1024);
+    LRN_CUDA(cudaGetLastError());
+    col_stats_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, P, g->fusion_b, nullptr);
+    LRN_CUDA(cudaGetLastError());
+    if ((st = transpose_bf16(dU, 1024, P, 1024, dUT, Pp, s))) return st;
+    if ((st = transpose_bf16(dZ, 1024, P, 1024, dZT, Pp, s))) return st;
+    // d(operand row) = dUf Wf  (columns >= 1984 of the padded transposed weight are zero)
+    if ((st = run_gemm_bf16(dU, 1024, P, 1024, ws + W.wft, 1024, kCat, nullptr, dA, kCat, 0, 0, s))) return st;
+    // dWf = dUf^T X   (K = points)
+    if ((st = run_gemm_bf16(dUT, Pp, 1024, Pp, XT, Pp, kCat, nullptr, gW, kCat, 1, 0, s))) return st;
+    LRN_CUDA(copy_sub(gW, kCat, 0, 1024, kFusionK, g->fusion_w));
+    // gate layer 2: dH = dZ Wg2, dWg2 = dZ^T H
+    if ((st = run_gemm_bf16(dZ, 1024, P, 1024, ws + W.wg2t, 1024, 128, nullptr, dHp, 128, 0, 0, s))) return st;
+    if ((st = run_gemm_bf16(dZT, Pp, 1024, Pp, XT + size_t(1920) * Pp, Pp, 128, nullptr, gW, 128, 1, 0, s))) return st;
+    LRN_CUDA(copy_sub(gW, 128, 64, 1024, 64, g->gate2_w));
+  }
+  // ---- chain, back to front: layer k consumes d(feat_k) = fusion dgrad slice (+ dgrad of layer k + 1)
+  for (int k = 5; k >= 1; --k) {
+    const int i = k - 1, C = kChan[k], uo = kUOff[i], xo = kCatOff[k];
+    const __nv_bfloat16* d2 = k < 5 ? dB : nullptr;
+    bn_bwd_reduce_kernel<<<stats_grid(C, P), 256, 0, s>>>(dA + xo, kCat, d2, 512, X + xo, kCat, U + uo, kULd, P, mean + uo,
+                                                          rstd + uo, S1 + uo, S2 + uo);
+    LRN_CUDA(cudaGetLastError());
+    LRN_CUDA(d2d(g->bn_b[i], S1 + uo, C));
+    LRN_CUDA(d2d(g->bn_w[i], S2 + uo, C));
+    bn_bwd_apply_kernel<<<elem_grid(P * C), 256, 0, s>>>(dA + xo, kCat, d2, 512, X + xo, kCat, U + uo, kULd, P, C, mean + uo,
+                                                         rstd + uo, pr->bn_w[i], S1 + uo, S2 + uo, dU, 1024);
+    LRN_CUDA(cudaGetLastError());
+    if (k == 1) break;
+    col_stats_kernel<<<stats_grid(C, P), 256, 0, s>>>(dU, 1024, P, g->conv_b[i], nullptr);
+    LRN_CUDA(cudaGetLastError());
+    if ((st = transpose_bf16(dU, 1024, P, C, dUT, Pp, s))) return st;
+    const int cin = kChan[k - 1], cin_p = std::max(cin, 128);
+    // dW_k = dU_k^T X_{k-1}
+    if ((st = run_gemm_bf16(dUT, Pp, C, Pp, XT + size_t(kCatOff[k - 1]) * Pp, Pp, cin_p, nullptr, gW, cin_p, 1, 0, s))) return st;
+    LRN_CUDA(copy_sub(gW, cin_p, 0, C, cin, g->conv_w[i]));
+    // d(feat_{k-1}) += dU_k W_k
+    if ((st = run_gemm_bf16(dU, 1024, P, C, ws + W.wt[k], C, cin_p, nullptr, dB, 512, 0, 0, s))) return st;
+  }
+  // ---- conv1 and gate layer 1 (fp32 reductions over the points)
+  conv1_gate1_bwd_kernel<<<int(std::min<int64_t>((P + 2047) / 2048, 1024)), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(context), P, dU, 1024, dHp, 128, X + kFusionK, kCat, g->conv_w[0], g->conv_b[0],
+      g->gate0_w, g->gate0_b);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+}  // extern "C"

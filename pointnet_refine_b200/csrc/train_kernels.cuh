@@ -1,0 +1,324 @@
+// CUDA-core kernels of the train-mode path (batch-statistic BatchNorm forward and the hand-written
+// backward).  All GEMMs of that path (forward, dgrad, wgrad) go through the tcgen05 pair kernels; these
+// kernels are the HBM-bound glue: statistics, normalisation, gate, masks, transposes, small reductions.
+// Reference semantics: torch.nn.BatchNorm1d in training mode (biased variance for normalisation, unbiased
+// for the running update, momentum 0.1) as used by src/model.py:16-20,25,43-51.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace lrn {
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// dst (bf16, row pitch ld) <- src fp32 (rows x cols), optionally transposed.  dst is zero-filled beforehand.
+__global__ void pack_bf16_kernel(const float* __restrict__ src, int rows, int cols, __nv_bfloat16* __restrict__ dst,
+                                 long long ld, int transpose) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<long long>(r) * cols);
+    dst[transpose ? c * ld + r : r * ld + c] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// conv1 pre-activation U1 = W1 x + b1 (raw fp32 point, no BatchNorm yet) and gate hidden H = relu(wg1 I + bg1).
+// 16 threads per point, 4 + 4 channels each (same mapping as point_embed_kernel).
+__global__ void __launch_bounds__(256)
+train_embed_kernel(const float4* __restrict__ ctx, long long rows, const float* __restrict__ w1,
+                   const float* __restrict__ b1, const float* __restrict__ wg1, const float* __restrict__ bg1,
+                   __nv_bfloat16* __restrict__ U, long long ldu, __nv_bfloat16* __restrict__ X, long long ldx) {
+  const int sub = threadIdx.x & 15;
+  float4 wr[4];
+  float br[4], gw[4], gb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    wr[j] = reinterpret_cast<const float4*>(w1)[4 * sub + j];
+    br[j] = b1[4 * sub + j];
+    gw[j] = wg1[4 * sub + j];
+    gb[j] = bg1[4 * sub + j];
+  }
+  const long long ppb = blockDim.x / 16;
+  for (long long pt = blockIdx.x * ppb + (threadIdx.x >> 4); pt < rows; pt += gridDim.x * ppb) {
+    const float4 x = __ldg(ctx + pt);
+    float u[4], h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      u[j] = fmaf(wr[j].x, x.x, fmaf(wr[j].y, x.y, fmaf(wr[j].z, x.z, fmaf(wr[j].w, x.w, br[j]))));
+      h[j] = fmaxf(fmaf(gw[j], x.w, gb[j]), 0.f);
+    }
+    *reinterpret_cast<uint2*>(U + pt * ldu + 4 * sub) = make_uint2(ptx::pack_bf16x2(u[0], u[1]), ptx::pack_bf16x2(u[2], u[3]));
+    *reinterpret_cast<uint2*>(X + pt * ldx + 1984 + 4 * sub) =
+        make_uint2(ptx::pack_bf16x2(h[0], h[1]), ptx::pack_bf16x2(h[2], h[3]));
+  }
+}
+
+// Per-column sum and sum of squares of a bf16 (rows x C) matrix -> fp32 atomics into sum[C], sumsq[C].
+// Block = 64 columns x 4 row lanes; grid = (C / 64, row slabs).
+__global__ void __launch_bounds__(256)
+col_stats_kernel(const __nv_bfloat16* __restrict__ A, long long ld, long long rows, float* __restrict__ sum,
+                 float* __restrict__ sumsq) {
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int lane_r = threadIdx.x >> 6;
+  float s = 0.f, q = 0.f;
+  for (long long r = blockIdx.y * 4ll + lane_r; r < rows; r += gridDim.y * 4ll) {
+    const float v = bf2f(A[r * ld + c]);
+    s += v;
+    q = fmaf(v, v, q);
+  }
+  __shared__ float sh[2][4][64];
+  sh[0][lane_r][threadIdx.x & 63] = s;
+  sh[1][lane_r][threadIdx.x & 63] = q;
+  __syncthreads();
+  if (lane_r == 0) {
+    const int t = threadIdx.x;
+    atomicAdd(sum + c, sh[0][0][t] + sh[0][1][t] + sh[0][2][t] + sh[0][3][t]);
+    if (sumsq) atomicAdd(sumsq + c, sh[1][0][t] + sh[1][1][t] + sh[1][2][t] + sh[1][3][t]);
+  }
+}
+
+// Batch statistics -> mean / rstd, the fused scale/shift of the normalisation, and the running-stat update.
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, long long rows, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float n = static_cast<float>(rows);
+  const float m = sum[c] / n;
+  const float var = fmaxf(sumsq[c] / n - m * m, 0.f);  // biased
+  const float r = rsqrtf(var + eps);
+  mean[c] = m;
+  rstd[c] = r;
+  scale[c] = gamma[c] * r;
+  shift[c] = beta[c] - m * gamma[c] * r;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (rows > 1 ? n / (n - 1.f) : 1.f);
+  }
+}
+
+// X[:, c] = relu(U[:, c] * scale[c] + shift[c]); 8 channels (16 bytes) per thread.
+__global__ void __launch_bounds__(256)
+bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ U, long long ldu, long long rows, int C,
+                     const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ X,
+                     long long ldx) {
+  const int groups = C / 8;
+  const long long total = rows * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / groups;
+    const int c0 = static_cast<int>(i - r * groups) * 8;
+    const uint4 raw = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
+    const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(&raw);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(bf2f(u[j]), scale[c0 + j], shift[c0 + j]), 0.f);
+    *reinterpret_cast<uint4*>(X + r * ldx + c0) =
+        make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
+                   ptx::pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// dst (C x ld_dst) = src^T, src (rows x C, pitch ld_src), bf16, 32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, long long rows, int C,
+                      __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const long long r0 = blockIdx.x * 32ll;
+  const int c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long r = r0 + ty + 8 * k;
+    tile[ty + 8 * k][tx] = (r < rows) ? src[r * ld_src + c0 + tx] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k;
+    const long long r = r0 + tx;
+    if (r < ld_dst) dst[static_cast<long long>(c) * ld_dst + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+
+// fused[b, c, n] = relu(Uf[p, c] * scale[c] + shift[c]) * (0.5 + 0.5 * sigmoid(Z[p, c])),  p = b * N + n
+// (src/model.py:51,54-55, train mode).  32 points x 32 channels per block, transposed through shared memory so
+// both the point-major reads and the channel-major (B,1024,N) writes are coalesced.
+__global__ void __launch_bounds__(256)
+fusion_gate_fwd_kernel(const __nv_bfloat16* __restrict__ Uf, long long ldu, const __nv_bfloat16* __restrict__ Z,
+                       long long ldz, long long rows, int npts, const float* __restrict__ scale,
+                       const float* __restrict__ shift, float* __restrict__ fused) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long p0 = blockIdx.x * 32ll;
+  const int c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long p = p0 + ty + 8 * k;
+    float v = 0.f;
+    if (p < rows) {
+      const int c = c0 + tx;
+      const float y = fmaxf(fmaf(bf2f(Uf[p * ldu + c]), scale[c], shift[c]), 0.f);
+      v = y * (0.5f + 0.5f * sigmoidf_fast(bf2f(Z[p * ldz + c])));
+    }
+    tile[ty + 8 * k][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k;
+    const long long p = p0 + tx;
+    if (p < rows) {
+      const long long b = p / npts, n = p - b * npts;
+      fused[(b * 1024 + c) * npts + n] = tile[tx][ty + 8 * k];
+    }
+  }
+}
+
+// Backward of the gate / ReLU at the fused output: with y0 = Uf*scale+shift, y = relu(y0), g = sigmoid(Z):
+//   dY[p,c] = dF * (0.5 + 0.5 g) * [y0 > 0]      (gradient w.r.t. the BatchNorm output)
+//   dZ[p,c] = dF * y * 0.5 * g * (1 - g)         (gradient w.r.t. the gate pre-activation)
+__global__ void __launch_bounds__(256)
+fusion_gate_bwd_kernel(const float* __restrict__ dfused, const __nv_bfloat16* __restrict__ Uf, long long ldu,
+                       const __nv_bfloat16* __restrict__ Z, long long ldz, long long rows, int npts,
+                       const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dY,
+                       __nv_bfloat16* __restrict__ dZ, long long ldd) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long p0 = blockIdx.x * 32ll;
+  const int c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // coalesced along n: tile[c][p]
+    const int c = c0 + ty + 8 * k;
+    const long long p = p0 + tx;
+    float v = 0.f;
+    if (p < rows) {
+      const long long b = p / npts, n = p - b * npts;
+      v = dfused[(b * 1024 + c) * npts + n];
+    }
+    tile[ty + 8 * k][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long p = p0 + ty + 8 * k;
+    if (p < rows) {
+      const int c = c0 + tx;
+      const float df = tile[tx][ty + 8 * k];
+      const float y0 = fmaf(bf2f(Uf[p * ldu + c]), scale[c], shift[c]);
+      const float g = sigmoidf_fast(bf2f(Z[p * ldz + c]));
+      dY[p * ldd + c] = __float2bfloat16_rn(y0 > 0.f ? df * (0.5f + 0.5f * g) : 0.f);
+      dZ[p * ldd + c] = __float2bfloat16_rn(df * fmaxf(y0, 0.f) * 0.5f * g * (1.f - g));
+    }
+  }
+}
+
+// BatchNorm backward, pass 1: S1[c] = sum_p dY, S2[c] = sum_p dY * xhat, where
+//   dY = (d1 + d2) * [X > 0]   (d2 / X optional: two gradient sources, ReLU mask from the stored activation)
+//   xhat = (U - mean) * rstd
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ d1, long long ld1, const __nv_bfloat16* __restrict__ d2,
+                     long long ld2, const __nv_bfloat16* __restrict__ X, long long ldx,
+                     const __nv_bfloat16* __restrict__ U, long long ldu, long long rows, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, float* __restrict__ S1, float* __restrict__ S2) {
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int lane_r = threadIdx.x >> 6;
+  const float m = mean[c], rs = rstd[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (long long r = blockIdx.y * 4ll + lane_r; r < rows; r += gridDim.y * 4ll) {
+    float d = bf2f(d1[r * ld1 + c]);
+    if (d2) d += bf2f(d2[r * ld2 + c]);
+    if (X && !(bf2f(X[r * ldx + c]) > 0.f)) d = 0.f;
+    s1 += d;
+    s2 = fmaf(d, (bf2f(U[r * ldu + c]) - m) * rs, s2);
+  }
+  __shared__ float sh[2][4][64];
+  sh[0][lane_r][threadIdx.x & 63] = s1;
+  sh[1][lane_r][threadIdx.x & 63] = s2;
+  __syncthreads();
+  if (lane_r == 0) {
+    const int t = threadIdx.x;
+    atomicAdd(S1 + c, sh[0][0][t] + sh[0][1][t] + sh[0][2][t] + sh[0][3][t]);
+    atomicAdd(S2 + c, sh[1][0][t] + sh[1][1][t] + sh[1][2][t] + sh[1][3][t]);
+  }
+}
+
+// BatchNorm backward, pass 2: dU = gamma * rstd * (dY - S1/P - xhat * S2/P)   (bf16, row-major)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ d1, long long ld1, const __nv_bfloat16* __restrict__ d2,
+                    long long ld2, const __nv_bfloat16* __restrict__ X, long long ldx,
+                    const __nv_bfloat16* __restrict__ U, long long ldu, long long rows, int C,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ S1, const float* __restrict__ S2, __nv_bfloat16* __restrict__ dU,
+                    long long ldo) {
+  const long long total = rows * C;
+  const float inv_n = 1.f / static_cast<float>(rows);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    float d = bf2f(d1[r * ld1 + c]);
+    if (d2) d += bf2f(d2[r * ld2 + c]);
+    if (X && !(bf2f(X[r * ldx + c]) > 0.f)) d = 0.f;
+    const float xh = (bf2f(U[r * ldu + c]) - mean[c]) * rstd[c];
+    dU[r * ldo + c] = __float2bfloat16_rn(gamma[c] * rstd[c] * (d - S1[c] * inv_n - xh * S2[c] * inv_n));
+  }
+}
+
+// conv1 / gate layer 1 parameter gradients (K = 4 resp. 1: plain reductions over the points):
+//   dW1[c, :] = sum_p dU1[p, c] * x[p, :]    db1[c] = sum_p dU1[p, c]
+//   dwg1[c]   = sum_p dH[p, c] * [H > 0] * I  dbg1[c] = sum_p dH[p, c] * [H > 0]
+__global__ void __launch_bounds__(256)
+conv1_gate1_bwd_kernel(const float4* __restrict__ ctx, long long rows, const __nv_bfloat16* __restrict__ dU1,
+                       long long ldu, const __nv_bfloat16* __restrict__ dH, long long ldh,
+                       const __nv_bfloat16* __restrict__ H, long long ldx, float* __restrict__ dW1,
+                       float* __restrict__ db1, float* __restrict__ dwg1, float* __restrict__ dbg1) {
+  const int c = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, ab = 0.f, g = 0.f, gb = 0.f;
+  for (long long r = blockIdx.x * 4ll + lane_r; r < rows; r += gridDim.x * 4ll) {
+    const float4 x = __ldg(ctx + r);
+    const float du = bf2f(dU1[r * ldu + c]);
+    a[0] = fmaf(du, x.x, a[0]);
+    a[1] = fmaf(du, x.y, a[1]);
+    a[2] = fmaf(du, x.z, a[2]);
+    a[3] = fmaf(du, x.w, a[3]);
+    ab += du;
+    const float dh = bf2f(H[r * ldx + c]) > 0.f ? bf2f(dH[r * ldh + c]) : 0.f;
+    g = fmaf(dh, x.w, g);
+    gb += dh;
+  }
+  __shared__ float sh[7][4][64];
+  sh[0][lane_r][c] = a[0]; sh[1][lane_r][c] = a[1]; sh[2][lane_r][c] = a[2]; sh[3][lane_r][c] = a[3];
+  sh[4][lane_r][c] = ab;   sh[5][lane_r][c] = g;    sh[6][lane_r][c] = gb;
+  __syncthreads();
+  if (lane_r == 0) {
+    float t[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t[k] = sh[k][0][c] + sh[k][1][c] + sh[k][2][c] + sh[k][3][c];
+    atomicAdd(dW1 + 4 * c + 0, t[0]);
+    atomicAdd(dW1 + 4 * c + 1, t[1]);
+    atomicAdd(dW1 + 4 * c + 2, t[2]);
+    atomicAdd(dW1 + 4 * c + 3, t[3]);
+    atomicAdd(db1 + c, t[4]);
+    atomicAdd(dwg1 + c, t[5]);
+    atomicAdd(dbg1 + c, t[6]);
+  }
+}
+
+// out[r, c] = src[r * ld + c0 + c] for c < cols  (fp32 sub-matrix copy: wgrad temporaries -> gradient tensors)
+__global__ void copy_submatrix_kernel(const float* __restrict__ src, long long ld, int c0, int rows, int cols,
+                                      float* __restrict__ dst) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<long long>(r) * cols);
+    dst[i] = src[r * ld + c0 + c];
+  }
+}
+
+}  // namespace lrn

@@ -9,8 +9,10 @@ What runs where
   * eval mode, CUDA tensors: the context encoder (+ pooling, + context_proj) and the regression
     heads run in the hand-written sm_100a library through the C ABI (ops.py).  The DETR decoder,
     point_mlp and pos_emb (SURVEY.md section 8f "next" rows) use stock PyTorch CUDA ops.
-  * train mode (batch-statistic BatchNorm, autograd): stock PyTorch ops on the same parameters;
-    the native backward is not part of this round (DESIGN.md "out of scope").
+  * train mode (batch-statistic BatchNorm, autograd): the context encoder runs natively too (train_ops.py:
+    batch-stat BN forward and a hand-written backward on the tcgen05 GEMMs, bf16 tier); the decoder and
+    context_proj are stock PyTorch ops.  `native_training = False` / LRN_NATIVE_TRAIN=0 or the tf32 tier use
+    the stock PyTorch formulation of the encoder instead.
   * CPU tensors: not supported -- there is no CPU path in the product (the oracle lives in oracle/).
 """
 from __future__ import annotations
@@ -73,6 +75,7 @@ class MultiScalePointNetEncoder(nn.Module):
         self.intensity_gate = nn.Sequential(nn.Conv1d(1, 64, 1), nn.ReLU(), nn.Conv1d(64, out_dim, 1), nn.Sigmoid())
         self.precision = _DEFAULT_PRECISION     # "bf16" | "tf32" (tensor-core operand tier)
         self.chunk_rows = 0                     # 0 = library default
+        self.native_training = os.environ.get("LRN_NATIVE_TRAIN", "1") != "0"   # train mode on the sm_100a kernels
         self._folded = None                     # (fingerprint, FoldedEncoder); never in the state_dict
         self._proj = None                       # optional nn.Linear(1024,256) folded alongside (set by LineRefineNet)
 
@@ -112,6 +115,9 @@ class MultiScalePointNetEncoder(nn.Module):
 
     def forward(self, x):
         _require_cuda(x, "MultiScalePointNetEncoder")
+        if self.training and self.native_training and self.precision == "bf16":
+            from .train_ops import encoder_train_forward   # batch-stat BN forward + hand-written backward
+            return encoder_train_forward(self, x.transpose(2, 1))
         if not _use_native(self, x):
             return self._forward_torch(x)
         out = self.run_native(x.transpose(2, 1), pool=True, fused=True)
@@ -208,7 +214,7 @@ class LineRefineNet(nn.Module):
     def forward(self, context, noisy_line):
         _require_cuda(context, "LineRefineNet")
         if not _use_native(self, context, noisy_line):
-            _, fused = self.context_encoder._forward_torch(context.transpose(2, 1))
+            _, fused = self.context_encoder(context.transpose(2, 1))   # train mode: native fwd/bwd (bf16 tier)
             memory = self.context_proj(fused.transpose(2, 1))
             return self._refine(context, noisy_line, memory, native_heads=False)
         outs = []

@@ -1,0 +1,118 @@
+"""Train-mode encoder as a torch.autograd.Function over the C ABI (lrn_encoder_train_forward/backward).
+
+Autograd only sees one node: inputs = the 28 encoder parameters (+ the context, which gets no gradient),
+output = `fused` (B,1024,N).  Pooling and context_proj stay ordinary differentiable torch ops of `fused`,
+so DDP's gradient hooks fire on the leaf parameters exactly as with the reference module
+(reference train_dist.py:147,188)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import lib
+from .ops import _aligned_bytes, _f32c, _stream_ptr
+
+
+class BnRunning(C.Structure):
+    _fields_ = [("mean", C.c_void_p * 6), ("var", C.c_void_p * 6)]
+
+
+class EncoderGrads(C.Structure):
+    _fields_ = ([(n, C.c_void_p * 5) for n in ("conv_w", "conv_b", "bn_w", "bn_b")]
+                + [(n, C.c_void_p) for n in ("fusion_w", "fusion_b", "fusion_bn_w", "fusion_bn_b",
+                                             "gate0_w", "gate0_b", "gate2_w", "gate2_b")])
+
+
+lib.lrn_train_workspace_bytes.restype = C.c_size_t
+lib.lrn_train_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+lib.lrn_encoder_train_forward.restype = C.c_int
+lib.lrn_encoder_train_forward.argtypes = [C.POINTER(_lib.EncoderParams), C.POINTER(BnRunning), C.c_float, C.c_void_p,
+                                          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+lib.lrn_encoder_train_backward.restype = C.c_int
+lib.lrn_encoder_train_backward.argtypes = [C.POINTER(_lib.EncoderParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                           C.POINTER(EncoderGrads), C.c_void_p, C.c_size_t, C.c_void_p]
+
+# parameter order of the autograd node (names relative to MultiScalePointNetEncoder)
+PARAM_NAMES = ([f"conv{k}.weight" for k in range(1, 6)] + [f"conv{k}.bias" for k in range(1, 6)]
+               + [f"bn{k}.weight" for k in range(1, 6)] + [f"bn{k}.bias" for k in range(1, 6)]
+               + ["fusion.0.weight", "fusion.0.bias", "fusion.1.weight", "fusion.1.bias",
+                  "intensity_gate.0.weight", "intensity_gate.0.bias", "intensity_gate.2.weight", "intensity_gate.2.bias"])
+
+
+def _params_struct(t):
+    """t: list of contiguous fp32 CUDA tensors in PARAM_NAMES order."""
+    p = _lib.EncoderParams()
+    for k in range(5):
+        p.conv_w[k], p.conv_b[k] = t[k].data_ptr(), t[5 + k].data_ptr()
+        p.bn_w[k], p.bn_b[k] = t[10 + k].data_ptr(), t[15 + k].data_ptr()
+    p.fusion_w, p.fusion_b, p.fusion_bn_w, p.fusion_bn_b = (x.data_ptr() for x in t[20:24])
+    p.gate0_w, p.gate0_b, p.gate2_w, p.gate2_b = (x.data_ptr() for x in t[24:28])
+    p.bn_eps = 1e-5
+    return p
+
+
+class EncoderTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, context, running, momentum, *params):
+        """context (B,N,4) fp32 CUDA; running = list of 12 buffers (6 running_mean, 6 running_var) updated in
+        place, or None; params in PARAM_NAMES order.  Returns fused (B,1024,N)."""
+        context = _f32c(context)
+        B, N, _ = context.shape
+        dev = context.device
+        t = [_f32c(p.detach()) for p in params]
+        ps = _params_struct(t)
+        nbytes = lib.lrn_train_workspace_bytes(B, N)
+        ws = _aligned_bytes(nbytes, dev)           # owned by this node until its backward has run
+        fused = torch.empty(B, 1024, N, dtype=torch.float32, device=dev)
+        rs = None
+        if running is not None:
+            rs = BnRunning()
+            for i in range(6):
+                rs.mean[i], rs.var[i] = running[i].data_ptr(), running[6 + i].data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(lib.lrn_encoder_train_forward(C.byref(ps), C.byref(rs) if rs is not None else None, momentum,
+                                                     context.data_ptr(), B, N, fused.data_ptr(), ws.data_ptr(),
+                                                     ws.numel(), _stream_ptr(dev)), "lrn_encoder_train_forward")
+        _lib.launch_counter += 12 + 1 + 6 * 2 + 5 + 6 + 1
+        ctx.save_for_backward(context, *t)
+        ctx.ws, ctx.shape = ws, (B, N)
+        return fused
+
+    @staticmethod
+    def backward(ctx, d_fused):
+        context, *t = ctx.saved_tensors
+        B, N = ctx.shape
+        dev = context.device
+        d_fused = _f32c(d_fused)
+        grads = [torch.empty_like(x) for x in t]
+        g = EncoderGrads()
+        for k in range(5):
+            g.conv_w[k], g.conv_b[k] = grads[k].data_ptr(), grads[5 + k].data_ptr()
+            g.bn_w[k], g.bn_b[k] = grads[10 + k].data_ptr(), grads[15 + k].data_ptr()
+        g.fusion_w, g.fusion_b, g.fusion_bn_w, g.fusion_bn_b = (x.data_ptr() for x in grads[20:24])
+        g.gate0_w, g.gate0_b, g.gate2_w, g.gate2_b = (x.data_ptr() for x in grads[24:28])
+        ps = _params_struct(t)
+        with torch.cuda.device(dev):
+            _lib.check(lib.lrn_encoder_train_backward(C.byref(ps), context.data_ptr(), B, N, d_fused.data_ptr(),
+                                                      C.byref(g), ctx.ws.data_ptr(), ctx.ws.numel(), _stream_ptr(dev)),
+                       "lrn_encoder_train_backward")
+        _lib.launch_counter += 60
+        ctx.ws = None
+        return (None, None, None, *grads)
+
+
+def encoder_train_forward(module, context):
+    """module: MultiScalePointNetEncoder in train mode; context (B,N,4).  Returns (global_feat, fused) with
+    autograd through the native backward; updates running statistics / num_batches_tracked like PyTorch."""
+    sd = dict(module.named_parameters())
+    params = [sd[n] for n in PARAM_NAMES]
+    bns = [module.bn1, module.bn2, module.bn3, module.bn4, module.bn5, module.fusion[1]]
+    running = [b.running_mean for b in bns] + [b.running_var for b in bns]
+    fused = EncoderTrainFn.apply(context, running, float(bns[0].momentum), *params)
+    with torch.no_grad():
+        for b in bns:
+            b.num_batches_tracked += 1
+    global_feat = torch.cat([fused.max(dim=2)[0], fused.mean(dim=2)], dim=1)   # src/model.py:58-60
+    return global_feat, fused
