@@ -111,3 +111,17 @@ def test_full_model_train_step_decreases_loss(dev):
     m.eval()
     with torch.no_grad():                       # the eval path re-folds the updated weights and running stats
         assert torch.isfinite(m(ctx, line)).all()
+
+
+def test_ddp_step_two_ranks():
+    """train_dist.py-style DDP step (NCCL gradient all-reduce) on the native encoder path; needs 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "ddp_check.py"), "8", "512"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ddp ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
