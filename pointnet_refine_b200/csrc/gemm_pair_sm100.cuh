@@ -121,8 +121,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int num_tiles = p.m_tiles * p.n_tiles;  // m_tiles counts 256-row pair tiles here
-  const int kb_total = p.kb_main + p.kb_gate;
+  // m_tiles counts 256-row pair tiles here; split-K (EPI_ACT, fp32 output) multiplies the tile count: work
+  // item w = split * (m_tiles * n_tiles) + output tile, each covering kb_per_split k-blocks
+  const int splits = (EPI == EPI_ACT && p.k_splits > 1) ? p.k_splits : 1;
+  const int out_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = out_tiles * splits;
+  const int kb_all = p.kb_main + p.kb_gate;
+  auto kb_begin = [&](int w) { return splits > 1 ? (w / out_tiles) * p.kb_per_split : 0; };
+  auto kb_count = [&](int w) { return splits > 1 ? min(p.kb_per_split, kb_all - kb_begin(w)) : kb_all; };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -149,11 +155,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      for (int work = cluster_id; work < num_tiles; work += num_clusters, ++it) {
+        const int tile = work % out_tiles;
         const int m_blk = tile / p.n_tiles;
         const int n_blk = tile - m_blk * p.n_tiles;
+        const int kb_total = kb_count(work), kb0 = kb_begin(work);
         for (int s = 0; s < kb_total; ++s) {
-          int kcol = s;
+          int kcol = kb0 + s;
           if (EPI == EPI_FUSION) {  // the gate k-blocks are the last columns of the operand row
             const KbSlot slot = fusion_slot(it, s, p.kb_main, p.kb_gate);
             kcol = slot.gate ? p.kb_main + slot.kb : slot.kb;
@@ -179,7 +187,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      for (int work = cluster_id; work < num_tiles; work += num_clusters, ++it) {
+        const int kb_total = kb_count(work);
         const bool stamp = p.dbg && cluster_id == 0 && lane == 0 && it < 16;
         if (stamp) p.dbg[it * 8 + 0] = clock64();  // tile start
         // EPI_ACT: accumulator stage it&1, completes every second tile.  EPI_FUSION: F_t lives in region
@@ -210,7 +219,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             ptx::tc_commit_pair(&bar_empty[stage], 3);  // frees this smem stage in BOTH CTAs
             if (slot.gate && slot.kb == p.kb_gate - 1) ptx::tc_commit_pair(&bar_tfull[rf ^ 1], 3);  // G_t complete
-            if (!slot.gate && slot.kb == p.kb_main - 1) {
+            if (!slot.gate && slot.kb == (EPI == EPI_FUSION ? p.kb_main : kb_total) - 1) {
               ptx::tc_commit_pair(&bar_tfull[rf], 3);                                               // F_t complete
               if (stamp) p.dbg[it * 8 + 1] = clock64();
             }
@@ -230,16 +239,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int col_lo = half * kHalfCols;
     int it = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    for (int work = cluster_id; work < num_tiles; work += num_clusters, ++it) {
+      const int tile = work % out_tiles;
       const int m_blk = tile / p.n_tiles;
       const int n_blk = tile - m_blk * p.n_tiles;
+      const bool add_bias = work < out_tiles;  // split-K: only the first split adds the bias
       float* sb = sbias + (it & 1) * 2 * BN;
       for (int c = et; c < BN; c += 32 * kPairEpiWarps) {
         if (EPI == EPI_FUSION) {
           sb[c] = p.bias_f[n_blk * BN + c];
           sb[BN + c] = p.bias_g[n_blk * BN + c];
         } else {
-          sb[c] = p.bias ? p.bias[n_blk * BN + c] : 0.f;
+          sb[c] = (p.bias && add_bias) ? p.bias[n_blk * BN + c] : 0.f;
         }
       }
       ptx::named_bar_sync(1, 32 * kPairEpiWarps);
@@ -285,6 +296,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               ptx::st_shared_v4(blk + (((cbase + t) ^ (rr & 7)) << 4), ptx::pack_bf16x2(v[8 * t], v[8 * t + 1]),
                                 ptx::pack_bf16x2(v[8 * t + 2], v[8 * t + 3]), ptx::pack_bf16x2(v[8 * t + 4], v[8 * t + 5]),
                                 ptx::pack_bf16x2(v[8 * t + 6], v[8 * t + 7]));
+          } else if (valid && splits > 1) {  // split-K partial product (fp32 output, zeroed by the host)
+            float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n_blk * BN + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
           } else if (valid) {
             store_row_chunk<TF32>(p.out, static_cast<long long>(row) * p.ldo + n_blk * BN + c0, v, p.out_f32 != 0,
                                   p.round_tf32 != 0);

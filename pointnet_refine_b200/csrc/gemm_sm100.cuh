@@ -47,6 +47,9 @@ struct GemmParams {
   int relu;
   int round_tf32;  // fp32 output is a TF32 operand of the next layer: round to nearest instead of truncating later
   int out_col0;    // pair kernels with staged TMA stores: first output column inside the output tensor map
+  int k_splits;    // pair EPI_ACT kernels, fp32 output: > 1 = split-K, every split atomically adds its partial
+                   // product into the (zeroed) output; 0 / 1 = one pass over K
+  int kb_per_split;
   // EPI_FUSION
   const float* bias_f;
   const float* bias_g;

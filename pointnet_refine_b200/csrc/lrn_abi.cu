@@ -175,9 +175,9 @@ int launch_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.m_tiles * p.n_tiles * std::max(p.k_splits, 1);
   if (tiles <= 0) return LRN_OK;
-  const int grid = 2 * std::min(tiles, sms / 2);  // one CTA pair (cluster of 2) per tile slot
+  const int grid = 2 * std::min(tiles, sms / 2);  // one CTA pair (cluster of 2) per work-item slot
   kern<<<grid, kPairThreads, L::kDynamic, stream>>>(ta, tb, tout, p);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
@@ -669,6 +669,17 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt,
   p.ldo = ldo;
   p.out_f32 = out_f32;
   p.relu = relu;
+  // Weight gradients: few output tiles, K = all points.  Split K over the idle CTA pairs; the splits add their
+  // partial products atomically into the zeroed fp32 output.
+  const int out_tiles = p.m_tiles * p.n_tiles, slots = dev.sms / 2;
+  if (g.pair && out_f32 && !relu && precision == LRN_PREC_BF16 && out_tiles < slots && p.kb_main >= 64) {
+    const int want = std::min((2 * slots + out_tiles - 1) / out_tiles, p.kb_main / 16);
+    if (want > 1) {
+      p.kb_per_split = (p.kb_main + want - 1) / want;
+      p.k_splits = (p.kb_main + p.kb_per_split - 1) / p.kb_per_split;
+      LRN_CUDA(cudaMemset2DAsync(out, size_t(ldo) * 4, 0, size_t(N) * 4, size_t(M), reinterpret_cast<cudaStream_t>(stream)));
+    }
+  }
   CUtensorMap tout;
   const bool staged_ok = precision == LRN_PREC_BF16 && !out_f32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                          (ldo * 2) % 16 == 0;
@@ -757,10 +768,14 @@ int pack_w(const float* src, int rows, int cols, void* dst, int64_t ld, bool tra
   return LRN_OK;
 }
 
-dim3 stats_grid(int C, int64_t rows) { return dim3(C / 64, unsigned(std::min<int64_t>((rows + 511) / 512, 512))); }
+// (column blocks of 64 channels, row slabs): enough blocks to fill the chip (~8 per SM) whatever C is
+dim3 stats_grid(int C, int64_t rows) {
+  const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (148 * 8) / (C / 64) + 1));
+  return dim3(C / 64, unsigned(slabs));
+}
 
 int transpose_bf16(const void* src, int64_t ld_src, int64_t rows, int C, void* dst, int64_t ld_dst, cudaStream_t s) {
-  dim3 grid(unsigned((ld_dst + 31) / 32), unsigned(C / 32));
+  dim3 grid(unsigned(ld_dst / 64), unsigned(C / 64));  // ld_dst (padded point count) is a multiple of 256
   transpose_bf16_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), ld_src, rows, C,
                                              static_cast<__nv_bfloat16*>(dst), ld_dst);
   LRN_CUDA(cudaGetLastError());
@@ -826,7 +841,7 @@ int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running
                                                        scale + uo, shift + uo);
     LRN_CUDA(cudaGetLastError());
     if (i == 5) break;
-    bn_relu_apply_kernel<<<elem_grid(P * C / 8), 256, 0, s>>>(U + uo, kULd, P, C, scale + uo, shift + uo, X + kCatOff[i + 1], kCat);
+    bn_relu_apply_kernel<<<stats_grid(C, P), 256, 0, s>>>(U + uo, kULd, P, C, scale + uo, shift + uo, X + kCatOff[i + 1], kCat);
     LRN_CUDA(cudaGetLastError());
     if (i < 4) {  // next layer's pre-activation: U_{k+1} = X_k W_{k+1}^T + b_{k+1}
       const int k = i + 2;
@@ -904,7 +919,7 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
     LRN_CUDA(cudaGetLastError());
     LRN_CUDA(d2d(g->fusion_bn_b, S1 + uo, 1024));
     LRN_CUDA(d2d(g->fusion_bn_w, S2 + uo, 1024));
-    bn_bwd_apply_kernel<<<elem_grid(P * 1024), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, 0, U + uo, kULd, P, 1024, mean + uo,
+    bn_bwd_apply_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, 0, U + uo, kULd, P, 1024, mean + uo,
                                                             rstd + uo, pr->fusion_bn_w, S1 + uo, S2 + uo, dU, 1024);
     LRN_CUDA(cudaGetLastError());
     col_stats_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, P, g->fusion_b, nullptr);
@@ -930,7 +945,7 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
     LRN_CUDA(cudaGetLastError());
     LRN_CUDA(d2d(g->bn_b[i], S1 + uo, C));
     LRN_CUDA(d2d(g->bn_w[i], S2 + uo, C));
-    bn_bwd_apply_kernel<<<elem_grid(P * C), 256, 0, s>>>(dA + xo, kCat, d2, 512, X + xo, kCat, U + uo, kULd, P, C, mean + uo,
+    bn_bwd_apply_kernel<<<stats_grid(C, P), 256, 0, s>>>(dA + xo, kCat, d2, 512, X + xo, kCat, U + uo, kULd, P, C, mean + uo,
                                                          rstd + uo, pr->bn_w[i], S1 + uo, S2 + uo, dU, 1024);
     LRN_CUDA(cudaGetLastError());
     if (k == 1) break;

@@ -55,26 +55,40 @@ train_embed_kernel(const float4* __restrict__ ctx, long long rows, const float* 
 }
 
 // Per-column sum and sum of squares of a bf16 (rows x C) matrix -> fp32 atomics into sum[C], sumsq[C].
-// Block = 64 columns x 4 row lanes; grid = (C / 64, row slabs).
+// Block = 64 columns (32 bf16 pairs) x 8 row lanes, 4 independent loads in flight per thread; grid = (C / 64, row slabs).
 __global__ void __launch_bounds__(256)
 col_stats_kernel(const __nv_bfloat16* __restrict__ A, long long ld, long long rows, float* __restrict__ sum,
                  float* __restrict__ sumsq) {
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int lane_r = threadIdx.x >> 6;
-  float s = 0.f, q = 0.f;
-  for (long long r = blockIdx.y * 4ll + lane_r; r < rows; r += gridDim.y * 4ll) {
-    const float v = bf2f(A[r * ld + c]);
-    s += v;
-    q = fmaf(v, v, q);
+  const int cp = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * cp;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const long long stride = gridDim.y * 8ll;
+  long long r = blockIdx.y * 8ll + lane_r;
+  for (; r + 3 * stride < rows; r += 4 * stride) {
+    __nv_bfloat162 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const __nv_bfloat162*>(A + (r + k * stride) * ld + c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(v[k]);
+      s0 += f.x; s1 += f.y;
+      q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+    }
   }
-  __shared__ float sh[2][4][64];
-  sh[0][lane_r][threadIdx.x & 63] = s;
-  sh[1][lane_r][threadIdx.x & 63] = q;
+  for (; r < rows; r += stride) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(A + r * ld + c));
+    s0 += f.x; s1 += f.y;
+    q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+  }
+  __shared__ float sh[4][8][32];
+  sh[0][lane_r][cp] = s0; sh[1][lane_r][cp] = s1; sh[2][lane_r][cp] = q0; sh[3][lane_r][cp] = q1;
   __syncthreads();
-  if (lane_r == 0) {
-    const int t = threadIdx.x;
-    atomicAdd(sum + c, sh[0][0][t] + sh[0][1][t] + sh[0][2][t] + sh[0][3][t]);
-    if (sumsq) atomicAdd(sumsq + c, sh[1][0][t] + sh[1][1][t] + sh[1][2][t] + sh[1][3][t]);
+  if (lane_r < 4) {  // warp w reduces quantity w over the 8 row lanes
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[lane_r][k][cp];
+    if (lane_r < 2) atomicAdd(sum + c + lane_r, t);
+    else if (sumsq) atomicAdd(sumsq + c + (lane_r - 2), t);
   }
 }
 
@@ -100,47 +114,50 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   }
 }
 
-// X[:, c] = relu(U[:, c] * scale[c] + shift[c]); 8 channels (16 bytes) per thread.
+// X[:, c] = relu(U[:, c] * scale[c] + shift[c]).  Channel-stationary threads: a thread owns 8 channels (its
+// scale / shift stay in registers) and walks down the rows; 8 threads cover 128 contiguous bytes of a row.
+// grid = (C / 64, row slabs), block = 8 channel groups x 32 row lanes.
 __global__ void __launch_bounds__(256)
 bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ U, long long ldu, long long rows, int C,
                      const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ X,
                      long long ldx) {
-  const int groups = C / 8;
-  const long long total = rows * groups;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / groups;
-    const int c0 = static_cast<int>(i - r * groups) * 8;
+  const int c0 = blockIdx.x * 64 + (threadIdx.x & 7) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+  for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
     const uint4 raw = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
     const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(&raw);
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(bf2f(u[j]), scale[c0 + j], shift[c0 + j]), 0.f);
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(bf2f(u[j]), sc[j], sh[j]), 0.f);
     *reinterpret_cast<uint4*>(X + r * ldx + c0) =
         make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
                    ptx::pack_bf16x2(v[6], v[7]));
   }
 }
 
-// dst (C x ld_dst) = src^T, src (rows x C, pitch ld_src), bf16, 32 x 32 tiles through shared memory.
+// dst (C x ld_dst) = src^T, src (rows x C, pitch ld_src), bf16.  64 x 64 tiles through shared memory, 16-byte global
+// loads and stores on both sides (C % 64 == 0, ld_dst % 64 == 0); rows >= `rows` are written as zeros.
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, long long rows, int C,
                       __nv_bfloat16* __restrict__ dst, long long ld_dst) {
-  __shared__ __nv_bfloat16 tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const long long r0 = blockIdx.x * 32ll;
-  const int c0 = blockIdx.y * 32;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const long long r = r0 + ty + 8 * k;
-    tile[ty + 8 * k][tx] = (r < rows) ? src[r * ld_src + c0 + tx] : __float2bfloat16_rn(0.f);
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];  // [point][channel], 144-byte rows
+  const long long r0 = blockIdx.x * 64ll;
+  const int c0 = blockIdx.y * 64;
+  for (int t = threadIdx.x; t < 512; t += 256) {  // 64 rows x 8 chunks of 8 channels
+    const int pr = t >> 3, ch = (t & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r0 + pr < rows) v = *reinterpret_cast<const uint4*>(src + (r0 + pr) * ld_src + c0 + ch);
+    *reinterpret_cast<uint4*>(&tile[pr][ch]) = v;
   }
   __syncthreads();
+  for (int t = threadIdx.x; t < 512; t += 256) {  // 64 channels x 8 chunks of 8 points
+    const int c = t >> 3, pc = (t & 7) * 8;
+    __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = c0 + ty + 8 * k;
-    const long long r = r0 + tx;
-    if (r < ld_dst) dst[static_cast<long long>(c) * ld_dst + r] = tile[tx][ty + 8 * k];
+    for (int j = 0; j < 8; ++j) o[j] = tile[pc + j][c];
+    *reinterpret_cast<uint4*>(dst + static_cast<long long>(c0 + c) * ld_dst + r0 + pc) = *reinterpret_cast<const uint4*>(o);
   }
 }
 
@@ -174,8 +191,8 @@ fusion_gate_fwd_kernel(const __nv_bfloat16* __restrict__ Uf, long long ldu, cons
     const int c = c0 + ty + 8 * k;
     const long long p = p0 + tx;
     if (p < rows) {
-      const long long b = p / npts, n = p - b * npts;
-      fused[(b * 1024 + c) * npts + n] = tile[tx][ty + 8 * k];
+      const unsigned b = static_cast<unsigned>(p) / static_cast<unsigned>(npts), n = static_cast<unsigned>(p) - b * npts;
+      fused[(static_cast<long long>(b) * 1024 + c) * npts + n] = tile[tx][ty + 8 * k];
     }
   }
 }
@@ -198,8 +215,8 @@ fusion_gate_bwd_kernel(const float* __restrict__ dfused, const __nv_bfloat16* __
     const long long p = p0 + tx;
     float v = 0.f;
     if (p < rows) {
-      const long long b = p / npts, n = p - b * npts;
-      v = dfused[(b * 1024 + c) * npts + n];
+      const unsigned b = static_cast<unsigned>(p) / static_cast<unsigned>(npts), n = static_cast<unsigned>(p) - b * npts;
+      v = dfused[(static_cast<long long>(b) * 1024 + c) * npts + n];
     }
     tile[ty + 8 * k][tx] = v;
   }
@@ -221,52 +238,85 @@ fusion_gate_bwd_kernel(const float* __restrict__ dfused, const __nv_bfloat16* __
 // BatchNorm backward, pass 1: S1[c] = sum_p dY, S2[c] = sum_p dY * xhat, where
 //   dY = (d1 + d2) * [X > 0]   (d2 / X optional: two gradient sources, ReLU mask from the stored activation)
 //   xhat = (U - mean) * rstd
+// Block = 64 columns (32 bf16 pairs) x 8 row lanes.
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ d1, long long ld1, const __nv_bfloat16* __restrict__ d2,
                      long long ld2, const __nv_bfloat16* __restrict__ X, long long ldx,
                      const __nv_bfloat16* __restrict__ U, long long ldu, long long rows, const float* __restrict__ mean,
                      const float* __restrict__ rstd, float* __restrict__ S1, float* __restrict__ S2) {
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int lane_r = threadIdx.x >> 6;
-  const float m = mean[c], rs = rstd[c];
-  float s1 = 0.f, s2 = 0.f;
-  for (long long r = blockIdx.y * 4ll + lane_r; r < rows; r += gridDim.y * 4ll) {
-    float d = bf2f(d1[r * ld1 + c]);
-    if (d2) d += bf2f(d2[r * ld2 + c]);
-    if (X && !(bf2f(X[r * ldx + c]) > 0.f)) d = 0.f;
-    s1 += d;
-    s2 = fmaf(d, (bf2f(U[r * ldu + c]) - m) * rs, s2);
+  const int cp = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * cp;
+  const float m0 = mean[c], m1 = mean[c + 1], rs0 = rstd[c], rs1 = rstd[c + 1];
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  const long long stride = gridDim.y * 8ll;
+#pragma unroll 2
+  for (long long r = blockIdx.y * 8ll + lane_r; r < rows; r += stride) {
+    float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d1 + r * ld1 + c));
+    const float2 u = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(U + r * ldu + c));
+    if (d2) {
+      const float2 e = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d2 + r * ld2 + c));
+      d.x += e.x; d.y += e.y;
+    }
+    if (X) {
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(X + r * ldx + c));
+      if (!(x.x > 0.f)) d.x = 0.f;
+      if (!(x.y > 0.f)) d.y = 0.f;
+    }
+    a0 += d.x; a1 += d.y;
+    b0 = fmaf(d.x, (u.x - m0) * rs0, b0);
+    b1 = fmaf(d.y, (u.y - m1) * rs1, b1);
   }
-  __shared__ float sh[2][4][64];
-  sh[0][lane_r][threadIdx.x & 63] = s1;
-  sh[1][lane_r][threadIdx.x & 63] = s2;
+  __shared__ float sh[4][8][32];
+  sh[0][lane_r][cp] = a0; sh[1][lane_r][cp] = a1; sh[2][lane_r][cp] = b0; sh[3][lane_r][cp] = b1;
   __syncthreads();
-  if (lane_r == 0) {
-    const int t = threadIdx.x;
-    atomicAdd(S1 + c, sh[0][0][t] + sh[0][1][t] + sh[0][2][t] + sh[0][3][t]);
-    atomicAdd(S2 + c, sh[1][0][t] + sh[1][1][t] + sh[1][2][t] + sh[1][3][t]);
+  if (lane_r < 4) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[lane_r][k][cp];
+    if (lane_r < 2) atomicAdd(S1 + c + lane_r, t);
+    else atomicAdd(S2 + c + (lane_r - 2), t);
   }
 }
 
-// BatchNorm backward, pass 2: dU = gamma * rstd * (dY - S1/P - xhat * S2/P)   (bf16, row-major)
+// BatchNorm backward, pass 2: dU = gamma * rstd * (dY - S1/P - xhat * S2/P) = A_c dY + B_c U + C_c with per-channel
+// coefficients kept in registers (channel-stationary threads as in bn_relu_apply_kernel).
+// d1 may alias dU (in place): every element is read before it is written by the same thread.
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ d1, long long ld1, const __nv_bfloat16* __restrict__ d2,
-                    long long ld2, const __nv_bfloat16* __restrict__ X, long long ldx,
-                    const __nv_bfloat16* __restrict__ U, long long ldu, long long rows, int C,
-                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                    const float* __restrict__ S1, const float* __restrict__ S2, __nv_bfloat16* __restrict__ dU,
-                    long long ldo) {
-  const long long total = rows * C;
+bn_bwd_apply_kernel(const __nv_bfloat16* d1, long long ld1, const __nv_bfloat16* __restrict__ d2, long long ld2,
+                    const __nv_bfloat16* __restrict__ X, long long ldx, const __nv_bfloat16* __restrict__ U,
+                    long long ldu, long long rows, int C, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ S1,
+                    const float* __restrict__ S2, __nv_bfloat16* dU, long long ldo) {
+  const int c0 = blockIdx.x * 64 + (threadIdx.x & 7) * 8;
   const float inv_n = 1.f / static_cast<float>(rows);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / C;
-    const int c = static_cast<int>(i - r * C);
-    float d = bf2f(d1[r * ld1 + c]);
-    if (d2) d += bf2f(d2[r * ld2 + c]);
-    if (X && !(bf2f(X[r * ldx + c]) > 0.f)) d = 0.f;
-    const float xh = (bf2f(U[r * ldu + c]) - mean[c]) * rstd[c];
-    dU[r * ldo + c] = __float2bfloat16_rn(gamma[c] * rstd[c] * (d - S1[c] * inv_n - xh * S2[c] * inv_n));
+  float A[8], Bc[8], Cc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float gr = gamma[c] * rstd[c];
+    A[j] = gr;
+    Bc[j] = -gr * rstd[c] * S2[c] * inv_n;
+    Cc[j] = -gr * S1[c] * inv_n - Bc[j] * mean[c];
+  }
+  for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
+    const uint4 r1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c0);
+    const uint4 ru = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
+    uint4 r2 = make_uint4(0, 0, 0, 0), rx = make_uint4(0, 0, 0, 0);
+    if (d2) r2 = *reinterpret_cast<const uint4*>(d2 + r * ld2 + c0);
+    if (X) rx = *reinterpret_cast<const uint4*>(X + r * ldx + c0);
+    const __nv_bfloat16 *p1 = reinterpret_cast<const __nv_bfloat16*>(&r1), *p2 = reinterpret_cast<const __nv_bfloat16*>(&r2),
+                        *px = reinterpret_cast<const __nv_bfloat16*>(&rx), *pu = reinterpret_cast<const __nv_bfloat16*>(&ru);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = bf2f(p1[j]);
+      if (d2) d += bf2f(p2[j]);
+      if (X && !(bf2f(px[j]) > 0.f)) d = 0.f;
+      v[j] = fmaf(A[j], d, fmaf(Bc[j], bf2f(pu[j]), Cc[j]));
+    }
+    *reinterpret_cast<uint4*>(dU + r * ldo + c0) =
+        make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
+                   ptx::pack_bf16x2(v[6], v[7]));
   }
 }
 
