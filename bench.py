@@ -231,6 +231,23 @@ def main():
             e2e_ms = float(t.item())
         e2e_value = world * B / (e2e_ms / e2e_steps * 1e-3)
 
+        # ---- informational: the whole LineRefineNet forward (encoder + context_proj + 6 decoder layers + heads)
+        full_model = None
+        if rank == 0:
+            fb = min(B, 256)
+            line = torch.randn(fb, 32, 3, device=dev, generator=gen)
+            for _ in range(2):
+                model(ctx[:fb], line)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                model(ctx[:fb], line)
+            torch.cuda.synchronize()
+            fm = (time.perf_counter() - t0) / 3
+            full_model = {"segments_per_sec": fb / fm, "ms_per_forward": fm * 1e3, "segments": fb, "points_per_segment": N,
+                          "note": "LineRefineNet.forward -> (6,B,32,3); encoder, context_proj, K/V projections and heads on the "
+                                  "sm_100a kernels, attention via torch SDPA, query side in stock PyTorch ops"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -272,7 +289,7 @@ def main():
         "config": config, "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": B * N * 16,
                 "d2h_bytes_per_step": B * 2048 * 4, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "full_model": full_model,
     }))
     if world > 1:
         dist.destroy_process_group()

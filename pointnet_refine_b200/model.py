@@ -187,6 +187,8 @@ class LineRefineNet(nn.Module):
         # context_proj is folded into the encoder's operand blob (tuple hides it from the module tree)
         self.context_encoder._proj = (self.context_proj,)
         self.segment_chunk = 256   # segments per decoder pass in eval mode (bounds the (B,N,256) temporaries)
+        self.fast_decoder = os.environ.get("LRN_FAST_DECODER", "1") != "0"   # bf16 tier: hoisted K/V GEMMs + SDPA
+        self._kv_cache = None
 
     @property
     def precision(self):
@@ -211,16 +213,68 @@ class LineRefineNet(nn.Module):
                 outs.append(current - noisy_line)
         return torch.stack(outs)
 
+    # -- context side of the decoder on the tcgen05 GEMMs ------------------------
+    def _kv_weights(self):
+        """bf16 copies of pos_emb.mlp.2 and of the K / V rows of all six cross-attention in_proj matrices
+        ([Wq; Wk; Wv] packing of nn.MultiheadAttention), re-made when a parameter changes."""
+        ps = [self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias]
+        for l in self.decoder_layers:
+            ps += [l.cross_attn.in_proj_weight, l.cross_attn.in_proj_bias]
+        fp = tuple((t.data_ptr(), t._version) for t in ps)
+        if getattr(self, "_kv_cache", None) is None or self._kv_cache[0] != fp:
+            d = self.d_model
+            wk = torch.cat([l.cross_attn.in_proj_weight[d:2 * d] for l in self.decoder_layers]).detach()
+            wv = torch.cat([l.cross_attn.in_proj_weight[2 * d:] for l in self.decoder_layers]).detach()
+            bk = torch.cat([l.cross_attn.in_proj_bias[d:2 * d] for l in self.decoder_layers]).detach()
+            bv = torch.cat([l.cross_attn.in_proj_bias[2 * d:] for l in self.decoder_layers]).detach()
+            self._kv_cache = (fp, wk.bfloat16().contiguous(), bk.float().contiguous(), wv.bfloat16().contiguous(),
+                              bv.float().contiguous(), self.pos_emb.mlp[2].weight.detach().bfloat16().contiguous())
+        return self._kv_cache[1:]
+
+    def _refine_fast(self, context, noisy_line, memory):
+        """Eval-mode decoder with the context-side work hoisted out of the layer loop: the memory positional
+        embedding and the K / V projections of ALL six cross-attention layers are three tcgen05 GEMMs over the
+        points (they do not depend on the decoder state, src/model.py:123-126), and every layer's cross
+        attention is one scaled_dot_product_attention call on bf16 K / V.  The query side (32 points per
+        segment) stays in stock PyTorch ops.  Same parameters and math as DetrTransformerDecoderLayer.forward
+        (src/model.py:104-135) in eval mode; bf16 tier only."""
+        B, N, _ = context.shape
+        d, H = self.d_model, 8
+        wk, bk, wv, bv, w2 = self._kv_weights()
+        mem = memory.reshape(B * N, d).bfloat16()
+        h = F.relu(self.pos_emb.mlp[0](context[:, :, :3])).reshape(B * N, d).bfloat16()
+        posm = ops.gemm_bias_act(h, w2, self.pos_emb.mlp[2].bias.detach(), out_dtype=torch.bfloat16)
+        k_all = ops.gemm_bias_act(mem + posm, wk, bk, out_dtype=torch.bfloat16).view(B, N, 6, H, d // H)
+        v_all = ops.gemm_bias_act(mem, wv, bv, out_dtype=torch.bfloat16).view(B, N, 6, H, d // H)
+        tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
+        current = noisy_line.clone()
+        outs = []
+        for i, (layer, head) in enumerate(zip(self.decoder_layers, self.reg_branches)):
+            qpos = self.pos_emb(current)
+            q = tgt + qpos
+            tgt = layer.norm1(tgt + layer.self_attn(q, q, value=tgt, need_weights=False)[0])
+            ca = layer.cross_attn
+            qh = F.linear(tgt + qpos, ca.in_proj_weight[:d], ca.in_proj_bias[:d]).view(B, -1, H, d // H).transpose(1, 2)
+            att = F.scaled_dot_product_attention(qh.bfloat16(), k_all[:, :, i].transpose(1, 2), v_all[:, :, i].transpose(1, 2))
+            att = att.transpose(1, 2).reshape(B, -1, d).float()
+            tgt = layer.norm2(tgt + ca.out_proj(att))
+            tgt = layer.norm3(tgt + layer.linear2(F.relu(layer.linear1(tgt))))
+            outs.append(ops.head_forward(head[0].weight, head[0].bias, head[2].weight, head[2].bias, tgt, current, noisy_line))
+        return torch.stack(outs)
+
     def forward(self, context, noisy_line):
         _require_cuda(context, "LineRefineNet")
         if not _use_native(self, context, noisy_line):
             _, fused = self.context_encoder(context.transpose(2, 1))   # train mode: native fwd/bwd (bf16 tier)
             memory = self.context_proj(fused.transpose(2, 1))
             return self._refine(context, noisy_line, memory, native_heads=False)
+        fast = self.precision == "bf16" and self.fast_decoder
+        N = context.shape[1]
+        chunk = max(1, min(self.segment_chunk, (1 << 20) // max(N, 1))) if fast else self.segment_chunk
         outs = []
-        for s in range(0, context.shape[0], self.segment_chunk):
-            ctx = context[s:s + self.segment_chunk].contiguous()
-            line = noisy_line[s:s + self.segment_chunk].contiguous()
+        for s in range(0, context.shape[0], chunk):
+            ctx = context[s:s + chunk].contiguous()
+            line = noisy_line[s:s + chunk].contiguous()
             memory = self.context_encoder.run_native(ctx, pool=False, memory=True)["memory"]
-            outs.append(self._refine(ctx, line, memory, native_heads=True))
+            outs.append(self._refine_fast(ctx, line, memory) if fast else self._refine(ctx, line, memory, native_heads=True))
         return torch.cat(outs, dim=1)
