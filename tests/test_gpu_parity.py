@@ -148,10 +148,10 @@ def test_encoder_vs_live_oracle(dev, B, N):
 # ------------------------------------------------------------------ size-independent properties at scale
 def test_properties_at_scale(dev):
     """Chunk invariance, permutation invariance within a segment, segment independence and
-    determinism of the max-pool at a size the oracle cannot run (1024 x 4096 points)."""
+    determinism of the max-pool at BASELINE.json's full configs[1] size (4096 x 4096 points)."""
     sd = synth.make_state_dict(0)
     m = _model(sd, dev, "bf16")
-    B, N = 1024, 4096
+    B, N = 4096, 4096                     # BASELINE.json configs[1], full size
     ctx = torch.randn(B, N, 4, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
     enc = m.context_encoder
     with torch.no_grad():
@@ -225,3 +225,16 @@ def test_refold_after_parameter_update(dev):
     o = orc.encoder_forward(sd2, ctx.cpu().numpy())[0]
     assert not torch.equal(a, b)
     assert np.abs(b.cpu().numpy() - o).max() <= 1e-3 * max(1.0, np.abs(o).max())
+
+
+def test_host_pipeline_matches_direct_call(dev):
+    """Chunked, copy/compute-overlapped host streaming returns exactly what one direct call returns."""
+    from pointnet_refine_b200.stream import HostEncoderPipeline
+    sd = synth.make_state_dict(0)
+    m = _model(sd, dev, "bf16")
+    host = torch.randn(700, 256, 4, generator=torch.Generator().manual_seed(9)).pin_memory()
+    with torch.no_grad():
+        direct = m.context_encoder.run_native(host.to(dev), pool=True)["global_feat"].cpu()
+    got = HostEncoderPipeline(m.context_encoder, segments_per_chunk=128).global_feat(host)
+    assert torch.equal(got[:, :1024], direct[:, :1024])
+    assert (got[:, 1024:] - direct[:, 1024:]).abs().max() <= 1e-5
