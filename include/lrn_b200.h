@@ -195,6 +195,13 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* W, 
                       void* out, int64_t ldo, int out_f32, int relu, int64_t M, int64_t N, int64_t K,
                       lrn_stream_t stream);
 
+/* out[M,N] (fp32) = At^T * Bt with At (K, M) and Bt (K, N) bf16 row-major ("MN-major" tcgen05 operands): the
+ * weight-gradient shape dW = dU^T X, K = points, read straight from the point-major buffers.  Few output tiles and a
+ * long K are split over the CTA pairs (fp32 atomic accumulation into the zeroed output).
+ * K % 64 == 0, M % 64 == 0, N % 128 == 0. */
+int lrn_gemm_tn(const void* At, int64_t lda, const void* Bt, int64_t ldb, float* out, int64_t ldo, int64_t M, int64_t N,
+                int64_t K, lrn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,7 +89,10 @@ __device__ __forceinline__ float gamma_hi(uint32_t q) { return __uint_as_float(0
 
 // GENERAL = false is the common fusion case (no argmax, every warp's 32 points valid and inside one
 // segment: N % 32 == 0); it drops the masked / 64-bit-key pooling paths and their registers.
-template <int BN, bool TF32, int EPI, int STAGES, bool GENERAL = true, bool STAGED = false>
+// MN = true (bf16, EPI_ACT): both operands are MN-major, i.e. the GEMM is  D[M x N] = A^T B  with A stored (K, M) and
+// B stored (K, N) row-major -- the weight-gradient shape dW = dU^T X (K = points) straight from the point-major
+// activation / gradient buffers, no transposed copies.  TMA boxes are [64 k-rows x 64 m/n] (128-byte rows).
+template <int BN, bool TF32, int EPI, int STAGES, bool GENERAL = true, bool STAGED = false, bool MN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const GemmParams p) {
@@ -100,7 +103,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t kTmemCols = 2 * BN;
   static_assert(kTmemCols == 256 || kTmemCols == 512, "TMEM columns must be a power of two");
   static_assert(EPI != EPI_FUSION || BN == 256, "fusion epilogue is laid out for BN = 256");
-  constexpr uint32_t kIdesc = ptx::make_idesc(TF32, 2 * BM, BN);
+  static_assert(!MN || (EPI == EPI_ACT && !TF32 && !STAGED), "MN-major operands: bf16 EPI_ACT only");
+  constexpr uint32_t kIdesc = ptx::make_idesc(TF32, 2 * BM, BN, MN);
   constexpr int kHalfCols = BN / 2;  // columns handled by one epilogue warp
   constexpr int kChunks = kHalfCols / 32;
 
@@ -173,8 +177,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (leader) ptx::mbar_arrive(&bar_full[stage]);
           } else {
             if (leader) ptx::mbar_arrive_expect_tx(&bar_full[stage], 2 * L::kStage);
-            ptx::tma_load_2d_pair(sa, &tmA, full_leader, p.a_col0 + kcol * BK, m_blk * 2 * BM + static_cast<int>(rank) * BM);
-            ptx::tma_load_2d_pair(sa + L::kA, &tmB, full_leader, kcol * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+            if (MN) {  // boxes of 64 k-rows x 64 m/n columns: this CTA's 128 m and BN/2 n
+#pragma unroll
+              for (int b = 0; b < 2; ++b)
+                ptx::tma_load_2d_pair(sa + b * 8192, &tmA, full_leader, m_blk * 2 * BM + static_cast<int>(rank) * BM + 64 * b,
+                                      kcol * BK);
+#pragma unroll
+              for (int b = 0; b < BN / 128; ++b)
+                ptx::tma_load_2d_pair(sa + L::kA + b * 8192, &tmB, full_leader,
+                                      n_blk * BN + static_cast<int>(rank) * (BN / 2) + 64 * b, kcol * BK);
+            } else {
+              ptx::tma_load_2d_pair(sa, &tmA, full_leader, p.a_col0 + kcol * BK, m_blk * 2 * BM + static_cast<int>(rank) * BM);
+              ptx::tma_load_2d_pair(sa + L::kA, &tmB, full_leader, kcol * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -209,13 +224,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::tc_fence_after();
           if (lane == 0) {
             const uint32_t a_addr = ptx::smem_u32(smem + stage * L::kStage);
-            const uint64_t da = ptx::make_smem_desc_sw128(a_addr);
-            const uint64_t db = ptx::make_smem_desc_sw128(a_addr + L::kA);
+            const uint64_t da = MN ? ptx::make_smem_desc_sw128_mn(a_addr, 8192) : ptx::make_smem_desc_sw128(a_addr);
+            const uint64_t db = MN ? ptx::make_smem_desc_sw128_mn(a_addr + L::kA, 8192) : ptx::make_smem_desc_sw128(a_addr + L::kA);
             const uint32_t d = slot.gate ? acc_gate : acc_main;
+            // K step of one MMA (16 bf16): 32 bytes along a K-major row, or 16 k-rows = 2048 bytes of an MN-major tile
+            constexpr int kStep = MN ? (2048 >> 4) : 2;
             if (!(EPI == EPI_FUSION && (p.flags & FUSE_DBG_NO_MMA))) {
 #pragma unroll
               for (int k = 0; k < kMmaPerKb; ++k)
-                ptx::tc_mma_ss_pair<TF32>(d, da + 2 * k, db + 2 * k, kIdesc, (slot.kb > 0 || k > 0) ? 1u : 0u);
+                ptx::tc_mma_ss_pair<TF32>(d, da + kStep * k, db + kStep * k, kIdesc, (slot.kb > 0 || k > 0) ? 1u : 0u);
             }
             ptx::tc_commit_pair(&bar_empty[stage], 3);  // frees this smem stage in BOTH CTAs
             if (slot.gate && slot.kb == p.kb_gate - 1) ptx::tc_commit_pair(&bar_tfull[rf ^ 1], 3);  // G_t complete

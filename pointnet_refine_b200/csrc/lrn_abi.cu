@@ -165,11 +165,11 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   return LRN_OK;
 }
 
-template <int BN, bool TF32, int EPI, int STAGES, bool GENERAL = true, bool STAGED = false>
+template <int BN, bool TF32, int EPI, int STAGES, bool GENERAL = true, bool STAGED = false, bool MN = false>
 int launch_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p, int sms,
                   cudaStream_t stream) {
   using L = PairSmem<BN, STAGES, EPI == EPI_FUSION, STAGED>;
-  auto kern = gemm_pair_kernel<BN, TF32, EPI, STAGES, GENERAL, STAGED>;
+  auto kern = gemm_pair_kernel<BN, TF32, EPI, STAGES, GENERAL, STAGED, MN>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
@@ -584,6 +584,56 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
   return LRN_OK;
 }
 
+// K-major tensor map helper's MN-major sibling: matrix stored (K rows, C cols) row-major, box = 64 cols x 64 rows
+static int make_tmap_mn(CUtensorMap* m, const void* base, int64_t k_rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc;
+  int st = get_encode_fn(&enc);
+  if (st) return st;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) return fail(LRN_ERR_MISALIGNED, "tensor map base/pitch");
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(k_rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld * 2)};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LRN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  return LRN_OK;
+}
+
+int lrn_gemm_tn(const void* At, int64_t lda, const void* Bt, int64_t ldb, float* out, int64_t ldo, int64_t M, int64_t N,
+                int64_t K, lrn_stream_t stream) {
+  if (!At || !Bt || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (M <= 0 || N <= 0 || K <= 0 || N % 128 || M % 64) return fail(LRN_ERR_BAD_SHAPE, "M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb;
+  if ((st = make_tmap_mn(&ta, At, K, M, lda))) return st;
+  if ((st = make_tmap_mn(&tb, Bt, K, N, ldb))) return st;
+  GemmParams p{};
+  p.M = int(M);
+  p.m_tiles = int((M + 2 * BM - 1) / (2 * BM));
+  p.n_tiles = int(N / bn);
+  p.kb_main = int((K + 63) / 64);  // rows beyond K are zero-filled by TMA
+  p.out = out;
+  p.ldo = ldo;
+  p.out_f32 = 1;
+  const int out_tiles = p.m_tiles * p.n_tiles, slots = dev.sms / 2;
+  if (out_tiles < slots && p.kb_main >= 64) {  // split K over the idle CTA pairs (fp32 atomic accumulation)
+    const int want = std::min((2 * slots + out_tiles - 1) / out_tiles, p.kb_main / 16);
+    if (want > 1) {
+      p.kb_per_split = (p.kb_main + want - 1) / want;
+      p.k_splits = (p.kb_main + p.kb_per_split - 1) / p.kb_per_split;
+      LRN_CUDA(cudaMemset2DAsync(out, size_t(ldo) * 4, 0, size_t(N) * 4, size_t(M), reinterpret_cast<cudaStream_t>(stream)));
+    }
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return bn == 256 ? launch_pair_t<256, false, EPI_ACT, 6, true, false, true>(ta, tb, ta, p, dev.sms, s)
+                   : launch_pair_t<128, false, EPI_ACT, 8, true, false, true>(ta, tb, ta, p, dev.sms, s);
+}
+
 int lrn_debug_ts_probe(const void* a_bf16 /* (128,64) */, const void* w_bf16 /* (64,64) */, float* out /* (128,64) */,
                        lrn_stream_t stream) {
   DeviceInfo dev;
@@ -717,7 +767,7 @@ struct TrainWs {
   // bf16 weights: W2..W5, Wf (1024 x 2048), Wg2 (1024 x 64), and transposed copies for the dgrads
   size_t w[6], wf, wg2, wt[6], wft, wg2t, wpack_end;
   // backward temporaries
-  size_t XT, dA, dB, dU, dUT, dZ, dZT, dHp, gW;
+  size_t dA, dB, dU, dZ, dHp, gW;
   size_t total;
 };
 
@@ -740,13 +790,10 @@ TrainWs train_layout(int64_t B, int64_t N) {
   W.wg2t = take(size_t(128) * 1024 * 2);
   W.wpack_end = off;
   (void)wstart;
-  W.XT = take(size_t(kCat) * W.Pp * 2);
   W.dA = take(size_t(W.Pp) * kCat * 2);
   W.dB = take(size_t(W.Pp) * 512 * 2);
   W.dU = take(size_t(W.Pp) * 1024 * 2);
-  W.dUT = take(size_t(1024) * W.Pp * 2);
   W.dZ = take(size_t(W.Pp) * 1024 * 2);
-  W.dZT = take(size_t(1024) * W.Pp * 2);
   W.dHp = take(size_t(W.Pp) * 128 * 2);
   W.gW = take(size_t(1024) * kCat * 4);
   W.total = off;
@@ -772,14 +819,6 @@ int pack_w(const float* src, int rows, int cols, void* dst, int64_t ld, bool tra
 dim3 stats_grid(int C, int64_t rows) {
   const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (148 * 8) / (C / 64) + 1));
   return dim3(C / 64, unsigned(slabs));
-}
-
-int transpose_bf16(const void* src, int64_t ld_src, int64_t rows, int C, void* dst, int64_t ld_dst, cudaStream_t s) {
-  dim3 grid(unsigned(ld_dst / 64), unsigned(C / 64));  // ld_dst (padded point count) is a multiple of 256
-  transpose_bf16_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), ld_src, rows, C,
-                                             static_cast<__nv_bfloat16*>(dst), ld_dst);
-  LRN_CUDA(cudaGetLastError());
-  return LRN_OK;
 }
 
 int elem_grid(long long total) { return int(std::min<long long>((total + 255) / 256, 148 * 32)); }
@@ -875,19 +914,16 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
   auto* X = reinterpret_cast<__nv_bfloat16*>(ws + W.X);
   auto* U = reinterpret_cast<__nv_bfloat16*>(ws + W.U);
   auto* Z = reinterpret_cast<__nv_bfloat16*>(ws + W.Z);
-  auto* XT = reinterpret_cast<__nv_bfloat16*>(ws + W.XT);
   auto* dA = reinterpret_cast<__nv_bfloat16*>(ws + W.dA);
   auto* dB = reinterpret_cast<__nv_bfloat16*>(ws + W.dB);
   auto* dU = reinterpret_cast<__nv_bfloat16*>(ws + W.dU);
-  auto* dUT = reinterpret_cast<__nv_bfloat16*>(ws + W.dUT);
   auto* dZ = reinterpret_cast<__nv_bfloat16*>(ws + W.dZ);
-  auto* dZT = reinterpret_cast<__nv_bfloat16*>(ws + W.dZT);
   auto* dHp = reinterpret_cast<__nv_bfloat16*>(ws + W.dHp);
   float* gW = reinterpret_cast<float*>(ws + W.gW);
   float* stats = reinterpret_cast<float*>(ws + W.stats);
   float *mean = stats + 2 * kStatLd, *rstd = stats + 3 * kStatLd, *scale = stats + 4 * kStatLd, *shift = stats + 5 * kStatLd,
         *S1 = stats + 6 * kStatLd, *S2 = stats + 7 * kStatLd, *Sz = stats + 8 * kStatLd;
-  const int64_t P = W.P, Pp = W.Pp;
+  const int64_t P = W.P;
   auto d2d = [&](float* dst, const float* src, int n) { return cudaMemcpyAsync(dst, src, size_t(n) * 4, cudaMemcpyDeviceToDevice, s); };
   auto copy_sub = [&](const float* src, int64_t ld, int c0, int rows, int cols, float* dst) {
     copy_submatrix_kernel<<<elem_grid(static_cast<long long>(rows) * cols), 256, 0, s>>>(src, ld, c0, rows, cols, dst);
@@ -901,8 +937,6 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
   LRN_CUDA(cudaMemsetAsync(g->gate0_b, 0, 64 * 4, s));
   for (int k = 1; k < 5; ++k) LRN_CUDA(cudaMemsetAsync(g->conv_b[k], 0, size_t(kChan[k + 1]) * 4, s));
   LRN_CUDA(cudaMemsetAsync(g->fusion_b, 0, 1024 * 4, s));
-  // operand rows, channel-major, for the weight gradients (K = points)
-  if ((st = transpose_bf16(X, kCat, P, kCat, XT, Pp, s))) return st;
 
   // ---- fused output: gate, ReLU, fusion BatchNorm
   {
@@ -924,16 +958,14 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
     LRN_CUDA(cudaGetLastError());
     col_stats_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, P, g->fusion_b, nullptr);
     LRN_CUDA(cudaGetLastError());
-    if ((st = transpose_bf16(dU, 1024, P, 1024, dUT, Pp, s))) return st;
-    if ((st = transpose_bf16(dZ, 1024, P, 1024, dZT, Pp, s))) return st;
     // d(operand row) = dUf Wf  (columns >= 1984 of the padded transposed weight are zero)
     if ((st = run_gemm_bf16(dU, 1024, P, 1024, ws + W.wft, 1024, kCat, nullptr, dA, kCat, 0, 0, s))) return st;
-    // dWf = dUf^T X   (K = points)
-    if ((st = run_gemm_bf16(dUT, Pp, 1024, Pp, XT, Pp, kCat, nullptr, gW, kCat, 1, 0, s))) return st;
+    // dWf = dUf^T X   (K = points; MN-major operands straight from the point-major buffers)
+    if ((st = lrn_gemm_tn(dU, 1024, X, kCat, gW, kCat, 1024, kCat, P, stream))) return st;
     LRN_CUDA(copy_sub(gW, kCat, 0, 1024, kFusionK, g->fusion_w));
     // gate layer 2: dH = dZ Wg2, dWg2 = dZ^T H
     if ((st = run_gemm_bf16(dZ, 1024, P, 1024, ws + W.wg2t, 1024, 128, nullptr, dHp, 128, 0, 0, s))) return st;
-    if ((st = run_gemm_bf16(dZT, Pp, 1024, Pp, XT + size_t(1920) * Pp, Pp, 128, nullptr, gW, 128, 1, 0, s))) return st;
+    if ((st = lrn_gemm_tn(dZ, 1024, X + 1920, kCat, gW, 128, 1024, 128, P, stream))) return st;
     LRN_CUDA(copy_sub(gW, 128, 64, 1024, 64, g->gate2_w));
   }
   // ---- chain, back to front: layer k consumes d(feat_k) = fusion dgrad slice (+ dgrad of layer k + 1)
@@ -951,10 +983,9 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
     if (k == 1) break;
     col_stats_kernel<<<stats_grid(C, P), 256, 0, s>>>(dU, 1024, P, g->conv_b[i], nullptr);
     LRN_CUDA(cudaGetLastError());
-    if ((st = transpose_bf16(dU, 1024, P, C, dUT, Pp, s))) return st;
     const int cin = kChan[k - 1], cin_p = std::max(cin, 128);
     // dW_k = dU_k^T X_{k-1}
-    if ((st = run_gemm_bf16(dUT, Pp, C, Pp, XT + size_t(kCatOff[k - 1]) * Pp, Pp, cin_p, nullptr, gW, cin_p, 1, 0, s))) return st;
+    if ((st = lrn_gemm_tn(dU, 1024, X + kCatOff[k - 1], kCat, gW, cin_p, C, cin_p, P, stream))) return st;
     LRN_CUDA(copy_sub(gW, cin_p, 0, C, cin, g->conv_w[i]));
     // d(feat_{k-1}) += dU_k W_k
     if ((st = run_gemm_bf16(dU, 1024, P, C, ws + W.wt[k], C, cin_p, nullptr, dB, 512, 0, 0, s))) return st;

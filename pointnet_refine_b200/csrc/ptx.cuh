@@ -248,10 +248,24 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same for an MN-major tile (the M/N index is the contiguous one): [64 k-rows x 64 mn-elements] bf16 boxes as TMA
+// writes them with the 128-byte swizzle (row = one k index, 128 bytes = 64 consecutive m/n).  Groups of 8 k-rows
+// are 1024 bytes apart (SBO); consecutive 64-element blocks along M/N are `mn_block_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(mn_block_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor (upper 32 bits of the "idesc" operand), dense, fp32 accumulate, both operands K-major.
 //   [4,6) c_format=1 (f32)  [7,10) a_format  [10,13) b_format  (1 = bf16, 2 = tf32)  [17,23) N>>3  [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc(bool tf32, uint32_t M, uint32_t N) {
-  return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+//   [15] a_major, [16] b_major: 0 = K-major, 1 = MN-major
+__host__ __device__ constexpr uint32_t make_idesc(bool tf32, uint32_t M, uint32_t N, bool mn_major = false) {
+  return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((N >> 3) << 17) | ((M >> 4) << 24) |
+         (mn_major ? (3u << 15) : 0u);
 }
 
 // ---------------------------------------------------------------- misc

@@ -1,6 +1,6 @@
 // CUDA-core kernels of the train-mode path (batch-statistic BatchNorm forward and the hand-written
 // backward).  All GEMMs of that path (forward, dgrad, wgrad) go through the tcgen05 pair kernels; these
-// kernels are the HBM-bound glue: statistics, normalisation, gate, masks, transposes, small reductions.
+// kernels are the HBM-bound glue: statistics, normalisation, gate, masks, small reductions.
 // Reference semantics: torch.nn.BatchNorm1d in training mode (biased variance for normalisation, unbiased
 // for the running update, momentum 0.1) as used by src/model.py:16-20,25,43-51.
 #pragma once
@@ -134,30 +134,6 @@ bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ U, long long ldu, long lo
     *reinterpret_cast<uint4*>(X + r * ldx + c0) =
         make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
                    ptx::pack_bf16x2(v[6], v[7]));
-  }
-}
-
-// dst (C x ld_dst) = src^T, src (rows x C, pitch ld_src), bf16.  64 x 64 tiles through shared memory, 16-byte global
-// loads and stores on both sides (C % 64 == 0, ld_dst % 64 == 0); rows >= `rows` are written as zeros.
-__global__ void __launch_bounds__(256)
-transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, long long rows, int C,
-                      __nv_bfloat16* __restrict__ dst, long long ld_dst) {
-  __shared__ __align__(16) __nv_bfloat16 tile[64][72];  // [point][channel], 144-byte rows
-  const long long r0 = blockIdx.x * 64ll;
-  const int c0 = blockIdx.y * 64;
-  for (int t = threadIdx.x; t < 512; t += 256) {  // 64 rows x 8 chunks of 8 channels
-    const int pr = t >> 3, ch = (t & 7) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r0 + pr < rows) v = *reinterpret_cast<const uint4*>(src + (r0 + pr) * ld_src + c0 + ch);
-    *reinterpret_cast<uint4*>(&tile[pr][ch]) = v;
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < 512; t += 256) {  // 64 channels x 8 chunks of 8 points
-    const int c = t >> 3, pc = (t & 7) * 8;
-    __align__(16) __nv_bfloat16 o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = tile[pc + j][c];
-    *reinterpret_cast<uint4*>(dst + static_cast<long long>(c0 + c) * ld_dst + r0 + pc) = *reinterpret_cast<const uint4*>(o);
   }
 }
 

@@ -22,7 +22,7 @@ ts_probe_kernel(const __grid_constant__ CUtensorMap tmW, const uint32_t* __restr
   __shared__ __align__(1024) uint8_t sW[64 * 128];
   __shared__ __align__(8) uint64_t bar_w, bar_d;
   __shared__ uint32_t tmem_ptr;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bar_w, 1);
     ptx::mbar_init(&bar_d, 1);

@@ -179,3 +179,17 @@ def profile_read() -> dict:
     n = (C.c_int64 * len(_lib.STAGES))()
     _lib.check(lib.lrn_profile_read(ms, n), "lrn_profile_read")
     return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(_lib.STAGES)}
+
+
+def gemm_tn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
+    """out (M,N) fp32 = at.T @ bt for bf16 at (K,M), bt (K,N) row-major (MN-major tcgen05 operands, split-K)."""
+    if at.dtype != torch.bfloat16 or bt.dtype != torch.bfloat16:
+        raise TypeError("bfloat16 operands expected")
+    K, M = at.shape
+    N = bt.shape[1]
+    out = torch.empty(M, N, dtype=torch.float32, device=at.device)
+    with torch.cuda.device(at.device):
+        _lib.check(lib.lrn_gemm_tn(at.data_ptr(), at.stride(0), bt.data_ptr(), bt.stride(0), out.data_ptr(), N, M, N, K,
+                                   _stream_ptr(at.device)), "lrn_gemm_tn")
+    _lib.launch_counter += 1
+    return out

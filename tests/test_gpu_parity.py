@@ -62,6 +62,18 @@ def test_gemm_tf32_matches_fp64(dev, M, N, K):
     assert (out.double() - ref).abs().max().item() <= 2e-5          # operands already TF32-exact
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1024, 2048, 2500), (64, 128, 30000), (512, 256, 4096)])
+def test_gemm_tn_mn_major_operands(dev, M, N, K):
+    """Weight-gradient shape: out = At^T Bt with both operands MN-major (K = points), split-K, ragged K."""
+    from pointnet_refine_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    at = torch.randn(K, M, device=dev, generator=g).bfloat16()
+    bt = (torch.randn(K, N, device=dev, generator=g) / K ** 0.5).bfloat16()
+    out = ops.gemm_tn(at, bt)
+    ref = at.double().T @ bt.double()
+    assert (out.double() - ref).abs().max().item() <= 5e-5
+
+
 # ------------------------------------------------------------------ encoder vs reference fixtures
 @pytest.mark.parametrize("prec", list(TIERS))
 @pytest.mark.parametrize("name", EVAL_CASES)
