@@ -116,3 +116,41 @@ def encoder_train_forward(module, context):
             b.num_batches_tracked += 1
     global_feat = torch.cat([fused.max(dim=2)[0], fused.mean(dim=2)], dim=1)   # src/model.py:58-60
     return global_feat, fused
+
+
+class LinearBf16Fn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMMs with bf16 operands and fp32 parameters / gradients:
+    forward `lrn_gemm_bias_act`, dgrad `dy W` (K-major GEMM on W^T), wgrad `dy^T x` (`lrn_gemm_tn`, MN-major operands,
+    split-K).  x (P, K) any float dtype, W (N, K) fp32, b (N) fp32; K % 64 == 0, N % 128 == 0.  Output bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import ops
+        xb = x.detach().to(torch.bfloat16).contiguous()
+        wb = weight.detach().to(torch.bfloat16).contiguous()
+        ctx.save_for_backward(xb, wb)
+        ctx.needs = (x.requires_grad, weight.requires_grad, bias is not None and bias.requires_grad)
+        ctx.x_dtype = x.dtype
+        return ops.gemm_bias_act(xb, wb, bias.detach() if bias is not None else None, out_dtype=torch.bfloat16)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        xb, wb = ctx.saved_tensors
+        dyb = dy.to(torch.bfloat16).contiguous()
+        need_x, need_w, need_b = ctx.needs
+        dx = dw = db = None
+        if need_x:
+            dx = ops.gemm_bias_act(dyb, wb.t().contiguous(), None, out_dtype=torch.bfloat16).to(ctx.x_dtype)
+        if need_w:
+            dw = ops.gemm_tn(dyb, xb)
+        if need_b:
+            db = dyb.float().sum(dim=0)
+        return dx, dw, db
+
+
+def linear_bf16(x, weight, bias):
+    """Differentiable bf16 tensor-core linear layer over the last dimension of x (leading dims flattened)."""
+    lead = x.shape[:-1]
+    y = LinearBf16Fn.apply(x.reshape(-1, x.shape[-1]), weight, bias)
+    return y.view(*lead, weight.shape[0])

@@ -125,3 +125,49 @@ def test_ddp_step_two_ranks():
                         "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "ddp_check.py"), "8", "512"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ddp ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_linear_bf16_autograd(dev):
+    """The differentiable tensor-core linear used for context_proj / K / V projections in train mode."""
+    from pointnet_refine_b200.train_ops import linear_bf16
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(5, 300, 256, device=dev, generator=g, requires_grad=True)
+    w = (torch.randn(1536, 256, device=dev, generator=g) / 16).requires_grad_()
+    b = torch.randn(1536, device=dev, generator=g, requires_grad=True)
+    r = torch.randn(5, 300, 1536, device=dev, generator=g)
+    (linear_bf16(x, w, b).float() * r).sum().backward()
+    gx, gw, gb = x.grad.clone(), w.grad.clone(), b.grad.clone()
+    x.grad = w.grad = b.grad = None
+    (torch.nn.functional.linear(x, w, b) * r).sum().backward()
+    for a, bb in ((gx, x.grad), (gw, w.grad), (gb, b.grad)):
+        assert float((a.float() - bb).norm() / bb.norm()) <= 1e-2
+
+
+def test_train_fast_decoder_close_to_stock(dev):
+    """model.train() with dropout disabled: the tensor-core decoder path gives the same loss and gradients
+    (relative L2) as the stock nn.MultiheadAttention formulation on the same native encoder."""
+    import pointnet_refine_b200 as prb
+    m = prb.LineRefineNet().to(dev)
+    m.load_state_dict(synth.to_torch(synth.make_state_dict(2)), strict=True)
+    m.train()
+    for mod in m.modules():                       # switch every dropout off, keep batch-stat BatchNorm
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, torch.nn.MultiheadAttention):
+            mod.dropout = 0.0
+    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(4, 512, seed=11))
+    tgt = 0.1 * torch.randn(4, 32, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    res = {}
+    for fast in (True, False):
+        m.fast_decoder = fast
+        m.zero_grad()
+        out = m(ctx, line)
+        loss = sum(torch.nn.functional.l1_loss(out[l], tgt) for l in range(6)) / 6
+        loss.backward()
+        res[fast] = (float(loss.detach()), {n: p.grad.clone() for n, p in m.named_parameters()})
+    assert abs(res[True][0] - res[False][0]) <= 2e-2 * abs(res[False][0])
+    for n in ("context_proj.weight", "pos_emb.mlp.2.weight", "decoder_layers.0.cross_attn.in_proj_weight",
+              "decoder_layers.5.linear1.weight", "reg_branches.5.0.weight"):
+        a, b = res[True][1][n].flatten().double(), res[False][1][n].flatten().double()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        assert cos >= 0.9, (n, cos)
