@@ -156,7 +156,8 @@ int lrn_profile_read(float* ms_per_stage /*[LRN_STAGE_COUNT]*/, int64_t* launche
  * stay with the caller (they are differentiable functions of `fused`).
  *   running     : running_mean / running_var of bn1..bn5 and fusion.1, updated in place like PyTorch
  *                 (momentum, unbiased variance); may be NULL.  num_batches_tracked is the caller's counter.
- *   fused       : (B,1024,N) fp32 output;  d_fused: its gradient.
+ *   fused       : fused_point_major = 0: (B,1024,N) fp32, the reference layout; 1: (B*N,1024) bf16 point-major
+ *                 (what context_proj consumes, no layout change).  d_fused: its gradient, same layout / type.
  *   grads       : fp32 gradient of every encoder parameter (same shapes as lrn_encoder_params).
  *   workspace   : lrn_train_workspace_bytes(B, N); the forward leaves the saved activations there and the
  *                 matching backward call must receive the same, untouched buffer. */
@@ -180,10 +181,10 @@ typedef struct lrn_encoder_grads {
 } lrn_encoder_grads;
 size_t lrn_train_workspace_bytes(int64_t B, int64_t N);
 int lrn_encoder_train_forward(const lrn_encoder_params* params, const lrn_bn_running* running, float momentum,
-                              const float* context, int64_t B, int64_t N, float* fused, void* workspace,
-                              size_t workspace_bytes, lrn_stream_t stream);
+                              const float* context, int64_t B, int64_t N, void* fused, int fused_point_major,
+                              void* workspace, size_t workspace_bytes, lrn_stream_t stream);
 int lrn_encoder_train_backward(const lrn_encoder_params* params, const float* context, int64_t B, int64_t N,
-                               const float* d_fused, const lrn_encoder_grads* grads, void* workspace,
+                               const void* d_fused, int fused_point_major, const lrn_encoder_grads* grads, void* workspace,
                                size_t workspace_bytes, lrn_stream_t stream);
 
 /* ---- building block, exported for unit tests and profiling ----

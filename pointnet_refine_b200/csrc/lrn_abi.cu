@@ -833,8 +833,8 @@ size_t lrn_train_workspace_bytes(int64_t B, int64_t N) {
 }
 
 int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running* running, float momentum,
-                              const float* context, int64_t B, int64_t N, float* fused, void* workspace,
-                              size_t workspace_bytes, lrn_stream_t stream) {
+                              const float* context, int64_t B, int64_t N, void* fused, int fused_point_major,
+                              void* workspace, size_t workspace_bytes, lrn_stream_t stream) {
   if (!pr || !context || !fused || !workspace) return fail(LRN_ERR_BAD_ARG, "null argument");
   if (B <= 0 || N <= 0 || B * N >= (int64_t(1) << 31) - 256) return fail(LRN_ERR_BAD_SHAPE, "B=%lld N=%lld", (long long)B, (long long)N);
   DeviceInfo dev;
@@ -894,14 +894,20 @@ int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running
       if (st) return st;
     }
   }
-  dim3 grid(unsigned((P + 31) / 32), 32);
-  fusion_gate_fwd_kernel<<<grid, 256, 0, s>>>(U + kUOff[5], kULd, Z, 1024, P, int(N), scale + kUOff[5], shift + kUOff[5], fused);
+  if (fused_point_major) {
+    fusion_gate_fwd_pm_kernel<<<stats_grid(1024, P), 256, 0, s>>>(U + kUOff[5], kULd, Z, 1024, P, scale + kUOff[5],
+                                                                   shift + kUOff[5], static_cast<__nv_bfloat16*>(fused));
+  } else {
+    dim3 grid(unsigned((P + 31) / 32), 32);
+    fusion_gate_fwd_kernel<<<grid, 256, 0, s>>>(U + kUOff[5], kULd, Z, 1024, P, int(N), scale + kUOff[5], shift + kUOff[5],
+                                                static_cast<float*>(fused));
+  }
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
 
 int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* context, int64_t B, int64_t N,
-                               const float* d_fused, const lrn_encoder_grads* g, void* workspace,
+                               const void* d_fused, int fused_point_major, const lrn_encoder_grads* g, void* workspace,
                                size_t workspace_bytes, lrn_stream_t stream) {
   if (!pr || !context || !d_fused || !g || !workspace) return fail(LRN_ERR_BAD_ARG, "null argument");
   DeviceInfo dev;
@@ -940,9 +946,15 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
 
   // ---- fused output: gate, ReLU, fusion BatchNorm
   {
-    dim3 grid(unsigned((P + 31) / 32), 32);
-    fusion_gate_bwd_kernel<<<grid, 256, 0, s>>>(d_fused, U + kUOff[5], kULd, Z, 1024, P, int(N), scale + kUOff[5],
-                                                shift + kUOff[5], dU, dZ, 1024);
+    if (fused_point_major) {
+      fusion_gate_bwd_pm_kernel<<<stats_grid(1024, P), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(d_fused), U + kUOff[5],
+                                                                     kULd, Z, 1024, P, scale + kUOff[5], shift + kUOff[5], dU,
+                                                                     dZ, 1024);
+    } else {
+      dim3 grid(unsigned((P + 31) / 32), 32);
+      fusion_gate_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(d_fused), U + kUOff[5], kULd, Z, 1024, P, int(N),
+                                                  scale + kUOff[5], shift + kUOff[5], dU, dZ, 1024);
+    }
     LRN_CUDA(cudaGetLastError());
     col_stats_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dZ, 1024, P, Sz, nullptr);  // d(gate layer 2 bias)
     LRN_CUDA(cudaGetLastError());

@@ -173,6 +173,60 @@ fusion_gate_fwd_kernel(const __nv_bfloat16* __restrict__ Uf, long long ldu, cons
   }
 }
 
+// Point-major variants (no layout change): fused_pm[p, c] bf16, channel-stationary threads like bn_relu_apply_kernel.
+__global__ void __launch_bounds__(256)
+fusion_gate_fwd_pm_kernel(const __nv_bfloat16* __restrict__ Uf, long long ldu, const __nv_bfloat16* __restrict__ Z,
+                          long long ldz, long long rows, const float* __restrict__ scale, const float* __restrict__ shift,
+                          __nv_bfloat16* __restrict__ fused_pm) {
+  const int c0 = blockIdx.x * 64 + (threadIdx.x & 7) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+  for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
+    const uint4 ru = *reinterpret_cast<const uint4*>(Uf + r * ldu + c0);
+    const uint4 rz = *reinterpret_cast<const uint4*>(Z + r * ldz + c0);
+    const __nv_bfloat16 *u = reinterpret_cast<const __nv_bfloat16*>(&ru), *z = reinterpret_cast<const __nv_bfloat16*>(&rz);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = fmaxf(fmaf(bf2f(u[j]), sc[j], sh[j]), 0.f) * (0.5f + 0.5f * sigmoidf_fast(bf2f(z[j])));
+    *reinterpret_cast<uint4*>(fused_pm + r * 1024 + c0) =
+        make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
+                   ptx::pack_bf16x2(v[6], v[7]));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fusion_gate_bwd_pm_kernel(const __nv_bfloat16* __restrict__ dfused_pm, const __nv_bfloat16* __restrict__ Uf, long long ldu,
+                          const __nv_bfloat16* __restrict__ Z, long long ldz, long long rows,
+                          const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dY,
+                          __nv_bfloat16* __restrict__ dZ, long long ldd) {
+  const int c0 = blockIdx.x * 64 + (threadIdx.x & 7) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+  for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
+    const uint4 rd = *reinterpret_cast<const uint4*>(dfused_pm + r * 1024 + c0);
+    const uint4 ru = *reinterpret_cast<const uint4*>(Uf + r * ldu + c0);
+    const uint4 rz = *reinterpret_cast<const uint4*>(Z + r * ldz + c0);
+    const __nv_bfloat16 *d = reinterpret_cast<const __nv_bfloat16*>(&rd), *u = reinterpret_cast<const __nv_bfloat16*>(&ru),
+                        *z = reinterpret_cast<const __nv_bfloat16*>(&rz);
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float df = bf2f(d[j]);
+      const float y0 = fmaf(bf2f(u[j]), sc[j], sh[j]);
+      const float g = sigmoidf_fast(bf2f(z[j]));
+      a[j] = y0 > 0.f ? df * (0.5f + 0.5f * g) : 0.f;
+      b[j] = df * fmaxf(y0, 0.f) * 0.5f * g * (1.f - g);
+    }
+    *reinterpret_cast<uint4*>(dY + r * ldd + c0) = make_uint4(ptx::pack_bf16x2(a[0], a[1]), ptx::pack_bf16x2(a[2], a[3]),
+                                                              ptx::pack_bf16x2(a[4], a[5]), ptx::pack_bf16x2(a[6], a[7]));
+    *reinterpret_cast<uint4*>(dZ + r * ldd + c0) = make_uint4(ptx::pack_bf16x2(b[0], b[1]), ptx::pack_bf16x2(b[2], b[3]),
+                                                              ptx::pack_bf16x2(b[4], b[5]), ptx::pack_bf16x2(b[6], b[7]));
+  }
+}
+
 // Backward of the gate / ReLU at the fused output: with y0 = Uf*scale+shift, y = relu(y0), g = sigmoid(Z):
 //   dY[p,c] = dF * (0.5 + 0.5 g) * [y0 > 0]      (gradient w.r.t. the BatchNorm output)
 //   dZ[p,c] = dF * y * 0.5 * g * (1 - g)         (gradient w.r.t. the gate pre-activation)

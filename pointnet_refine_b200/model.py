@@ -262,7 +262,7 @@ class LineRefineNet(nn.Module):
             outs.append(ops.head_forward(head[0].weight, head[0].bias, head[2].weight, head[2].bias, tgt, current, noisy_line))
         return torch.stack(outs)
 
-    def _refine_fast_train(self, context, noisy_line, fused):
+    def _refine_fast_train(self, context, noisy_line, fused_pm):
         """Autograd-capable twin of _refine_fast for model.train(): context_proj, the memory positional embedding
         and the K / V projections of all six cross-attention layers run as differentiable bf16 tensor-core linears
         (train_ops.linear_bf16: tcgen05 forward, dgrad and wgrad), the cross attention through
@@ -277,11 +277,12 @@ class LineRefineNet(nn.Module):
         wv = torch.cat([l.cross_attn.in_proj_weight[2 * d:] for l in self.decoder_layers])
         bk = torch.cat([l.cross_attn.in_proj_bias[d:2 * d] for l in self.decoder_layers])
         bv = torch.cat([l.cross_attn.in_proj_bias[2 * d:] for l in self.decoder_layers])
-        mem = linear_bf16(fused.transpose(2, 1), self.context_proj.weight, self.context_proj.bias)      # (B,N,256) bf16
+        mem = linear_bf16(fused_pm, self.context_proj.weight, self.context_proj.bias)      # (B,N,256) bf16
         h = F.relu(self.pos_emb.mlp[0](context[:, :, :3]))
         posm = linear_bf16(h, self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias)
-        k_all = linear_bf16(mem + posm, wk, bk).view(B, N, 6, H, d // H)
-        v_all = linear_bf16(mem, wv, bv).view(B, N, 6, H, d // H)
+        # unbind (not six slices): its backward is one stack instead of six zero-filled full-size gradients
+        k_l = linear_bf16(mem + posm, wk, bk).view(B, N, 6, H, d // H).unbind(2)
+        v_l = linear_bf16(mem, wv, bv).view(B, N, 6, H, d // H).unbind(2)
         tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
         current = noisy_line
         outs = []
@@ -291,7 +292,7 @@ class LineRefineNet(nn.Module):
             tgt = layer.norm1(tgt + layer.dropout1(layer.self_attn(q, q, value=tgt, need_weights=False)[0]))
             ca = layer.cross_attn
             qh = F.linear(tgt + qpos, ca.in_proj_weight[:d], ca.in_proj_bias[:d]).view(B, -1, H, d // H).transpose(1, 2)
-            att = F.scaled_dot_product_attention(qh.bfloat16(), k_all[:, :, i].transpose(1, 2), v_all[:, :, i].transpose(1, 2),
+            att = F.scaled_dot_product_attention(qh.bfloat16(), k_l[i].transpose(1, 2), v_l[i].transpose(1, 2),
                                                  dropout_p=ca.dropout if self.training else 0.0)
             att = att.transpose(1, 2).reshape(B, -1, d).float()
             tgt = layer.norm2(tgt + layer.dropout2(ca.out_proj(att)))
@@ -303,9 +304,11 @@ class LineRefineNet(nn.Module):
     def forward(self, context, noisy_line):
         _require_cuda(context, "LineRefineNet")
         if not _use_native(self, context, noisy_line):
-            _, fused = self.context_encoder(context.transpose(2, 1))   # train mode: native fwd/bwd (bf16 tier)
             if self.training and self.fast_decoder and self.precision == "bf16" and self.context_encoder.native_training:
-                return self._refine_fast_train(context, noisy_line, fused)
+                from .train_ops import encoder_train_forward
+                _, fused_pm = encoder_train_forward(self.context_encoder, context, point_major=True)
+                return self._refine_fast_train(context, noisy_line, fused_pm)
+            _, fused = self.context_encoder(context.transpose(2, 1))   # train mode: native fwd/bwd (bf16 tier)
             memory = self.context_proj(fused.transpose(2, 1))
             return self._refine(context, noisy_line, memory, native_heads=False)
         fast = self.precision == "bf16" and self.fast_decoder

@@ -29,10 +29,10 @@ lib.lrn_train_workspace_bytes.restype = C.c_size_t
 lib.lrn_train_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
 lib.lrn_encoder_train_forward.restype = C.c_int
 lib.lrn_encoder_train_forward.argtypes = [C.POINTER(_lib.EncoderParams), C.POINTER(BnRunning), C.c_float, C.c_void_p,
-                                          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+                                          C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.lrn_encoder_train_backward.restype = C.c_int
 lib.lrn_encoder_train_backward.argtypes = [C.POINTER(_lib.EncoderParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
-                                           C.POINTER(EncoderGrads), C.c_void_p, C.c_size_t, C.c_void_p]
+                                           C.c_int, C.POINTER(EncoderGrads), C.c_void_p, C.c_size_t, C.c_void_p]
 
 # parameter order of the autograd node (names relative to MultiScalePointNetEncoder)
 PARAM_NAMES = ([f"conv{k}.weight" for k in range(1, 6)] + [f"conv{k}.bias" for k in range(1, 6)]
@@ -55,9 +55,10 @@ def _params_struct(t):
 
 class EncoderTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, context, running, momentum, *params):
+    def forward(ctx, context, running, momentum, point_major, *params):
         """context (B,N,4) fp32 CUDA; running = list of 12 buffers (6 running_mean, 6 running_var) updated in
-        place, or None; params in PARAM_NAMES order.  Returns fused (B,1024,N)."""
+        place, or None; params in PARAM_NAMES order.  Returns fused (B,1024,N) fp32, or with point_major the
+        (B,N,1024) bf16 tensor context_proj consumes."""
         context = _f32c(context)
         B, N, _ = context.shape
         dev = context.device
@@ -65,7 +66,8 @@ class EncoderTrainFn(torch.autograd.Function):
         ps = _params_struct(t)
         nbytes = lib.lrn_train_workspace_bytes(B, N)
         ws = _aligned_bytes(nbytes, dev)           # owned by this node until its backward has run
-        fused = torch.empty(B, 1024, N, dtype=torch.float32, device=dev)
+        fused = (torch.empty(B, N, 1024, dtype=torch.bfloat16, device=dev) if point_major
+                 else torch.empty(B, 1024, N, dtype=torch.float32, device=dev))
         rs = None
         if running is not None:
             rs = BnRunning()
@@ -73,11 +75,12 @@ class EncoderTrainFn(torch.autograd.Function):
                 rs.mean[i], rs.var[i] = running[i].data_ptr(), running[6 + i].data_ptr()
         with torch.cuda.device(dev):
             _lib.check(lib.lrn_encoder_train_forward(C.byref(ps), C.byref(rs) if rs is not None else None, momentum,
-                                                     context.data_ptr(), B, N, fused.data_ptr(), ws.data_ptr(),
-                                                     ws.numel(), _stream_ptr(dev)), "lrn_encoder_train_forward")
+                                                     context.data_ptr(), B, N, fused.data_ptr(), int(point_major),
+                                                     ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
+                       "lrn_encoder_train_forward")
         _lib.launch_counter += 12 + 1 + 6 * 2 + 5 + 6 + 1
         ctx.save_for_backward(context, *t)
-        ctx.ws, ctx.shape = ws, (B, N)
+        ctx.ws, ctx.shape, ctx.point_major = ws, (B, N), bool(point_major)
         return fused
 
     @staticmethod
@@ -85,7 +88,7 @@ class EncoderTrainFn(torch.autograd.Function):
         context, *t = ctx.saved_tensors
         B, N = ctx.shape
         dev = context.device
-        d_fused = _f32c(d_fused)
+        d_fused = d_fused.to(torch.bfloat16).contiguous() if ctx.point_major else _f32c(d_fused)
         grads = [torch.empty_like(x) for x in t]
         g = EncoderGrads()
         for k in range(5):
@@ -96,24 +99,27 @@ class EncoderTrainFn(torch.autograd.Function):
         ps = _params_struct(t)
         with torch.cuda.device(dev):
             _lib.check(lib.lrn_encoder_train_backward(C.byref(ps), context.data_ptr(), B, N, d_fused.data_ptr(),
-                                                      C.byref(g), ctx.ws.data_ptr(), ctx.ws.numel(), _stream_ptr(dev)),
-                       "lrn_encoder_train_backward")
+                                                      int(ctx.point_major), C.byref(g), ctx.ws.data_ptr(), ctx.ws.numel(),
+                                                      _stream_ptr(dev)), "lrn_encoder_train_backward")
         _lib.launch_counter += 60
         ctx.ws = None
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
-def encoder_train_forward(module, context):
+def encoder_train_forward(module, context, point_major=False):
     """module: MultiScalePointNetEncoder in train mode; context (B,N,4).  Returns (global_feat, fused) with
-    autograd through the native backward; updates running statistics / num_batches_tracked like PyTorch."""
+    autograd through the native backward; updates running statistics / num_batches_tracked like PyTorch.
+    point_major=True returns (None, fused_pm (B,N,1024) bf16) for LineRefineNet, which never uses global_feat."""
     sd = dict(module.named_parameters())
     params = [sd[n] for n in PARAM_NAMES]
     bns = [module.bn1, module.bn2, module.bn3, module.bn4, module.bn5, module.fusion[1]]
     running = [b.running_mean for b in bns] + [b.running_var for b in bns]
-    fused = EncoderTrainFn.apply(context, running, float(bns[0].momentum), *params)
+    fused = EncoderTrainFn.apply(context, running, float(bns[0].momentum), point_major, *params)
     with torch.no_grad():
         for b in bns:
             b.num_batches_tracked += 1
+    if point_major:
+        return None, fused
     global_feat = torch.cat([fused.max(dim=2)[0], fused.mean(dim=2)], dim=1)   # src/model.py:58-60
     return global_feat, fused
 
