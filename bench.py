@@ -5,7 +5,7 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- encoder forward (shared MLP, fusion, gate,
 max+mean pooling -> global_feat) over 4096 segments x 4096 context points per GPU, synthetic
-N(0,1) points, random-init weights (oracle/synth.py), bf16 tensor-core tier.  A "step" is one
+N(0,1) points, random-init weights (PyTorch default init, seed 0), bf16 tensor-core tier.  A "step" is one
 pass over that batch.  N > 1 (under torchrun): every rank runs the same per-GPU workload on its
 own shard, no data-path collective (segments are independent) -> weak scaling.
 
@@ -152,8 +152,7 @@ def main():
     import torch.distributed as dist
 
     import pointnet_refine_b200 as prb
-    from oracle import synth   # synthetic weights only (numpy RNG); the oracle is not on the timed path
-    from pointnet_refine_b200 import _lib, ops
+    from pointnet_refine_b200 import _lib, ops      # nothing under oracle/ is imported by the native arm
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -165,8 +164,16 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    model = prb.LineRefineNet().to(dev).eval()
-    model.load_state_dict(synth.to_torch(synth.make_state_dict(0)), strict=True)
+    torch.manual_seed(0)                            # random-init weights of the reference architecture (PyTorch default
+    model = prb.LineRefineNet()                     # init), BatchNorm affine / running statistics randomised so that the
+    with torch.no_grad():                           # folding is not the identity
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0.0, 0.1)
+                mod.running_mean.normal_(0.0, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+    model = model.to(dev).eval()
     model.precision = args.precision
     enc = model.context_encoder
     B, N = args.segments, args.points

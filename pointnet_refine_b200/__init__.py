@@ -8,4 +8,6 @@ from . import _lib, ops  # noqa: F401  (loads liblrn_b200.so; raises if missing)
 from .model import (DetrTransformerDecoderLayer, LineRefineNet, MultiScalePointNetEncoder,  # noqa: F401
                     PositionalEncoding)
 
-__all__ = ["LineRefineNet", "MultiScalePointNetEncoder", "PositionalEncoding", "DetrTransformerDecoderLayer", "ops"]
+from .graph import GraphedLineRefineNet  # noqa: F401,E402
+
+__all__ = ["GraphedLineRefineNet", "LineRefineNet", "MultiScalePointNetEncoder", "PositionalEncoding", "DetrTransformerDecoderLayer", "ops"]
