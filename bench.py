@@ -214,6 +214,22 @@ def main():
         prof = ops.profile_read()
         ops.profile_enable(False)
 
+        # ---- HBM roofline of the stand-alone point loader + first layer (north_star evidence item; the bf16 tier's
+        #      default path has this stage inside the fused chain kernel): 16 B in + 256 B out per point
+        rows_hbm = min(B * N, 4 * 1024 * 1024)
+        folded = enc.folded()
+        pts = ctx.reshape(-1, 4)[:rows_hbm]
+        for _ in range(2):
+            ops.point_embed(folded, pts)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(5):
+            ops.point_embed(folded, pts)
+        h1.record()
+        torch.cuda.synchronize()
+        embed_ms = h0.elapsed_time(h1) / 5
+        embed_bytes = rows_hbm * (16 + 2 * 64 * (2 if args.precision == "bf16" else 4))
+
         # ---- end to end through the module API from pinned host buffers
         host_ctx = torch.empty(B, N, 4, dtype=torch.float32).pin_memory()
         host_ctx.copy_(ctx)
@@ -298,7 +314,14 @@ def main():
         "config": config, "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": B * N * 16,
                 "d2h_bytes_per_step": B * 2048 * 4, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "full_model": full_model,
+        "roofline": roofline,
+        "roofline_hbm": {"bound": "hbm", "kernel": "point_embed_kernel (point loading + conv1 + gate layer 1, stand-alone)",
+                         "achieved": embed_bytes / (embed_ms * 1e-3) / 1e9, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
+                         "frac": embed_bytes / (embed_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]), "traffic": None,
+                         "points": rows_hbm, "algorithmic_bytes_per_point": embed_bytes // rows_hbm,
+                         "note": "torch allocation of the (P,2048) operand rows is outside the events' kernel time but inside "
+                                 "the loop; the default bf16 path runs this stage inside chain_pair_kernel"},
+        "cpu_baseline": cpu_baseline, "full_model": full_model,
     }))
     if world > 1:
         dist.destroy_process_group()

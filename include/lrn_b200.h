@@ -117,6 +117,13 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
                         float* global_feat, float* fused, int64_t* argmax, float* memory, int64_t chunk_rows,
                         void* workspace, size_t workspace_bytes, lrn_stream_t stream);
 
+/* ---- point loading + first layer, stand-alone (tf32 tier, per-layer path, and bench.py's HBM roofline line) ----
+ * Replaces: relu(bn1(conv1(x))) and the gate's Conv1d(1,64)+ReLU, src/model.py:43,33-34, in fp32 FMA on the raw points:
+ * reads 16 B/point, writes feat1 -> operand columns [0,64) and the gate hidden block -> [1984,2048) of
+ * `operand_rows` ((rows, 2048) in the tier's operand type).  HBM-bound: 16 + 256 B (bf16) / 16 + 512 B (tf32) per point. */
+int lrn_point_embed(const void* packed, int precision, const float* context, int64_t rows, void* operand_rows,
+                    lrn_stream_t stream);
+
 /* ---- regression head + cumulative-offset bookkeeping ----
  * Replaces: reg_branches[i](tgt) and the coordinate update of LineRefineNet.forward,
  * src/model.py:172-179,220,227-231:

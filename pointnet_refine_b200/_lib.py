@@ -24,7 +24,7 @@ EXPORTS = [
     "lrn_abi_version", "lrn_status_string", "lrn_last_error", "lrn_device_check",
     "lrn_encoder_packed_bytes", "lrn_encoder_fold", "lrn_encoder_workspace_bytes", "lrn_encoder_forward",
     "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe", "lrn_train_workspace_bytes",
-    "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn",
+    "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
 
@@ -67,6 +67,8 @@ def _load():
     lib.lrn_profile_enable.argtypes = [ci]
     lib.lrn_profile_read.restype = ci
     lib.lrn_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+    lib.lrn_point_embed.restype = ci
+    lib.lrn_point_embed.argtypes = [vp, ci, vp, i64, vp, vp]
     lib.lrn_gemm_tn.restype = ci
     lib.lrn_gemm_tn.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp]
     lib.lrn_debug_ts_probe.restype = ci

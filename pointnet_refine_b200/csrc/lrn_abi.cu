@@ -675,6 +675,26 @@ int lrn_profile_read(float* ms_per_stage, int64_t* launches_per_stage) {
   return LRN_OK;
 }
 
+int lrn_point_embed(const void* packed, int precision, const float* context, int64_t rows, void* operand_rows,
+                    lrn_stream_t stream) {
+  if (bad_precision(precision) || !packed || !context || !operand_rows || rows <= 0) return fail(LRN_ERR_BAD_ARG, "bad argument");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const PackedLayout L = packed_layout(precision);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  EmbedWeights ew{reinterpret_cast<const float*>(pk + L.w1), reinterpret_cast<const float*>(pk + L.b1),
+                  reinterpret_cast<const float*>(pk + L.wg1), reinterpret_cast<const float*>(pk + L.bg1)};
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = int(std::min<int64_t>((rows + 15) / 16, int64_t(dev.sms) * 16));
+  if (precision == LRN_PREC_TF32)
+    point_embed_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context), rows, ew, operand_rows, kCat);
+  else
+    point_embed_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context), rows, ew, operand_rows, kCat);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
 int lrn_head_forward(const float* w1, const float* b1, const float* w2, const float* b2, const float* tgt,
                      int64_t rows, float* current, const float* noisy, float* cum_out, lrn_stream_t stream) {
   if (!w1 || !b1 || !w2 || !b2 || !tgt || !current || !noisy || !cum_out) return fail(LRN_ERR_BAD_ARG, "null pointer");

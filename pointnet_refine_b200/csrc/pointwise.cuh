@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(256) point_embed_kernel(const float4* __restri
     gb[j] = w.bg1[4 * sub + j];
   }
   const long long pts_per_block = blockDim.x / 16;
-  for (long long pt = blockIdx.x * pts_per_block + (threadIdx.x >> 4); pt < rows; pt += gridDim.x * pts_per_block) {
-    const float4 x = __ldg(ctx + pt);
+  const long long stride = gridDim.x * pts_per_block;
+  auto emit = [&](long long pt, const float4& x) {
     float f[4], h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -83,7 +83,17 @@ __global__ void __launch_bounds__(256) point_embed_kernel(const float4* __restri
       *reinterpret_cast<uint2*>(row + 1984 + 4 * sub) =
           make_uint2(ptx::pack_bf16x2(h[0], h[1]), ptx::pack_bf16x2(h[2], h[3]));
     }
+  };
+  // four points (loads) in flight per thread: the kernel is HBM-latency-bound otherwise
+  long long pt = blockIdx.x * pts_per_block + (threadIdx.x >> 4);
+  for (; pt + 3 * stride < rows; pt += 4 * stride) {
+    float4 x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = __ldg(ctx + pt + k * stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(pt + k * stride, x[k]);
   }
+  for (; pt < rows; pt += stride) emit(pt, __ldg(ctx + pt));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -193,3 +193,17 @@ def gemm_tn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
                                    _stream_ptr(at.device)), "lrn_gemm_tn")
     _lib.launch_counter += 1
     return out
+
+
+def point_embed(folded: FoldedEncoder, context: torch.Tensor) -> torch.Tensor:
+    """Stand-alone first layer (+ gate layer 1): context (P, 4) or (B, N, 4) fp32 -> operand rows (P, 2048) in the
+    tier's operand type with columns [0,64) and [1984,2048) written (the rest is left uninitialised)."""
+    context = _f32c(context).reshape(-1, 4)
+    P = context.shape[0]
+    dt = torch.float32 if folded.precision == "tf32" else torch.bfloat16
+    rows = torch.empty(P, 2048, dtype=dt, device=context.device)
+    with torch.cuda.device(context.device):
+        _lib.check(lib.lrn_point_embed(folded.blob.data_ptr(), folded.prec_id, context.data_ptr(), P, rows.data_ptr(),
+                                       _stream_ptr(context.device)), "lrn_point_embed")
+    _lib.launch_counter += 1
+    return rows
