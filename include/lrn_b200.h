@@ -56,6 +56,8 @@ enum lrn_encoder_flags {
   LRN_OUT_ARGMAX = 2, /* argmax (B,1024) int64, first index on ties   src/model.py:58 (torch.max indices) */
   LRN_OUT_FUSED = 4,  /* fused fp32 in the reference layout (B,1024,N) src/model.py:55,62 */
   LRN_OUT_MEMORY = 8, /* memory fp32 (B,N,256) = context_proj(fused^T) src/model.py:194   */
+  LRN_OUT_MEMORY_BF16 = 16, /* with LRN_OUT_MEMORY (bf16 tier): memory is written as bf16 into rows of pitch 512
+                               elements, columns [0,256); columns [256,512) are left to the caller (lrn_pos_hidden) */
 };
 
 /* Raw fp32 parameters of the reference module, exactly as they sit in its state_dict
@@ -108,13 +110,13 @@ int lrn_encoder_fold(const lrn_encoder_params* params, int precision, void* pack
  *   global_feat  : (B, 2048) fp32               required iff LRN_OUT_POOL or LRN_OUT_ARGMAX
  *   fused        : (B, 1024, N) fp32            required iff LRN_OUT_FUSED
  *   argmax       : (B, 1024) int64              required iff LRN_OUT_ARGMAX
- *   memory       : (B, N, 256) fp32             required iff LRN_OUT_MEMORY
+ *   memory       : (B, N, 256) fp32             required iff LRN_OUT_MEMORY  ((B, N, 512) bf16 with LRN_OUT_MEMORY_BF16)
  *   chunk_rows   : points processed per wave (0 = library default); a tuning knob only.
  * B >= 1, N >= 1, B*N < 2^31.  Empty input (B == 0 or N == 0) returns LRN_ERR_BAD_SHAPE, like
  * the reference, whose torch.max over an empty dimension raises. */
 size_t lrn_encoder_workspace_bytes(int64_t B, int64_t N, int precision, int flags, int64_t chunk_rows);
 int lrn_encoder_forward(const void* packed, int precision, const float* context, int64_t B, int64_t N, int flags,
-                        float* global_feat, float* fused, int64_t* argmax, float* memory, int64_t chunk_rows,
+                        float* global_feat, float* fused, int64_t* argmax, void* memory, int64_t chunk_rows,
                         void* workspace, size_t workspace_bytes, lrn_stream_t stream);
 
 /* ---- point loading + first layer, stand-alone (tf32 tier, per-layer path, and bench.py's HBM roofline line) ----
@@ -209,6 +211,25 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* W, 
  * K % 64 == 0, M % 64 == 0, N % 128 == 0. */
 int lrn_gemm_tn(const void* At, int64_t lda, const void* Bt, int64_t ldb, float* out, int64_t ldo, int64_t M, int64_t N,
                 int64_t K, lrn_stream_t stream);
+
+/* Cross attention of the 32 polyline queries of every segment over its N context points, all 8 heads, without
+ * materialising K or V (replaces nn.MultiheadAttention cross_attn inside DetrTransformerDecoderLayer.forward,
+ * src/model.py:123-128, for the eval path).
+ *   qfold (B*256, 256) bf16: row h*32+q = log2(e)/sqrt(32) * (q_h[q] Wk_h), Wk_h = in_proj_weight[256+32h : 256+32h+32]
+ *   kp    (B*N, 256)  bf16, row pitch ld_kp: memory + positional embedding     mem (B*N, 256) bf16, row pitch ld_mem: memory
+ *   out   (B*splits*256, 256) fp32: softmax(qfold kp^T) mem per split, normalised inside the split
+ *   lse   (B*splits*256) fp32: log2 of the split's sum of 2^score (to merge splits; splits = 1: final result)
+ * The caller applies Wv_h / bv_h to `out` (rows of the softmax sum to one, so the bias passes through).
+ * lrn_ctx_attention_splits(B, N) is the split count the library would pick (few segments: several clusters each). */
+int lrn_ctx_attention_splits(int B, int N);
+int lrn_ctx_attention(const void* qfold, const void* kp, int64_t ld_kp, const void* mem, int64_t ld_mem, int B, int N,
+                      int splits, float* out, float* lse, lrn_stream_t stream);
+
+/* out[pt][0:256) = bf16(relu(W1 xyz + b1)): first layer of PositionalEncoding (src/model.py:66-75) on the context points
+ * (context (P,4) fp32, xyz = first three columns; src/model.py:197).  out rows have a pitch of ld_out bf16 elements, so
+ * it can fill columns [256,512) of the LRN_OUT_MEMORY_BF16 buffer: one GEMM with [I | W2] then yields memory + pos. */
+int lrn_pos_hidden(const float* w1, const float* b1, const float* context, int64_t P, void* out, int64_t ld_out,
+                   lrn_stream_t stream);
 
 #ifdef __cplusplus
 }

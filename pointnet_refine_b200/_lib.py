@@ -17,7 +17,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "lrn_b200.h")
 # enums of include/lrn_b200.h
 LRN_OK = 0
 PREC_BF16, PREC_TF32 = 0, 1
-OUT_POOL, OUT_ARGMAX, OUT_FUSED, OUT_MEMORY = 1, 2, 4, 8
+OUT_POOL, OUT_ARGMAX, OUT_FUSED, OUT_MEMORY, OUT_MEMORY_BF16 = 1, 2, 4, 8, 16
 PRECISIONS = {"bf16": PREC_BF16, "tf32": PREC_TF32}
 
 EXPORTS = [
@@ -25,6 +25,7 @@ EXPORTS = [
     "lrn_encoder_packed_bytes", "lrn_encoder_fold", "lrn_encoder_workspace_bytes", "lrn_encoder_forward",
     "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe", "lrn_train_workspace_bytes",
     "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
+    "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
 
@@ -71,6 +72,12 @@ def _load():
     lib.lrn_point_embed.argtypes = [vp, ci, vp, i64, vp, vp]
     lib.lrn_gemm_tn.restype = ci
     lib.lrn_gemm_tn.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp]
+    lib.lrn_ctx_attention_splits.restype = ci
+    lib.lrn_ctx_attention_splits.argtypes = [ci, ci]
+    lib.lrn_ctx_attention.restype = ci
+    lib.lrn_ctx_attention.argtypes = [vp, vp, i64, vp, i64, ci, ci, ci, vp, vp, vp]
+    lib.lrn_pos_hidden.restype = ci
+    lib.lrn_pos_hidden.argtypes = [vp, vp, vp, i64, vp, i64, vp]
     lib.lrn_debug_ts_probe.restype = ci
     lib.lrn_debug_ts_probe.argtypes = [vp, vp, vp, vp]
     lib.lrn_debug_timeline.restype = ci

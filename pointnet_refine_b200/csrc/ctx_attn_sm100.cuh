@@ -1,0 +1,284 @@
+// Cross attention of the 32 polyline queries of a segment over its N context points (SURVEY.md §8f row 1;
+// reference: nn.MultiheadAttention cross_attn in DetrTransformerDecoderLayer.forward, src/model.py:123-128),
+// without ever materialising K or V:
+//
+//   scores_h = (q_h / sqrt(32)) K_h^T,  K_h = (memory + pos) Wk_h^T + bk_h
+//            = [(q_h Wk_h) / sqrt(32)] (memory + pos)^T + const(row)          -- the bias term is softmax-invariant
+//   out_h    = softmax(scores_h) V_h,   V_h = memory Wv_h^T + bv_h
+//            = [softmax(scores_h) memory] Wv_h^T + bv_h                       -- rows of the softmax sum to 1
+//
+// so the 8 heads x 32 queries of one segment become 256 "folded" queries of width 256 (the host folds Wk and the
+// 1/sqrt(32) * log2(e) scale into them), and the kernel is one flash-style pass over the segment's points:
+//
+//   S = Qf Kp^T        tcgen05.mma cta_group::2, 256 folded queries x 128 points x K = 256 (Qf resident in smem)
+//   P = exp2(S - m)    one thread per folded query (TMEM lane), lazily rescaled running maximum
+//   O += P Mem         tcgen05.mma with P (bf16) as the A operand in TENSOR MEMORY, Mem as an MN-major smem operand
+//
+// Per layer the only HBM traffic is Kp = memory + pos and Mem = memory (bf16, 1 KB per point) plus 256 KB of output per
+// segment.  One cluster of two CTAs per (segment, split); a segment can be split over several clusters (few segments),
+// the host merges the partial results with their log-sum-exp.
+#pragma once
+#include "ptx.cuh"
+#include "chain_pair_sm100.cuh"  // tc_mma_ts_pair
+
+namespace lrn {
+
+constexpr int kAttnThreads = 192;  // warp 0 TMA, warp 1 MMA / TMEM alloc, warps 2..5 softmax (one TMEM lane per thread)
+constexpr int kAttnStep = 128;     // points per step
+
+struct AttnSmem {
+  static constexpr uint32_t kQ = 0;                   // 4 k-blocks x [128 folded queries x 128 B]
+  static constexpr uint32_t kKp = kQ + 65536;         // 2 stages x 4 k-blocks x [64 points x 128 B]
+  static constexpr uint32_t kV = kKp + 2 * 32768;     // 2 stages x 2 point-blocks x 2 dim-blocks x [64 points x 128 B]
+  static constexpr uint32_t kScratch = kV + 2 * 32768;  // 4 warps x [32][33] floats (output transpose)
+  static constexpr uint32_t kBar = kScratch + 4 * 32 * 33 * 4;
+  static constexpr uint32_t kTmemPtr = kBar + 16 * 8;
+  static constexpr uint32_t kDynamic = kTmemPtr + 16 + 1024;
+};
+
+struct AttnParams {
+  int N;          // points per segment
+  int splits;     // clusters per segment
+  int steps_per_split;
+  float* out;     // (B * splits * 256, 256) fp32: normalised partial attention over memory
+  float* lse;     // (B * splits * 256) fp32: log2-sum-exp2 of the scaled scores of the split
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAttnThreads, 1)
+ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKp,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using L = AttnSmem;
+  constexpr uint32_t kIdescS = ptx::make_idesc(false, 256, 128);
+  constexpr uint32_t kIdescO = ptx::make_idesc(false, 256, 256) | (1u << 16);  // B operand (memory) MN-major
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* q_full = bars;         // leader: folded queries of both CTAs landed
+  uint64_t* kp_full = bars + 1;    // [2] leader: Kp stage landed (both CTAs' halves)
+  uint64_t* v_full = bars + 3;     // [2] leader: Mem stage landed
+  uint64_t* s_full = bars + 5;     // [2] both: S buffer written by the tensor pipe (also: Kp stage consumed)
+  uint64_t* p_ready = bars + 7;    // [2] leader: P written to tensor memory by the softmax warps of both CTAs
+  uint64_t* o_done = bars + 9;     // [2] both: O += P Mem of that step finished (also: Mem stage and S buffer free)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int item = blockIdx.x >> 1;
+  const int seg = item / p.splits;
+  const int split = item - seg * p.splits;
+  const int total_steps = (p.N + kAttnStep - 1) / kAttnStep;
+  const int step0 = split * p.steps_per_split;
+  const int steps = min(p.steps_per_split, total_steps - step0);  // >= 1 by construction of `splits`
+  const int64_t seg_row0 = static_cast<int64_t>(seg) * p.N;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmKp);
+    ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&kp_full[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_ready[i], 8);
+      ptx::mbar_init(&o_done[i], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_pair<512>(tmem_ptr);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      const uint32_t q_leader = ptx::mapa(ptx::smem_u32(q_full), 0);
+      if (leader) ptx::mbar_arrive_expect_tx(q_full, 2 * 65536);
+      for (int kb = 0; kb < 4; ++kb)
+        ptx::tma_load_2d_pair(smem + L::kQ + kb * 16384, &tmQ, q_leader, kb * 64, seg * 256 + static_cast<int>(rank) * 128);
+      for (int j = 0; j < steps; ++j) {
+        const int st = j & 1;
+        const uint32_t prev = ((j - 2) >> 1) & 1;  // parity of the phase that step j - 2 completed
+        const int row = static_cast<int>(seg_row0) + (step0 + j) * kAttnStep;
+        // Kp: this CTA's 64 points of the step (the B operand of S is split by points across the pair)
+        if (j >= 2) ptx::mbar_wait(&s_full[st], prev);
+        const uint32_t kp_leader = ptx::mapa(ptx::smem_u32(&kp_full[st]), 0);
+        if (leader) ptx::mbar_arrive_expect_tx(&kp_full[st], 2 * 32768);
+        for (int kb = 0; kb < 4; ++kb)
+          ptx::tma_load_2d_pair(smem + L::kKp + st * 32768 + kb * 8192, &tmKp, kp_leader, kb * 64, row + static_cast<int>(rank) * 64);
+        // Mem: all 128 points, this CTA's 128 of the 256 output dims (the B operand of O is split by dims)
+        if (j >= 2) ptx::mbar_wait(&o_done[st], prev);
+        const uint32_t v_leader = ptx::mapa(ptx::smem_u32(&v_full[st]), 0);
+        if (leader) ptx::mbar_arrive_expect_tx(&v_full[st], 2 * 32768);
+        for (int pb = 0; pb < 2; ++pb)
+          for (int db = 0; db < 2; ++db)
+            ptx::tma_load_2d_pair(smem + L::kV + st * 32768 + pb * 16384 + db * 8192, &tmV, v_leader,
+                                  static_cast<int>(rank) * 128 + db * 64, row + pb * 64);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (leader) {
+      auto issue_s = [&](int j) {  // S_j = Qf Kp_j^T -> S buffer j & 1
+        const int st = j & 1;
+        ptx::mbar_wait(&kp_full[st], (j >> 1) & 1);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t d = tmem_base + st * 128;
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + L::kQ + kb * 16384));
+            const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + L::kKp + st * 32768 + kb * 8192));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::tc_mma_ss_pair<false>(d, da + 2 * k, db + 2 * k, kIdescS, (kb | k) ? 1u : 0u);
+          }
+          ptx::tc_commit_pair(&s_full[st], 3);
+        }
+        __syncwarp();
+      };
+      ptx::mbar_wait(q_full, 0);
+      issue_s(0);
+      if (steps > 1) issue_s(1);
+      for (int j = 0; j < steps; ++j) {
+        const int st = j & 1;
+        const uint32_t par = (j >> 1) & 1;
+        ptx::mbar_wait(&p_ready[st], par);
+        ptx::mbar_wait(&v_full[st], par);
+        ptx::tc_fence_after();
+        if (lane == 0) {  // O += P_j Mem_j : A = P_j in the first 64 columns of S buffer st (2 points per column)
+#pragma unroll
+          for (int pb = 0; pb < 2; ++pb) {
+            const uint64_t db = ptx::make_smem_desc_sw128_mn(ptx::smem_u32(smem + L::kV + st * 32768 + pb * 16384), 8192);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_ts_pair(tmem_o, tmem_base + st * 128 + pb * 32 + k * 8, db + 128 * k, kIdescO, (j | pb | k) ? 1u : 0u);
+          }
+          ptx::tc_commit_pair(&o_done[st], 3);
+        }
+        __syncwarp();
+        if (j + 2 < steps) issue_s(j + 2);  // in order behind O_j on the tensor pipe, which is still reading P_j
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warps (both CTAs): thread = folded query
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t ready_leader[2] = {ptx::mapa(ptx::smem_u32(&p_ready[0]), 0), ptx::mapa(ptx::smem_u32(&p_ready[1]), 0)};
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < steps; ++j) {
+      const int st = j & 1;
+      const uint32_t t_s = t_lane + st * 128;
+      const int valid = min(kAttnStep, p.N - (step0 + j) * kAttnStep);
+      ptx::mbar_wait(&s_full[st], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      // pass 1: maximum of this row over the step's points
+      float m_t = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_s + 32 * c, r);
+        ptx::tmem_ld_wait();
+        if (valid >= 32 * c + 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m_t = fmaxf(m_t, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * c + i < valid) m_t = fmaxf(m_t, __uint_as_float(r[i]));
+        }
+      }
+      // Lazy rescale: the reference maximum only moves when the row maximum grew by more than 2^8 (p <= 256 stays
+      // exact enough in bf16 / fp32); then this row of O and its running sum are scaled down once.
+      const bool grow = m_t > m_ref + 8.f;
+      if (j == 0) {
+        m_ref = m_t;
+      } else if (__any_sync(0xffffffffu, grow)) {
+        const float f = grow ? ex2_approx(m_ref - m_t) : 1.f;
+        ptx::mbar_wait(&o_done[st ^ 1], ((j - 1) >> 1) & 1);  // O_{j-1} has been accumulated
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          ptx::tmem_st_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
+        }
+        l_sum *= f;
+        if (grow) m_ref = m_t;
+      }
+      // pass 2: P = exp2(S - m_ref) as bf16 pairs over the first 64 columns of the same buffer (writes trail reads)
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t a[32], b[32], o[32];
+        ptx::tmem_ld_32x32b_x32(t_s + 64 * h, a);
+        ptx::tmem_ld_32x32b_x32(t_s + 64 * h + 32, b);
+        ptx::tmem_ld_wait();
+        const int c0 = 64 * h;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float e0 = ex2_approx(__uint_as_float(a[2 * i]) - m_ref), e1 = ex2_approx(__uint_as_float(a[2 * i + 1]) - m_ref);
+          float e2 = ex2_approx(__uint_as_float(b[2 * i]) - m_ref), e3 = ex2_approx(__uint_as_float(b[2 * i + 1]) - m_ref);
+          if (valid < kAttnStep) {
+            if (c0 + 2 * i >= valid) e0 = 0.f;
+            if (c0 + 2 * i + 1 >= valid) e1 = 0.f;
+            if (c0 + 32 + 2 * i >= valid) e2 = 0.f;
+            if (c0 + 32 + 2 * i + 1 >= valid) e3 = 0.f;
+          }
+          l_sum += (e0 + e1) + (e2 + e3);
+          o[i] = ptx::pack_bf16x2(e0, e1);
+          o[16 + i] = ptx::pack_bf16x2(e2, e3);
+        }
+        ptx::tmem_st_32x32b_x32(t_s + 32 * h, o);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ready_leader[st]);
+    }
+    // ---- epilogue: O / l -> global (through a per-warp transpose so that rows are written 128 B at a time)
+    {
+      const int last = steps - 1;
+      ptx::mbar_wait(&o_done[last & 1], (last >> 1) & 1);
+      ptx::tc_fence_after();
+      const float inv = 1.f / l_sum;
+      float* scratch = reinterpret_cast<float*>(smem + L::kScratch) + (warp - 2) * 32 * 33;
+      const int64_t out_row0 = (static_cast<int64_t>(item) * 256 + rank * 128 + q * 32);
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = __uint_as_float(r[i]) * inv;
+        __syncwarp();
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) p.out[(out_row0 + rr) * 256 + 32 * c + lane] = scratch[rr * 33 + lane];
+        __syncwarp();
+      }
+      p.lse[out_row0 + lane] = m_ref + log2f(l_sum);
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+}  // namespace lrn

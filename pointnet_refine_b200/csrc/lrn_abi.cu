@@ -18,6 +18,7 @@
 #include "gemm_pair_sm100.cuh"
 #include "chain_pair_sm100.cuh"
 #include "ts_probe.cuh"
+#include "ctx_attn_sm100.cuh"
 #include "pointwise.cuh"
 
 namespace {
@@ -396,9 +397,11 @@ size_t lrn_encoder_workspace_bytes(int64_t B, int64_t N, int precision, int flag
 }
 
 int lrn_encoder_forward(const void* packed, int precision, const float* context, int64_t B, int64_t N, int flags,
-                        float* global_feat, float* fused, int64_t* argmax, float* memory, int64_t chunk_rows,
+                        float* global_feat, float* fused, int64_t* argmax, void* memory, int64_t chunk_rows,
                         void* workspace, size_t workspace_bytes, lrn_stream_t stream) {
   if (bad_precision(precision)) return fail(LRN_ERR_BAD_ARG, "bad precision %d", precision);
+  if ((flags & LRN_OUT_MEMORY_BF16) && (precision != LRN_PREC_BF16 || !(flags & LRN_OUT_MEMORY)))
+    return fail(LRN_ERR_BAD_ARG, "LRN_OUT_MEMORY_BF16 needs LRN_OUT_MEMORY and the bf16 tier");
   if (B <= 0 || N <= 0) return fail(LRN_ERR_BAD_SHAPE, "empty input B=%lld N=%lld", (long long)B, (long long)N);
   if (B * N >= (int64_t(1) << 31) - 128) return fail(LRN_ERR_BAD_SHAPE, "B*N = %lld must be < 2^31", (long long)(B * N));
   if (!packed || !context || !workspace) return fail(LRN_ERR_BAD_ARG, "null packed/context/workspace");
@@ -567,12 +570,22 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.kb_main = 1024 / bk;
       p.a_col0 = 0;
       p.bias = reinterpret_cast<const float*>(pk + L.bp);
-      p.out = memory + r0 * 256;
-      p.ldo = 256;
-      p.out_f32 = 1;
       p.relu = 0;
+      CUtensorMap tmem_out;
+      const bool mem_bf16 = flags & LRN_OUT_MEMORY_BF16;
+      if (mem_bf16) {  // bf16 rows of pitch 512: [memory | 256 columns left to the caller], TMA-store epilogue
+        p.out = reinterpret_cast<uint16_t*>(memory) + r0 * 512;
+        p.ldo = 512;
+        p.out_f32 = 0;
+        st = make_tmap(&tmem_out, precision, p.out, rows, 256, 512, BM);
+        if (st) return st;
+      } else {
+        p.out = reinterpret_cast<float*>(memory) + r0 * 256;
+        p.ldo = 256;
+        p.out_f32 = 1;
+      }
       StageTimer timer(LRN_STAGE_PROJ, s);
-      st = launch_gemm(precision, plan_p, EPI_ACT, tpm, twp, p, dev.sms, s);
+      st = launch_gemm(precision, plan_p, EPI_ACT, tpm, twp, p, dev.sms, s, mem_bf16 ? &tmem_out : nullptr);
       if (st) return st;
     }
   }
@@ -632,6 +645,64 @@ int lrn_gemm_tn(const void* At, int64_t lda, const void* Bt, int64_t ldb, float*
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return bn == 256 ? launch_pair_t<256, false, EPI_ACT, 6, true, false, true>(ta, tb, ta, p, dev.sms, s)
                    : launch_pair_t<128, false, EPI_ACT, 8, true, false, true>(ta, tb, ta, p, dev.sms, s);
+}
+
+int lrn_ctx_attention_splits(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  DeviceInfo dev;
+  if (device_info(&dev)) return 0;
+  const int total = (N + kAttnStep - 1) / kAttnStep, slots = dev.sms / 2;
+  int splits = std::max(1, std::min((slots + B - 1) / B, total));
+  const int per = (total + splits - 1) / splits;
+  return (total + per - 1) / per;
+}
+
+int lrn_ctx_attention(const void* qfold, const void* kp, int64_t ld_kp, const void* mem, int64_t ld_mem, int B, int N,
+                      int splits, float* out, float* lse, lrn_stream_t stream) {
+  if (!qfold || !kp || !mem || !out || !lse) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (B <= 0 || N <= 0 || int64_t(B) * N >= (int64_t(1) << 31) - 256) return fail(LRN_ERR_BAD_SHAPE, "B=%d N=%d", B, N);
+  if (ld_kp < 256 || ld_mem < 256) return fail(LRN_ERR_BAD_ARG, "row pitch below 256");
+  const int total = (N + kAttnStep - 1) / kAttnStep;
+  if (splits < 1 || splits > total) return fail(LRN_ERR_BAD_ARG, "splits=%d (1..%d)", splits, total);
+  const int per = (total + splits - 1) / splits;
+  if ((splits - 1) * per >= total) return fail(LRN_ERR_BAD_ARG, "splits=%d leaves an empty split (use lrn_ctx_attention_splits)", splits);
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  CUtensorMap tq, tk, tv;
+  if ((st = make_tmap(&tq, LRN_PREC_BF16, qfold, int64_t(B) * 256, 256, 256, 128))) return st;
+  if ((st = make_tmap(&tk, LRN_PREC_BF16, kp, int64_t(B) * N, 256, ld_kp, 64))) return st;
+  if ((st = make_tmap_mn(&tv, mem, int64_t(B) * N, 256, ld_mem))) return st;
+  AttnParams p{};
+  p.N = N;
+  p.splits = splits;
+  p.steps_per_split = per;
+  p.out = out;
+  p.lse = lse;
+  static bool configured = false;
+  if (!configured) {
+    LRN_CUDA(cudaFuncSetAttribute(ctx_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kDynamic));
+    configured = true;
+  }
+  ctx_attn_kernel<<<2 * B * splits, kAttnThreads, AttnSmem::kDynamic, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_pos_hidden(const float* w1, const float* b1, const float* context, int64_t P, void* out, int64_t ld_out,
+                   lrn_stream_t stream) {
+  if (!w1 || !b1 || !context || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (P <= 0) return fail(LRN_ERR_BAD_SHAPE, "P=%lld", (long long)P);
+  if ((reinterpret_cast<uintptr_t>(context) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || ld_out < 256 || (ld_out * 2) % 16)
+    return fail(LRN_ERR_MISALIGNED, "context / out need 16-byte alignment, ld_out >= 256 and a multiple of 8");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const int grid = int(std::min<int64_t>((P + 7) / 8, int64_t(dev.sms) * 8));
+  pos_hidden_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(context), P, w1, b1,
+                                                                              reinterpret_cast<uint16_t*>(out), ld_out);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
 }
 
 int lrn_debug_ts_probe(const void* a_bf16 /* (128,64) */, const void* w_bf16 /* (64,64) */, float* out /* (128,64) */,

@@ -97,6 +97,43 @@ __global__ void __launch_bounds__(256) point_embed_kernel(const float4* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// First layer of the positional embedding on the context points (reference PositionalEncoding.mlp[0] + ReLU,
+// src/model.py:66-75 applied to context[:, :, :3] at :197): out[pt][0:256) = bf16(relu(W1 xyz + b1)).
+// One warp writes one point's 512-byte row; lane = 8 consecutive channels, their weights live in registers.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pos_hidden_kernel(const float4* __restrict__ ctx, long long rows,
+                                                         const float* __restrict__ w1 /* (256,3) */,
+                                                         const float* __restrict__ b1, uint16_t* __restrict__ out, long long ld) {
+  const int lane = threadIdx.x & 31;
+  float wx[8], wy[8], wz[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = 8 * lane + j;
+    wx[j] = w1[3 * c];
+    wy[j] = w1[3 * c + 1];
+    wz[j] = w1[3 * c + 2];
+    bb[j] = b1[c];
+  }
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  long long pt = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  auto emit = [&](long long q, const float4& x) {
+    float h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = fmaxf(fmaf(wx[j], x.x, fmaf(wy[j], x.y, fmaf(wz[j], x.z, bb[j]))), 0.f);
+    *reinterpret_cast<uint4*>(out + q * ld + 8 * lane) = make_uint4(ptx::pack_bf16x2(h[0], h[1]), ptx::pack_bf16x2(h[2], h[3]),
+                                                                    ptx::pack_bf16x2(h[4], h[5]), ptx::pack_bf16x2(h[6], h[7]));
+  };
+  for (; pt + 3 * warps < rows; pt += 4 * warps) {
+    float4 x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = __ldg(ctx + pt + k * warps);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(pt + k * warps, x[k]);
+  }
+  for (; pt < rows; pt += warps) emit(pt, __ldg(ctx + pt));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Unpack argmax keys: key = (float bits << 32) | (0xFFFFFFFF - n)  ->  max value and int64 index.
 // ---------------------------------------------------------------------------------------------
 __global__ void argmax_finalize_kernel(const unsigned long long* __restrict__ keys, long long B,

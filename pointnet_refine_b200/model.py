@@ -17,6 +17,7 @@ What runs where
 """
 from __future__ import annotations
 
+import math
 import os
 
 import torch
@@ -187,7 +188,8 @@ class LineRefineNet(nn.Module):
         # context_proj is folded into the encoder's operand blob (tuple hides it from the module tree)
         self.context_encoder._proj = (self.context_proj,)
         self.segment_chunk = 256   # segments per decoder pass in eval mode (bounds the (B,N,256) temporaries)
-        self.fast_decoder = os.environ.get("LRN_FAST_DECODER", "1") != "0"   # bf16 tier: hoisted K/V GEMMs + SDPA
+        self.fast_decoder = os.environ.get("LRN_FAST_DECODER", "1") != "0"   # bf16 tier: context side on the tensor cores
+        self.ctx_attention = os.environ.get("LRN_CTX_ATTN", "1") != "0"      # ... folded-query attention kernel (else K/V GEMMs + SDPA)
         self._kv_cache = None
 
     @property
@@ -262,6 +264,80 @@ class LineRefineNet(nn.Module):
             outs.append(ops.head_forward(head[0].weight, head[0].bias, head[2].weight, head[2].bias, tgt, current, noisy_line))
         return torch.stack(outs)
 
+    # -- cross attention without K / V: folded queries + lrn_ctx_attention ------------------------------------
+    def _attn_weights(self):
+        """Per cross-attention layer, the query and output sides with the K / V projections folded in
+        (csrc/ctx_attn_sm100.cuh):  Wqk (2048,256), bqk: (tgt+qpos) -> 8 heads x 256 folded query (scores come out
+        in log2 units, 1/sqrt(32) included);  Wvo (256,2048), bvo: 8 heads x (softmax . memory) -> out_proj output.
+        Plus [I | pos_emb.mlp.2.weight] (256,512) bf16, so that one GEMM over [memory | pos hidden] rows gives
+        memory + pos.  Re-made when a parameter changes."""
+        ps = [self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias]
+        for l in self.decoder_layers:
+            ps += [l.cross_attn.in_proj_weight, l.cross_attn.in_proj_bias, l.cross_attn.out_proj.weight, l.cross_attn.out_proj.bias]
+        fp = tuple((t.data_ptr(), t._version) for t in ps)
+        if getattr(self, "_attn_cache", None) is None or self._attn_cache[0] != fp:
+            d, H = self.d_model, 8
+            hd = d // H
+            scale = math.log2(math.e) / math.sqrt(hd)
+            layers = []
+            for l in self.decoder_layers:
+                ca = l.cross_attn
+                w, b = ca.in_proj_weight.detach().double(), ca.in_proj_bias.detach().double()
+                wq, wk, wv = w[:d].view(H, hd, d), w[d:2 * d].view(H, hd, d), w[2 * d:].view(H, hd, d)
+                bq, bv = b[:d].view(H, hd), b[2 * d:]
+                wo, bo = ca.out_proj.weight.detach().double(), ca.out_proj.bias.detach().double()
+                wqk = scale * torch.einsum("hcd,hce->hde", wk, wq).reshape(H * d, d)          # row h*256+j: folded dim j of head h
+                bqk = scale * torch.einsum("hc,hcd->hd", bq, wk).reshape(H * d)
+                wvo = torch.einsum("ohc,hcd->ohd", wo.view(d, H, hd), wv).reshape(d, H * d)
+                bvo = wo @ bv + bo
+                layers.append(tuple(t.float().contiguous() for t in (wqk, bqk, wvo, bvo)))
+            w2 = self.pos_emb.mlp[2].weight.detach()
+            wx = torch.cat([torch.eye(d, device=w2.device, dtype=w2.dtype), w2], dim=1).bfloat16().contiguous()
+            self._attn_cache = (fp, layers, wx, self.pos_emb.mlp[2].bias.detach().float().contiguous())
+        return self._attn_cache[1:]
+
+    def _refine_attn(self, context, noisy_line, memx):
+        """Eval-mode decoder, bf16 tier, M = 32: per layer the cross attention is ONE lrn_ctx_attention launch over
+        kp = memory + pos and memory (bf16), with Wk / Wv folded into the 32 x 8 queries and into out_proj - K and V
+        of nn.MultiheadAttention (src/model.py:123-128) are never formed.  `memx` (B,N,512) bf16 is the encoder's
+        LRN_OUT_MEMORY_BF16 buffer: [memory | room for the positional hidden layer].  The linears of the query side
+        (self-attention projections, FFN, pos_emb layer 2, the folded query / output maps) run on the tcgen05 GEMM
+        in its tf32 tier; the 32 x 32 self attention, LayerNorms and residual adds are stock PyTorch ops.
+        Same parameters and math as DetrTransformerDecoderLayer.forward (src/model.py:104-135) in eval mode."""
+        B, N, _ = context.shape
+        d, H = self.d_model, 8
+        layers_w, wx, b2 = self._attn_weights()
+        ops.pos_hidden(self.pos_emb.mlp[0].weight.detach(), self.pos_emb.mlp[0].bias.detach(), context, memx[:, :, d:])
+        kp = ops.gemm_bias_act(memx.view(B * N, 2 * d), wx, b2, out_dtype=torch.bfloat16).view(B, N, d)
+        mem = memx[:, :, :d]
+        rows = B * noisy_line.shape[1]
+
+        def lin(x, w, b, relu=False):   # (B,32,K) fp32 -> (B,32,N) fp32
+            if rows < 256:
+                y = F.linear(x, w, b)
+                return F.relu(y) if relu else y
+            return ops.gemm_bias_act(x.reshape(rows, -1), w.detach(), b.detach(), relu=relu).view(B, -1, w.shape[0])
+
+        pe0, pe2 = self.pos_emb.mlp[0], self.pos_emb.mlp[2]
+        tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
+        current = noisy_line.clone()
+        outs = []
+        for layer, head, (wqk, bqk, wvo, bvo) in zip(self.decoder_layers, self.reg_branches, layers_w):
+            qpos = lin(F.relu(pe0(current)), pe2.weight, pe2.bias)
+            q = tgt + qpos
+            sa = layer.self_attn
+            qk = lin(q, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d]).view(B, -1, 2, H, d // H)
+            v = lin(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:]).view(B, -1, H, d // H)
+            att = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
+            tgt = layer.norm1(tgt + lin(att.transpose(1, 2).reshape(B, -1, d), sa.out_proj.weight, sa.out_proj.bias))
+            # folded queries: row q * 8 + h of the segment's 256 (any row order works, rows are independent)
+            qf = lin(tgt + qpos, wqk, bqk).bfloat16().view(B, H * 32, d)
+            o = ops.ctx_attention(qf, kp, mem).view(B, 32, H * d)
+            tgt = layer.norm2(tgt + lin(o, wvo, bvo))
+            tgt = layer.norm3(tgt + lin(lin(tgt, layer.linear1.weight, layer.linear1.bias, relu=True), layer.linear2.weight, layer.linear2.bias))
+            outs.append(ops.head_forward(head[0].weight, head[0].bias, head[2].weight, head[2].bias, tgt, current, noisy_line))
+        return torch.stack(outs)
+
     def _refine_fast_train(self, context, noisy_line, fused_pm):
         """Autograd-capable twin of _refine_fast for model.train(): context_proj, the memory positional embedding
         and the K / V projections of all six cross-attention layers run as differentiable bf16 tensor-core linears
@@ -318,6 +394,10 @@ class LineRefineNet(nn.Module):
         for s in range(0, context.shape[0], chunk):
             ctx = context[s:s + chunk].contiguous()
             line = noisy_line[s:s + chunk].contiguous()
+            if fast and self.ctx_attention and line.shape[1] == 32:
+                memx = self.context_encoder.run_native(ctx, pool=False, memory=True, memory_bf16=True)["memory"]
+                outs.append(self._refine_attn(ctx, line, memx))
+                continue
             memory = self.context_encoder.run_native(ctx, pool=False, memory=True)["memory"]
             outs.append(self._refine_fast(ctx, line, memory) if fast else self._refine(ctx, line, memory, native_heads=True))
         return torch.cat(outs, dim=1)

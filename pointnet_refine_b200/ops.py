@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import OUT_ARGMAX, OUT_FUSED, OUT_MEMORY, OUT_POOL, PRECISIONS, lib
+from ._lib import OUT_ARGMAX, OUT_FUSED, OUT_MEMORY, OUT_MEMORY_BF16, OUT_POOL, PRECISIONS, lib
 
 DEFAULT_CHUNK_ROWS = 148 * 128 * 4   # keep in sync with kDefaultChunkRows (csrc/lrn_abi.cu)
 
@@ -85,9 +85,11 @@ def _workspace(nbytes: int, device):
 
 
 def encoder_forward(folded: FoldedEncoder, context: torch.Tensor, *, pool=True, argmax=False, fused=False,
-                    memory=False, chunk_rows: int = 0):
+                    memory=False, memory_bf16=False, chunk_rows: int = 0):
     """Run the fused encoder on context (B, N, 4) float32 CUDA.  Returns a dict with the requested
-    outputs: global_feat (B,2048), argmax (B,1024) int64, fused (B,1024,N), memory (B,N,256)."""
+    outputs: global_feat (B,2048), argmax (B,1024) int64, fused (B,1024,N), memory (B,N,256).
+    memory_bf16 (bf16 tier): memory is returned as a (B,N,512) bfloat16 buffer whose columns [0,256) hold it and
+    whose columns [256,512) are uninitialised (filled by pos_hidden for the decoder's context side)."""
     if context.dim() != 3 or context.shape[-1] != 4:
         raise ValueError(f"context must be (B, N, 4), got {tuple(context.shape)}")
     context = _f32c(context)
@@ -96,7 +98,7 @@ def encoder_forward(folded: FoldedEncoder, context: torch.Tensor, *, pool=True, 
         raise ValueError("empty context (the reference's torch.max over an empty dimension raises too)")
     dev = context.device
     flags = (OUT_POOL if pool else 0) | (OUT_ARGMAX if argmax else 0) | (OUT_FUSED if fused else 0) | \
-            (OUT_MEMORY if memory else 0)
+            (OUT_MEMORY if memory else 0) | (OUT_MEMORY_BF16 if memory and memory_bf16 else 0)
     if memory and not folded.has_proj:
         raise ValueError("memory output needs context_proj weights in the folded blob")
     out = {}
@@ -108,7 +110,8 @@ def encoder_forward(folded: FoldedEncoder, context: torch.Tensor, *, pool=True, 
     if fused:
         out["fused"] = fz = torch.empty(B, 1024, N, dtype=torch.float32, device=dev)
     if memory:
-        out["memory"] = mem = torch.empty(B, N, 256, dtype=torch.float32, device=dev)
+        out["memory"] = mem = (torch.empty(B, N, 512, dtype=torch.bfloat16, device=dev) if memory_bf16 else
+                               torch.empty(B, N, 256, dtype=torch.float32, device=dev))
     nbytes = lib.lrn_encoder_workspace_bytes(B, N, folded.prec_id, flags, chunk_rows)
     ws = _workspace(nbytes, dev)
     dp = lambda t: t.data_ptr() if t is not None else None
@@ -191,6 +194,54 @@ def gemm_tn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(at.device):
         _lib.check(lib.lrn_gemm_tn(at.data_ptr(), at.stride(0), bt.data_ptr(), bt.stride(0), out.data_ptr(), N, M, N, K,
                                    _stream_ptr(at.device)), "lrn_gemm_tn")
+    _lib.launch_counter += 1
+    return out
+
+
+def ctx_attention(qfold: torch.Tensor, kp: torch.Tensor, mem: torch.Tensor, splits: int | None = None) -> torch.Tensor:
+    """softmax(qfold @ kp^T) @ mem per segment on the tensor cores, K / V never materialised (lrn_ctx_attention).
+    qfold (B, 256, 256) bf16 folded queries (scores in log2 units), kp / mem (B, N, 256) bf16 (rows may be strided
+    views of a wider buffer) -> (B, 256, 256) fp32."""
+    for t in (qfold, kp, mem):
+        if t.dtype != torch.bfloat16 or not t.is_cuda:
+            raise TypeError("ctx_attention expects CUDA bfloat16 tensors")
+    B, N, d = kp.shape
+    if d != 256 or tuple(qfold.shape) != (B, 256, 256) or mem.shape != kp.shape:
+        raise ValueError(f"ctx_attention shapes: qfold {tuple(qfold.shape)}, kp {tuple(kp.shape)}, mem {tuple(mem.shape)}")
+
+    def rows(t):  # (B, N, 256) view with unit column stride and segments back to back -> row pitch
+        if t.stride(2) != 1 or (B > 1 and t.stride(0) != N * t.stride(1)):
+            t = t.contiguous()
+        return t, t.stride(1)
+    qfold = qfold.contiguous()
+    (kp, ld_kp), (mem, ld_mem) = rows(kp), rows(mem)
+    if splits is None:
+        splits = lib.lrn_ctx_attention_splits(B, N)
+    out = torch.empty(B, splits, 256, 256, dtype=torch.float32, device=kp.device)
+    lse = torch.empty(B, splits, 256, dtype=torch.float32, device=kp.device)
+    with torch.cuda.device(kp.device):
+        _lib.check(lib.lrn_ctx_attention(qfold.data_ptr(), kp.data_ptr(), ld_kp, mem.data_ptr(), ld_mem, B, N, splits,
+                                         out.data_ptr(), lse.data_ptr(), _stream_ptr(kp.device)), "lrn_ctx_attention")
+    _lib.launch_counter += 1
+    if splits == 1:
+        return out[:, 0]
+    w = torch.softmax(lse * 0.6931471805599453, dim=1)  # lse is in log2 units
+    return (out * w.unsqueeze(-1)).sum(1)
+
+
+def pos_hidden(w1: torch.Tensor, b1: torch.Tensor, context: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[..., :] = bf16(relu(context[..., :3] @ w1.T + b1)) (lrn_pos_hidden); `out` is a (B, N, 256) bf16 view whose
+    rows may be strided (e.g. columns [256,512) of encoder_forward's memory_bf16 buffer)."""
+    context = _f32c(context)
+    P = context.numel() // 4
+    if out.dtype != torch.bfloat16 or out.shape[-1] != 256 or out.stride(-1) != 1 or out.numel() != P * 256:
+        raise ValueError("pos_hidden: out must be a bfloat16 (..., 256) view with unit column stride")
+    ld = out.stride(-2)
+    if out.dim() == 3 and out.shape[0] > 1 and out.stride(0) != out.shape[1] * ld:
+        raise ValueError("pos_hidden: segments of `out` must be back to back")
+    with torch.cuda.device(context.device):
+        _lib.check(lib.lrn_pos_hidden(_f32c(w1).data_ptr(), _f32c(b1).data_ptr(), context.data_ptr(), P, out.data_ptr(), ld,
+                                      _stream_ptr(context.device)), "lrn_pos_hidden")
     _lib.launch_counter += 1
     return out
 

@@ -142,6 +142,67 @@ def test_heads_match_oracle(dev):
         np.testing.assert_allclose(cum.cpu().numpy(), cur + delta - noisy, rtol=0, atol=2e-5)
 
 
+# ------------------------------------------------------------------ context side of the decoder
+@pytest.mark.parametrize("B,N,splits,ramp", [(1, 128, None, False), (2, 127, None, False), (3, 300, 1, False), (3, 300, 3, False),
+                                             (1, 4096, None, False), (5, 1000, 2, True), (300, 3, None, False), (2, 65536, None, True)])
+def test_ctx_attention_matches_fp64(dev, B, N, splits, ramp):
+    """softmax(qfold kp^T) mem (lrn_ctx_attention) against fp64 on the same bf16 inputs; `ramp` makes the scores grow
+    along the points so that the lazily rescaled running maximum is exercised; splits > 1 covers the merge."""
+    from pointnet_refine_b200 import ops
+    gen = torch.Generator(device=dev).manual_seed(B * 1000 + N)
+    r = lambda *s: torch.randn(*s, device=dev, generator=gen)
+    qf = (r(B, 256, 256) * (4.0 if ramp else 1.0) / 16).bfloat16()
+    mem = r(B, N, 256).bfloat16()
+    kp = mem.float() + 0.5 * r(B, N, 256)
+    if ramp:
+        kp = kp * torch.linspace(0.2, 3.0, N, device=dev)[None, :, None]
+    kp = kp.bfloat16()
+    out = ops.ctx_attention(qf, kp, mem, splits)
+    ref = torch.softmax(qf.double() @ kp.double().transpose(1, 2) * np.log(2.0), dim=-1) @ mem.double()
+    assert torch.isfinite(out).all()
+    assert float((out.double() - ref).abs().max()) <= 1e-2 * max(1.0, float(ref.abs().max()))
+    # strided views of a wider buffer (the layout LineRefineNet uses): same result, bit for bit
+    wide = torch.empty(B, N, 512, dtype=torch.bfloat16, device=dev)
+    wide[:, :, :256] = mem
+    assert torch.equal(ops.ctx_attention(qf, kp, wide[:, :, :256], splits), out)
+
+
+def test_pos_hidden_and_bf16_memory(dev):
+    from pointnet_refine_b200 import ops
+    g, sd, ctx, _, _ = load_case("b3_n1000_ragged")
+    m = _model(sd, dev, "bf16")
+    c = torch.from_numpy(ctx).to(dev)
+    with torch.no_grad():
+        mem32 = m.context_encoder.run_native(c, pool=False, memory=True)["memory"]
+        memx = m.context_encoder.run_native(c, pool=False, memory=True, memory_bf16=True)["memory"]
+        assert memx.shape == (3, 1000, 512) and memx.dtype == torch.bfloat16
+        assert torch.equal(memx[:, :, :256], mem32.bfloat16())          # same accumulators, rounded once
+        w1, b1 = m.pos_emb.mlp[0].weight, m.pos_emb.mlp[0].bias
+        ops.pos_hidden(w1, b1, c, memx[:, :, 256:])
+        ref = torch.relu(c[:, :, :3].double() @ w1.double().T + b1.double())
+        assert float((memx[:, :, 256:].double() - ref).abs().max()) <= 2 ** -8 * max(1.0, float(ref.abs().max()))
+        assert torch.equal(memx[:, :, :256], mem32.bfloat16())          # the memory half is left alone
+
+
+@pytest.mark.parametrize("B,N", [(9, 300), (16, 1024)])
+def test_full_forward_batched_vs_live_oracle(dev, B, N):
+    """B * 32 >= 256 query rows: the query-side linears take the tcgen05 tf32 GEMM (smaller batches use F.linear)."""
+    sd = synth.make_state_dict(21)
+    ctx, line = synth.make_inputs(B, N, seed=5)
+    ref = orc.line_refine_forward(sd, ctx, line)
+    rng = max(1.0, float(np.abs(ref).max()))
+    m = _model(sd, dev, "bf16")
+    assert m.fast_decoder and m.ctx_attention
+    with torch.no_grad():
+        out = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
+        m.ctx_attention = False
+        out_kv = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
+        m.fast_decoder = False
+        out_stock = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
+    for o in (out, out_kv, out_stock):
+        assert np.abs(o.cpu().numpy() - ref).max() <= 5e-2 * rng
+
+
 # ------------------------------------------------------------------ live oracle, odd shapes
 @pytest.mark.parametrize("B,N", [(1, 127), (1, 129), (7, 300), (4, 4096), (300, 3)])
 def test_encoder_vs_live_oracle(dev, B, N):

@@ -28,4 +28,7 @@ for name in ("b2_n1024", "b3_n1000_ragged", "b5_n37_tiny"):
     assert np.array_equal(gf[:, :1024], fused.max(axis=2)), name
     assert np.array_equal(out2["global_feat"][:, :1024].cpu().numpy(), gf[:, :1024]), name
     assert np.array_equal(out2["argmax"].cpu().numpy(), fused.argmax(axis=2)), name
+    with torch.no_grad():   # whole forward on the selected decoder path (LRN_FAST_DECODER / LRN_CTX_ATTN)
+        full = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev)).cpu().numpy()
+    assert np.abs(full - g["out"]).max() <= 5e-2 * max(1.0, float(np.abs(g["out"]).max())), name
 print("variant ok", {k: v for k, v in os.environ.items() if k.startswith("LRN_")})
