@@ -343,10 +343,12 @@ class LineRefineNet(nn.Module):
         and the K / V projections of all six cross-attention layers run as differentiable bf16 tensor-core linears
         (train_ops.linear_bf16: tcgen05 forward, dgrad and wgrad), the cross attention through
         scaled_dot_product_attention with the reference's dropout rate on the attention weights
-        (src/model.py:84, nn.MultiheadAttention(dropout=0.1)); query side and the sub-layer dropouts are the
-        module's own stock ops.  Same parameters as DetrTransformerDecoderLayer; dropout draws differ from the
-        reference's RNG stream (they would from run to run there, too)."""
-        from .train_ops import linear_bf16
+        (src/model.py:84, nn.MultiheadAttention(dropout=0.1)); the query-side linears (self-attention projections,
+        FFN, pos_emb layer 2, cross-attention q / out_proj) take the same bf16 tensor-core linear when the batch has
+        >= 256 query rows; the 32 x 32 self attention, LayerNorms, dropouts and heads are stock ops.  Same parameters
+        as DetrTransformerDecoderLayer; dropout draws differ from the reference's RNG stream (they would from run to
+        run there, too)."""
+        from .train_ops import kv_proj, linear_bf16
         B, N, _ = context.shape
         d, H = self.d_model, 8
         wk = torch.cat([l.cross_attn.in_proj_weight[d:2 * d] for l in self.decoder_layers])
@@ -356,23 +358,35 @@ class LineRefineNet(nn.Module):
         mem = linear_bf16(fused_pm, self.context_proj.weight, self.context_proj.bias)      # (B,N,256) bf16
         h = F.relu(self.pos_emb.mlp[0](context[:, :, :3]))
         posm = linear_bf16(h, self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias)
-        # unbind (not six slices): its backward is one stack instead of six zero-filled full-size gradients
-        k_l = linear_bf16(mem + posm, wk, bk).view(B, N, 6, H, d // H).unbind(2)
-        v_l = linear_bf16(mem, wv, bv).view(B, N, 6, H, d // H).unbind(2)
+        k_l = kv_proj(mem + posm, wk, bk, 6, H)     # six (B, H, N, 32) views of one (B, N, 6, H, 32) GEMM result
+        v_l = kv_proj(mem, wv, bv, 6, H)
+        rows = B * noisy_line.shape[1]
+        tc = rows >= 256 and rows % 64 == 0   # query-side linears on the bf16 tensor-core path (fwd, dgrad, wgrad)
+
+        def lin(x, w, b):
+            return linear_bf16(x, w, b).float() if tc else F.linear(x, w, b)
+
+        pe0, pe2 = self.pos_emb.mlp[0], self.pos_emb.mlp[2]
         tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
         current = noisy_line
         outs = []
         for i, (layer, head) in enumerate(zip(self.decoder_layers, self.reg_branches)):
-            qpos = self.pos_emb(current)
+            qpos = lin(F.relu(pe0(current)), pe2.weight, pe2.bias)
             q = tgt + qpos
-            tgt = layer.norm1(tgt + layer.dropout1(layer.self_attn(q, q, value=tgt, need_weights=False)[0]))
+            sa = layer.self_attn
+            qk = lin(q, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d]).view(B, -1, 2, H, d // H)
+            v = lin(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:]).view(B, -1, H, d // H)
+            att = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2),
+                                                 dropout_p=sa.dropout if self.training else 0.0)
+            att = lin(att.transpose(1, 2).reshape(B, -1, d), sa.out_proj.weight, sa.out_proj.bias)
+            tgt = layer.norm1(tgt + layer.dropout1(att))
             ca = layer.cross_attn
-            qh = F.linear(tgt + qpos, ca.in_proj_weight[:d], ca.in_proj_bias[:d]).view(B, -1, H, d // H).transpose(1, 2)
-            att = F.scaled_dot_product_attention(qh.bfloat16(), k_l[i].transpose(1, 2), v_l[i].transpose(1, 2),
-                                                 dropout_p=ca.dropout if self.training else 0.0)
+            qh = lin(tgt + qpos, ca.in_proj_weight[:d], ca.in_proj_bias[:d]).view(B, -1, H, d // H).transpose(1, 2)
+            att = F.scaled_dot_product_attention(qh.bfloat16(), k_l[i], v_l[i], dropout_p=ca.dropout if self.training else 0.0)
             att = att.transpose(1, 2).reshape(B, -1, d).float()
-            tgt = layer.norm2(tgt + layer.dropout2(ca.out_proj(att)))
-            tgt = layer.norm3(tgt + layer.dropout3(layer.linear2(layer.dropout(F.relu(layer.linear1(tgt))))))
+            tgt = layer.norm2(tgt + layer.dropout2(lin(att, ca.out_proj.weight, ca.out_proj.bias)))
+            ffn = lin(layer.dropout(F.relu(lin(tgt, layer.linear1.weight, layer.linear1.bias))), layer.linear2.weight, layer.linear2.bias)
+            tgt = layer.norm3(tgt + layer.dropout3(ffn))
             current = current + head(tgt)
             outs.append(current - noisy_line)
         return torch.stack(outs)

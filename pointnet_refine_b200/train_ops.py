@@ -151,8 +151,55 @@ class LinearBf16Fn(torch.autograd.Function):
         if need_w:
             dw = ops.gemm_tn(dyb, xb)
         if need_b:
-            db = dyb.float().sum(dim=0)
+            db = dyb.sum(dim=0, dtype=torch.float32)
         return dx, dw, db
+
+
+class KVProjFn(torch.autograd.Function):
+    """K (or V) projections of all L cross-attention layers as ONE bf16 tensor-core linear over the context points,
+    handed to scaled_dot_product_attention as L views (B, H, N, hd) of the (B, N, L, H, hd) result.  The backward
+    gathers the L attention gradients straight into that layout (one strided copy each) instead of autograd's
+    stack + contiguous round trip over the 3 KB/point gradient, then runs dgrad / wgrad like LinearBf16Fn.
+    x (B, N, K) bf16 or fp32, weight (L*H*hd, K) fp32, bias fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, L, H):
+        from . import ops
+        B, N, K = x.shape
+        xb = x.detach().to(torch.bfloat16).contiguous().view(B * N, K)
+        wb = weight.detach().to(torch.bfloat16).contiguous()
+        ctx.save_for_backward(xb, wb)
+        ctx.needs = (x.requires_grad, weight.requires_grad, bias.requires_grad)
+        ctx.meta = (B, N, K, L, H, x.dtype)
+        y = ops.gemm_bias_act(xb, wb, bias.detach(), out_dtype=torch.bfloat16).view(B, N, L, H, -1)
+        return tuple(y[:, :, i].transpose(1, 2) for i in range(L))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        from . import ops
+        xb, wb = ctx.saved_tensors
+        B, N, K, L, H, x_dtype = ctx.meta
+        dy = torch.empty(B, N, L, H, wb.shape[0] // (L * H), dtype=torch.bfloat16, device=xb.device)
+        for i, g in enumerate(grads):
+            if g is None:
+                dy[:, :, i].zero_()
+            else:
+                dy[:, :, i].copy_(g.transpose(1, 2))
+        dyb = dy.view(B * N, -1)
+        need_x, need_w, need_b = ctx.needs
+        dx = dw = db = None
+        if need_x:
+            dx = ops.gemm_bias_act(dyb, wb.t().contiguous(), None, out_dtype=torch.bfloat16).view(B, N, K).to(x_dtype)
+        if need_w:
+            dw = ops.gemm_tn(dyb, xb)
+        if need_b:
+            db = dyb.sum(dim=0, dtype=torch.float32)
+        return dx, dw, db, None, None
+
+
+def kv_proj(x, weight, bias, layers: int, heads: int):
+    """(B, N, K) -> tuple of `layers` tensors (B, heads, N, hd), see KVProjFn."""
+    return KVProjFn.apply(x, weight, bias, layers, heads)
 
 
 def linear_bf16(x, weight, bias):

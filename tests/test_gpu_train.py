@@ -143,9 +143,11 @@ def test_linear_bf16_autograd(dev):
         assert float((a.float() - bb).norm() / bb.norm()) <= 1e-2
 
 
-def test_train_fast_decoder_close_to_stock(dev):
+@pytest.mark.parametrize("B", [4, 8])
+def test_train_fast_decoder_close_to_stock(dev, B):
     """model.train() with dropout disabled: the tensor-core decoder path gives the same loss and gradients
-    (relative L2) as the stock nn.MultiheadAttention formulation on the same native encoder."""
+    (relative L2) as the stock nn.MultiheadAttention formulation on the same native encoder.  B = 8 (256 query rows)
+    also takes the bf16 tensor-core linears on the query side."""
     import pointnet_refine_b200 as prb
     m = prb.LineRefineNet().to(dev)
     m.load_state_dict(synth.to_torch(synth.make_state_dict(2)), strict=True)
@@ -155,8 +157,8 @@ def test_train_fast_decoder_close_to_stock(dev):
             mod.p = 0.0
         if isinstance(mod, torch.nn.MultiheadAttention):
             mod.dropout = 0.0
-    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(4, 512, seed=11))
-    tgt = 0.1 * torch.randn(4, 32, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(B, 512, seed=11))
+    tgt = 0.1 * torch.randn(B, 32, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
     res = {}
     for fast in (True, False):
         m.fast_decoder = fast
