@@ -231,6 +231,26 @@ int lrn_ctx_attention(const void* qfold, const void* kp, int64_t ld_kp, const vo
 int lrn_pos_hidden(const float* w1, const float* b1, const float* context, int64_t P, void* out, int64_t ld_out,
                    lrn_stream_t stream);
 
+/* Scene preprocessing for all L lines of one scene: the tube crop, weighted sampling and centroid
+ * normalisation of LaneRefineDataset.__getitem__ steps 4-6 (src/dataset.py:214-237, weighted_sampling :78-130) and of
+ * process_single_line (inference_whole_scene.py:95-121), which the reference runs on the host with one KD-tree per line.
+ *   scene     (S, 4) fp32 [x, y, z, intensity] device        dense200 (L, 200, 3) f64: resample_polyline(raw, 200)
+ *   line32    (L, 32, 3) f64: resample_polyline(raw, 32)      centers  (L, 3) f64: mean of the 32 points
+ *   context   (L, N, 4) fp32 out: sampled points, xyz - center (float64 subtraction, rounded once), intensity
+ *   indices   (L, N) int64 out: scene index of every sample (-1: the zero points of an empty crop)
+ *   counts    (L) int32 out: points inside the tube (distance to the 200-point polyline < crop_radius, float64 compare)
+ *   status    (2) int64 out: [0] total candidates, [1] bit 0: `capacity` < [0] -> nothing was sampled, call again with
+ *             capacity >= status[0]; bit 1: more than 2^k - N candidates tie exactly at a line's threshold key
+ *   coord_extent: largest |coordinate| of the scene (sizes the band in which the fp32 pre-filter defers to float64)
+ * The draw follows the RNG contract documented in oracle/scene_oracle.py (counter-based hash of seed, line, scene index;
+ * Efraimidis-Spirakis keys; samples in descending key order): same distribution as the reference's
+ * np.random.choice(replace=False, p), reproducible and independent of thread order.  N <= 4096, L <= 65535. */
+size_t lrn_scene_workspace_bytes(int L, int64_t capacity);
+int lrn_scene_segments(const float* scene, int64_t S, const double* dense200, const double* line32, const double* centers,
+                       int L, int N, double crop_radius, double decay_scale, double coord_extent, uint64_t seed, int64_t capacity,
+                       float* context, int64_t* indices, int32_t* counts, int64_t* status, void* workspace, size_t workspace_bytes,
+                       lrn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,7 @@ EXPORTS = [
     "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe", "lrn_train_workspace_bytes",
     "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
     "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden",
+    "lrn_scene_workspace_bytes", "lrn_scene_segments",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
 
@@ -76,6 +77,11 @@ def _load():
     lib.lrn_ctx_attention_splits.argtypes = [ci, ci]
     lib.lrn_ctx_attention.restype = ci
     lib.lrn_ctx_attention.argtypes = [vp, vp, i64, vp, i64, ci, ci, ci, vp, vp, vp]
+    lib.lrn_scene_workspace_bytes.restype = sz
+    lib.lrn_scene_workspace_bytes.argtypes = [ci, i64]
+    lib.lrn_scene_segments.restype = ci
+    lib.lrn_scene_segments.argtypes = [vp, i64, vp, vp, vp, ci, ci, C.c_double, C.c_double, C.c_double, C.c_uint64, i64,
+                                       vp, vp, vp, vp, vp, sz, vp]
     lib.lrn_pos_hidden.restype = ci
     lib.lrn_pos_hidden.argtypes = [vp, vp, vp, i64, vp, i64, vp]
     lib.lrn_debug_ts_probe.restype = ci

@@ -19,6 +19,7 @@
 #include "chain_pair_sm100.cuh"
 #include "ts_probe.cuh"
 #include "ctx_attn_sm100.cuh"
+#include "scene_kernels.cuh"
 #include "pointwise.cuh"
 
 namespace {
@@ -701,6 +702,101 @@ int lrn_pos_hidden(const float* w1, const float* b1, const float* context, int64
   const int grid = int(std::min<int64_t>((P + 7) / 8, int64_t(dev.sms) * 8));
   pos_hidden_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(context), P, w1, b1,
                                                                               reinterpret_cast<uint16_t*>(out), ld_out);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+// ---------------------------------------------------------------- scene preprocessing (section 8f row 3)
+namespace {
+struct SceneLayout {
+  size_t aabb, dense_f, count, fill, imin, imax, offset, cand, keys, total;
+};
+SceneLayout scene_layout(int L, int64_t capacity) {
+  SceneLayout w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  w.aabb = take(size_t(L) * 6 * 4);
+  w.dense_f = take(size_t(L) * scene::kDense * 3 * 4);
+  w.count = take(size_t(L) * 4);
+  w.fill = take(size_t(L) * 4);
+  w.imin = take(size_t(L) * 4);
+  w.imax = take(size_t(L) * 4);
+  w.offset = take(size_t(L + 1) * 8);
+  w.cand = take(size_t(capacity) * 4);
+  w.keys = take(size_t(capacity) * 8);
+  w.total = off;
+  return w;
+}
+int scene_cap(int N) {
+  int c = 2;
+  while (c < 2 * N) c <<= 1;
+  return c;
+}
+}  // namespace
+
+size_t lrn_scene_workspace_bytes(int L, int64_t capacity) {
+  if (L <= 0 || capacity <= 0) return 0;
+  return scene_layout(L, capacity).total;
+}
+
+int lrn_scene_segments(const float* scene_pts, int64_t S, const double* dense200, const double* line32, const double* centers,
+                       int L, int N, double crop_radius, double decay_scale, double coord_extent, uint64_t seed, int64_t capacity,
+                       float* context, int64_t* indices, int32_t* counts, int64_t* status, void* workspace, size_t workspace_bytes,
+                       lrn_stream_t stream) {
+  if (!scene_pts || !dense200 || !line32 || !centers || !context || !indices || !counts || !status || !workspace)
+    return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (S <= 0 || S >= (int64_t(1) << 31) || L <= 0 || L > 65535 || N <= 0 || N > 4096 || capacity <= 0)
+    return fail(LRN_ERR_BAD_SHAPE, "S=%lld L=%d N=%d capacity=%lld (S < 2^31, L <= 65535, N <= 4096)", (long long)S, L, N, (long long)capacity);
+  if (!(crop_radius > 0) || !(decay_scale > 0) || !(coord_extent >= 0) || (crop_radius + 2.0) / decay_scale > 25.0)
+    return fail(LRN_ERR_BAD_ARG, "crop_radius=%g decay_scale=%g: (radius + 2) / decay must stay <= 25 (weights must not underflow)",
+                crop_radius, decay_scale);
+  if ((reinterpret_cast<uintptr_t>(scene_pts) & 15) || (reinterpret_cast<uintptr_t>(context) & 15) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return fail(LRN_ERR_MISALIGNED, "scene / context need 16-byte, workspace 256-byte alignment");
+  const SceneLayout w = scene_layout(L, capacity);
+  if (workspace_bytes < w.total) return fail(LRN_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, w.total);
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* aabb = reinterpret_cast<float*>(ws + w.aabb);
+  float* dense_f = reinterpret_cast<float*>(ws + w.dense_f);
+  int* count = reinterpret_cast<int*>(ws + w.count);
+  int* fill = reinterpret_cast<int*>(ws + w.fill);
+  int* imin = reinterpret_cast<int*>(ws + w.imin);
+  int* imax = reinterpret_cast<int*>(ws + w.imax);
+  long long* offset = reinterpret_cast<long long*>(ws + w.offset);
+  uint32_t* cand = reinterpret_cast<uint32_t*>(ws + w.cand);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(ws + w.keys);
+  long long* stat = reinterpret_cast<long long*>(status);
+  // fp32 pre-filter: decides `distance < radius` outside a band of +-eps, the band is evaluated in double
+  const double eps = 1e-3 + 4e-6 * coord_extent;
+  const double rlo = std::max(crop_radius - eps, 0.0), rhi = crop_radius + eps;
+  const float r2_lo = float(rlo * rlo * (1.0 - 1e-6)), r2_hi = float(rhi * rhi * (1.0 + 1e-6));
+  const float4* pts = reinterpret_cast<const float4*>(scene_pts);
+  scene::prep_kernel<<<L, 128, 0, s>>>(dense200, L, float(rhi * (1.0 + 1e-6)), aabb, dense_f, count, fill, imin, imax);
+  LRN_CUDA(cudaGetLastError());
+  const int grid = int((S + 255) / 256);
+  scene::tube_crop_kernel<false><<<grid, 256, 0, s>>>(pts, S, L, aabb, dense_f, dense200, crop_radius, r2_lo, r2_hi, count, imin, imax,
+                                                      fill, offset, capacity, cand);
+  LRN_CUDA(cudaGetLastError());
+  scene::scan_kernel<<<1, 1024, 0, s>>>(count, L, capacity, offset, stat);
+  LRN_CUDA(cudaGetLastError());
+  scene::tube_crop_kernel<true><<<grid, 256, 0, s>>>(pts, S, L, aabb, dense_f, dense200, crop_radius, r2_lo, r2_hi, count, imin, imax,
+                                                     fill, offset, capacity, cand);
+  LRN_CUDA(cudaGetLastError());
+  scene::sample_keys_kernel<<<dim3(32, L), 256, 0, s>>>(pts, line32, count, offset, imin, imax, N, decay_scale, seed, stat, cand, keys);
+  LRN_CUDA(cudaGetLastError());
+  const int cap = scene_cap(N);
+  const size_t smem = size_t(cap) * 12;
+  static size_t configured = 0;
+  if (smem > configured) {
+    LRN_CUDA(cudaFuncSetAttribute(scene::select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    configured = smem;
+  }
+  scene::select_kernel<<<L, 256, smem, s>>>(pts, centers, count, offset, N, cap, seed, stat, cand, keys, context,
+                                            reinterpret_cast<long long*>(indices), counts);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

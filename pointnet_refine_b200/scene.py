@@ -1,0 +1,95 @@
+"""Whole-scene front end of LineRefineNet on the GPU.
+
+The reference builds the network input for ONE line at a time on the host: KD-tree over a 200-point resampling of the
+line, distance query for every scene point, crop, weighted sampling, centroid normalisation
+(src/dataset.py:78-130,214-237; inference_whole_scene.py:95-121), then a B = 1 forward per line (:124-142).
+`build_segments` does the crop / sampling / normalisation for all lines of a scene in one pass on the device
+(`lrn_scene_segments`, csrc/scene_kernels.cuh) and `refine_scene` runs the lines of a scene as one batch.
+
+Only the polyline resampling stays on the host (a few hundred points per line, float64 like the reference).  The draw
+follows the reproducible RNG contract documented in include/lrn_b200.h (the reference uses the global unseeded
+np.random stream): same sampling distribution, fixed by (seed, line number, scene index).
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib
+from .ops import _aligned_bytes, _stream_ptr
+
+
+def resample_polyline(points, num_points: int = 32) -> np.ndarray:
+    """Arc-length-uniform linear resampling of a polyline (reference src/dataset.py:8-30): float64 (num_points, 3);
+    zeros for fewer than two vertices."""
+    pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    if pts.shape[0] < 2:
+        return np.zeros((num_points, 3))
+    arc = np.concatenate(([0.0], np.cumsum(np.linalg.norm(np.diff(pts, axis=0), axis=1))))
+    at = np.linspace(0, arc[-1], num_points)
+    return np.column_stack([np.interp(at, arc, pts[:, k]) for k in range(3)])
+
+
+class SceneSegments(NamedTuple):
+    context: torch.Tensor      # (L, N, 4) fp32 CUDA: sampled points, xyz centred on the line, intensity
+    noisy_line: torch.Tensor   # (L, 32, 3) fp32 CUDA: the resampled line, centred
+    centers: np.ndarray        # (L, 3) float64 host
+    line32: np.ndarray         # (L, 32, 3) float64 host, scene coordinates
+    indices: torch.Tensor      # (L, N) int64 CUDA: scene index of every sample, -1 for an empty crop's zero points
+    counts: torch.Tensor       # (L,) int32 CUDA: scene points inside each tube
+
+
+def build_segments(scene: torch.Tensor, raw_lines: Sequence, num_context_points: int = 1024, crop_radius: float = 0.3,
+                   decay_scale: float = 2.0, seed: int = 0, capacity: int | None = None) -> SceneSegments:
+    """scene (S, 4) fp32 CUDA [x, y, z, intensity]; raw_lines: polylines (n_i, 3) in scene coordinates.  Defaults are
+    inference_whole_scene.py's (:21-22, weighted_sampling's decay_scale); LaneRefineDataset uses 2048 / 4.0 / 2.0."""
+    if not scene.is_cuda or scene.dtype != torch.float32 or scene.dim() != 2 or scene.shape[1] != 4:
+        raise TypeError("scene must be a CUDA float32 (S, 4) tensor")
+    scene = scene.contiguous()
+    S, L, N = scene.shape[0], len(raw_lines), int(num_context_points)
+    if S == 0 or L == 0:
+        raise ValueError("empty scene or no lines")
+    line32 = np.stack([resample_polyline(r, 32) for r in raw_lines])
+    dense = np.stack([resample_polyline(r, 200) for r in raw_lines])
+    centers = line32.mean(axis=1)
+    dev = scene.device
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_dense, d_line, d_cent = up(dense), up(line32), up(centers)
+    extent = float(max(np.abs(dense).max(), float(scene[:, :3].abs().max())))
+    context = torch.empty(L, N, 4, dtype=torch.float32, device=dev)
+    indices = torch.empty(L, N, dtype=torch.int64, device=dev)
+    counts = torch.empty(L, dtype=torch.int32, device=dev)
+    status = torch.zeros(2, dtype=torch.int64, device=dev)
+    cap = int(capacity) if capacity else max(1 << 20, min(S * L, 8 * L * N))
+    for _ in range(2):
+        ws = _aligned_bytes(lib.lrn_scene_workspace_bytes(L, cap), dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.lrn_scene_segments(scene.data_ptr(), S, d_dense.data_ptr(), d_line.data_ptr(), d_cent.data_ptr(), L, N,
+                                              float(crop_radius), float(decay_scale), extent, int(seed) & (2 ** 64 - 1), cap,
+                                              context.data_ptr(), indices.data_ptr(), counts.data_ptr(), status.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "lrn_scene_segments")
+        _lib.launch_counter += 6
+        total, flags = (int(v) for v in status.tolist())        # synchronises
+        if flags & 2:
+            raise RuntimeError("lrn_scene_segments: too many candidates tie exactly at a threshold key")
+        if not flags & 1:
+            break
+        cap = total                                                # candidate buffer was too small: exact size now
+    else:
+        raise RuntimeError("lrn_scene_segments: candidate buffer overflow after resizing")
+    noisy = torch.from_numpy((line32 - centers[:, None, :]).astype(np.float32)).to(dev)
+    return SceneSegments(context, noisy, centers, line32, indices, counts)
+
+
+@torch.no_grad()
+def refine_scene(model, scene: torch.Tensor, raw_lines: Sequence, num_context_points: int = 1024, crop_radius: float = 0.3,
+                 decay_scale: float = 2.0, seed: int = 0) -> np.ndarray:
+    """All lines of a scene through the model in one batch: (L, 32, 3) float64 refined polylines in scene coordinates
+    = resampled line + last decoder layer's cumulative offset (inference_whole_scene.py:137-147)."""
+    seg = build_segments(scene, raw_lines, num_context_points, crop_radius, decay_scale, seed)
+    model.eval()
+    offsets = model(seg.context, seg.noisy_line)[-1]
+    return seg.line32 + offsets.double().cpu().numpy()
