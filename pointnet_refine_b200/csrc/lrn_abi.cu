@@ -715,7 +715,7 @@ SceneLayout scene_layout(int L, int64_t capacity) {
   SceneLayout w{};
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  w.aabb = take(size_t(L) * 6 * 4);
+  w.aabb = take(size_t(L) * scene::kBoxFloats * 4);
   w.dense_f = take(size_t(L) * scene::kDense * 3 * 4);
   w.count = take(size_t(L) * 4);
   w.fill = take(size_t(L) * 4);

@@ -15,6 +15,9 @@ namespace scene {
 constexpr int kDense = 200;  // points of the crop polyline (src/dataset.py:217)
 constexpr int kLine = 32;    // points of the sampling polyline
 constexpr int kLineTile = 256;
+constexpr int kSub = 8;                    // the crop polyline is tested in 8 pieces of 25 points, each with its own box
+constexpr int kSubLen = kDense / kSub;
+constexpr int kBoxFloats = 6 * (1 + kSub);  // per line: whole-line box, then the piece boxes
 
 // ------------------------------------------------------------------------------------------------ RNG contract
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -74,46 +77,42 @@ __device__ __forceinline__ double dist2_exact(double px, double py, double pz, c
 }
 
 // ------------------------------------------------------------------------------------------------ per-line setup
-// Bounding box of every crop polyline grown by (radius + eps), fp32 copy of its points, counters reset.
+// Bounding boxes (whole polyline and its kSub pieces) grown by (radius + eps), fp32 copy of the points, counters reset.
+// A scene point within the radius of some polyline point lies inside that point's piece box, so testing only the
+// pieces whose box contains the scene point decides `distance < radius` exactly.
 __global__ void prep_kernel(const double* __restrict__ dense, int L, float grow, float* __restrict__ aabb,
                             float* __restrict__ dense_f, int* __restrict__ count, int* __restrict__ fill,
                             int* __restrict__ imin, int* __restrict__ imax) {
   const int l = blockIdx.x;
   if (l >= L) return;
-  __shared__ float red[6][32];
-  float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-  for (int i = threadIdx.x; i < kDense; i += blockDim.x) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double v = dense[(static_cast<size_t>(l) * kDense + i) * 3 + k];
-      dense_f[(static_cast<size_t>(l) * kDense + i) * 3 + k] = static_cast<float>(v);
-      lo[k] = fminf(lo[k], __double2float_rd(v));
-      hi[k] = fmaxf(hi[k], __double2float_ru(v));
+  __shared__ float lo_s[kSub][3], hi_s[kSub][3];
+  for (int i = threadIdx.x; i < kDense * 3; i += blockDim.x)
+    dense_f[static_cast<size_t>(l) * kDense * 3 + i] = static_cast<float>(dense[static_cast<size_t>(l) * kDense * 3 + i]);
+  if (threadIdx.x < kSub * 3) {
+    const int sub = threadIdx.x / 3, k = threadIdx.x % 3;
+    float lo = 3.4e38f, hi = -3.4e38f;
+    for (int i = 0; i < kSubLen; ++i) {
+      const double v = dense[(static_cast<size_t>(l) * kDense + sub * kSubLen + i) * 3 + k];
+      lo = fminf(lo, __double2float_rd(v));
+      hi = fmaxf(hi, __double2float_ru(v));
     }
+    lo_s[sub][k] = lo;
+    hi_s[sub][k] = hi;
+    aabb[l * kBoxFloats + 6 * (1 + sub) + k] = lo - grow;
+    aabb[l * kBoxFloats + 6 * (1 + sub) + 3 + k] = hi + grow;
   }
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-    for (int o = 16; o; o >>= 1) {
-      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
-      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
-    }
-  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if ((threadIdx.x & 31) == 0)
-    for (int k = 0; k < 3; ++k) {
-      red[k][w] = lo[k];
-      red[3 + k][w] = hi[k];
-    }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 0; k < 3; ++k) {
-      float a = red[k][0], b = red[3 + k][0];
-      for (int i = 1; i < nw; ++i) {
-        a = fminf(a, red[k][i]);
-        b = fmaxf(b, red[3 + k][i]);
-      }
-      aabb[l * 6 + k] = a - grow;
-      aabb[l * 6 + 3 + k] = b + grow;
+  if (threadIdx.x < 3) {
+    const int k = threadIdx.x;
+    float lo = lo_s[0][k], hi = hi_s[0][k];
+    for (int sub = 1; sub < kSub; ++sub) {
+      lo = fminf(lo, lo_s[sub][k]);
+      hi = fmaxf(hi, hi_s[sub][k]);
     }
+    aabb[l * kBoxFloats + k] = lo - grow;
+    aabb[l * kBoxFloats + 3 + k] = hi + grow;
+  }
+  if (threadIdx.x == 0) {
     count[l] = 0;
     fill[l] = 0;
     imin[l] = 0x7FFFFFFF;
@@ -122,8 +121,9 @@ __global__ void prep_kernel(const double* __restrict__ dense, int L, float grow,
 }
 
 // ------------------------------------------------------------------------------------------------ tube crop
-// One thread per scene point, all lines: box test, fp32 minimum distance to the 200-point polyline, and the exact
-// double evaluation only inside the band where fp32 cannot decide `distance < radius`.
+// One thread per scene point, all lines: box tests (line, then pieces), fp32 minimum distance to the points of the
+// pieces whose box contains it, and the exact double evaluation only inside the band where fp32 cannot decide
+// `distance < radius`.
 // FILL = false: count the candidates of every line (+ intensity range).  FILL = true: write their scene indices.
 template <bool FILL>
 __global__ void __launch_bounds__(256) tube_crop_kernel(const float4* __restrict__ pts, long long S, int L,
@@ -136,27 +136,38 @@ __global__ void __launch_bounds__(256) tube_crop_kernel(const float4* __restrict
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < S) p = pts[i];
+  auto inside = [&](const float* b) { return !(p.x < b[0] || p.y < b[1] || p.z < b[2] || p.x > b[3] || p.y > b[4] || p.z > b[5]); };
   for (int l0 = 0; l0 < L; l0 += kLineTile) {
     const int nl = min(kLineTile, L - l0);
     __syncthreads();
-    for (int t = threadIdx.x; t < nl * 6; t += blockDim.x) box[t] = aabb[l0 * 6 + t];
+    for (int t = threadIdx.x; t < nl * 6; t += blockDim.x) box[t] = aabb[(l0 + t / 6) * kBoxFloats + t % 6];
     __syncthreads();
     if (i >= S) continue;
     for (int j = 0; j < nl; ++j) {
-      const float* b = box + j * 6;
-      if (p.x < b[0] || p.y < b[1] || p.z < b[2] || p.x > b[3] || p.y > b[4] || p.z > b[5]) continue;
+      if (!inside(box + j * 6)) continue;
       const int l = l0 + j;
+      const float* sb = aabb + l * kBoxFloats + 6;
       const float* q = dense_f + static_cast<size_t>(l) * kDense * 3;
       float best = 3.4e38f;
-      for (int k = 0; k < kDense; ++k) {
-        const float dx = p.x - __ldg(q + 3 * k), dy = p.y - __ldg(q + 3 * k + 1), dz = p.z - __ldg(q + 3 * k + 2);
-        best = fminf(best, dx * dx + dy * dy + dz * dz);
+      uint32_t pieces = 0;
+      for (int sub = 0; sub < kSub; ++sub) {
+        float b6[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) b6[k] = __ldg(sb + 6 * sub + k);
+        if (!inside(b6)) continue;
+        pieces |= 1u << sub;
+        for (int k = sub * kSubLen; k < (sub + 1) * kSubLen; ++k) {
+          const float dx = p.x - __ldg(q + 3 * k), dy = p.y - __ldg(q + 3 * k + 1), dz = p.z - __ldg(q + 3 * k + 2);
+          best = fminf(best, dx * dx + dy * dy + dz * dz);
+        }
       }
       if (best > r2_hi) continue;
       if (best >= r2_lo) {  // undecidable in fp32: the reference's float64 comparison
         const double* qd = dense + static_cast<size_t>(l) * kDense * 3;
         double bd = 1e300;
-        for (int k = 0; k < kDense; ++k) bd = fmin(bd, dist2_exact(p.x, p.y, p.z, qd + 3 * k));
+        for (int sub = 0; sub < kSub; ++sub)
+          if (pieces >> sub & 1)
+            for (int k = sub * kSubLen; k < (sub + 1) * kSubLen; ++k) bd = fmin(bd, dist2_exact(p.x, p.y, p.z, qd + 3 * k));
         if (!(sqrt(bd) < radius)) continue;
       }
       if (!FILL) {
