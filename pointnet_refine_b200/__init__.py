@@ -9,5 +9,6 @@ from .model import (DetrTransformerDecoderLayer, LineRefineNet, MultiScalePointN
                     PositionalEncoding)
 
 from .graph import GraphedLineRefineNet  # noqa: F401,E402
+from . import scene  # noqa: F401,E402  (whole-scene front end: build_segments, refine_scene)
 
-__all__ = ["GraphedLineRefineNet", "LineRefineNet", "MultiScalePointNetEncoder", "PositionalEncoding", "DetrTransformerDecoderLayer", "ops"]
+__all__ = ["GraphedLineRefineNet", "LineRefineNet", "MultiScalePointNetEncoder", "PositionalEncoding", "DetrTransformerDecoderLayer", "ops", "scene"]
