@@ -161,8 +161,13 @@ int lrn_profile_read(float* ms_per_stage /*[LRN_STAGE_COUNT]*/, int64_t* launche
 /* ---- train mode: batch-statistic BatchNorm forward + hand-written backward of the context encoder ----
  * Replaces: MultiScalePointNetEncoder.forward under model.train() (src/model.py:39-55 with nn.BatchNorm1d in
  * training mode) and its autograd backward, as driven by train.py:56-72 / train_dist.py:168-189.  bf16
- * tensor-core operands, fp32 parameters and gradients.  The pooling (src/model.py:58-60) and context_proj
- * stay with the caller (they are differentiable functions of `fused`).
+ * tensor-core operands, fp32 parameters and gradients.  context_proj stays with the caller (a differentiable
+ * function of `fused`).
+ *   global_feat : optional (fused_point_major = 0): (B, 2048) fp32 = [max_n | mean_n] of fused (src/model.py:58-60),
+ *                 with argmax (B, 1024) int64 = first maximal point per (segment, channel).  The backward takes
+ *                 d_global_feat + that argmax and scatters the max gradient to its argmax point / spreads the mean
+ *                 gradient as 1/N inside its first kernel; d_fused may be NULL when only the pooled features carry
+ *                 gradient (no dense (B,1024,N) gradient is built for the pooling).
  *   running     : running_mean / running_var of bn1..bn5 and fusion.1, updated in place like PyTorch
  *                 (momentum, unbiased variance); may be NULL.  num_batches_tracked is the caller's counter.
  *   fused       : fused_point_major = 0: (B,1024,N) fp32, the reference layout; 1: (B*N,1024) bf16 point-major
@@ -191,9 +196,11 @@ typedef struct lrn_encoder_grads {
 size_t lrn_train_workspace_bytes(int64_t B, int64_t N);
 int lrn_encoder_train_forward(const lrn_encoder_params* params, const lrn_bn_running* running, float momentum,
                               const float* context, int64_t B, int64_t N, void* fused, int fused_point_major,
-                              void* workspace, size_t workspace_bytes, lrn_stream_t stream);
+                              float* global_feat, int64_t* argmax, void* workspace, size_t workspace_bytes,
+                              lrn_stream_t stream);
 int lrn_encoder_train_backward(const lrn_encoder_params* params, const float* context, int64_t B, int64_t N,
-                               const void* d_fused, int fused_point_major, const lrn_encoder_grads* grads, void* workspace,
+                               const void* d_fused, int fused_point_major, const float* d_global_feat,
+                               const int64_t* argmax, const lrn_encoder_grads* grads, void* workspace,
                                size_t workspace_bytes, lrn_stream_t stream);
 
 /* ---- building block, exported for unit tests and profiling ----

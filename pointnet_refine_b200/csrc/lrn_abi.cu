@@ -1021,8 +1021,11 @@ size_t lrn_train_workspace_bytes(int64_t B, int64_t N) {
 
 int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running* running, float momentum,
                               const float* context, int64_t B, int64_t N, void* fused, int fused_point_major,
-                              void* workspace, size_t workspace_bytes, lrn_stream_t stream) {
+                              float* global_feat, int64_t* argmax, void* workspace, size_t workspace_bytes,
+                              lrn_stream_t stream) {
   if (!pr || !context || !fused || !workspace) return fail(LRN_ERR_BAD_ARG, "null argument");
+  if ((global_feat != nullptr) != (argmax != nullptr) || (global_feat && fused_point_major))
+    return fail(LRN_ERR_BAD_ARG, "global_feat and argmax come together and need the (B,1024,N) fused layout");
   if (B <= 0 || N <= 0 || B * N >= (int64_t(1) << 31) - 256) return fail(LRN_ERR_BAD_SHAPE, "B=%lld N=%lld", (long long)B, (long long)N);
   DeviceInfo dev;
   int st = device_info(&dev);
@@ -1088,15 +1091,24 @@ int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running
     dim3 grid(unsigned((P + 31) / 32), 32);
     fusion_gate_fwd_kernel<<<grid, 256, 0, s>>>(U + kUOff[5], kULd, Z, 1024, P, int(N), scale + kUOff[5], shift + kUOff[5],
                                                 static_cast<float*>(fused));
+    if (global_feat) {
+      LRN_CUDA(cudaGetLastError());
+      pool_rows_kernel<<<int(std::min<int64_t>((B * 1024 + 7) / 8, int64_t(dev.sms) * 16)), 256, 0, s>>>(
+          static_cast<const float*>(fused), B * 1024, int(N), global_feat, reinterpret_cast<long long*>(argmax));
+    }
   }
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
 
 int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* context, int64_t B, int64_t N,
-                               const void* d_fused, int fused_point_major, const lrn_encoder_grads* g, void* workspace,
-                               size_t workspace_bytes, lrn_stream_t stream) {
-  if (!pr || !context || !d_fused || !g || !workspace) return fail(LRN_ERR_BAD_ARG, "null argument");
+                               const void* d_fused, int fused_point_major, const float* d_global_feat,
+                               const int64_t* argmax, const lrn_encoder_grads* g, void* workspace, size_t workspace_bytes,
+                               lrn_stream_t stream) {
+  if (!pr || !context || !g || !workspace) return fail(LRN_ERR_BAD_ARG, "null argument");
+  if (!d_fused && !d_global_feat) return fail(LRN_ERR_BAD_ARG, "no output gradient (d_fused and d_global_feat are null)");
+  if (d_global_feat && (!argmax || fused_point_major))
+    return fail(LRN_ERR_BAD_ARG, "d_global_feat needs the forward's argmax and the (B,1024,N) fused layout");
   DeviceInfo dev;
   int st = device_info(&dev);
   if (st) return st;
@@ -1139,7 +1151,8 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
                                                                      dZ, 1024);
     } else {
       dim3 grid(unsigned((P + 31) / 32), 32);
-      fusion_gate_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(d_fused), U + kUOff[5], kULd, Z, 1024, P, int(N),
+      fusion_gate_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(d_fused), d_global_feat,
+                                                  reinterpret_cast<const long long*>(argmax), U + kUOff[5], kULd, Z, 1024, P, int(N),
                                                   scale + kUOff[5], shift + kUOff[5], dU, dZ, 1024);
     }
     LRN_CUDA(cudaGetLastError());

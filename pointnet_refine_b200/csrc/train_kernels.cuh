@@ -173,6 +173,45 @@ fusion_gate_fwd_kernel(const __nv_bfloat16* __restrict__ Uf, long long ldu, cons
   }
 }
 
+// Dual pooling of the train-mode output (src/model.py:58-60): one warp per (segment, channel) row of fused (B,1024,N):
+// global_feat[b, c] = max_n, global_feat[b, 1024 + c] = mean_n, argmax[b, c] = first maximal n (torch.max's rule) -
+// the index the backward scatters the max gradient to.
+__global__ void __launch_bounds__(256)
+pool_rows_kernel(const float* __restrict__ fused, long long rows /* B * 1024 */, int npts, float* __restrict__ global_feat,
+                 long long* __restrict__ argmax) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const float* row = fused + r * npts;
+    float best = -INFINITY, sum = 0.f;
+    int arg = 0x7FFFFFFF;
+    for (int n = lane; n < npts; n += 32) {
+      const float v = row[n];
+      sum += v;
+      if (v > best) {   // strictly greater: the first index wins inside a lane
+        best = v;
+        arg = n;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (ob > best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    if (lane == 0) {
+      const long long b = r >> 10, c = r & 1023;
+      global_feat[b * 2048 + c] = best;
+      global_feat[b * 2048 + 1024 + c] = sum / static_cast<float>(npts);
+      argmax[r] = arg;
+    }
+  }
+}
+
 // Point-major variants (no layout change): fused_pm[p, c] bf16, channel-stationary threads like bn_relu_apply_kernel.
 __global__ void __launch_bounds__(256)
 fusion_gate_fwd_pm_kernel(const __nv_bfloat16* __restrict__ Uf, long long ldu, const __nv_bfloat16* __restrict__ Z,
@@ -230,8 +269,12 @@ fusion_gate_bwd_pm_kernel(const __nv_bfloat16* __restrict__ dfused_pm, const __n
 // Backward of the gate / ReLU at the fused output: with y0 = Uf*scale+shift, y = relu(y0), g = sigmoid(Z):
 //   dY[p,c] = dF * (0.5 + 0.5 g) * [y0 > 0]      (gradient w.r.t. the BatchNorm output)
 //   dZ[p,c] = dF * y * 0.5 * g * (1 - g)         (gradient w.r.t. the gate pre-activation)
+// The gradient of the pooled features is folded in here (hand-written backward of src/model.py:58-60): the max gradient
+// is scattered to its argmax point, the mean gradient spread as 1/N - `dfused` may then be null (pooled loss only),
+// no dense (B,1024,N) gradient is ever built for the pooling.
 __global__ void __launch_bounds__(256)
-fusion_gate_bwd_kernel(const float* __restrict__ dfused, const __nv_bfloat16* __restrict__ Uf, long long ldu,
+fusion_gate_bwd_kernel(const float* __restrict__ dfused, const float* __restrict__ dgf, const long long* __restrict__ argmax,
+                       const __nv_bfloat16* __restrict__ Uf, long long ldu,
                        const __nv_bfloat16* __restrict__ Z, long long ldz, long long rows, int npts,
                        const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dY,
                        __nv_bfloat16* __restrict__ dZ, long long ldd) {
@@ -246,7 +289,11 @@ fusion_gate_bwd_kernel(const float* __restrict__ dfused, const __nv_bfloat16* __
     float v = 0.f;
     if (p < rows) {
       const unsigned b = static_cast<unsigned>(p) / static_cast<unsigned>(npts), n = static_cast<unsigned>(p) - b * npts;
-      v = dfused[(static_cast<long long>(b) * 1024 + c) * npts + n];
+      if (dfused) v = dfused[(static_cast<long long>(b) * 1024 + c) * npts + n];
+      if (dgf) {
+        v += dgf[static_cast<long long>(b) * 2048 + 1024 + c] / static_cast<float>(npts);
+        if (argmax[static_cast<long long>(b) * 1024 + c] == n) v += dgf[static_cast<long long>(b) * 2048 + c];
+      }
     }
     tile[ty + 8 * k][tx] = v;
   }

@@ -29,10 +29,12 @@ lib.lrn_train_workspace_bytes.restype = C.c_size_t
 lib.lrn_train_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
 lib.lrn_encoder_train_forward.restype = C.c_int
 lib.lrn_encoder_train_forward.argtypes = [C.POINTER(_lib.EncoderParams), C.POINTER(BnRunning), C.c_float, C.c_void_p,
-                                          C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+                                          C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]
 lib.lrn_encoder_train_backward.restype = C.c_int
 lib.lrn_encoder_train_backward.argtypes = [C.POINTER(_lib.EncoderParams), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
-                                           C.c_int, C.POINTER(EncoderGrads), C.c_void_p, C.c_size_t, C.c_void_p]
+                                           C.c_int, C.c_void_p, C.c_void_p, C.POINTER(EncoderGrads), C.c_void_p, C.c_size_t,
+                                           C.c_void_p]
 
 # parameter order of the autograd node (names relative to MultiScalePointNetEncoder)
 PARAM_NAMES = ([f"conv{k}.weight" for k in range(1, 6)] + [f"conv{k}.bias" for k in range(1, 6)]
@@ -57,8 +59,8 @@ class EncoderTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, context, running, momentum, point_major, *params):
         """context (B,N,4) fp32 CUDA; running = list of 12 buffers (6 running_mean, 6 running_var) updated in
-        place, or None; params in PARAM_NAMES order.  Returns fused (B,1024,N) fp32, or with point_major the
-        (B,N,1024) bf16 tensor context_proj consumes."""
+        place, or None; params in PARAM_NAMES order.  Returns (global_feat (B,2048), fused (B,1024,N)) fp32, or with
+        point_major the (B,N,1024) bf16 tensor context_proj consumes (LineRefineNet never uses global_feat)."""
         context = _f32c(context)
         B, N, _ = context.shape
         dev = context.device
@@ -68,6 +70,10 @@ class EncoderTrainFn(torch.autograd.Function):
         ws = _aligned_bytes(nbytes, dev)           # owned by this node until its backward has run
         fused = (torch.empty(B, N, 1024, dtype=torch.bfloat16, device=dev) if point_major
                  else torch.empty(B, 1024, N, dtype=torch.float32, device=dev))
+        gf = am = None
+        if not point_major:
+            gf = torch.empty(B, 2048, dtype=torch.float32, device=dev)
+            am = torch.empty(B, 1024, dtype=torch.int64, device=dev)
         rs = None
         if running is not None:
             rs = BnRunning()
@@ -76,19 +82,28 @@ class EncoderTrainFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.lrn_encoder_train_forward(C.byref(ps), C.byref(rs) if rs is not None else None, momentum,
                                                      context.data_ptr(), B, N, fused.data_ptr(), int(point_major),
+                                                     gf.data_ptr() if gf is not None else None,
+                                                     am.data_ptr() if am is not None else None,
                                                      ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
                        "lrn_encoder_train_forward")
-        _lib.launch_counter += 12 + 1 + 6 * 2 + 5 + 6 + 1
+        _lib.launch_counter += 12 + 1 + 6 * 2 + 5 + 6 + 1 + (0 if point_major else 1)
         ctx.save_for_backward(context, *t)
-        ctx.ws, ctx.shape, ctx.point_major = ws, (B, N), bool(point_major)
-        return fused
+        ctx.ws, ctx.shape, ctx.point_major, ctx.argmax = ws, (B, N), bool(point_major), am
+        if point_major:
+            return fused
+        ctx.mark_non_differentiable(am)
+        return gf, fused, am
 
     @staticmethod
-    def backward(ctx, d_fused):
+    def backward(ctx, *douts):
         context, *t = ctx.saved_tensors
         B, N = ctx.shape
         dev = context.device
-        d_fused = d_fused.to(torch.bfloat16).contiguous() if ctx.point_major else _f32c(d_fused)
+        if ctx.point_major:
+            d_gf, d_fused = None, douts[0].to(torch.bfloat16).contiguous()
+        else:
+            d_gf = _f32c(douts[0]) if douts[0] is not None else None
+            d_fused = _f32c(douts[1]) if douts[1] is not None else None
         grads = [torch.empty_like(x) for x in t]
         g = EncoderGrads()
         for k in range(5):
@@ -98,8 +113,11 @@ class EncoderTrainFn(torch.autograd.Function):
         g.gate0_w, g.gate0_b, g.gate2_w, g.gate2_b = (x.data_ptr() for x in grads[24:28])
         ps = _params_struct(t)
         with torch.cuda.device(dev):
-            _lib.check(lib.lrn_encoder_train_backward(C.byref(ps), context.data_ptr(), B, N, d_fused.data_ptr(),
-                                                      int(ctx.point_major), C.byref(g), ctx.ws.data_ptr(), ctx.ws.numel(),
+            _lib.check(lib.lrn_encoder_train_backward(C.byref(ps), context.data_ptr(), B, N,
+                                                      d_fused.data_ptr() if d_fused is not None else None, int(ctx.point_major),
+                                                      d_gf.data_ptr() if d_gf is not None else None,
+                                                      ctx.argmax.data_ptr() if d_gf is not None else None,
+                                                      C.byref(g), ctx.ws.data_ptr(), ctx.ws.numel(),
                                                       _stream_ptr(dev)), "lrn_encoder_train_backward")
         _lib.launch_counter += 60
         ctx.ws = None
@@ -114,13 +132,13 @@ def encoder_train_forward(module, context, point_major=False):
     params = [sd[n] for n in PARAM_NAMES]
     bns = [module.bn1, module.bn2, module.bn3, module.bn4, module.bn5, module.fusion[1]]
     running = [b.running_mean for b in bns] + [b.running_var for b in bns]
-    fused = EncoderTrainFn.apply(context, running, float(bns[0].momentum), point_major, *params)
+    out = EncoderTrainFn.apply(context, running, float(bns[0].momentum), point_major, *params)
     with torch.no_grad():
         for b in bns:
             b.num_batches_tracked += 1
     if point_major:
-        return None, fused
-    global_feat = torch.cat([fused.max(dim=2)[0], fused.mean(dim=2)], dim=1)   # src/model.py:58-60
+        return None, out
+    global_feat, fused, _ = out      # pooling (src/model.py:58-60) and its argmax-scatter backward are native too
     return global_feat, fused
 
 

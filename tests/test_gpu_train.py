@@ -71,6 +71,27 @@ def test_train_forward_backward_matches_torch(dev, B, N):
         assert rel <= 0.3 and cos >= 0.95, (name, rel, cos)   # worst: conv1 (end of the chain), rel 0.23 / cos 0.974
 
 
+def test_train_pooled_loss_uses_native_argmax_scatter(dev):
+    """Loss on global_feat only: the backward receives no d_fused at all; the max gradient is scattered to the argmax
+    point and the mean gradient spread as 1/N inside the native backward (hand-written backward of src/model.py:58-60)."""
+    enc, ref = _pair(dev)
+    B, N = 3, 500
+    ctx = torch.from_numpy(synth.make_inputs(B, N, seed=77)[0]).to(dev)
+    R2 = torch.randn(B, 2048, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    res = {}
+    for name, e in (("native", enc), ("torch", ref)):
+        gf, fused = e(ctx.transpose(2, 1))
+        if name == "native":
+            assert torch.equal(gf[:, :1024].detach(), fused.detach().max(dim=2)[0])   # pooled in the native forward
+            assert float((gf[:, 1024:] - fused.mean(dim=2)).detach().abs().max()) <= 1e-5
+        (gf * R2).sum().backward()
+        res[name] = {n: p.grad.flatten().double() for n, p in e.named_parameters()}
+    for n in ("fusion.0.weight", "fusion.1.weight", "intensity_gate.2.weight", "conv5.weight", "conv3.weight", "bn2.bias"):
+        a, b = res["native"][n], res["torch"][n]
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        assert float((a - b).norm() / b.norm()) <= 0.3 and cos >= 0.95, (n, cos)
+
+
 def test_train_matches_reference_golden(dev):
     """Train-mode forward against the fixture generated from the unmodified reference (oracle/make_golden.py)."""
     g, sd, ctx, _, (sc, sn) = load_case("train_b2_n512")

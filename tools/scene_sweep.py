@@ -17,6 +17,7 @@ ap.add_argument("--segments", type=int, default=1_000_000)
 ap.add_argument("--points", type=int, default=2048)
 ap.add_argument("--chunk", type=int, default=512)
 ap.add_argument("--encoder", action="store_true")
+ap.add_argument("--graph", action="store_true", help="replay the chunk forward as a CUDA graph")
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -31,6 +32,7 @@ gen = torch.Generator(device=dev).manual_seed(1234 + rank)
 ctx = torch.randn(args.chunk, args.points, 4, device=dev, generator=gen)
 line = torch.randn(args.chunk, 32, 3, device=dev, generator=gen)
 acc = torch.zeros((), device=dev, dtype=torch.float64)
+graphed = prb.GraphedLineRefineNet(m, args.chunk, args.points) if args.graph and not args.encoder else None
 
 def run(n_seg):
     done = 0
@@ -38,6 +40,8 @@ def run(n_seg):
         n = min(args.chunk, n_seg - done)
         if args.encoder:
             out = m.context_encoder.run_native(ctx[:n], pool=True)["global_feat"]
+        elif graphed is not None and n == args.chunk:
+            out = graphed(ctx, line)[-1]
         else:
             out = m(ctx[:n], line[:n])[-1]
         acc.add_(out.double().sum())            # consume the result on the device
@@ -61,7 +65,7 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"config": "scene sweep (BASELINE configs[2])", "segments": args.segments, "points": args.points, "n_gpus": world,
-                      "what": "encoder + pooling" if args.encoder else "LineRefineNet.forward (6,B,32,3)", "chunk": args.chunk,
+                      "what": "encoder + pooling" if args.encoder else "LineRefineNet.forward (6,B,32,3)", "chunk": args.chunk, "cuda_graph": bool(graphed),
                       "seconds": round(float(t), 3), "segments_per_sec": round(args.segments / float(t), 1),
                       "points_per_sec": round(args.segments * args.points / float(t), 1), "finite": bool(torch.isfinite(acc))}))
 if world > 1:
