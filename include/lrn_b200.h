@@ -258,6 +258,16 @@ int lrn_scene_segments(const float* scene, int64_t S, const double* dense200, co
                        float* context, int64_t* indices, int32_t* counts, int64_t* status, void* workspace, size_t workspace_bytes,
                        lrn_stream_t stream);
 
+/* ---- training-loop machinery ----
+ * One Adam step over a flat fp32 buffer holding every parameter (train.py:40 optim.Adam(model.parameters(), lr);
+ * torch.optim.Adam semantics without amsgrad, weight decay added to the gradient); step counts from 1. */
+int lrn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, lrn_stream_t stream);
+/* Deep-supervision loss of train.py:63-69: loss[0] = (1/L) sum_l L1Loss(pred[l], target) for pred (L, n) and target (n)
+ * (n = B*M*3 elements per decoder layer), and its gradient dpred (L, n) = sign(pred - target) / (L n); dpred may be NULL. */
+int lrn_l1_deep_supervision(const float* pred, const float* target, int L, int64_t n, float* loss, float* dpred,
+                            lrn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

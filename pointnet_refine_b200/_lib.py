@@ -26,7 +26,7 @@ EXPORTS = [
     "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe", "lrn_train_workspace_bytes",
     "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
     "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden",
-    "lrn_scene_workspace_bytes", "lrn_scene_segments",
+    "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_adam_step", "lrn_l1_deep_supervision",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
 
@@ -82,6 +82,10 @@ def _load():
     lib.lrn_scene_segments.restype = ci
     lib.lrn_scene_segments.argtypes = [vp, i64, vp, vp, vp, ci, ci, C.c_double, C.c_double, C.c_double, C.c_uint64, i64,
                                        vp, vp, vp, vp, vp, sz, vp]
+    lib.lrn_adam_step.restype = ci
+    lib.lrn_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]
+    lib.lrn_l1_deep_supervision.restype = ci
+    lib.lrn_l1_deep_supervision.argtypes = [vp, vp, ci, i64, vp, vp, vp]
     lib.lrn_pos_hidden.restype = ci
     lib.lrn_pos_hidden.argtypes = [vp, vp, vp, i64, vp, i64, vp]
     lib.lrn_debug_ts_probe.restype = ci

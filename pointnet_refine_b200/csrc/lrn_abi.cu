@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1206,6 +1207,36 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
   conv1_gate1_bwd_kernel<<<int(std::min<int64_t>((P + 2047) / 2048, 1024)), 256, 0, s>>>(
       reinterpret_cast<const float4*>(context), P, dU, 1024, dHp, 128, X + kFusionK, kCat, g->conv_w[0], g->conv_b[0],
       g->gate0_w, g->gate0_b);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, lrn_stream_t stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (n <= 0 || step < 1) return fail(LRN_ERR_BAD_SHAPE, "n=%lld step=%lld", (long long)n, (long long)step);
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const double bc1 = 1.0 - pow(double(beta1), double(step)), bc2 = 1.0 - pow(double(beta2), double(step));
+  const int grid = int(std::min<int64_t>((n + 255) / 256, int64_t(dev.sms) * 16));
+  adam_step_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, float(double(lr) / bc1),
+                                                                              beta1, beta2, eps, weight_decay, float(1.0 / sqrt(bc2)));
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_l1_deep_supervision(const float* pred, const float* target, int L, int64_t n, float* loss, float* dpred,
+                            lrn_stream_t stream) {
+  if (!pred || !target || !loss) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (L <= 0 || n <= 0) return fail(LRN_ERR_BAD_SHAPE, "L=%d n=%lld", L, (long long)n);
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  LRN_CUDA(cudaMemsetAsync(loss, 0, 4, s));
+  const int grid = int(std::min<int64_t>((int64_t(L) * n + 255) / 256, int64_t(dev.sms) * 4));
+  l1_deep_supervision_kernel<<<grid, 256, 0, s>>>(pred, target, L, n, loss, dpred);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

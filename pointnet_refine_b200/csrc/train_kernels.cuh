@@ -448,4 +448,50 @@ __global__ void copy_submatrix_kernel(const float* __restrict__ src, long long l
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Training-loop machinery: Adam over one flat parameter buffer and the L1 deep-supervision loss.
+// ---------------------------------------------------------------------------------------------
+// torch.optim.Adam (train.py:40, no amsgrad), same operation order as its single-tensor path:
+//   g += wd * p;  m = m + (1 - b1) (g - m);  v = b2 v + (1 - b2) g g;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                 float step_size, float b1, float b2, float eps, float wd, float inv_bc2_sqrt) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = fmaf(1.f - b1, gi - m[i], m[i]);
+    const float vi = fmaf(1.f - b2, gi * gi, b2 * v[i]);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * (mi / (sqrtf(vi) * inv_bc2_sqrt + eps));
+  }
+}
+
+// loss = (1 / L) sum_l mean_i |pred[l][i] - target[i]|   (train.py:63-69, criterion = L1Loss);
+// dpred[l][i] = sign(pred[l][i] - target[i]) / (L n)       (0 at equality, like torch)
+__global__ void __launch_bounds__(256)
+l1_deep_supervision_kernel(const float* __restrict__ pred, const float* __restrict__ target, int L, long long n,
+                           float* __restrict__ loss, float* __restrict__ dpred) {
+  __shared__ float red[8];
+  const float w = 1.f / (static_cast<float>(L) * static_cast<float>(n));
+  const long long total = static_cast<long long>(L) * n, stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const float d = pred[i] - target[i % n];
+    acc += fabsf(d);
+    if (dpred) dpred[i] = d > 0.f ? w : (d < 0.f ? -w : 0.f);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(loss, t * w);
+  }
+}
+
 }  // namespace lrn

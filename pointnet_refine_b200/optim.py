@@ -1,0 +1,104 @@
+"""Training-loop machinery on the native kernels.
+
+`FlatAdam` is a drop-in for `optim.Adam(model.parameters(), lr=LR)` (reference train.py:40, train_dist.py:149): every
+parameter becomes a view of ONE flat fp32 buffer (and its `.grad` a view of one flat gradient buffer), so a step is one
+`lrn_adam_step` launch instead of a multi-tensor sweep, and `zero_grad` is one memset.
+`deep_supervision_l1` is the loss of train.py:63-69 (mean over decoder layers of L1Loss) as one fused forward+backward
+kernel."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import lib
+from .ops import _stream_ptr
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        params = [p for p in params]
+        if not params:
+            raise ValueError("FlatAdam got an empty parameter list")
+        if any((not p.is_cuda) or p.dtype != torch.float32 for p in params):
+            raise TypeError("FlatAdam expects CUDA float32 parameters (no CPU fallback)")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        dev = params[0].device
+        pad = lambda n: (n + 63) // 64 * 64         # every parameter starts 256-byte aligned (TMA / float4 consumers)
+        total = sum(pad(p.numel()) for p in params)
+        self._flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._views = []
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                self._flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self._flat[off:off + n].view(p.shape)          # the module keeps its Parameter objects
+                self._views.append((p, self._grad[off:off + n].view(p.shape)))
+                off += pad(n)
+        self._step = 0
+        self._attach()
+
+    def _attach(self):
+        for p, g in self._views:
+            if p.grad is not g:
+                if p.grad is not None:
+                    g.copy_(p.grad)            # a gradient that arrived while .grad was detached
+                p.grad = g
+
+    def zero_grad(self, set_to_none: bool = False):
+        self._grad.zero_()
+        self._attach()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self._attach()
+        g = self.param_groups[0]
+        self._step += 1
+        dev = self._flat.device
+        with torch.cuda.device(dev):
+            _lib.check(lib.lrn_adam_step(self._flat.data_ptr(), self._grad.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
+                                         self._flat.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                         float(g["eps"]), float(g["weight_decay"]), self._step, _stream_ptr(dev)), "lrn_adam_step")
+        _lib.launch_counter += 1
+        # the kernel wrote through raw pointers: tell autograd / the weight-folding caches (data_ptr + _version
+        # fingerprints in model.py) that every parameter changed
+        torch.autograd.graph.increment_version([p for p, _ in self._views])
+        return loss
+
+
+class _DeepSupervisionL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        L = pred.shape[0]
+        pred_c, tgt_c = pred.detach().float().contiguous(), target.detach().float().contiguous()
+        n = tgt_c.numel()
+        if pred_c.numel() != L * n:
+            raise ValueError(f"pred {tuple(pred.shape)} is not (L, *target.shape) for target {tuple(target.shape)}")
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        dpred = torch.empty_like(pred_c)
+        with torch.cuda.device(pred.device):
+            _lib.check(lib.lrn_l1_deep_supervision(pred_c.data_ptr(), tgt_c.data_ptr(), L, n, loss.data_ptr(), dpred.data_ptr(),
+                                                   _stream_ptr(pred.device)), "lrn_l1_deep_supervision")
+        _lib.launch_counter += 1
+        ctx.save_for_backward(dpred)
+        ctx.pred_dtype = pred.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dpred,) = ctx.saved_tensors
+        return (dpred * dloss).to(ctx.pred_dtype), None
+
+
+def deep_supervision_l1(pred_stack: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """sum_l L1Loss(pred_stack[l], target) / L for pred_stack (L, B, M, 3), target (B, M, 3) (train.py:63-69)."""
+    if not pred_stack.is_cuda:
+        raise TypeError("deep_supervision_l1 expects CUDA tensors (no CPU fallback)")
+    return _DeepSupervisionL1.apply(pred_stack, target)

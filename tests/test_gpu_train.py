@@ -194,3 +194,63 @@ def test_train_fast_decoder_close_to_stock(dev, B):
         a, b = res[True][1][n].flatten().double(), res[False][1][n].flatten().double()
         cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
         assert cos >= 0.9, (n, cos)
+
+
+def test_flat_adam_and_fused_l1_match_torch(dev):
+    """FlatAdam (one lrn_adam_step launch over a flat buffer) and deep_supervision_l1 against torch.optim.Adam and the
+    reference's loss loop (train.py:40,63-72) over several steps of the same small model."""
+    import copy
+    import pointnet_refine_b200 as prb
+    from pointnet_refine_b200.optim import FlatAdam, deep_supervision_l1
+    torch.manual_seed(0)
+    net_a = torch.nn.Sequential(torch.nn.Linear(96, 64), torch.nn.ReLU(), torch.nn.Linear(64, 6 * 96)).to(dev)
+    net_b = copy.deepcopy(net_a)
+    opt_a = FlatAdam(net_a.parameters(), lr=1e-3, weight_decay=1e-2)
+    opt_b = torch.optim.Adam(net_b.parameters(), lr=1e-3, weight_decay=1e-2)
+    x = torch.randn(16, 96, device=dev)
+    tgt = torch.randn(16, 32, 3, device=dev)
+    for it in range(5):
+        losses = []
+        for net, opt, fused in ((net_a, opt_a, True), (net_b, opt_b, False)):
+            opt.zero_grad()
+            pred = net(x).view(16, 6, 32, 3).permute(1, 0, 2, 3)                       # (L, B, M, 3)
+            if fused:
+                loss = deep_supervision_l1(pred, tgt)
+            else:
+                loss = sum(torch.nn.functional.l1_loss(pred[l], tgt) for l in range(6)) / 6
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[1]), (it, losses)
+    for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+        assert float((pa - pb).detach().abs().max()) <= 2e-6, float((pa - pb).detach().abs().max())
+        assert pa._version > 0
+
+
+def test_flat_adam_trains_line_refine_net(dev):
+    """train.py loop body with FlatAdam + the fused loss on the native train path; eval afterwards re-folds the updated
+    weights (the optimizer bumps the parameters' version counters)."""
+    import pointnet_refine_b200 as prb
+    from pointnet_refine_b200.optim import FlatAdam, deep_supervision_l1
+    torch.manual_seed(0)
+    m = prb.LineRefineNet().to(dev).train()
+    opt = FlatAdam(m.parameters(), lr=1e-3)
+    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(8, 512, seed=5))
+    tgt = 0.1 * torch.randn(8, 32, 3, device=dev)
+    m.eval()
+    with torch.no_grad():
+        before = m(ctx, line).clone()
+    m.train()
+    losses = []
+    for _ in range(10):
+        opt.zero_grad()
+        loss = deep_supervision_l1(m(ctx, line), tgt)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < losses[0]
+    assert len(m.state_dict()) == 205                                        # same checkpoint interface
+    m.eval()
+    with torch.no_grad():
+        after = m(ctx, line)
+    assert torch.isfinite(after).all() and float((after - before).abs().max()) > 1e-4
