@@ -206,7 +206,7 @@ int lrn_encoder_train_backward(const lrn_encoder_params* params, const float* co
 /* ---- building block, exported for unit tests and profiling ----
  * out[M,N] = act(A[M,K] * W[N,K]^T + bias) on the tcgen05 tensor-core path.
  *   precision BF16: A, W bfloat16, out bfloat16 (out_f32 = 0) or fp32 (out_f32 = 1)
- *   precision TF32: A, W fp32,     out fp32
+ *   precision TF32: A, W fp32,     out fp32 (out_f32 = 1) or bfloat16 (out_f32 = 0)
  * lda/ldw/ldo in elements; K % 64 == 0 (bf16) or K % 32 == 0 (tf32); N % 128 == 0. */
 int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                       void* out, int64_t ldo, int out_f32, int relu, int64_t M, int64_t N, int64_t K,
@@ -257,6 +257,20 @@ int lrn_scene_segments(const float* scene, int64_t S, const double* dense200, co
                        int L, int N, double crop_radius, double decay_scale, double coord_extent, uint64_t seed, int64_t capacity,
                        float* context, int64_t* indices, int32_t* counts, int64_t* status, void* workspace, size_t workspace_bytes,
                        lrn_stream_t stream);
+
+/* ---- query side of the decoder (DetrTransformerDecoderLayer.forward, src/model.py:104-135) ----
+ * out = LayerNorm(x + y) * gamma + beta over rows of 256 (norm1 / norm2 / norm3 with their residual adds, :117,:129,:134);
+ * y may be NULL; cols must be 256 (d_model). */
+int lrn_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, float eps, float* out,
+                      int64_t rows, int64_t cols, lrn_stream_t stream);
+/* Self attention over the 32 polyline points of each of B segments, 8 heads x 32 (self_attn, src/model.py:113-117, eval):
+ * qk (B*32, 512) fp32 = [q | k] in-projections, v (B*32, 256) -> out (B*32, 256) heads concatenated (before out_proj). */
+int lrn_self_attention32(const float* qk, const float* v, float* out, int B, lrn_stream_t stream);
+/* Second layer of reg_branches[i] + the cumulative-offset update (src/model.py:220,227-231) for `rows` polyline points:
+ * delta = hidden (rows,128) W2^T + b2; current += delta (in place); cum = current - noisy.  (lrn_head_forward does both
+ * layers in one latency-oriented kernel; for thousands of rows layer 1 runs as a tensor-core GEMM and this finishes.) */
+int lrn_head_update(const float* hidden, const float* w2, const float* b2, int64_t rows, float* current, const float* noisy,
+                    float* cum, lrn_stream_t stream);
 
 /* ---- training-loop machinery ----
  * One Adam step over a flat fp32 buffer holding every parameter (train.py:40 optim.Adam(model.parameters(), lr);

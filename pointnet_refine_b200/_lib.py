@@ -27,6 +27,7 @@ EXPORTS = [
     "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
     "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden",
     "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_adam_step", "lrn_l1_deep_supervision",
+    "lrn_add_layernorm", "lrn_self_attention32", "lrn_head_update",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
 
@@ -82,6 +83,12 @@ def _load():
     lib.lrn_scene_segments.restype = ci
     lib.lrn_scene_segments.argtypes = [vp, i64, vp, vp, vp, ci, ci, C.c_double, C.c_double, C.c_double, C.c_uint64, i64,
                                        vp, vp, vp, vp, vp, sz, vp]
+    lib.lrn_add_layernorm.restype = ci
+    lib.lrn_add_layernorm.argtypes = [vp, vp, vp, vp, C.c_float, vp, i64, i64, vp]
+    lib.lrn_self_attention32.restype = ci
+    lib.lrn_self_attention32.argtypes = [vp, vp, vp, ci, vp]
+    lib.lrn_head_update.restype = ci
+    lib.lrn_head_update.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     lib.lrn_adam_step.restype = ci
     lib.lrn_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]
     lib.lrn_l1_deep_supervision.restype = ci

@@ -406,7 +406,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.npts] = v[j];
             }
             if ((p.flags & FUSE_STORE_PM) && valid)
-              store_row_chunk<TF32>(p.fused_pm, static_cast<long long>(row) * 1024 + ch0, v, false, TF32);
+              store_row_chunk<TF32>(p.fused_pm, static_cast<long long>(row) * 1024 + ch0, v, TF32, TF32);
             if (p.flags & (FUSE_POOL | FUSE_ARGMAX)) {
               if (!GENERAL || (uniform && !(p.flags & FUSE_ARGMAX))) {
                 float mx, sm;

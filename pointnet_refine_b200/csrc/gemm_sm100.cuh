@@ -133,7 +133,7 @@ __device__ __forceinline__ void pool_chunk(const float (&v)[32], bool mask, long
 template <bool TF32>
 __device__ __forceinline__ void store_row_chunk(void* out, long long elem_off, const float (&v)[32], bool as_f32,
                                                 bool rna_tf32) {
-  if (TF32 || as_f32) {
+  if (as_f32) {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + elem_off);
     if (rna_tf32) {
 #pragma unroll
@@ -326,7 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.npts] = v[j];
           }
           if ((p.flags & FUSE_STORE_PM) && valid)
-            store_row_chunk<TF32>(p.fused_pm, static_cast<long long>(row) * 1024 + ch0, v, false, TF32);
+            store_row_chunk<TF32>(p.fused_pm, static_cast<long long>(row) * 1024 + ch0, v, TF32, TF32);
           if (p.flags & (FUSE_POOL | FUSE_ARGMAX)) {
             if (uniform) {
               pool_chunk(v, true, seg_lo, n_in_seg, ch0, lane, p);

@@ -21,6 +21,7 @@
 #include "ts_probe.cuh"
 #include "ctx_attn_sm100.cuh"
 #include "scene_kernels.cuh"
+#include "query_kernels.cuh"
 #include "pointwise.cuh"
 
 namespace {
@@ -887,7 +888,6 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt,
   const int bk = int(128 / es);
   if (M <= 0 || N <= 0 || K <= 0 || K % bk || N % 128 || M >= (int64_t(1) << 31))
     return fail(LRN_ERR_BAD_SHAPE, "M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
-  if (precision == LRN_PREC_TF32 && !out_f32) return fail(LRN_ERR_BAD_ARG, "tf32 tier writes fp32");
   DeviceInfo dev;
   int st = device_info(&dev);
   if (st) return st;
@@ -1237,6 +1237,52 @@ int lrn_l1_deep_supervision(const float* pred, const float* target, int L, int64
   LRN_CUDA(cudaMemsetAsync(loss, 0, 4, s));
   const int grid = int(std::min<int64_t>((int64_t(L) * n + 255) / 256, int64_t(dev.sms) * 4));
   l1_deep_supervision_kernel<<<grid, 256, 0, s>>>(pred, target, L, n, loss, dpred);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, float eps, float* out,
+                      int64_t rows, int64_t cols, lrn_stream_t stream) {
+  if (!x || !gamma || !beta || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (rows <= 0 || cols != 256) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld cols=%lld (d_model = 256)", (long long)rows, (long long)cols);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out) |
+       reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15)
+    return fail(LRN_ERR_MISALIGNED, "16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const int grid = int(std::min<int64_t>((rows + 7) / 8, int64_t(dev.sms) * 8));
+  add_layernorm256_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, gamma, beta, eps, out, rows);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_self_attention32(const float* qk, const float* v, float* out, int B, lrn_stream_t stream) {
+  if (!qk || !v || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (B <= 0) return fail(LRN_ERR_BAD_SHAPE, "B=%d", B);
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  static bool configured = false;
+  if (!configured) {
+    LRN_CUDA(cudaFuncSetAttribute(self_attn32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelfAttnSmem));
+    configured = true;
+  }
+  self_attn32_kernel<<<std::min(B, dev.sms * 2), 256, kSelfAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(qk, v, out, B);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_head_update(const float* hidden, const float* w2, const float* b2, int64_t rows, float* current, const float* noisy,
+                    float* cum, lrn_stream_t stream) {
+  if (!hidden || !w2 || !b2 || !current || !noisy || !cum) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (rows <= 0) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld", (long long)rows);
+  if ((reinterpret_cast<uintptr_t>(hidden) | reinterpret_cast<uintptr_t>(w2)) & 15) return fail(LRN_ERR_MISALIGNED, "hidden / w2 need 16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const int grid = int(std::min<int64_t>((rows + 7) / 8, int64_t(dev.sms) * 8));
+  head_update_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hidden, w2, b2, rows, current, noisy, cum);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

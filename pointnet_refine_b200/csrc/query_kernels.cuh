@@ -1,0 +1,132 @@
+// Query side of the decoder: the small per-polyline-point operations between the tensor-core
+// linears of DetrTransformerDecoderLayer.forward (reference src/model.py:104-135), each as one HBM-bound kernel:
+// residual add + LayerNorm, the 32 x 32 self attention of one segment's polyline points (8 heads x 32), and the second
+// layer of a regression head with the cumulative-offset update (src/model.py:220,227-231).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lrn {
+
+// out[r, :] = LayerNorm(x[r, :] + y[r, :]) * gamma + beta over 256 columns (norm1/2/3, eps 1e-5, biased variance).
+// One warp per row; lane l holds columns [4l, 4l+4) and [128+4l, 128+4l+4).  y may be null.
+__global__ void __launch_bounds__(256)
+add_layernorm256_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, float* __restrict__ out, long long rows) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float4 g0 = reinterpret_cast<const float4*>(gamma)[lane], g1 = reinterpret_cast<const float4*>(gamma)[32 + lane];
+  const float4 b0 = reinterpret_cast<const float4*>(beta)[lane], b1 = reinterpret_cast<const float4*>(beta)[32 + lane];
+  for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + r * 256);
+    float4 a = xr[lane], b = xr[32 + lane];
+    if (y) {
+      const float4* yr = reinterpret_cast<const float4*>(y + r * 256);
+      const float4 c = yr[lane], d = yr[32 + lane];
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+    float s = (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / 256.f);
+    a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
+    b.x -= mean; b.y -= mean; b.z -= mean; b.w -= mean;
+    float q = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w) + (b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / 256.f) + eps);
+    float4* orow = reinterpret_cast<float4*>(out + r * 256);
+    orow[lane] = make_float4(a.x * rstd * g0.x + b0.x, a.y * rstd * g0.y + b0.y, a.z * rstd * g0.z + b0.z, a.w * rstd * g0.w + b0.w);
+    orow[32 + lane] = make_float4(b.x * rstd * g1.x + b1.x, b.y * rstd * g1.y + b1.y, b.z * rstd * g1.z + b1.z, b.w * rstd * g1.w + b1.w);
+  }
+}
+
+// Self attention over the 32 polyline points of one segment, 8 heads of 32 channels (nn.MultiheadAttention self_attn in
+// eval mode, src/model.py:113-117): qk (B*32, 512) = [q | k] projections, v (B*32, 256) -> out (B*32, 256), heads
+// concatenated.  One block per segment, warp = head, lane = query; K / V of the head in shared memory (broadcast reads).
+constexpr int kSelfAttnSmem = 8 * 3 * 32 * 33 * 4;
+__global__ void __launch_bounds__(256)
+self_attn32_kernel(const float* __restrict__ qk, const float* __restrict__ v, float* __restrict__ out, int B) {
+  extern __shared__ float sm[];
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qs = sm + h * 3 * 32 * 33;
+  float* ks = qs + 32 * 33;
+  float* vs = ks + 32 * 33;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const long long row0 = static_cast<long long>(b) * 32;
+    __syncwarp();
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {  // coalesced 128-byte rows
+      qs[j * 33 + lane] = qk[(row0 + j) * 512 + h * 32 + lane];
+      ks[j * 33 + lane] = qk[(row0 + j) * 512 + 256 + h * 32 + lane];
+      vs[j * 33 + lane] = v[(row0 + j) * 256 + h * 32 + lane];
+    }
+    __syncwarp();
+    float q[32], s[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) q[c] = qs[lane * 33 + c] * 0.17677669529663688f;  // 1 / sqrt(32)
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc = fmaf(q[c], ks[j * 33 + c], acc);
+      s[j] = acc;
+      m = fmaxf(m, acc);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      s[j] = expf(s[j] - m);
+      l += s[j];
+    }
+    const float inv = 1.f / l;
+    float o[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float pj = s[j] * inv;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o[c] = fmaf(pj, vs[j * 33 + c], o[c]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) qs[lane * 33 + c] = o[c];  // stage through shared memory for coalesced rows
+    __syncwarp();
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) out[(row0 + j) * 256 + h * 32 + lane] = qs[j * 33 + lane];
+  }
+}
+
+// Second layer of a regression head + cumulative-offset bookkeeping (src/model.py:220,227-231):
+//   delta = hidden[r, :] W2^T + b2 (128 -> 3);  current[r] += delta;  cum[r] = current[r] - noisy[r].  One warp per row.
+__global__ void __launch_bounds__(256)
+head_update_kernel(const float* __restrict__ hidden, const float* __restrict__ w2 /* (3,128) */, const float* __restrict__ b2,
+                   long long rows, float* __restrict__ current, const float* __restrict__ noisy, float* __restrict__ cum) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float4 wx = reinterpret_cast<const float4*>(w2)[lane], wy = reinterpret_cast<const float4*>(w2 + 128)[lane],
+               wz = reinterpret_cast<const float4*>(w2 + 256)[lane];
+  for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const float4 hv = reinterpret_cast<const float4*>(hidden + r * 128)[lane];
+    float dx = hv.x * wx.x + hv.y * wx.y + hv.z * wx.z + hv.w * wx.w;
+    float dy = hv.x * wy.x + hv.y * wy.y + hv.z * wy.z + hv.w * wy.w;
+    float dz = hv.x * wz.x + hv.y * wz.y + hv.z * wz.z + hv.w * wz.w;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      dx += __shfl_xor_sync(0xffffffffu, dx, o);
+      dy += __shfl_xor_sync(0xffffffffu, dy, o);
+      dz += __shfl_xor_sync(0xffffffffu, dz, o);
+    }
+    if (lane < 3) {
+      const float d = (lane == 0 ? dx : lane == 1 ? dy : dz) + b2[lane];
+      const float c = current[r * 3 + lane] + d;
+      current[r * 3 + lane] = c;
+      cum[r * 3 + lane] = c - noisy[r * 3 + lane];
+    }
+  }
+}
+
+}  // namespace lrn

@@ -312,30 +312,43 @@ class LineRefineNet(nn.Module):
         mem = memx[:, :, :d]
         rows = B * noisy_line.shape[1]
 
-        def lin(x, w, b, relu=False):   # (B,32,K) fp32 -> (B,32,N) fp32
+        def lin(x, w, b, relu=False, out_dtype=None):   # (B,32,K) fp32 -> (B,32,N) fp32 (or out_dtype)
             if rows < 256:
                 y = F.linear(x, w, b)
-                return F.relu(y) if relu else y
-            return ops.gemm_bias_act(x.reshape(rows, -1), w.detach(), b.detach(), relu=relu).view(B, -1, w.shape[0])
+                y = F.relu(y) if relu else y
+                return y if out_dtype is None else y.to(out_dtype)
+            return ops.gemm_bias_act(x.reshape(rows, -1), w.detach(), b.detach(), relu=relu, out_dtype=out_dtype).view(B, -1, w.shape[0])
 
         pe0, pe2 = self.pos_emb.mlp[0], self.pos_emb.mlp[2]
         tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
         current = noisy_line.clone()
         outs = []
+        big = rows >= 256     # thousands of rows: every step below is one native kernel; else latency-oriented stock ops
         for layer, head, (wqk, bqk, wvo, bvo) in zip(self.decoder_layers, self.reg_branches, layers_w):
             qpos = lin(F.relu(pe0(current)), pe2.weight, pe2.bias)
             q = tgt + qpos
             sa = layer.self_attn
-            qk = lin(q, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d]).view(B, -1, 2, H, d // H)
-            v = lin(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:]).view(B, -1, H, d // H)
-            att = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
-            tgt = layer.norm1(tgt + lin(att.transpose(1, 2).reshape(B, -1, d), sa.out_proj.weight, sa.out_proj.bias))
+            qk = lin(q, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d])
+            v = lin(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:])
+            if big:
+                att = ops.self_attention32(qk, v)
+                tgt = ops.add_layernorm(tgt, lin(att, sa.out_proj.weight, sa.out_proj.bias), layer.norm1)
+            else:
+                qk5 = qk.view(B, -1, 2, H, d // H)
+                att = F.scaled_dot_product_attention(qk5[:, :, 0].transpose(1, 2), qk5[:, :, 1].transpose(1, 2),
+                                                     v.view(B, -1, H, d // H).transpose(1, 2))
+                tgt = layer.norm1(tgt + lin(att.transpose(1, 2).reshape(B, -1, d), sa.out_proj.weight, sa.out_proj.bias))
             # folded queries: row q * 8 + h of the segment's 256 (any row order works, rows are independent)
-            qf = lin(tgt + qpos, wqk, bqk).bfloat16().view(B, H * 32, d)
+            qf = lin(tgt + qpos, wqk, bqk, out_dtype=torch.bfloat16).view(B, H * 32, d)   # tf32 accumulate, rounded once
             o = ops.ctx_attention(qf, kp, mem).view(B, 32, H * d)
-            tgt = layer.norm2(tgt + lin(o, wvo, bvo))
-            tgt = layer.norm3(tgt + lin(lin(tgt, layer.linear1.weight, layer.linear1.bias, relu=True), layer.linear2.weight, layer.linear2.bias))
-            outs.append(ops.head_forward(head[0].weight, head[0].bias, head[2].weight, head[2].bias, tgt, current, noisy_line))
+            ffn_in = ops.add_layernorm(tgt, lin(o, wvo, bvo), layer.norm2) if big else layer.norm2(tgt + lin(o, wvo, bvo))
+            ffn = lin(lin(ffn_in, layer.linear1.weight, layer.linear1.bias, relu=True), layer.linear2.weight, layer.linear2.bias)
+            tgt = ops.add_layernorm(ffn_in, ffn, layer.norm3) if big else layer.norm3(ffn_in + ffn)
+            if big:
+                hid = lin(tgt, head[0].weight, head[0].bias, relu=True)
+                outs.append(ops.head_update(hid, head[2].weight, head[2].bias, current, noisy_line))
+            else:
+                outs.append(ops.head_forward(head[0].weight, head[0].bias, head[2].weight, head[2].bias, tgt, current, noisy_line))
         return torch.stack(outs)
 
     def _refine_fast_train(self, context, noisy_line, fused_pm):
@@ -403,7 +416,12 @@ class LineRefineNet(nn.Module):
             return self._refine(context, noisy_line, memory, native_heads=False)
         fast = self.precision == "bf16" and self.fast_decoder
         N = context.shape[1]
-        chunk = max(1, min(self.segment_chunk, (1 << 20) // max(N, 1))) if fast else self.segment_chunk
+        if fast and self.ctx_attention and noisy_line.shape[1] == 32:
+            # ~1M context points per pass, up to 2048 segments: the query-side GEMMs (32 rows per segment) need
+            # thousands of rows to fill the 74 CTA pairs, and no (B,N,1536) K / V temporaries exist on this path
+            chunk = max(1, min(8 * self.segment_chunk, (1 << 20) // max(N, 1)))
+        else:
+            chunk = max(1, min(self.segment_chunk, (1 << 20) // max(N, 1))) if fast else self.segment_chunk
         outs = []
         for s in range(0, context.shape[0], chunk):
             ctx = context[s:s + chunk].contiguous()

@@ -246,6 +246,48 @@ def pos_hidden(w1: torch.Tensor, b1: torch.Tensor, context: torch.Tensor, out: t
     return out
 
 
+def add_layernorm(x: torch.Tensor, y, norm: torch.nn.LayerNorm) -> torch.Tensor:
+    """norm(x + y) for fp32 (..., 256) tensors in one kernel (lrn_add_layernorm); y may be None."""
+    x = _f32c(x)
+    y = _f32c(y) if y is not None else None
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lrn_add_layernorm(x.data_ptr(), y.data_ptr() if y is not None else None, _f32c(norm.weight.detach()).data_ptr(),
+                                         _f32c(norm.bias.detach()).data_ptr(), float(norm.eps), out.data_ptr(),
+                                         x.numel() // x.shape[-1], x.shape[-1], _stream_ptr(x.device)), "lrn_add_layernorm")
+    _lib.launch_counter += 1
+    return out
+
+
+def self_attention32(qk: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """Softmax attention among the 32 polyline points of every segment, 8 heads x 32 (lrn_self_attention32):
+    qk (B, 32, 512) = [q | k] projections, v (B, 32, 256) -> (B, 32, 256), heads concatenated."""
+    qk, v = _f32c(qk), _f32c(v)
+    B = qk.shape[0]
+    if tuple(qk.shape) != (B, 32, 512) or tuple(v.shape) != (B, 32, 256):
+        raise ValueError(f"self_attention32 shapes {tuple(qk.shape)}, {tuple(v.shape)}")
+    out = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        _lib.check(lib.lrn_self_attention32(qk.data_ptr(), v.data_ptr(), out.data_ptr(), B, _stream_ptr(v.device)),
+                   "lrn_self_attention32")
+    _lib.launch_counter += 1
+    return out
+
+
+def head_update(hidden: torch.Tensor, w2, b2, current: torch.Tensor, noisy: torch.Tensor) -> torch.Tensor:
+    """Second head layer + cumulative-offset update (lrn_head_update): `current` (B,M,3) is updated in place; returns the
+    cumulative offset (B,M,3)."""
+    hidden = _f32c(hidden)
+    rows = hidden.numel() // 128
+    cum = torch.empty_like(current)
+    with torch.cuda.device(hidden.device):
+        _lib.check(lib.lrn_head_update(hidden.data_ptr(), _f32c(w2.detach()).data_ptr(), _f32c(b2.detach()).data_ptr(), rows,
+                                       current.data_ptr(), _f32c(noisy).data_ptr(), cum.data_ptr(), _stream_ptr(hidden.device)),
+                   "lrn_head_update")
+    _lib.launch_counter += 1
+    return cum
+
+
 def point_embed(folded: FoldedEncoder, context: torch.Tensor) -> torch.Tensor:
     """Stand-alone first layer (+ gate layer 1): context (P, 4) or (B, N, 4) fp32 -> operand rows (P, 2048) in the
     tier's operand type with columns [0,64) and [1984,2048) written (the rest is left uninitialised)."""

@@ -184,6 +184,34 @@ def test_pos_hidden_and_bf16_memory(dev):
         assert torch.equal(memx[:, :, :256], mem32.bfloat16())          # the memory half is left alone
 
 
+def test_query_side_kernels_match_torch(dev):
+    """add + LayerNorm, the 32 x 32 self attention and the head update against the stock modules."""
+    import torch.nn.functional as F
+    from pointnet_refine_b200 import ops
+    gen = torch.Generator(device=dev).manual_seed(3)
+    r = lambda *s: torch.randn(*s, device=dev, generator=gen)
+    for B in (1, 7, 300):
+        x, y = r(B, 32, 256) * 3 + 1, r(B, 32, 256)
+        ln = torch.nn.LayerNorm(256).to(dev)
+        with torch.no_grad():
+            ln.weight.copy_(r(256)); ln.bias.copy_(r(256))
+            assert float((ops.add_layernorm(x, y, ln) - ln(x + y)).abs().max()) <= 2e-5
+            assert float((ops.add_layernorm(x, None, ln) - ln(x)).abs().max()) <= 2e-5
+            mha = torch.nn.MultiheadAttention(256, 8, batch_first=True).to(dev).eval()
+            q_in, v_in = r(B, 32, 256), r(B, 32, 256)
+            ref = mha(q_in, q_in, value=v_in, need_weights=False)[0]
+            W, bias = mha.in_proj_weight, mha.in_proj_bias
+            qk = F.linear(q_in, W[:512], bias[:512])
+            v = F.linear(v_in, W[512:], bias[512:])
+            got = mha.out_proj(ops.self_attention32(qk, v))
+            assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+            hid, w2, b2 = r(B * 32, 128), r(3, 128), r(3)
+            cur, noisy = r(B, 32, 3), r(B, 32, 3)
+            want = cur + (hid.double() @ w2.double().T + b2.double()).view(B, 32, 3).float()
+            cum = ops.head_update(hid, w2, b2, cur, noisy)
+            assert float((cur - want).abs().max()) <= 1e-4 and float((cum - (want - noisy)).abs().max()) <= 1e-4
+
+
 @pytest.mark.parametrize("B,N", [(9, 300), (16, 1024)])
 def test_full_forward_batched_vs_live_oracle(dev, B, N):
     """B * 32 >= 256 query rows: the query-side linears take the tcgen05 tf32 GEMM (smaller batches use F.linear)."""
