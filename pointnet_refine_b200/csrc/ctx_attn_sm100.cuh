@@ -15,8 +15,10 @@
 //   O += P Mem         tcgen05.mma with P (bf16) as the A operand in TENSOR MEMORY, Mem as an MN-major smem operand
 //
 // Per layer the only HBM traffic is Kp = memory + pos and Mem = memory (bf16, 1 KB per point) plus 256 KB of output per
-// segment.  One cluster of two CTAs per (segment, split); a segment can be split over several clusters (few segments),
-// the host merges the partial results with their log-sum-exp.
+// segment.  Work item = (segment, split): a segment can be split over several items (few segments), the host merges the
+// partial results with their log-sum-exp.  The kernel is persistent - one cluster of two CTAs per SM pair loops over the
+// items with one running step counter for all pipeline barriers, so the next item's folded queries and first point tiles
+// load, and its first S products run, while the softmax warps still write the previous item's output.
 #pragma once
 #include "ptx.cuh"
 #include "chain_pair_sm100.cuh"  // tc_mma_ts_pair
@@ -37,6 +39,7 @@ struct AttnSmem {
 };
 
 struct AttnParams {
+  int items;      // work items = segments * splits
   int N;          // points per segment
   int splits;     // clusters per segment
   int steps_per_split;
@@ -72,13 +75,13 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
-  const int item = blockIdx.x >> 1;
-  const int seg = item / p.splits;
-  const int split = item - seg * p.splits;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
   const int total_steps = (p.N + kAttnStep - 1) / kAttnStep;
-  const int step0 = split * p.steps_per_split;
-  const int steps = min(p.steps_per_split, total_steps - step0);  // >= 1 by construction of `splits`
-  const int64_t seg_row0 = static_cast<int64_t>(seg) * p.N;
+  // item -> (segment, first step, number of steps); every role walks the same item sequence
+  auto item_seg = [&](int item) { return item / p.splits; };
+  auto item_step0 = [&](int item) { return (item % p.splits) * p.steps_per_split; };
+  auto item_steps = [&](int item) { return min(p.steps_per_split, total_steps - item_step0(item)); };  // >= 1 by construction
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
@@ -105,36 +108,43 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       const uint32_t q_leader = ptx::mapa(ptx::smem_u32(q_full), 0);
-      if (leader) ptx::mbar_arrive_expect_tx(q_full, 2 * 65536);
-      for (int kb = 0; kb < 4; ++kb)
-        ptx::tma_load_2d_pair(smem + L::kQ + kb * 16384, &tmQ, q_leader, kb * 64, seg * 256 + static_cast<int>(rank) * 128);
-      for (int j = 0; j < steps; ++j) {
-        const int st = j & 1;
-        const uint32_t prev = ((j - 2) >> 1) & 1;  // parity of the phase that step j - 2 completed
-        const int row = static_cast<int>(seg_row0) + (step0 + j) * kAttnStep;
-        // Kp: this CTA's 64 points of the step (the B operand of S is split by points across the pair)
-        if (j >= 2) ptx::mbar_wait(&s_full[st], prev);
-        const uint32_t kp_leader = ptx::mapa(ptx::smem_u32(&kp_full[st]), 0);
-        if (leader) ptx::mbar_arrive_expect_tx(&kp_full[st], 2 * 32768);
+      int g = 0;  // running step counter over all items of this cluster: stage = g & 1, phase = (g >> 1) & 1
+      for (int item = cluster_id; item < p.items; item += num_clusters) {
+        const int seg = item_seg(item), step0 = item_step0(item), steps = item_steps(item);
+        const int64_t seg_row0 = static_cast<int64_t>(seg) * p.N;
+        // the previous item's last S product has finished reading the folded queries
+        if (g >= 1) ptx::mbar_wait(&s_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+        if (leader) ptx::mbar_arrive_expect_tx(q_full, 2 * 65536);
         for (int kb = 0; kb < 4; ++kb)
-          ptx::tma_load_2d_pair(smem + L::kKp + st * 32768 + kb * 8192, &tmKp, kp_leader, kb * 64, row + static_cast<int>(rank) * 64);
-        // Mem: all 128 points, this CTA's 128 of the 256 output dims (the B operand of O is split by dims)
-        if (j >= 2) ptx::mbar_wait(&o_done[st], prev);
-        const uint32_t v_leader = ptx::mapa(ptx::smem_u32(&v_full[st]), 0);
-        if (leader) ptx::mbar_arrive_expect_tx(&v_full[st], 2 * 32768);
-        for (int pb = 0; pb < 2; ++pb)
-          for (int db = 0; db < 2; ++db)
-            ptx::tma_load_2d_pair(smem + L::kV + st * 32768 + pb * 16384 + db * 8192, &tmV, v_leader,
-                                  static_cast<int>(rank) * 128 + db * 64, row + pb * 64);
+          ptx::tma_load_2d_pair(smem + L::kQ + kb * 16384, &tmQ, q_leader, kb * 64, seg * 256 + static_cast<int>(rank) * 128);
+        for (int j = 0; j < steps; ++j, ++g) {
+          const int st = g & 1;
+          const uint32_t prev = ((g - 2) >> 1) & 1;  // parity of the phase that step g - 2 completed
+          const int row = static_cast<int>(seg_row0) + (step0 + j) * kAttnStep;
+          // Kp: this CTA's 64 points of the step (the B operand of S is split by points across the pair)
+          if (g >= 2) ptx::mbar_wait(&s_full[st], prev);
+          const uint32_t kp_leader = ptx::mapa(ptx::smem_u32(&kp_full[st]), 0);
+          if (leader) ptx::mbar_arrive_expect_tx(&kp_full[st], 2 * 32768);
+          for (int kb = 0; kb < 4; ++kb)
+            ptx::tma_load_2d_pair(smem + L::kKp + st * 32768 + kb * 8192, &tmKp, kp_leader, kb * 64, row + static_cast<int>(rank) * 64);
+          // Mem: all 128 points, this CTA's 128 of the 256 output dims (the B operand of O is split by dims)
+          if (g >= 2) ptx::mbar_wait(&o_done[st], prev);
+          const uint32_t v_leader = ptx::mapa(ptx::smem_u32(&v_full[st]), 0);
+          if (leader) ptx::mbar_arrive_expect_tx(&v_full[st], 2 * 32768);
+          for (int pb = 0; pb < 2; ++pb)
+            for (int db = 0; db < 2; ++db)
+              ptx::tma_load_2d_pair(smem + L::kV + st * 32768 + pb * 16384 + db * 8192, &tmV, v_leader,
+                                    static_cast<int>(rank) * 128 + db * 64, row + pb * 64);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA)
     if (leader) {
-      auto issue_s = [&](int j) {  // S_j = Qf Kp_j^T -> S buffer j & 1
-        const int st = j & 1;
-        ptx::mbar_wait(&kp_full[st], (j >> 1) & 1);
+      auto issue_s = [&](int g) {  // S = Qf Kp^T of running step g -> S buffer g & 1
+        const int st = g & 1;
+        ptx::mbar_wait(&kp_full[st], (g >> 1) & 1);
         ptx::tc_fence_after();
         if (lane == 0) {
           const uint32_t d = tmem_base + st * 128;
@@ -149,27 +159,33 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         __syncwarp();
       };
-      ptx::mbar_wait(q_full, 0);
-      issue_s(0);
-      if (steps > 1) issue_s(1);
-      for (int j = 0; j < steps; ++j) {
-        const int st = j & 1;
-        const uint32_t par = (j >> 1) & 1;
-        ptx::mbar_wait(&p_ready[st], par);
-        ptx::mbar_wait(&v_full[st], par);
-        ptx::tc_fence_after();
-        if (lane == 0) {  // O += P_j Mem_j : A = P_j in the first 64 columns of S buffer st (2 points per column)
+      int g0 = 0, it = 0;
+      for (int item = cluster_id; item < p.items; item += num_clusters, ++it) {
+        const int steps = item_steps(item);
+        ptx::mbar_wait(q_full, it & 1);
+        issue_s(g0);
+        if (steps > 1) issue_s(g0 + 1);
+        for (int j = 0; j < steps; ++j) {
+          const int g = g0 + j, st = g & 1;
+          const uint32_t par = (g >> 1) & 1;
+          // P_j written by the softmax warps of both CTAs (for j = 0 this also says: the previous item's O was read out)
+          ptx::mbar_wait(&p_ready[st], par);
+          ptx::mbar_wait(&v_full[st], par);
+          ptx::tc_fence_after();
+          if (lane == 0) {  // O += P_j Mem_j : A = P_j in the first 64 columns of S buffer st (2 points per column)
 #pragma unroll
-          for (int pb = 0; pb < 2; ++pb) {
-            const uint64_t db = ptx::make_smem_desc_sw128_mn(ptx::smem_u32(smem + L::kV + st * 32768 + pb * 16384), 8192);
+            for (int pb = 0; pb < 2; ++pb) {
+              const uint64_t db = ptx::make_smem_desc_sw128_mn(ptx::smem_u32(smem + L::kV + st * 32768 + pb * 16384), 8192);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_ts_pair(tmem_o, tmem_base + st * 128 + pb * 32 + k * 8, db + 128 * k, kIdescO, (j | pb | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                tc_mma_ts_pair(tmem_o, tmem_base + st * 128 + pb * 32 + k * 8, db + 128 * k, kIdescO, (j | pb | k) ? 1u : 0u);
+            }
+            ptx::tc_commit_pair(&o_done[st], 3);
           }
-          ptx::tc_commit_pair(&o_done[st], 3);
+          __syncwarp();
+          if (j + 2 < steps) issue_s(g + 2);  // in order behind O_j on the tensor pipe, which is still reading P_j
         }
-        __syncwarp();
-        if (j + 2 < steps) issue_s(j + 2);  // in order behind O_j on the tensor pipe, which is still reading P_j
+        g0 += steps;
       }
     }
   } else {
@@ -177,12 +193,16 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t ready_leader[2] = {ptx::mapa(ptx::smem_u32(&p_ready[0]), 0), ptx::mapa(ptx::smem_u32(&p_ready[1]), 0)};
+    int g0 = 0;
+    for (int item = cluster_id; item < p.items; item += num_clusters) {
+    const int step0 = item_step0(item), steps = item_steps(item);
     float m_ref = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < steps; ++j) {
-      const int st = j & 1;
+      const int g = g0 + j;
+      const int st = g & 1;
       const uint32_t t_s = t_lane + st * 128;
       const int valid = min(kAttnStep, p.N - (step0 + j) * kAttnStep);
-      ptx::mbar_wait(&s_full[st], (j >> 1) & 1);
+      ptx::mbar_wait(&s_full[st], (g >> 1) & 1);
       ptx::tc_fence_after();
       // pass 1: maximum of this row over the step's points
       float m_t = -INFINITY;
@@ -207,7 +227,7 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         m_ref = m_t;
       } else if (__any_sync(0xffffffffu, grow)) {
         const float f = grow ? ex2_approx(m_ref - m_t) : 1.f;
-        ptx::mbar_wait(&o_done[st ^ 1], ((j - 1) >> 1) & 1);  // O_{j-1} has been accumulated
+        ptx::mbar_wait(&o_done[st ^ 1], ((g - 1) >> 1) & 1);  // O_{j-1} has been accumulated
         ptx::tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
@@ -252,7 +272,7 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     // ---- epilogue: O / l -> global (through a per-warp transpose so that rows are written 128 B at a time)
     {
-      const int last = steps - 1;
+      const int last = g0 + steps - 1;
       ptx::mbar_wait(&o_done[last & 1], (last >> 1) & 1);
       ptx::tc_fence_after();
       const float inv = 1.f / l_sum;
@@ -272,6 +292,8 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       p.lse[out_row0 + lane] = m_ref + log2f(l_sum);
     }
+    g0 += steps;
+    }  // items
   }
   ptx::tc_fence_before();
   ptx::cluster_sync();

@@ -677,6 +677,7 @@ int lrn_ctx_attention(const void* qfold, const void* kp, int64_t ld_kp, const vo
   if ((st = make_tmap(&tk, LRN_PREC_BF16, kp, int64_t(B) * N, 256, ld_kp, 64))) return st;
   if ((st = make_tmap_mn(&tv, mem, int64_t(B) * N, 256, ld_mem))) return st;
   AttnParams p{};
+  p.items = B * splits;
   p.N = N;
   p.splits = splits;
   p.steps_per_split = per;
@@ -687,7 +688,8 @@ int lrn_ctx_attention(const void* qfold, const void* kp, int64_t ld_kp, const vo
     LRN_CUDA(cudaFuncSetAttribute(ctx_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kDynamic));
     configured = true;
   }
-  ctx_attn_kernel<<<2 * B * splits, kAttnThreads, AttnSmem::kDynamic, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  const int clusters = std::min(B * splits, dev.sms / 2);  // persistent: one cluster per SM pair walks the items
+  ctx_attn_kernel<<<2 * clusters, kAttnThreads, AttnSmem::kDynamic, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
