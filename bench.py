@@ -271,8 +271,8 @@ def main():
             fm = (time.perf_counter() - t0) / 3
             full_model = {"segments_per_sec": fb / fm, "ms_per_forward": fm * 1e3, "segments": fb, "points_per_segment": N,
                           "note": "LineRefineNet.forward -> (6,B,32,3); encoder, context_proj, folded-query cross attention "
-                                  "(K/V never materialised), query-side linears and heads on the sm_100a kernels; 32x32 self "
-                                  "attention, LayerNorms and adds in stock PyTorch ops"}
+                                  "(K/V never materialised), query side (linears, 32x32 self attention, add+LayerNorm, heads) on "
+                                  "the sm_100a kernels; point_mlp and the K=3 pos_emb layer are stock PyTorch ops"}
 
     if rank != 0:
         if world > 1:
