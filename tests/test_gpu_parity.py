@@ -311,6 +311,31 @@ def test_errors_are_loud(dev):
     assert st == 1                                                   # empty input -> LRN_ERR_BAD_SHAPE
     with pytest.raises(TypeError):
         ops.gemm_bias_act(torch.zeros(8, 64, device=dev), torch.zeros(128, 64, device=dev).bfloat16(), None)
+    # decoder context side / scene front end: wrong types, shapes and parameters are refused, not worked around
+    bf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(TypeError):
+        ops.ctx_attention(torch.zeros(1, 256, 256, device=dev), bf(1, 64, 256), bf(1, 64, 256))
+    with pytest.raises(ValueError):
+        ops.ctx_attention(bf(1, 128, 256), bf(1, 64, 256), bf(1, 64, 256))
+    with pytest.raises(RuntimeError):
+        ops.ctx_attention(bf(1, 256, 256), bf(1, 64, 256), bf(1, 64, 256), splits=5)          # more splits than point tiles
+    with pytest.raises(RuntimeError):
+        m.precision = "tf32"
+        try:
+            m.context_encoder.run_native(torch.zeros(1, 16, 4, device=dev), pool=False, memory=True, memory_bf16=True)
+        finally:
+            m.precision = "bf16"
+    from pointnet_refine_b200 import scene as sc
+    pts = torch.zeros(100, 4, device=dev)
+    line = [[0.0, 0.0, 0.0], [1.0, 0.0, 0.0]]
+    with pytest.raises(TypeError):
+        sc.build_segments(pts.cpu(), [line])
+    with pytest.raises(ValueError):
+        sc.build_segments(pts, [])
+    with pytest.raises(RuntimeError):
+        sc.build_segments(pts, [line], num_context_points=5000)                                  # N <= 4096
+    with pytest.raises(RuntimeError):
+        sc.build_segments(pts, [line], crop_radius=100.0, decay_scale=1.0)                       # weights would underflow
 
 
 def test_refold_after_parameter_update(dev):

@@ -99,3 +99,18 @@ def test_sharded_run_equals_unsharded_gloo_world2():
     ctx, _ = synth.make_inputs(B, 64, seed=99)
     want = orc.encoder_forward(synth.make_state_dict(0), ctx)[0]
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+
+
+def test_scene_host_resampling_equals_oracle():
+    """The product's polyline resampling (host side of scene.build_segments) and the pinned oracle agree bit for bit."""
+    import numpy as np
+    from oracle import scene_oracle as so
+    from pointnet_refine_b200 import scene as sc
+    rs = np.random.default_rng(0)
+    for i in range(300):
+        nv = int(rs.integers(1, 30))
+        pts = np.cumsum(rs.normal(0, 3, (nv, 3)), axis=0) + rs.normal(0, 100, 3)
+        if i % 5 == 0 and nv > 3:
+            pts[nv // 2] = pts[nv // 2 - 1]                  # a zero-length segment
+        for n in (32, 200):
+            np.testing.assert_array_equal(sc.resample_polyline(pts, n), so.resample_polyline(pts, n))
