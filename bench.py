@@ -128,7 +128,7 @@ def main():
                 f"per GPU (BASELINE.json configs[1])")
     config = {"workload": workload, "segments_per_gpu": args.segments, "points_per_segment": args.points,
               "tier": args.precision, "parallelism": f"dp{world} (independent segment shards, no collective)",
-              "l2": "input batch (268 MB/GPU at the default size) and per-wave operand buffer (310 MB) exceed the 126 MB L2"}
+              "l2": "input batch (268 MB/GPU at the default size) and per-wave operand buffer (1.24 GB) exceed the 126 MB L2"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":

@@ -9,7 +9,7 @@ import torch
 from . import _lib
 from ._lib import OUT_ARGMAX, OUT_FUSED, OUT_MEMORY, OUT_MEMORY_BF16, OUT_POOL, PRECISIONS, lib
 
-DEFAULT_CHUNK_ROWS = 148 * 128 * 4   # keep in sync with kDefaultChunkRows (csrc/lrn_abi.cu)
+DEFAULT_CHUNK_ROWS = 148 * 128 * 16   # keep in sync with kDefaultChunkRows (csrc/lrn_abi.cu)
 
 
 def _stream_ptr(device) -> int:
