@@ -252,6 +252,12 @@ int lrn_pos_hidden(const float* w1, const float* b1, const float* context, int64
  * The draw follows the RNG contract documented in oracle/scene_oracle.py (counter-based hash of seed, line, scene index;
  * Efraimidis-Spirakis keys; samples in descending key order): same distribution as the reference's
  * np.random.choice(replace=False, p), reproducible and independent of thread order.  N <= 4096, L <= 65535. */
+/* resample_polyline (src/dataset.py:8-30) of L polylines to 32 and to 200 points on the device, bit-equal to the numpy
+ * formulation: vertices (total, 3) f64 = all polylines back to back, offsets (L+1) int64 = first vertex of each line;
+ * outputs line32 (L,32,3), dense200 (L,200,3), centers (L,3) f64 and noisy_centered (L,32,3) fp32 = line32 - center
+ * (src/dataset.py:232-237).  A polyline with fewer than two vertices gives zeros; at most 2048 vertices per line. */
+int lrn_scene_resample(const double* vertices, const int64_t* offsets, int L, int max_vertices, double* line32, double* dense200,
+                       double* centers, float* noisy_centered, lrn_stream_t stream);
 size_t lrn_scene_workspace_bytes(int L, int64_t capacity);
 int lrn_scene_segments(const float* scene, int64_t S, const double* dense200, const double* line32, const double* centers,
                        int L, int N, double crop_radius, double decay_scale, double coord_extent, uint64_t seed, int64_t capacity,

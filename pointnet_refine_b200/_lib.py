@@ -26,7 +26,7 @@ EXPORTS = [
     "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe", "lrn_train_workspace_bytes",
     "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
     "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden",
-    "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_adam_step", "lrn_l1_deep_supervision",
+    "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_scene_resample", "lrn_adam_step", "lrn_l1_deep_supervision",
     "lrn_add_layernorm", "lrn_self_attention32", "lrn_head_update",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
@@ -78,6 +78,8 @@ def _load():
     lib.lrn_ctx_attention_splits.argtypes = [ci, ci]
     lib.lrn_ctx_attention.restype = ci
     lib.lrn_ctx_attention.argtypes = [vp, vp, i64, vp, i64, ci, ci, ci, vp, vp, vp]
+    lib.lrn_scene_resample.restype = ci
+    lib.lrn_scene_resample.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.lrn_scene_workspace_bytes.restype = sz
     lib.lrn_scene_workspace_bytes.argtypes = [ci, i64]
     lib.lrn_scene_segments.restype = ci

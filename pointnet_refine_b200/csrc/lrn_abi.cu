@@ -739,6 +739,20 @@ int scene_cap(int N) {
 }
 }  // namespace
 
+int lrn_scene_resample(const double* vertices, const int64_t* offsets, int L, int max_vertices, double* line32, double* dense200,
+                       double* centers, float* noisy_centered, lrn_stream_t stream) {
+  if (!vertices || !offsets || !line32 || !dense200 || !centers || !noisy_centered) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (L <= 0 || max_vertices < 0 || max_vertices > scene::kMaxVertices)
+    return fail(LRN_ERR_BAD_SHAPE, "L=%d, longest polyline %d vertices (limit %d)", L, max_vertices, scene::kMaxVertices);
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  scene::resample_kernel<<<L, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(vertices, reinterpret_cast<const long long*>(offsets), L,
+                                                                                line32, dense200, centers, noisy_centered);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
 size_t lrn_scene_workspace_bytes(int L, int64_t capacity) {
   if (L <= 0 || capacity <= 0) return 0;
   return scene_layout(L, capacity).total;

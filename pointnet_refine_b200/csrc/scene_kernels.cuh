@@ -76,6 +76,82 @@ __device__ __forceinline__ double dist2_exact(double px, double py, double pz, c
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
+// ------------------------------------------------------------------------------------------------ polyline resampling
+// resample_polyline (src/dataset.py:8-30) for every line to 32 and to 200 points, the centroid of the 32 (src/dataset.py:
+// 232) and the centred line - the same IEEE double operations in the same order as numpy (norm = sqrt((dx^2+dy^2)+dz^2),
+// sequential cumsum, linspace = i * (total / (n-1)) with the last point pinned, np.interp = slope * (t - x_j) + f_j with
+// the exact-hit and right-edge rules), so the results are bit-equal to the host formulation.  One block per line.
+constexpr int kMaxVertices = 2048;
+__global__ void __launch_bounds__(256)
+resample_kernel(const double* __restrict__ verts, const long long* __restrict__ offsets, int L, double* __restrict__ line32,
+                double* __restrict__ dense, double* __restrict__ centers, float* __restrict__ noisy_centered) {
+  __shared__ double cum[kMaxVertices];
+  __shared__ double l32[kLine * 3];
+  __shared__ double ctr[3];
+  const int l = blockIdx.x;
+  if (l >= L) return;
+  const double* v = verts + offsets[l] * 3;
+  const int n = static_cast<int>(offsets[l + 1] - offsets[l]);
+  if (threadIdx.x == 0 && n >= 2) {
+    double c = 0.0;
+    cum[0] = 0.0;
+    for (int i = 1; i < n; ++i) {
+      const double dx = __dsub_rn(v[3 * i], v[3 * i - 3]), dy = __dsub_rn(v[3 * i + 1], v[3 * i - 2]), dz = __dsub_rn(v[3 * i + 2], v[3 * i - 1]);
+      const double seg = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+      c = i == 1 ? seg : __dadd_rn(c, seg);
+      cum[i] = c;
+    }
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < kLine + kDense) {
+    const int num = t < kLine ? kLine : kDense;
+    const int i = t < kLine ? t : t - kLine;
+    double out[3] = {0.0, 0.0, 0.0};
+    if (n >= 2) {
+      const double total = cum[n - 1];
+      const double step = __ddiv_rn(total, static_cast<double>(num - 1));
+      double x = step == 0.0 ? __dmul_rn(__ddiv_rn(static_cast<double>(i), static_cast<double>(num - 1)), total)
+                             : __dmul_rn(static_cast<double>(i), step);
+      if (i == num - 1) x = total;
+      // j = last vertex with cum[j] <= x
+      int lo = 0, hi = n - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (cum[mid] <= x) lo = mid; else hi = mid - 1;
+      }
+      const int j = lo;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (j >= n - 1) {
+          out[k] = v[3 * (n - 1) + k];
+        } else if (cum[j] == x) {
+          out[k] = v[3 * j + k];
+        } else {
+          const double slope = __ddiv_rn(__dsub_rn(v[3 * j + 3 + k], v[3 * j + k]), __dsub_rn(cum[j + 1], cum[j]));
+          out[k] = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, cum[j])), v[3 * j + k]);
+        }
+      }
+    }
+    double* dst = t < kLine ? line32 + (static_cast<size_t>(l) * kLine + i) * 3 : dense + (static_cast<size_t>(l) * kDense + i) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dst[k] = out[k];
+      if (t < kLine) l32[3 * i + k] = out[k];
+    }
+  }
+  __syncthreads();
+  if (t < 3) {
+    double s = l32[t];
+    for (int i = 1; i < kLine; ++i) s = __dadd_rn(s, l32[3 * i + t]);
+    s = __ddiv_rn(s, static_cast<double>(kLine));
+    ctr[t] = s;
+    centers[l * 3 + t] = s;
+  }
+  __syncthreads();
+  if (t < kLine * 3) noisy_centered[static_cast<size_t>(l) * kLine * 3 + t] = static_cast<float>(__dsub_rn(l32[t], ctr[t % 3]));
+}
+
 // ------------------------------------------------------------------------------------------------ per-line setup
 // Bounding boxes (whole polyline and its kSub pieces) grown by (radius + eps), fp32 copy of the points, counters reset.
 // A scene point within the radius of some polyline point lies inside that point's piece box, so testing only the

@@ -6,8 +6,8 @@ line, distance query for every scene point, crop, weighted sampling, centroid no
 `build_segments` does the crop / sampling / normalisation for all lines of a scene in one pass on the device
 (`lrn_scene_segments`, csrc/scene_kernels.cuh) and `refine_scene` runs the lines of a scene as one batch.
 
-Only the polyline resampling stays on the host (a few hundred points per line, float64 like the reference).  The draw
-follows the reproducible RNG contract documented in include/lrn_b200.h (the reference uses the global unseeded
+The polyline resampling runs on the device too (`lrn_scene_resample`, bit-equal to the numpy formulation; the host
+`resample_polyline` below is kept for callers and tests).  The draw follows the reproducible RNG contract documented in include/lrn_b200.h (the reference uses the global unseeded
 np.random stream): same sampling distribution, fixed by (seed, line number, scene index).
 """
 from __future__ import annotations
@@ -52,13 +52,25 @@ def build_segments(scene: torch.Tensor, raw_lines: Sequence, num_context_points:
     S, L, N = scene.shape[0], len(raw_lines), int(num_context_points)
     if S == 0 or L == 0:
         raise ValueError("empty scene or no lines")
-    line32 = np.stack([resample_polyline(r, 32) for r in raw_lines])
-    dense = np.stack([resample_polyline(r, 200) for r in raw_lines])
-    centers = line32.mean(axis=1)
     dev = scene.device
-    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    d_dense, d_line, d_cent = up(dense), up(line32), up(centers)
-    extent = float(max(np.abs(dense).max(), float(scene[:, :3].abs().max())))
+    # polylines back to back -> one upload; resampling, centroids and the centred lines happen on the device
+    arrs = [np.asarray(r, dtype=np.float64).reshape(-1, 3) for r in raw_lines]
+    lens = np.fromiter((a.shape[0] for a in arrs), dtype=np.int64, count=L)
+    offsets = np.zeros(L + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    verts = np.concatenate(arrs) if offsets[-1] > 0 else np.zeros((1, 3))
+    extent_lines = float(np.abs(verts).max())
+    d_verts, d_off = torch.from_numpy(verts).to(dev), torch.from_numpy(offsets).to(dev)
+    d_line = torch.empty(L, 32, 3, dtype=torch.float64, device=dev)
+    d_dense = torch.empty(L, 200, 3, dtype=torch.float64, device=dev)
+    d_cent = torch.empty(L, 3, dtype=torch.float64, device=dev)
+    noisy = torch.empty(L, 32, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lrn_scene_resample(d_verts.data_ptr(), d_off.data_ptr(), L, int(lens.max()), d_line.data_ptr(),
+                                          d_dense.data_ptr(), d_cent.data_ptr(), noisy.data_ptr(), _stream_ptr(dev)),
+                   "lrn_scene_resample")
+    _lib.launch_counter += 1
+    extent = float(max(extent_lines, float(scene[:, :3].abs().max())))
     context = torch.empty(L, N, 4, dtype=torch.float32, device=dev)
     indices = torch.empty(L, N, dtype=torch.int64, device=dev)
     counts = torch.empty(L, dtype=torch.int32, device=dev)
@@ -80,8 +92,7 @@ def build_segments(scene: torch.Tensor, raw_lines: Sequence, num_context_points:
         cap = total                                                # candidate buffer was too small: exact size now
     else:
         raise RuntimeError("lrn_scene_segments: candidate buffer overflow after resizing")
-    noisy = torch.from_numpy((line32 - centers[:, None, :]).astype(np.float32)).to(dev)
-    return SceneSegments(context, noisy, centers, line32, indices, counts)
+    return SceneSegments(context, noisy, d_cent.cpu().numpy(), d_line.cpu().numpy(), indices, counts)
 
 
 @torch.no_grad()

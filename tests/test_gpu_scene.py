@@ -22,6 +22,7 @@ def _check_against_oracle(scene, lines, seg, N, r, decay, seed):
         o_ctx, o_noisy, o_center, o_idx, o_count = so.build_segment(scene, raw, N, r, decay, seed, l)
         assert cnt[l] == o_count, (l, cnt[l], o_count)
         np.testing.assert_array_equal(seg.centers[l], o_center)
+        np.testing.assert_array_equal(seg.line32[l], so.resample_polyline(raw, 32))      # device resampling == numpy
         np.testing.assert_array_equal(idx[l], o_idx, err_msg=f"line {l}")
         np.testing.assert_array_equal(ctx[l].view(np.uint32), o_ctx.view(np.uint32), err_msg=f"line {l}")
         np.testing.assert_array_equal(noisy[l], o_noisy)
@@ -94,3 +95,28 @@ def test_refine_scene_runs_lines_as_one_batch(dev):
     with torch.no_grad():
         one = m(seg.context[3:4], seg.noisy_line[3:4])[-1][0].double().cpu().numpy()      # B = 1, like the reference loop
     np.testing.assert_allclose(refined[3], seg.line32[3] + one, atol=5e-2)
+
+
+def test_device_resampling_is_bit_equal_to_numpy(dev):
+    """lrn_scene_resample against the reference formulation (np.interp / linspace / cumsum) on awkward polylines:
+    single vertex, repeated vertices, float32-valued vertices, long lines."""
+    from pointnet_refine_b200 import scene as sc
+    rs = np.random.default_rng(3)
+    lines = []
+    for i in range(200):
+        nv = int(rs.integers(1, 60)) if i % 17 else 1500
+        pts = np.cumsum(rs.normal(0, 2, (nv, 3)), axis=0) + rs.normal(0, 200, 3)
+        if i % 5 == 0 and nv > 3:
+            pts[nv // 2] = pts[nv // 2 - 1]
+        if i % 7 == 0:
+            pts = pts.astype(np.float32).astype(np.float64)
+        if i % 13 == 0 and nv > 1:
+            pts[:] = pts[0]                                        # zero total length
+        lines.append(pts)
+    scene = torch.zeros(64, 4, device=dev)
+    seg = sc.build_segments(scene, lines, 16, 0.5, 2.0, seed=0)
+    for l, raw in enumerate(lines):
+        p32 = so.resample_polyline(raw, 32)
+        np.testing.assert_array_equal(seg.line32[l], p32, err_msg=f"line {l} ({len(raw)} vertices)")
+        np.testing.assert_array_equal(seg.centers[l], p32.mean(axis=0))
+        np.testing.assert_array_equal(seg.noisy_line[l].cpu().numpy(), (p32 - p32.mean(axis=0)).astype(np.float32))

@@ -53,7 +53,7 @@ with torch.no_grad():
             m(seg.context[l:l + 1], seg.noisy_line[l:l + 1])[-1].cpu()
     t_loop = dev_time(loop, n=2) / min(L, 32)
 print(json.dumps({"scene_points": S, "lines": L, "N": N, "crop_radius": r, "candidates": cand,
-                  "build_segments_ms": round(t_build * 1e3, 2), "of_which_host_resampling_ms": round(t_resample * 1e3, 2), "ms_per_line": round(t_build * 1e3 / L, 4),
+                  "build_segments_ms": round(t_build * 1e3, 2), "numpy_resampling_of_all_lines_ms": round(t_resample * 1e3, 2), "ms_per_line": round(t_build * 1e3 / L, 4),
                   "scene_points_x_lines_per_s": round(S * L / t_build, 1),
                   "host_oracle_ms_per_line": round(t_oracle * 1e3, 1), "host_kdtree_ms_per_line": None if t_kd is None else round(t_kd * 1e3, 1),
                   "refine_scene_ms": round(t_refine * 1e3, 2), "b1_forward_loop_ms_per_line": round(t_loop * 1e3, 3),
