@@ -248,6 +248,9 @@ int lrn_pos_hidden(const float* w1, const float* b1, const float* context, int64
  *   counts    (L) int32 out: points inside the tube (distance to the 200-point polyline < crop_radius, float64 compare)
  *   status    (2) int64 out: [0] total candidates, [1] bit 0: `capacity` < [0] -> nothing was sampled, call again with
  *             capacity >= status[0]; bit 1: more than 2^k - N candidates tie exactly at a line's threshold key
+ *   scene_sorted / perm: optional (both or neither): the same points in a spatially coherent order (e.g. Morton order of
+ *             x, y) with perm[i] = scene index of scene_sorted[i]; the crop then walks this copy, so that the 32 points of a
+ *             warp are neighbours and only enter the tests of the lines that pass near them.  Results are identical.
  *   coord_extent: largest |coordinate| of the scene (sizes the band in which the fp32 pre-filter defers to float64)
  * The draw follows the RNG contract documented in oracle/scene_oracle.py (counter-based hash of seed, line, scene index;
  * Efraimidis-Spirakis keys; samples in descending key order): same distribution as the reference's
@@ -259,7 +262,7 @@ int lrn_pos_hidden(const float* w1, const float* b1, const float* context, int64
 int lrn_scene_resample(const double* vertices, const int64_t* offsets, int L, int max_vertices, double* line32, double* dense200,
                        double* centers, float* noisy_centered, lrn_stream_t stream);
 size_t lrn_scene_workspace_bytes(int L, int64_t capacity);
-int lrn_scene_segments(const float* scene, int64_t S, const double* dense200, const double* line32, const double* centers,
+int lrn_scene_segments(const float* scene, int64_t S, const float* scene_sorted, const int32_t* perm, const double* dense200, const double* line32, const double* centers,
                        int L, int N, double crop_radius, double decay_scale, double coord_extent, uint64_t seed, int64_t capacity,
                        float* context, int64_t* indices, int32_t* counts, int64_t* status, void* workspace, size_t workspace_bytes,
                        lrn_stream_t stream);

@@ -83,7 +83,7 @@ def _load():
     lib.lrn_scene_workspace_bytes.restype = sz
     lib.lrn_scene_workspace_bytes.argtypes = [ci, i64]
     lib.lrn_scene_segments.restype = ci
-    lib.lrn_scene_segments.argtypes = [vp, i64, vp, vp, vp, ci, ci, C.c_double, C.c_double, C.c_double, C.c_uint64, i64,
+    lib.lrn_scene_segments.argtypes = [vp, i64, vp, vp, vp, vp, vp, ci, ci, C.c_double, C.c_double, C.c_double, C.c_uint64, i64,
                                        vp, vp, vp, vp, vp, sz, vp]
     lib.lrn_add_layernorm.restype = ci
     lib.lrn_add_layernorm.argtypes = [vp, vp, vp, vp, C.c_float, vp, i64, i64, vp]

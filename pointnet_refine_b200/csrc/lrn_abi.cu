@@ -758,7 +758,7 @@ size_t lrn_scene_workspace_bytes(int L, int64_t capacity) {
   return scene_layout(L, capacity).total;
 }
 
-int lrn_scene_segments(const float* scene_pts, int64_t S, const double* dense200, const double* line32, const double* centers,
+int lrn_scene_segments(const float* scene_pts, int64_t S, const float* scene_sorted, const int32_t* perm, const double* dense200, const double* line32, const double* centers,
                        int L, int N, double crop_radius, double decay_scale, double coord_extent, uint64_t seed, int64_t capacity,
                        float* context, int64_t* indices, int32_t* counts, int64_t* status, void* workspace, size_t workspace_bytes,
                        lrn_stream_t stream) {
@@ -794,16 +794,19 @@ int lrn_scene_segments(const float* scene_pts, int64_t S, const double* dense200
   const double rlo = std::max(crop_radius - eps, 0.0), rhi = crop_radius + eps;
   const float r2_lo = float(rlo * rlo * (1.0 - 1e-6)), r2_hi = float(rhi * rhi * (1.0 + 1e-6));
   const float4* pts = reinterpret_cast<const float4*>(scene_pts);
+  if ((scene_sorted != nullptr) != (perm != nullptr)) return fail(LRN_ERR_BAD_ARG, "scene_sorted and perm come together");
+  if (reinterpret_cast<uintptr_t>(scene_sorted) & 15) return fail(LRN_ERR_MISALIGNED, "scene_sorted needs 16-byte alignment");
+  const float4* crop_pts = scene_sorted ? reinterpret_cast<const float4*>(scene_sorted) : pts;
   scene::prep_kernel<<<L, 128, 0, s>>>(dense200, L, float(rhi * (1.0 + 1e-6)), aabb, dense_f, count, fill, imin, imax);
   LRN_CUDA(cudaGetLastError());
   const int grid = int((S + 255) / 256);
-  scene::tube_crop_kernel<false><<<grid, 256, 0, s>>>(pts, S, L, aabb, dense_f, dense200, crop_radius, r2_lo, r2_hi, count, imin, imax,
-                                                      fill, offset, capacity, cand);
+  scene::tube_crop_kernel<false><<<grid, 256, 0, s>>>(crop_pts, S, L, aabb, dense_f, dense200, crop_radius, r2_lo, r2_hi, count, imin,
+                                                      imax, fill, offset, capacity, perm, cand);
   LRN_CUDA(cudaGetLastError());
   scene::scan_kernel<<<1, 1024, 0, s>>>(count, L, capacity, offset, stat);
   LRN_CUDA(cudaGetLastError());
-  scene::tube_crop_kernel<true><<<grid, 256, 0, s>>>(pts, S, L, aabb, dense_f, dense200, crop_radius, r2_lo, r2_hi, count, imin, imax,
-                                                     fill, offset, capacity, cand);
+  scene::tube_crop_kernel<true><<<grid, 256, 0, s>>>(crop_pts, S, L, aabb, dense_f, dense200, crop_radius, r2_lo, r2_hi, count, imin,
+                                                     imax, fill, offset, capacity, perm, cand);
   LRN_CUDA(cudaGetLastError());
   scene::sample_keys_kernel<<<dim3(32, L), 256, 0, s>>>(pts, line32, count, offset, imin, imax, N, decay_scale, seed, stat, cand, keys);
   LRN_CUDA(cudaGetLastError());

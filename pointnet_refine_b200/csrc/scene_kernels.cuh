@@ -197,6 +197,9 @@ __global__ void prep_kernel(const double* __restrict__ dense, int L, float grow,
 }
 
 // ------------------------------------------------------------------------------------------------ tube crop
+// `pts` may be the scene in any order (`perm[i]` = scene index of pts[i], or null for the identity): in a spatially sorted
+// order (Morton, scene.prepare_scene) the 32 points of a warp are neighbours, so a warp only enters the piece tests of
+// the few lines that actually pass near it instead of diverging on most lines.
 // One thread per scene point, all lines: box tests (line, then pieces), fp32 minimum distance to the points of the
 // pieces whose box contains it, and the exact double evaluation only inside the band where fp32 cannot decide
 // `distance < radius`.
@@ -207,7 +210,8 @@ __global__ void __launch_bounds__(256) tube_crop_kernel(const float4* __restrict
                                                         const double* __restrict__ dense, double radius, float r2_lo, float r2_hi,
                                                         int* __restrict__ count, int* __restrict__ imin, int* __restrict__ imax,
                                                         int* __restrict__ fill, const long long* __restrict__ offset,
-                                                        long long capacity, uint32_t* __restrict__ cand) {
+                                                        long long capacity, const int* __restrict__ perm,
+                                                        uint32_t* __restrict__ cand) {
   __shared__ float box[kLineTile * 6];
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(256) tube_crop_kernel(const float4* __restrict
         atomicMax(&imax[l], o);
       } else {
         const long long pos = offset[l] + atomicAdd(&fill[l], 1);
-        if (pos < capacity) cand[pos] = static_cast<uint32_t>(i);
+        if (pos < capacity) cand[pos] = perm ? static_cast<uint32_t>(perm[i]) : static_cast<uint32_t>(i);
       }
     }
   }

@@ -33,6 +33,36 @@ def resample_polyline(points, num_points: int = 32) -> np.ndarray:
     return np.column_stack([np.interp(at, arc, pts[:, k]) for k in range(3)])
 
 
+class PreparedScene(NamedTuple):
+    """A scene plus a spatially sorted copy (Morton order of x, y): prepare once, crop many line sets."""
+    points: torch.Tensor          # (S, 4) fp32 CUDA, caller's order (what `indices` refer to)
+    sorted_points: torch.Tensor   # (S, 4) the same points in Morton order
+    perm: torch.Tensor            # (S,) int32: sorted_points[i] = points[perm[i]]
+    extent: float                 # largest |coordinate|
+
+
+def prepare_scene(scene: torch.Tensor, sort: bool = True) -> PreparedScene:
+    if not scene.is_cuda or scene.dtype != torch.float32 or scene.dim() != 2 or scene.shape[1] != 4:
+        raise TypeError("scene must be a CUDA float32 (S, 4) tensor")
+    scene = scene.contiguous()
+    if scene.shape[0] == 0:
+        raise ValueError("empty scene")
+    extent = float(scene[:, :3].abs().max())
+    if not sort:
+        return PreparedScene(scene, None, None, extent)
+    xy = scene[:, :2]
+    lo, hi = xy.min(dim=0).values, xy.max(dim=0).values
+    q = ((xy - lo) / (hi - lo).clamp_min(1e-6) * 65535.0).to(torch.int64).clamp_(0, 65535)
+
+    def spread(v):   # 16 bits -> every other bit of 32
+        v = (v | (v << 8)) & 0x00FF00FF
+        v = (v | (v << 4)) & 0x0F0F0F0F
+        v = (v | (v << 2)) & 0x33333333
+        return (v | (v << 1)) & 0x55555555
+    perm = torch.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << 1))
+    return PreparedScene(scene, scene[perm].contiguous(), perm.to(torch.int32), extent)
+
+
 class SceneSegments(NamedTuple):
     context: torch.Tensor      # (L, N, 4) fp32 CUDA: sampled points, xyz centred on the line, intensity
     noisy_line: torch.Tensor   # (L, 32, 3) fp32 CUDA: the resampled line, centred
@@ -42,16 +72,16 @@ class SceneSegments(NamedTuple):
     counts: torch.Tensor       # (L,) int32 CUDA: scene points inside each tube
 
 
-def build_segments(scene: torch.Tensor, raw_lines: Sequence, num_context_points: int = 1024, crop_radius: float = 0.3,
+def build_segments(scene, raw_lines: Sequence, num_context_points: int = 1024, crop_radius: float = 0.3,
                    decay_scale: float = 2.0, seed: int = 0, capacity: int | None = None) -> SceneSegments:
-    """scene (S, 4) fp32 CUDA [x, y, z, intensity]; raw_lines: polylines (n_i, 3) in scene coordinates.  Defaults are
-    inference_whole_scene.py's (:21-22, weighted_sampling's decay_scale); LaneRefineDataset uses 2048 / 4.0 / 2.0."""
-    if not scene.is_cuda or scene.dtype != torch.float32 or scene.dim() != 2 or scene.shape[1] != 4:
-        raise TypeError("scene must be a CUDA float32 (S, 4) tensor")
-    scene = scene.contiguous()
+    """scene (S, 4) fp32 CUDA [x, y, z, intensity] or a PreparedScene (several line sets over one scene: sort it once);
+    raw_lines: polylines (n_i, 3) in scene coordinates.  Defaults are inference_whole_scene.py's (:21-22,
+    weighted_sampling's decay_scale); LaneRefineDataset uses 2048 / 4.0 / 2.0."""
+    prepared = scene if isinstance(scene, PreparedScene) else prepare_scene(scene)
+    scene = prepared.points
     S, L, N = scene.shape[0], len(raw_lines), int(num_context_points)
-    if S == 0 or L == 0:
-        raise ValueError("empty scene or no lines")
+    if L == 0:
+        raise ValueError("no lines")
     dev = scene.device
     # polylines back to back -> one upload; resampling, centroids and the centred lines happen on the device
     arrs = [np.asarray(r, dtype=np.float64).reshape(-1, 3) for r in raw_lines]
@@ -70,7 +100,7 @@ def build_segments(scene: torch.Tensor, raw_lines: Sequence, num_context_points:
                                           d_dense.data_ptr(), d_cent.data_ptr(), noisy.data_ptr(), _stream_ptr(dev)),
                    "lrn_scene_resample")
     _lib.launch_counter += 1
-    extent = float(max(extent_lines, float(scene[:, :3].abs().max())))
+    extent = max(extent_lines, prepared.extent)
     context = torch.empty(L, N, 4, dtype=torch.float32, device=dev)
     indices = torch.empty(L, N, dtype=torch.int64, device=dev)
     counts = torch.empty(L, dtype=torch.int32, device=dev)
@@ -79,7 +109,10 @@ def build_segments(scene: torch.Tensor, raw_lines: Sequence, num_context_points:
     for _ in range(2):
         ws = _aligned_bytes(lib.lrn_scene_workspace_bytes(L, cap), dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.lrn_scene_segments(scene.data_ptr(), S, d_dense.data_ptr(), d_line.data_ptr(), d_cent.data_ptr(), L, N,
+            _lib.check(lib.lrn_scene_segments(scene.data_ptr(), S,
+                                              prepared.sorted_points.data_ptr() if prepared.perm is not None else None,
+                                              prepared.perm.data_ptr() if prepared.perm is not None else None,
+                                              d_dense.data_ptr(), d_line.data_ptr(), d_cent.data_ptr(), L, N,
                                               float(crop_radius), float(decay_scale), extent, int(seed) & (2 ** 64 - 1), cap,
                                               context.data_ptr(), indices.data_ptr(), counts.data_ptr(), status.data_ptr(),
                                               ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "lrn_scene_segments")
@@ -96,7 +129,7 @@ def build_segments(scene: torch.Tensor, raw_lines: Sequence, num_context_points:
 
 
 @torch.no_grad()
-def refine_scene(model, scene: torch.Tensor, raw_lines: Sequence, num_context_points: int = 1024, crop_radius: float = 0.3,
+def refine_scene(model, scene, raw_lines: Sequence, num_context_points: int = 1024, crop_radius: float = 0.3,
                  decay_scale: float = 2.0, seed: int = 0) -> np.ndarray:
     """All lines of a scene through the model in one batch: (L, 32, 3) float64 refined polylines in scene coordinates
     = resampled line + last decoder layer's cumulative offset (inference_whole_scene.py:137-147)."""

@@ -43,6 +43,20 @@ def test_segments_match_oracle_bit_for_bit(dev, S, L, N, r):
         assert ((cnt[:-1] > 0) & (cnt[:-1] <= N)).any()                       # ... and the with-replacement branch
 
 
+def test_sorted_and_unsorted_scene_give_identical_segments(dev):
+    """The Morton-sorted copy only changes the order in which the crop visits the points."""
+    from pointnet_refine_b200 import scene as sc
+    scene, lines = so.synth_scene(150_000, 8, seed=21)
+    d_scene = torch.from_numpy(scene).to(dev)
+    prep = sc.prepare_scene(d_scene)
+    assert torch.equal(prep.sorted_points, d_scene[prep.perm.long()])
+    a = sc.build_segments(prep, lines, 512, 1.5, 2.0, seed=9)
+    b = sc.build_segments(sc.prepare_scene(d_scene, sort=False), lines, 512, 1.5, 2.0, seed=9)
+    c = sc.build_segments(d_scene, lines, 512, 1.5, 2.0, seed=9)
+    for x in (b, c):
+        assert torch.equal(a.indices, x.indices) and torch.equal(a.context, x.context) and torch.equal(a.counts, x.counts)
+
+
 def test_capacity_overflow_is_retried_and_seed_matters(dev):
     from pointnet_refine_b200 import scene as sc
     scene, lines = so.synth_scene(80_000, 6, seed=5)

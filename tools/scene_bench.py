@@ -21,7 +21,10 @@ def dev_time(f, n=3):
     for _ in range(n): f()
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n
-t_build = dev_time(lambda: sc.build_segments(d_scene, lines, N, r, 2.0, seed=1))
+t_prep = dev_time(lambda: sc.prepare_scene(d_scene))
+prep = sc.prepare_scene(d_scene)
+t_unsorted = dev_time(lambda: sc.build_segments(sc.prepare_scene(d_scene, sort=False), lines, N, r, 2.0, seed=1))
+t_build = dev_time(lambda: sc.build_segments(prep, lines, N, r, 2.0, seed=1))
 t0 = time.perf_counter()
 for raw in lines: sc.resample_polyline(raw, 32); sc.resample_polyline(raw, 200)
 t_resample = time.perf_counter() - t0
@@ -46,14 +49,14 @@ except ImportError:
     pass
 torch.manual_seed(0)
 m = prb.LineRefineNet().to(dev).eval()
-t_refine = dev_time(lambda: sc.refine_scene(m, d_scene, lines, N, r, 2.0, seed=1), n=2)
+t_refine = dev_time(lambda: sc.refine_scene(m, prep, lines, N, r, 2.0, seed=1), n=2)
 with torch.no_grad():
     def loop():
         for l in range(min(L, 32)):
             m(seg.context[l:l + 1], seg.noisy_line[l:l + 1])[-1].cpu()
     t_loop = dev_time(loop, n=2) / min(L, 32)
 print(json.dumps({"scene_points": S, "lines": L, "N": N, "crop_radius": r, "candidates": cand,
-                  "build_segments_ms": round(t_build * 1e3, 2), "numpy_resampling_of_all_lines_ms": round(t_resample * 1e3, 2), "ms_per_line": round(t_build * 1e3 / L, 4),
+                  "prepare_scene_ms": round(t_prep * 1e3, 2), "build_segments_unsorted_ms": round(t_unsorted * 1e3, 2), "build_segments_ms": round(t_build * 1e3, 2), "numpy_resampling_of_all_lines_ms": round(t_resample * 1e3, 2), "ms_per_line": round(t_build * 1e3 / L, 4),
                   "scene_points_x_lines_per_s": round(S * L / t_build, 1),
                   "host_oracle_ms_per_line": round(t_oracle * 1e3, 1), "host_kdtree_ms_per_line": None if t_kd is None else round(t_kd * 1e3, 1),
                   "refine_scene_ms": round(t_refine * 1e3, 2), "b1_forward_loop_ms_per_line": round(t_loop * 1e3, 3),
