@@ -231,6 +231,27 @@ def test_full_forward_batched_vs_live_oracle(dev, B, N):
         assert np.abs(o.cpu().numpy() - ref).max() <= 5e-2 * rng
 
 
+def test_full_forward_chunking_and_segment_independence_at_scale(dev):
+    """600 segments x 700 points: the decoder pass size (segments per pass, which also changes the attention kernel's
+    split count) and the order of the segments must not matter beyond rounding; every segment is independent."""
+    sd = synth.make_state_dict(4)
+    m = _model(sd, dev, "bf16")
+    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(600, 700, seed=31))
+    with torch.no_grad():
+        full = m(ctx, line)
+        m.segment_chunk = 5                               # 40 segments per pass on the attention path
+        small = m(ctx, line)
+        m.segment_chunk = 256
+        perm = torch.randperm(600, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+        shuffled = m(ctx[perm], line[perm])
+        alone = m(ctx[17:18], line[17:18])                # B = 1: stock-op query side, attention split over clusters
+    rng = max(1.0, float(full.abs().max()))
+    assert torch.isfinite(full).all()
+    assert float((small - full).abs().max()) <= 5e-3 * rng
+    assert float((shuffled - full[:, perm]).abs().max()) <= 5e-3 * rng
+    assert float((alone[:, 0] - full[:, 17]).abs().max()) <= 5e-3 * rng
+
+
 # ------------------------------------------------------------------ live oracle, odd shapes
 @pytest.mark.parametrize("B,N", [(1, 127), (1, 129), (7, 300), (4, 4096), (300, 3)])
 def test_encoder_vs_live_oracle(dev, B, N):
