@@ -63,6 +63,28 @@ def prepare_scene(scene: torch.Tensor, sort: bool = True) -> PreparedScene:
     return PreparedScene(scene, scene[perm].contiguous(), perm.to(torch.int32), extent)
 
 
+def _resample_on_device(raw_lines: Sequence, dev):
+    """Polylines back to back -> one upload -> lrn_scene_resample: (line32 (L,32,3) f64, dense200 (L,200,3) f64,
+    centers (L,3) f64, centred line32 (L,32,3) fp32, largest |vertex coordinate|)."""
+    L = len(raw_lines)
+    arrs = [np.asarray(r, dtype=np.float64).reshape(-1, 3) for r in raw_lines]
+    lens = np.fromiter((a.shape[0] for a in arrs), dtype=np.int64, count=L)
+    offsets = np.zeros(L + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    verts = np.concatenate(arrs) if offsets[-1] > 0 else np.zeros((1, 3))
+    d_verts, d_off = torch.from_numpy(verts).to(dev), torch.from_numpy(offsets).to(dev)
+    d_line = torch.empty(L, 32, 3, dtype=torch.float64, device=dev)
+    d_dense = torch.empty(L, 200, 3, dtype=torch.float64, device=dev)
+    d_cent = torch.empty(L, 3, dtype=torch.float64, device=dev)
+    centred = torch.empty(L, 32, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lrn_scene_resample(d_verts.data_ptr(), d_off.data_ptr(), L, int(lens.max()), d_line.data_ptr(),
+                                          d_dense.data_ptr(), d_cent.data_ptr(), centred.data_ptr(), _stream_ptr(dev)),
+                   "lrn_scene_resample")
+    _lib.launch_counter += 1
+    return d_line, d_dense, d_cent, centred, float(np.abs(verts).max())
+
+
 class SceneSegments(NamedTuple):
     context: torch.Tensor      # (L, N, 4) fp32 CUDA: sampled points, xyz centred on the line, intensity
     noisy_line: torch.Tensor   # (L, 32, 3) fp32 CUDA: the resampled line, centred
@@ -83,23 +105,7 @@ def build_segments(scene, raw_lines: Sequence, num_context_points: int = 1024, c
     if L == 0:
         raise ValueError("no lines")
     dev = scene.device
-    # polylines back to back -> one upload; resampling, centroids and the centred lines happen on the device
-    arrs = [np.asarray(r, dtype=np.float64).reshape(-1, 3) for r in raw_lines]
-    lens = np.fromiter((a.shape[0] for a in arrs), dtype=np.int64, count=L)
-    offsets = np.zeros(L + 1, dtype=np.int64)
-    np.cumsum(lens, out=offsets[1:])
-    verts = np.concatenate(arrs) if offsets[-1] > 0 else np.zeros((1, 3))
-    extent_lines = float(np.abs(verts).max())
-    d_verts, d_off = torch.from_numpy(verts).to(dev), torch.from_numpy(offsets).to(dev)
-    d_line = torch.empty(L, 32, 3, dtype=torch.float64, device=dev)
-    d_dense = torch.empty(L, 200, 3, dtype=torch.float64, device=dev)
-    d_cent = torch.empty(L, 3, dtype=torch.float64, device=dev)
-    noisy = torch.empty(L, 32, 3, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.lrn_scene_resample(d_verts.data_ptr(), d_off.data_ptr(), L, int(lens.max()), d_line.data_ptr(),
-                                          d_dense.data_ptr(), d_cent.data_ptr(), noisy.data_ptr(), _stream_ptr(dev)),
-                   "lrn_scene_resample")
-    _lib.launch_counter += 1
+    d_line, d_dense, d_cent, noisy, extent_lines = _resample_on_device(raw_lines, dev)
     extent = max(extent_lines, prepared.extent)
     context = torch.empty(L, N, 4, dtype=torch.float32, device=dev)
     indices = torch.empty(L, N, dtype=torch.int64, device=dev)
@@ -126,6 +132,23 @@ def build_segments(scene, raw_lines: Sequence, num_context_points: int = 1024, c
     else:
         raise RuntimeError("lrn_scene_segments: candidate buffer overflow after resizing")
     return SceneSegments(context, noisy, d_cent.cpu().numpy(), d_line.cpu().numpy(), indices, counts)
+
+
+def build_training_batch(scene, noisy_lines: Sequence, gt_lines: Sequence, num_context_points: int = 2048,
+                         crop_radius: float = 4.0, decay_scale: float = 2.0, seed: int = 0):
+    """One scene's training samples as a batch, what LaneRefineDataset.__getitem__ (src/dataset.py:177-253) returns per
+    sample: {'context' (L,N,4), 'noisy_line' (L,32,3), 'target_offset' (L,32,3)} fp32 CUDA, with
+    target_offset = (gt32 - center) - (noisy32 - center) in float64, rounded once (src/dataset.py:239-243).
+    Defaults are LaneRefineDataset's (num_context_points 2048, crop_radius 4.0, decay_scale 2.0)."""
+    if len(noisy_lines) != len(gt_lines):
+        raise ValueError("one ground-truth polyline per noisy polyline")
+    seg = build_segments(scene, noisy_lines, num_context_points, crop_radius, decay_scale, seed)
+    dev = seg.context.device
+    gt32, _, _, _, _ = _resample_on_device(gt_lines, dev)
+    center = torch.from_numpy(seg.centers).to(dev)[:, None, :]
+    noisy32 = torch.from_numpy(seg.line32).to(dev)
+    target = ((gt32 - center) - (noisy32 - center)).float()
+    return {"context": seg.context, "noisy_line": seg.noisy_line, "target_offset": target}
 
 
 @torch.no_grad()

@@ -134,3 +134,18 @@ def test_device_resampling_is_bit_equal_to_numpy(dev):
         np.testing.assert_array_equal(seg.line32[l], p32, err_msg=f"line {l} ({len(raw)} vertices)")
         np.testing.assert_array_equal(seg.centers[l], p32.mean(axis=0))
         np.testing.assert_array_equal(seg.noisy_line[l].cpu().numpy(), (p32 - p32.mean(axis=0)).astype(np.float32))
+
+
+def test_training_batch_matches_dataset_item(dev):
+    """build_training_batch = LaneRefineDataset.__getitem__ steps 3-6 for all samples of a scene (src/dataset.py:204-243)."""
+    from pointnet_refine_b200 import scene as sc
+    scene, lines = so.synth_scene(80_000, 6, seed=12)
+    rs = np.random.default_rng(1)
+    gts = [l + rs.normal(0, 0.2, l.shape) for l in lines]
+    batch = sc.build_training_batch(torch.from_numpy(scene).to(dev), lines, gts, 512, 2.0, 2.0, seed=7)
+    for l, (raw, gt) in enumerate(zip(lines, gts)):
+        o_ctx, o_noisy, center, _, _ = so.build_segment(scene, raw, 512, 2.0, 2.0, 7, l)
+        target = ((so.resample_polyline(gt, 32) - center) - (so.resample_polyline(raw, 32) - center)).astype(np.float32)
+        np.testing.assert_array_equal(batch["context"][l].cpu().numpy(), o_ctx)
+        np.testing.assert_array_equal(batch["noisy_line"][l].cpu().numpy(), o_noisy)
+        np.testing.assert_array_equal(batch["target_offset"][l].cpu().numpy(), target)
