@@ -195,105 +195,105 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t ready_leader[2] = {ptx::mapa(ptx::smem_u32(&p_ready[0]), 0), ptx::mapa(ptx::smem_u32(&p_ready[1]), 0)};
     int g0 = 0;
     for (int item = cluster_id; item < p.items; item += num_clusters) {
-    const int step0 = item_step0(item), steps = item_steps(item);
-    float m_ref = -INFINITY, l_sum = 0.f;
-    for (int j = 0; j < steps; ++j) {
-      const int g = g0 + j;
-      const int st = g & 1;
-      const uint32_t t_s = t_lane + st * 128;
-      const int valid = min(kAttnStep, p.N - (step0 + j) * kAttnStep);
-      ptx::mbar_wait(&s_full[st], (g >> 1) & 1);
-      ptx::tc_fence_after();
-      // pass 1: maximum of this row over the step's points
-      float m_t = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_s + 32 * c, r);
-        ptx::tmem_ld_wait();
-        if (valid >= 32 * c + 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m_t = fmaxf(m_t, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (32 * c + i < valid) m_t = fmaxf(m_t, __uint_as_float(r[i]));
-        }
-      }
-      // Lazy rescale: the reference maximum only moves when the row maximum grew by more than 2^8 (p <= 256 stays
-      // exact enough in bf16 / fp32); then this row of O and its running sum are scaled down once.
-      const bool grow = m_t > m_ref + 8.f;
-      if (j == 0) {
-        m_ref = m_t;
-      } else if (__any_sync(0xffffffffu, grow)) {
-        const float f = grow ? ex2_approx(m_ref - m_t) : 1.f;
-        ptx::mbar_wait(&o_done[st ^ 1], ((g - 1) >> 1) & 1);  // O_{j-1} has been accumulated
+      const int step0 = item_step0(item), steps = item_steps(item);
+      float m_ref = -INFINITY, l_sum = 0.f;
+      for (int j = 0; j < steps; ++j) {
+        const int g = g0 + j;
+        const int st = g & 1;
+        const uint32_t t_s = t_lane + st * 128;
+        const int valid = min(kAttnStep, p.N - (step0 + j) * kAttnStep);
+        ptx::mbar_wait(&s_full[st], (g >> 1) & 1);
         ptx::tc_fence_after();
+        // pass 1: maximum of this row over the step's points
+        float m_t = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_s + 32 * c, r);
+          ptx::tmem_ld_wait();
+          if (valid >= 32 * c + 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m_t = fmaxf(m_t, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (32 * c + i < valid) m_t = fmaxf(m_t, __uint_as_float(r[i]));
+          }
+        }
+        // Lazy rescale: the reference maximum only moves when the row maximum grew by more than 2^8 (p <= 256 stays
+        // exact enough in bf16 / fp32); then this row of O and its running sum are scaled down once.
+        const bool grow = m_t > m_ref + 8.f;
+        if (j == 0) {
+          m_ref = m_t;
+        } else if (__any_sync(0xffffffffu, grow)) {
+          const float f = grow ? ex2_approx(m_ref - m_t) : 1.f;
+          ptx::mbar_wait(&o_done[st ^ 1], ((g - 1) >> 1) & 1);  // O_{j-1} has been accumulated
+          ptx::tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            ptx::tmem_st_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
+          }
+          l_sum *= f;
+          if (grow) m_ref = m_t;
+        }
+        // pass 2: P = exp2(S - m_ref) as bf16 pairs over the first 64 columns of the same buffer (writes trail reads)
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t a[32], b[32], o[32];
+          ptx::tmem_ld_32x32b_x32(t_s + 64 * h, a);
+          ptx::tmem_ld_32x32b_x32(t_s + 64 * h + 32, b);
+          ptx::tmem_ld_wait();
+          const int c0 = 64 * h;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float e0 = ex2_approx(__uint_as_float(a[2 * i]) - m_ref), e1 = ex2_approx(__uint_as_float(a[2 * i + 1]) - m_ref);
+            float e2 = ex2_approx(__uint_as_float(b[2 * i]) - m_ref), e3 = ex2_approx(__uint_as_float(b[2 * i + 1]) - m_ref);
+            if (valid < kAttnStep) {
+              if (c0 + 2 * i >= valid) e0 = 0.f;
+              if (c0 + 2 * i + 1 >= valid) e1 = 0.f;
+              if (c0 + 32 + 2 * i >= valid) e2 = 0.f;
+              if (c0 + 32 + 2 * i + 1 >= valid) e3 = 0.f;
+            }
+            l_sum += (e0 + e1) + (e2 + e3);
+            o[i] = ptx::pack_bf16x2(e0, e1);
+            o[16 + i] = ptx::pack_bf16x2(e2, e3);
+          }
+          ptx::tmem_st_32x32b_x32(t_s + 32 * h, o);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ready_leader[st]);
+      }
+      // ---- epilogue: O / l -> global (through a per-warp transpose so that rows are written 128 B at a time)
+      {
+        const int last = g0 + steps - 1;
+        ptx::mbar_wait(&o_done[last & 1], (last >> 1) & 1);
+        ptx::tc_fence_after();
+        const float inv = 1.f / l_sum;
+        float* scratch = reinterpret_cast<float*>(smem + L::kScratch) + (warp - 2) * 32 * 33;
+        const int64_t out_row0 = (static_cast<int64_t>(item) * 256 + rank * 128 + q * 32);
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-          ptx::tmem_st_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
-        }
-        l_sum *= f;
-        if (grow) m_ref = m_t;
-      }
-      // pass 2: P = exp2(S - m_ref) as bf16 pairs over the first 64 columns of the same buffer (writes trail reads)
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        uint32_t a[32], b[32], o[32];
-        ptx::tmem_ld_32x32b_x32(t_s + 64 * h, a);
-        ptx::tmem_ld_32x32b_x32(t_s + 64 * h + 32, b);
-        ptx::tmem_ld_wait();
-        const int c0 = 64 * h;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float e0 = ex2_approx(__uint_as_float(a[2 * i]) - m_ref), e1 = ex2_approx(__uint_as_float(a[2 * i + 1]) - m_ref);
-          float e2 = ex2_approx(__uint_as_float(b[2 * i]) - m_ref), e3 = ex2_approx(__uint_as_float(b[2 * i + 1]) - m_ref);
-          if (valid < kAttnStep) {
-            if (c0 + 2 * i >= valid) e0 = 0.f;
-            if (c0 + 2 * i + 1 >= valid) e1 = 0.f;
-            if (c0 + 32 + 2 * i >= valid) e2 = 0.f;
-            if (c0 + 32 + 2 * i + 1 >= valid) e3 = 0.f;
-          }
-          l_sum += (e0 + e1) + (e2 + e3);
-          o[i] = ptx::pack_bf16x2(e0, e1);
-          o[16 + i] = ptx::pack_bf16x2(e2, e3);
-        }
-        ptx::tmem_st_32x32b_x32(t_s + 32 * h, o);
-      }
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ready_leader[st]);
-    }
-    // ---- epilogue: O / l -> global (through a per-warp transpose so that rows are written 128 B at a time)
-    {
-      const int last = g0 + steps - 1;
-      ptx::mbar_wait(&o_done[last & 1], (last >> 1) & 1);
-      ptx::tc_fence_after();
-      const float inv = 1.f / l_sum;
-      float* scratch = reinterpret_cast<float*>(smem + L::kScratch) + (warp - 2) * 32 * 33;
-      const int64_t out_row0 = (static_cast<int64_t>(item) * 256 + rank * 128 + q * 32);
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = __uint_as_float(r[i]) * inv;
-        __syncwarp();
+          for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = __uint_as_float(r[i]) * inv;
+          __syncwarp();
 #pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) p.out[(out_row0 + rr) * 256 + 32 * c + lane] = scratch[rr * 33 + lane];
-        __syncwarp();
+          for (int rr = 0; rr < 32; ++rr) p.out[(out_row0 + rr) * 256 + 32 * c + lane] = scratch[rr * 33 + lane];
+          __syncwarp();
+        }
+        p.lse[out_row0 + lane] = m_ref + log2f(l_sum);
       }
-      p.lse[out_row0 + lane] = m_ref + log2f(l_sum);
+      g0 += steps;
     }
-    g0 += steps;
-    }  // items
   }
   ptx::tc_fence_before();
   ptx::cluster_sync();
