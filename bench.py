@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_POINT_ENCODER = 5_587_584
 FLOP_PER_POINT_FUSION_KERNEL = 2 * (1984 + 64) * 1024   # fusion conv + gate layer 2 = 4,194,304
+FLOP_PER_POINT_CHAIN_KERNEL = 2 * (64 * 128 + 128 * 256 + 256 * 512 + 512 * 1024)   # conv2..conv5 = 1,392,640
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -299,6 +300,16 @@ def main():
             roofline["traffic"] = json.load(f).get("fusion_dram_bytes_per_launch")
     except Exception:
         pass
+    # second tensor-bound kernel: the fused conv1..conv5 chain (its tensor-core work = conv2..conv5; contains the
+    # widest shared-MLP layer, conv5 512 -> 1024).  Only when the chain kernel is the path taken (bf16 tier, defaults).
+    c_ms, c_n = prof["conv5"]
+    chain_path = args.precision == "bf16" and all(prof[k][1] == 0 for k in ("conv2", "conv3", "conv4")) and c_n > 0
+    if chain_path and c_ms > 0:
+        c_ach = FLOP_PER_POINT_CHAIN_KERNEL * B * N * min(args.steps, 3) / (c_ms * 1e-3) / 1e12
+        roofline["chain_kernel"] = {"kernel": "chain_pair_kernel<true> (conv1 FMA + conv2..conv5 on tcgen05, conv5 with A in TMEM)",
+                                    "achieved": c_ach, "peak": peak, "unit": "TFLOP/s", "frac": c_ach / peak,
+                                    "kernel_ms_per_launch": c_ms / c_n, "kernel_share_of_step": c_ms / total_ms if total_ms else None,
+                                    "algorithmic_flop_per_point": FLOP_PER_POINT_CHAIN_KERNEL}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
