@@ -216,51 +216,71 @@ class LineRefineNet(nn.Module):
         return torch.stack(outs)
 
     # -- context side of the decoder on the tcgen05 GEMMs ------------------------
-    def _kv_weights(self):
-        """bf16 copies of pos_emb.mlp.2 and of the K / V rows of all six cross-attention in_proj matrices
-        ([Wq; Wk; Wv] packing of nn.MultiheadAttention), re-made when a parameter changes."""
+    @staticmethod
+    def _rna_tf32(t):
+        """fp32 -> nearest TF32 value (ties away from zero in magnitude), still stored as fp32: the tensor core would
+        otherwise truncate the low 13 mantissa bits of every operand, a bias that adds up over K."""
+        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    def _kv_weights(self, op):
+        """Copies in the operand type `op` (bf16 or fp32 for the tf32 tier) of pos_emb.mlp.2 and of the K / V rows of
+        all six cross-attention in_proj matrices ([Wq; Wk; Wv] packing of nn.MultiheadAttention), re-made when a
+        parameter changes."""
         ps = [self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias]
         for l in self.decoder_layers:
             ps += [l.cross_attn.in_proj_weight, l.cross_attn.in_proj_bias]
-        fp = tuple((t.data_ptr(), t._version) for t in ps)
+        fp = (op,) + tuple((t.data_ptr(), t._version) for t in ps)
         if getattr(self, "_kv_cache", None) is None or self._kv_cache[0] != fp:
             d = self.d_model
             wk = torch.cat([l.cross_attn.in_proj_weight[d:2 * d] for l in self.decoder_layers]).detach()
             wv = torch.cat([l.cross_attn.in_proj_weight[2 * d:] for l in self.decoder_layers]).detach()
             bk = torch.cat([l.cross_attn.in_proj_bias[d:2 * d] for l in self.decoder_layers]).detach()
             bv = torch.cat([l.cross_attn.in_proj_bias[2 * d:] for l in self.decoder_layers]).detach()
-            self._kv_cache = (fp, wk.bfloat16().contiguous(), bk.float().contiguous(), wv.bfloat16().contiguous(),
-                              bv.float().contiguous(), self.pos_emb.mlp[2].weight.detach().bfloat16().contiguous())
+            cast = (lambda t: t.bfloat16().contiguous()) if op == torch.bfloat16 else (lambda t: self._rna_tf32(t.float()))
+            self._kv_cache = (fp, cast(wk), bk.float().contiguous(), cast(wv), bv.float().contiguous(),
+                              cast(self.pos_emb.mlp[2].weight.detach()))
         return self._kv_cache[1:]
 
     def _refine_fast(self, context, noisy_line, memory):
         """Eval-mode decoder with the context-side work hoisted out of the layer loop: the memory positional
         embedding and the K / V projections of ALL six cross-attention layers are three tcgen05 GEMMs over the
         points (they do not depend on the decoder state, src/model.py:123-126), and every layer's cross
-        attention is one scaled_dot_product_attention call on bf16 K / V.  The query side (32 points per
-        segment) stays in stock PyTorch ops.  Same parameters and math as DetrTransformerDecoderLayer.forward
-        (src/model.py:104-135) in eval mode; bf16 tier only."""
+        attention is one scaled_dot_product_attention call on those K / V.  Operands are bf16 in the bf16 tier
+        (when the folded-query kernel is switched off) and fp32 / TF32 tensor cores in the tf32 tier; the larger
+        query-side linears take the tf32 GEMM too.  Same parameters and math as DetrTransformerDecoderLayer.forward
+        (src/model.py:104-135) in eval mode."""
         B, N, _ = context.shape
         d, H = self.d_model, 8
-        wk, bk, wv, bv, w2 = self._kv_weights()
-        mem = memory.reshape(B * N, d).bfloat16()
-        h = F.relu(self.pos_emb.mlp[0](context[:, :, :3])).reshape(B * N, d).bfloat16()
-        posm = ops.gemm_bias_act(h, w2, self.pos_emb.mlp[2].bias.detach(), out_dtype=torch.bfloat16)
-        k_all = ops.gemm_bias_act(mem + posm, wk, bk, out_dtype=torch.bfloat16).view(B, N, 6, H, d // H)
-        v_all = ops.gemm_bias_act(mem, wv, bv, out_dtype=torch.bfloat16).view(B, N, 6, H, d // H)
+        op = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        wk, bk, wv, bv, w2 = self._kv_weights(op)
+        cast = (lambda t: t.bfloat16()) if op == torch.bfloat16 else self._rna_tf32
+        mem = memory.reshape(B * N, d)
+        h = cast(F.relu(self.pos_emb.mlp[0](context[:, :, :3])).reshape(B * N, d))
+        posm = ops.gemm_bias_act(h, w2, self.pos_emb.mlp[2].bias.detach(), out_dtype=op)
+        k_all = ops.gemm_bias_act(cast(mem + posm), wk, bk, out_dtype=op).view(B, N, 6, H, d // H)
+        v_all = ops.gemm_bias_act(cast(mem), wv, bv, out_dtype=op).view(B, N, 6, H, d // H)
+        rows = B * noisy_line.shape[1]
+
+        def lin(mod, x, relu=False):   # nn.Linear on the tf32 tensor-core GEMM once there are enough rows
+            if rows < 256:
+                y = mod(x)
+                return F.relu(y) if relu else y
+            return ops.gemm_bias_act(self._rna_tf32(x.reshape(rows, -1)), self._rna_tf32(mod.weight.detach()), mod.bias.detach(),
+                                     relu=relu).view(B, -1, mod.out_features)
+
         tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
         current = noisy_line.clone()
         outs = []
         for i, (layer, head) in enumerate(zip(self.decoder_layers, self.reg_branches)):
-            qpos = self.pos_emb(current)
+            qpos = lin(self.pos_emb.mlp[2], F.relu(self.pos_emb.mlp[0](current)))
             q = tgt + qpos
             tgt = layer.norm1(tgt + layer.self_attn(q, q, value=tgt, need_weights=False)[0])
             ca = layer.cross_attn
             qh = F.linear(tgt + qpos, ca.in_proj_weight[:d], ca.in_proj_bias[:d]).view(B, -1, H, d // H).transpose(1, 2)
-            att = F.scaled_dot_product_attention(qh.bfloat16(), k_all[:, :, i].transpose(1, 2), v_all[:, :, i].transpose(1, 2))
+            att = F.scaled_dot_product_attention(qh.to(op), k_all[:, :, i].transpose(1, 2), v_all[:, :, i].transpose(1, 2))
             att = att.transpose(1, 2).reshape(B, -1, d).float()
-            tgt = layer.norm2(tgt + ca.out_proj(att))
-            tgt = layer.norm3(tgt + layer.linear2(F.relu(layer.linear1(tgt))))
+            tgt = layer.norm2(tgt + lin(ca.out_proj, att))
+            tgt = layer.norm3(tgt + lin(layer.linear2, lin(layer.linear1, tgt, relu=True)))
             outs.append(ops.head_forward(head[0].weight, head[0].bias, head[2].weight, head[2].bias, tgt, current, noisy_line))
         return torch.stack(outs)
 
@@ -414,9 +434,10 @@ class LineRefineNet(nn.Module):
             _, fused = self.context_encoder(context.transpose(2, 1))   # train mode: native fwd/bwd (bf16 tier)
             memory = self.context_proj(fused.transpose(2, 1))
             return self._refine(context, noisy_line, memory, native_heads=False)
-        fast = self.precision == "bf16" and self.fast_decoder
+        fast = self.fast_decoder            # both tiers; the folded-query attention kernel below is bf16 only
+        attn = fast and self.precision == "bf16" and self.ctx_attention and noisy_line.shape[1] == 32
         N = context.shape[1]
-        if fast and self.ctx_attention and noisy_line.shape[1] == 32:
+        if attn:
             # ~1M context points per pass, up to 2048 segments: the query-side GEMMs (32 rows per segment) need
             # thousands of rows to fill the 74 CTA pairs, and no (B,N,1536) K / V temporaries exist on this path
             chunk = max(1, min(8 * self.segment_chunk, (1 << 20) // max(N, 1)))
@@ -426,7 +447,7 @@ class LineRefineNet(nn.Module):
         for s in range(0, context.shape[0], chunk):
             ctx = context[s:s + chunk].contiguous()
             line = noisy_line[s:s + chunk].contiguous()
-            if fast and self.ctx_attention and line.shape[1] == 32:
+            if attn:
                 memx = self.context_encoder.run_native(ctx, pool=False, memory=True, memory_bf16=True)["memory"]
                 outs.append(self._refine_attn(ctx, line, memx))
                 continue

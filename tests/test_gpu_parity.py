@@ -229,6 +229,14 @@ def test_full_forward_batched_vs_live_oracle(dev, B, N):
         out_stock = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
     for o in (out, out_kv, out_stock):
         assert np.abs(o.cpu().numpy() - ref).max() <= 5e-2 * rng
+    # tf32 tier: K / V GEMMs + SDPA in fp32 with RNA-rounded TF32 operands (fast) vs the stock decoder
+    m32 = _model(sd, dev, "tf32")
+    with torch.no_grad():
+        fast32 = m32(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
+        m32.fast_decoder = False
+        stock32 = m32(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
+    assert np.abs(fast32.cpu().numpy() - ref).max() <= 2e-3 * rng
+    assert np.abs(stock32.cpu().numpy() - ref).max() <= 2e-3 * rng
 
 
 def test_full_forward_chunking_and_segment_independence_at_scale(dev):
