@@ -255,6 +255,11 @@ int lrn_pos_hidden(const float* w1, const float* b1, const float* context, int64
  * The draw follows the RNG contract documented in oracle/scene_oracle.py (counter-based hash of seed, line, scene index;
  * Efraimidis-Spirakis keys; samples in descending key order): same distribution as the reference's
  * np.random.choice(replace=False, p), reproducible and independent of thread order.  N <= 4096, L <= 65535. */
+/* Parameter gradients of lrn_pos_hidden (train mode): d_w1 (256,3), d_b1 (256) fp32 (zeroed here) from the bf16 hidden
+ * activations (ReLU mask) and their bf16 gradient, both (P, 256) with row pitches in elements. */
+int lrn_pos_hidden_backward(const float* context, int64_t P, const void* hidden, int64_t ld_hidden, const void* d_hidden,
+                            int64_t ld_d, float* d_w1, float* d_b1, lrn_stream_t stream);
+
 /* resample_polyline (src/dataset.py:8-30) of L polylines to 32 and to 200 points on the device, bit-equal to the numpy
  * formulation: vertices (total, 3) f64 = all polylines back to back, offsets (L+1) int64 = first vertex of each line;
  * outputs line32 (L,32,3), dense200 (L,200,3), centers (L,3) f64 and noisy_centered (L,32,3) fp32 = line32 - center
@@ -271,7 +276,12 @@ int lrn_scene_segments(const float* scene, int64_t S, const float* scene_sorted,
  * out = LayerNorm(x + y) * gamma + beta over rows of 256 (norm1 / norm2 / norm3 with their residual adds, :117,:129,:134);
  * y may be NULL; cols must be 256 (d_model). */
 int lrn_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, float eps, float* out,
-                      int64_t rows, int64_t cols, lrn_stream_t stream);
+                      float* stats /* optional (rows, 2): mean, rstd for the backward */, int64_t rows, int64_t cols,
+                      lrn_stream_t stream);
+/* Its backward (train mode): dz (rows,256) = gradient of x and of y, dgamma / dbeta (256) fp32 (zeroed here, then
+ * accumulated); x, y, stats as in the forward call. */
+int lrn_add_layernorm_backward(const float* dy, const float* x, const float* y, const float* stats, const float* gamma, float* dz,
+                               float* dgamma, float* dbeta, int64_t rows, int64_t cols, lrn_stream_t stream);
 /* Self attention over the 32 polyline points of each of B segments, 8 heads x 32 (self_attn, src/model.py:113-117, eval):
  * qk (B*32, 512) fp32 = [q | k] in-projections, v (B*32, 256) -> out (B*32, 256) heads concatenated (before out_proj). */
 int lrn_self_attention32(const float* qk, const float* v, float* out, int B, lrn_stream_t stream);

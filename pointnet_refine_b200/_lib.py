@@ -25,9 +25,9 @@ EXPORTS = [
     "lrn_encoder_packed_bytes", "lrn_encoder_fold", "lrn_encoder_workspace_bytes", "lrn_encoder_forward",
     "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe", "lrn_train_workspace_bytes",
     "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
-    "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden",
+    "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden", "lrn_pos_hidden_backward",
     "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_scene_resample", "lrn_adam_step", "lrn_l1_deep_supervision",
-    "lrn_add_layernorm", "lrn_self_attention32", "lrn_head_update",
+    "lrn_add_layernorm", "lrn_add_layernorm_backward", "lrn_self_attention32", "lrn_head_update",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
 
@@ -86,7 +86,9 @@ def _load():
     lib.lrn_scene_segments.argtypes = [vp, i64, vp, vp, vp, vp, vp, ci, ci, C.c_double, C.c_double, C.c_double, C.c_uint64, i64,
                                        vp, vp, vp, vp, vp, sz, vp]
     lib.lrn_add_layernorm.restype = ci
-    lib.lrn_add_layernorm.argtypes = [vp, vp, vp, vp, C.c_float, vp, i64, i64, vp]
+    lib.lrn_add_layernorm.argtypes = [vp, vp, vp, vp, C.c_float, vp, vp, i64, i64, vp]
+    lib.lrn_add_layernorm_backward.restype = ci
+    lib.lrn_add_layernorm_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
     lib.lrn_self_attention32.restype = ci
     lib.lrn_self_attention32.argtypes = [vp, vp, vp, ci, vp]
     lib.lrn_head_update.restype = ci
@@ -95,6 +97,8 @@ def _load():
     lib.lrn_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]
     lib.lrn_l1_deep_supervision.restype = ci
     lib.lrn_l1_deep_supervision.argtypes = [vp, vp, ci, i64, vp, vp, vp]
+    lib.lrn_pos_hidden_backward.restype = ci
+    lib.lrn_pos_hidden_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp]
     lib.lrn_pos_hidden.restype = ci
     lib.lrn_pos_hidden.argtypes = [vp, vp, vp, i64, vp, i64, vp]
     lib.lrn_debug_ts_probe.restype = ci

@@ -711,6 +711,26 @@ int lrn_pos_hidden(const float* w1, const float* b1, const float* context, int64
   return LRN_OK;
 }
 
+int lrn_pos_hidden_backward(const float* context, int64_t P, const void* hidden, int64_t ld_hidden, const void* d_hidden,
+                            int64_t ld_d, float* d_w1, float* d_b1, lrn_stream_t stream) {
+  if (!context || !hidden || !d_hidden || !d_w1 || !d_b1) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (P <= 0) return fail(LRN_ERR_BAD_SHAPE, "P=%lld", (long long)P);
+  if ((reinterpret_cast<uintptr_t>(context) | reinterpret_cast<uintptr_t>(hidden) | reinterpret_cast<uintptr_t>(d_hidden)) & 15 ||
+      ld_hidden % 8 || ld_d % 8 || ld_hidden < 256 || ld_d < 256)
+    return fail(LRN_ERR_MISALIGNED, "16-byte alignment, row pitches >= 256 and multiples of 8");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  LRN_CUDA(cudaMemsetAsync(d_w1, 0, 256 * 3 * 4, s));
+  LRN_CUDA(cudaMemsetAsync(d_b1, 0, 256 * 4, s));
+  const int grid = int(std::min<int64_t>((P + 7) / 8, int64_t(dev.sms) * 4));
+  pos_hidden_bwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context), P, reinterpret_cast<const uint16_t*>(hidden),
+                                             ld_hidden, reinterpret_cast<const uint16_t*>(d_hidden), ld_d, d_w1, d_b1);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
 // ---------------------------------------------------------------- scene preprocessing (section 8f row 3)
 namespace {
 struct SceneLayout {
@@ -1262,7 +1282,7 @@ int lrn_l1_deep_supervision(const float* pred, const float* target, int L, int64
 }
 
 int lrn_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, float eps, float* out,
-                      int64_t rows, int64_t cols, lrn_stream_t stream) {
+                      float* stats, int64_t rows, int64_t cols, lrn_stream_t stream) {
   if (!x || !gamma || !beta || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
   if (rows <= 0 || cols != 256) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld cols=%lld (d_model = 256)", (long long)rows, (long long)cols);
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out) |
@@ -1272,7 +1292,26 @@ int lrn_add_layernorm(const float* x, const float* y, const float* gamma, const 
   int st = device_info(&dev);
   if (st) return st;
   const int grid = int(std::min<int64_t>((rows + 7) / 8, int64_t(dev.sms) * 8));
-  add_layernorm256_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, gamma, beta, eps, out, rows);
+  add_layernorm256_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, gamma, beta, eps, out, stats, rows);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_add_layernorm_backward(const float* dy, const float* x, const float* y, const float* stats, const float* gamma, float* dz,
+                               float* dgamma, float* dbeta, int64_t rows, int64_t cols, lrn_stream_t stream) {
+  if (!dy || !x || !stats || !gamma || !dz || !dgamma || !dbeta) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (rows <= 0 || cols != 256) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld cols=%lld (d_model = 256)", (long long)rows, (long long)cols);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dz) |
+       reinterpret_cast<uintptr_t>(gamma)) & 15)
+    return fail(LRN_ERR_MISALIGNED, "16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  LRN_CUDA(cudaMemsetAsync(dgamma, 0, 256 * 4, s));
+  LRN_CUDA(cudaMemsetAsync(dbeta, 0, 256 * 4, s));
+  const int grid = int(std::min<int64_t>((rows + 7) / 8, int64_t(dev.sms) * 4));
+  add_layernorm256_bwd_kernel<<<grid, 256, 0, s>>>(dy, x, y, stats, gamma, dz, dgamma, dbeta, rows);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

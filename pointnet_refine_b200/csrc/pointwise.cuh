@@ -133,6 +133,44 @@ __global__ void __launch_bounds__(256) pos_hidden_kernel(const float4* __restric
   for (; pt < rows; pt += warps) emit(pt, __ldg(ctx + pt));
 }
 
+// Backward of pos_hidden_kernel w.r.t. its parameters (train mode): with m = [h > 0],
+//   dW1[c][k] += sum_p dh[p][c] * m * xyz[p][k],   db1[c] += sum_p dh[p][c] * m.
+// Same thread layout (warp per point, lane = 8 channels); every warp keeps its partial sums in registers over all its
+// points and issues one atomicAdd per (channel, term) at the end.  dW1 / db1 are zeroed by the caller.
+__global__ void __launch_bounds__(256) pos_hidden_bwd_kernel(const float4* __restrict__ ctx, long long rows,
+                                                             const uint16_t* __restrict__ h, long long ldh,
+                                                             const uint16_t* __restrict__ dh, long long ldd,
+                                                             float* __restrict__ dw1 /* (256,3) */, float* __restrict__ db1) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float ax[8], ay[8], az[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ax[j] = ay[j] = az[j] = ab[j] = 0.f;
+  auto bf = [](uint32_t w, int hi) { return __uint_as_float(hi ? (w & 0xFFFF0000u) : (w << 16)); };
+  for (long long pt = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; pt < rows; pt += warps) {
+    const float4 x = __ldg(ctx + pt);
+    const uint4 hv = *reinterpret_cast<const uint4*>(h + pt * ldh + 8 * lane);
+    const uint4 dv = *reinterpret_cast<const uint4*>(dh + pt * ldd + 8 * lane);
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float g = bf(hw[j >> 1], j & 1) > 0.f ? bf(dw[j >> 1], j & 1) : 0.f;
+      ax[j] = fmaf(g, x.x, ax[j]);
+      ay[j] = fmaf(g, x.y, ay[j]);
+      az[j] = fmaf(g, x.z, az[j]);
+      ab[j] += g;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = 8 * lane + j;
+    atomicAdd(dw1 + 3 * c, ax[j]);
+    atomicAdd(dw1 + 3 * c + 1, ay[j]);
+    atomicAdd(dw1 + 3 * c + 2, az[j]);
+    atomicAdd(db1 + c, ab[j]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Unpack argmax keys: key = (float bits << 32) | (0xFFFFFFFF - n)  ->  max value and int64 index.
 // ---------------------------------------------------------------------------------------------

@@ -10,9 +10,11 @@ namespace lrn {
 
 // out[r, :] = LayerNorm(x[r, :] + y[r, :]) * gamma + beta over 256 columns (norm1/2/3, eps 1e-5, biased variance).
 // One warp per row; lane l holds columns [4l, 4l+4) and [128+4l, 128+4l+4).  y may be null.
+// `stats` (optional, (rows, 2) = mean, rstd) is what the backward kernel needs besides x + y.
 __global__ void __launch_bounds__(256)
 add_layernorm256_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, float eps, float* __restrict__ out, long long rows) {
+                        const float* __restrict__ beta, float eps, float* __restrict__ out, float* __restrict__ stats,
+                        long long rows) {
   const int lane = threadIdx.x & 31;
   const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const float4 g0 = reinterpret_cast<const float4*>(gamma)[lane], g1 = reinterpret_cast<const float4*>(gamma)[32 + lane];
@@ -36,9 +38,68 @@ add_layernorm256_kernel(const float* __restrict__ x, const float* __restrict__ y
 #pragma unroll
     for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q * (1.f / 256.f) + eps);
+    if (stats && lane == 0) {
+      stats[2 * r] = mean;
+      stats[2 * r + 1] = rstd;
+    }
     float4* orow = reinterpret_cast<float4*>(out + r * 256);
     orow[lane] = make_float4(a.x * rstd * g0.x + b0.x, a.y * rstd * g0.y + b0.y, a.z * rstd * g0.z + b0.z, a.w * rstd * g0.w + b0.w);
     orow[32 + lane] = make_float4(b.x * rstd * g1.x + b1.x, b.y * rstd * g1.y + b1.y, b.z * rstd * g1.z + b1.z, b.w * rstd * g1.w + b1.w);
+  }
+}
+
+// Backward of out = LayerNorm(x + y) * gamma + beta over 256 columns.  With z = x + y, xh = (z - mean) * rstd, g = gamma * dy:
+//   dz = rstd * (g - mean_c(g) - xh * mean_c(g * xh))    (the gradient of both x and y)
+//   dgamma += sum_rows dy * xh,  dbeta += sum_rows dy    (per-warp register partial sums, one atomicAdd per warp and column)
+__global__ void __launch_bounds__(256)
+add_layernorm256_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                            const float* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ dz,
+                            float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float4 g0 = reinterpret_cast<const float4*>(gamma)[lane], g1 = reinterpret_cast<const float4*>(gamma)[32 + lane];
+  float ag[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ab[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    float4 a = reinterpret_cast<const float4*>(x + r * 256)[lane], b = reinterpret_cast<const float4*>(x + r * 256)[32 + lane];
+    if (y) {
+      const float4 c = reinterpret_cast<const float4*>(y + r * 256)[lane], d = reinterpret_cast<const float4*>(y + r * 256)[32 + lane];
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+    const float4 d0 = reinterpret_cast<const float4*>(dy + r * 256)[lane], d1 = reinterpret_cast<const float4*>(dy + r * 256)[32 + lane];
+    const float xh[8] = {(a.x - mean) * rstd, (a.y - mean) * rstd, (a.z - mean) * rstd, (a.w - mean) * rstd,
+                         (b.x - mean) * rstd, (b.y - mean) * rstd, (b.z - mean) * rstd, (b.w - mean) * rstd};
+    const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float g[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      g[i] = gm[i] * dv[i];
+      s1 += g[i];
+      s2 += g[i] * xh[i];
+      ag[i] += dv[i] * xh[i];
+      ab[i] += dv[i];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 *= (1.f / 256.f);
+    s2 *= (1.f / 256.f);
+    float o8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o8[i] = rstd * (g[i] - s1 - xh[i] * s2);
+    reinterpret_cast<float4*>(dz + r * 256)[lane] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+    reinterpret_cast<float4*>(dz + r * 256)[32 + lane] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(dgamma + 4 * lane + i, ag[i]);
+    atomicAdd(dgamma + 128 + 4 * lane + i, ag[4 + i]);
+    atomicAdd(dbeta + 4 * lane + i, ab[i]);
+    atomicAdd(dbeta + 128 + 4 * lane + i, ab[4 + i]);
   }
 }
 

@@ -381,7 +381,7 @@ class LineRefineNet(nn.Module):
         >= 256 query rows; the 32 x 32 self attention, LayerNorms, dropouts and heads are stock ops.  Same parameters
         as DetrTransformerDecoderLayer; dropout draws differ from the reference's RNG stream (they would from run to
         run there, too)."""
-        from .train_ops import kv_proj, linear_bf16
+        from .train_ops import add_layernorm, kv_proj, linear_bf16, pos_hidden_train
         B, N, _ = context.shape
         d, H = self.d_model, 8
         wk = torch.cat([l.cross_attn.in_proj_weight[d:2 * d] for l in self.decoder_layers])
@@ -389,7 +389,7 @@ class LineRefineNet(nn.Module):
         bk = torch.cat([l.cross_attn.in_proj_bias[d:2 * d] for l in self.decoder_layers])
         bv = torch.cat([l.cross_attn.in_proj_bias[2 * d:] for l in self.decoder_layers])
         mem = linear_bf16(fused_pm, self.context_proj.weight, self.context_proj.bias)      # (B,N,256) bf16
-        h = F.relu(self.pos_emb.mlp[0](context[:, :, :3]))
+        h = pos_hidden_train(context, self.pos_emb.mlp[0].weight, self.pos_emb.mlp[0].bias)    # (B,N,256) bf16
         posm = linear_bf16(h, self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias)
         k_l = kv_proj(mem + posm, wk, bk, 6, H)     # six (B, H, N, 32) views of one (B, N, 6, H, 32) GEMM result
         v_l = kv_proj(mem, wv, bv, 6, H)
@@ -412,14 +412,14 @@ class LineRefineNet(nn.Module):
             att = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2),
                                                  dropout_p=sa.dropout if self.training else 0.0)
             att = lin(att.transpose(1, 2).reshape(B, -1, d), sa.out_proj.weight, sa.out_proj.bias)
-            tgt = layer.norm1(tgt + layer.dropout1(att))
+            tgt = add_layernorm(tgt, layer.dropout1(att), layer.norm1)
             ca = layer.cross_attn
             qh = lin(tgt + qpos, ca.in_proj_weight[:d], ca.in_proj_bias[:d]).view(B, -1, H, d // H).transpose(1, 2)
             att = F.scaled_dot_product_attention(qh.bfloat16(), k_l[i], v_l[i], dropout_p=ca.dropout if self.training else 0.0)
             att = att.transpose(1, 2).reshape(B, -1, d).float()
-            tgt = layer.norm2(tgt + layer.dropout2(lin(att, ca.out_proj.weight, ca.out_proj.bias)))
+            tgt = add_layernorm(tgt, layer.dropout2(lin(att, ca.out_proj.weight, ca.out_proj.bias)), layer.norm2)
             ffn = lin(layer.dropout(F.relu(lin(tgt, layer.linear1.weight, layer.linear1.bias))), layer.linear2.weight, layer.linear2.bias)
-            tgt = layer.norm3(tgt + layer.dropout3(ffn))
+            tgt = add_layernorm(tgt, layer.dropout3(ffn), layer.norm3)
             current = current + head(tgt)
             outs.append(current - noisy_line)
         return torch.stack(outs)

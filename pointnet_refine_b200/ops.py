@@ -253,7 +253,7 @@ def add_layernorm(x: torch.Tensor, y, norm: torch.nn.LayerNorm) -> torch.Tensor:
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
         _lib.check(lib.lrn_add_layernorm(x.data_ptr(), y.data_ptr() if y is not None else None, _f32c(norm.weight.detach()).data_ptr(),
-                                         _f32c(norm.bias.detach()).data_ptr(), float(norm.eps), out.data_ptr(),
+                                         _f32c(norm.bias.detach()).data_ptr(), float(norm.eps), out.data_ptr(), None,
                                          x.numel() // x.shape[-1], x.shape[-1], _stream_ptr(x.device)), "lrn_add_layernorm")
     _lib.launch_counter += 1
     return out

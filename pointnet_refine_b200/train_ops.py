@@ -220,6 +220,79 @@ def kv_proj(x, weight, bias, layers: int, heads: int):
     return KVProjFn.apply(x, weight, bias, layers, heads)
 
 
+class PosHiddenFn(torch.autograd.Function):
+    """relu(W1 xyz + b1) on the context points as bf16 (lrn_pos_hidden), with the parameter gradients from
+    lrn_pos_hidden_backward; the context itself gets no gradient (PositionalEncoding.mlp[0], src/model.py:66-75,197)."""
+
+    @staticmethod
+    def forward(ctx, context, w1, b1):
+        context = _f32c(context)
+        B, N, _ = context.shape
+        h = torch.empty(B, N, 256, dtype=torch.bfloat16, device=context.device)
+        with torch.cuda.device(context.device):
+            _lib.check(lib.lrn_pos_hidden(_f32c(w1.detach()).data_ptr(), _f32c(b1.detach()).data_ptr(), context.data_ptr(), B * N,
+                                          h.data_ptr(), 256, _stream_ptr(context.device)), "lrn_pos_hidden")
+        _lib.launch_counter += 1
+        ctx.save_for_backward(context, h)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        context, h = ctx.saved_tensors
+        dh = dh.to(torch.bfloat16).contiguous()
+        dw = torch.empty(256, 3, dtype=torch.float32, device=h.device)
+        db = torch.empty(256, dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            _lib.check(lib.lrn_pos_hidden_backward(context.data_ptr(), h.numel() // 256, h.data_ptr(), 256, dh.data_ptr(), 256,
+                                                   dw.data_ptr(), db.data_ptr(), _stream_ptr(h.device)), "lrn_pos_hidden_backward")
+        _lib.launch_counter += 1
+        return None, dw, db
+
+
+def pos_hidden_train(context, w1, b1):
+    return PosHiddenFn.apply(context, w1, b1)
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """LayerNorm(x + y) over 256 columns with the residual add fused in, forward and backward on the native kernels
+    (lrn_add_layernorm / lrn_add_layernorm_backward); norm1 / norm2 / norm3 of DetrTransformerDecoderLayer in training."""
+
+    @staticmethod
+    def forward(ctx, x, y, gamma, beta, eps):
+        x, y = _f32c(x), _f32c(y)
+        g, b = _f32c(gamma.detach()), _f32c(beta.detach())
+        rows = x.numel() // 256
+        out = torch.empty_like(x)
+        stats = torch.empty(rows, 2, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.lrn_add_layernorm(x.data_ptr(), y.data_ptr(), g.data_ptr(), b.data_ptr(), float(eps), out.data_ptr(),
+                                             stats.data_ptr(), rows, 256, _stream_ptr(x.device)), "lrn_add_layernorm")
+        _lib.launch_counter += 1
+        ctx.save_for_backward(x, y, stats, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, stats, g = ctx.saved_tensors
+        dout = _f32c(dout)
+        dz = torch.empty_like(x)
+        dgamma = torch.empty(256, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(256, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.lrn_add_layernorm_backward(dout.data_ptr(), x.data_ptr(), y.data_ptr(), stats.data_ptr(), g.data_ptr(),
+                                                      dz.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), x.numel() // 256, 256,
+                                                      _stream_ptr(x.device)), "lrn_add_layernorm_backward")
+        _lib.launch_counter += 1
+        return dz, dz, dgamma, dbeta, None
+
+
+def add_layernorm(x, y, norm: torch.nn.LayerNorm):
+    """norm(x + y), differentiable, for (..., 256) fp32 CUDA tensors."""
+    if x.shape[-1] != 256 or x.shape != y.shape:
+        raise ValueError(f"add_layernorm: shapes {tuple(x.shape)}, {tuple(y.shape)} (last dim must be 256)")
+    return AddLayerNormFn.apply(x, y, norm.weight, norm.bias, norm.eps)
+
+
 def linear_bf16(x, weight, bias):
     """Differentiable bf16 tensor-core linear layer over the last dimension of x (leading dims flattened)."""
     lead = x.shape[:-1]

@@ -254,3 +254,37 @@ def test_flat_adam_trains_line_refine_net(dev):
     with torch.no_grad():
         after = m(ctx, line)
     assert torch.isfinite(after).all() and float((after - before).abs().max()) > 1e-4
+
+
+def test_add_layernorm_and_pos_hidden_autograd(dev):
+    """Native forward + backward of LayerNorm(x + y) and of the positional hidden layer against stock autograd."""
+    from pointnet_refine_b200.train_ops import add_layernorm, pos_hidden_train
+    gen = torch.Generator(device=dev).manual_seed(11)
+    r = lambda *s: torch.randn(*s, device=dev, generator=gen)
+    for rows in (32, 1000, 40000):
+        ln = torch.nn.LayerNorm(256).to(dev)
+        with torch.no_grad():
+            ln.weight.copy_(1 + 0.3 * r(256)); ln.bias.copy_(0.2 * r(256))
+        x, y, w = r(rows // 32, 32, 256) * 2 + 0.5, r(rows // 32, 32, 256), r(rows // 32, 32, 256)
+        res = []
+        for native in (True, False):
+            xa, ya = x.clone().requires_grad_(), y.clone().requires_grad_()
+            ln.zero_grad()
+            out = add_layernorm(xa, ya, ln) if native else ln(xa + ya)
+            (out * w).sum().backward()
+            res.append((out.detach(), xa.grad, ya.grad, ln.weight.grad.clone(), ln.bias.grad.clone()))
+        for a, b in zip(*res):
+            assert float((a - b).abs().max()) <= 2e-4 * max(1.0, float(b.abs().max())), rows
+    lin = torch.nn.Linear(3, 256).to(dev)
+    ctx = r(5, 700, 4)
+    wgt = r(5, 700, 256)
+    h = pos_hidden_train(ctx, lin.weight, lin.bias)
+    assert h.dtype == torch.bfloat16
+    (h.float() * wgt).sum().backward()
+    gw, gb = lin.weight.grad.clone(), lin.bias.grad.clone()
+    lin.zero_grad()
+    href = torch.relu(lin(ctx[:, :, :3]))
+    (href * wgt.bfloat16().float()).sum().backward()
+    assert float((h.float() - href).detach().abs().max()) <= 2 ** -8 * max(1.0, float(href.detach().abs().max()))
+    for a, b in ((gw, lin.weight.grad), (gb, lin.bias.grad)):
+        assert float((a - b).norm() / b.norm()) <= 1e-2
