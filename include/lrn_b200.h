@@ -291,6 +291,10 @@ int lrn_self_attention32(const float* qk, const float* v, float* out, int B, lrn
 int lrn_head_update(const float* hidden, const float* w2, const float* b2, int64_t rows, float* current, const float* noisy,
                     float* cum, lrn_stream_t stream);
 
+/* out[c] = sum over rows of the bf16 matrix A (rows, cols), row pitch ld: the bias gradient of a linear layer whose output
+ * gradient is bf16 (cols % 64 == 0). */
+int lrn_col_sum_bf16(const void* A, int64_t ld, int64_t rows, int64_t cols, float* out, lrn_stream_t stream);
+
 /* ---- training-loop machinery ----
  * One Adam step over a flat fp32 buffer holding every parameter (train.py:40 optim.Adam(model.parameters(), lr);
  * torch.optim.Adam semantics without amsgrad, weight decay added to the gradient); step counts from 1. */

@@ -1346,4 +1346,14 @@ int lrn_head_update(const float* hidden, const float* w2, const float* b2, int64
   return LRN_OK;
 }
 
+int lrn_col_sum_bf16(const void* A, int64_t ld, int64_t rows, int64_t cols, float* out, lrn_stream_t stream) {
+  if (!A || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (rows <= 0 || cols <= 0 || cols % 64 || ld < cols || ld % 2) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld cols=%lld ld=%lld (cols %% 64 == 0)", (long long)rows, (long long)cols, (long long)ld);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  LRN_CUDA(cudaMemsetAsync(out, 0, size_t(cols) * 4, s));
+  col_stats_kernel<<<stats_grid(int(cols), rows), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(A), ld, rows, out, nullptr);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
 }  // extern "C"

@@ -50,7 +50,7 @@ add_layernorm256_kernel(const float* __restrict__ x, const float* __restrict__ y
 
 // Backward of out = LayerNorm(x + y) * gamma + beta over 256 columns.  With z = x + y, xh = (z - mean) * rstd, g = gamma * dy:
 //   dz = rstd * (g - mean_c(g) - xh * mean_c(g * xh))    (the gradient of both x and y)
-//   dgamma += sum_rows dy * xh,  dbeta += sum_rows dy    (per-warp register partial sums, one atomicAdd per warp and column)
+//   dgamma += sum_rows dy * xh,  dbeta += sum_rows dy    (register partial sums per warp, reduced per block)
 __global__ void __launch_bounds__(256)
 add_layernorm256_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
                             const float* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ dz,
@@ -94,12 +94,22 @@ add_layernorm256_bwd_kernel(const float* __restrict__ dy, const float* __restric
     reinterpret_cast<float4*>(dz + r * 256)[lane] = make_float4(o8[0], o8[1], o8[2], o8[3]);
     reinterpret_cast<float4*>(dz + r * 256)[32 + lane] = make_float4(o8[4], o8[5], o8[6], o8[7]);
   }
+  // block-level reduction of the 8 warps' partial sums, then one atomicAdd per block and column
+  __shared__ float red[8][512];
+  const int w = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    atomicAdd(dgamma + 4 * lane + i, ag[i]);
-    atomicAdd(dgamma + 128 + 4 * lane + i, ag[4 + i]);
-    atomicAdd(dbeta + 4 * lane + i, ab[i]);
-    atomicAdd(dbeta + 128 + 4 * lane + i, ab[4 + i]);
+    red[w][4 * lane + i] = ag[i];
+    red[w][128 + 4 * lane + i] = ag[4 + i];
+    red[w][256 + 4 * lane + i] = ab[i];
+    red[w][384 + 4 * lane + i] = ab[4 + i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 512; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][c];
+    atomicAdd((c < 256 ? dgamma : dbeta - 256) + c, t);
   }
 }
 

@@ -142,6 +142,19 @@ def encoder_train_forward(module, context, point_major=False):
     return global_feat, fused
 
 
+def _col_sum(dyb):
+    """Column sums (fp32) of a contiguous bf16 matrix: the bias gradient."""
+    rows, cols = dyb.shape
+    if cols % 64:
+        return dyb.sum(dim=0, dtype=torch.float32)
+    out = torch.empty(cols, dtype=torch.float32, device=dyb.device)
+    with torch.cuda.device(dyb.device):
+        _lib.check(lib.lrn_col_sum_bf16(dyb.data_ptr(), dyb.stride(0), rows, cols, out.data_ptr(), _stream_ptr(dyb.device)),
+                   "lrn_col_sum_bf16")
+    _lib.launch_counter += 1
+    return out
+
+
 class LinearBf16Fn(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 GEMMs with bf16 operands and fp32 parameters / gradients:
     forward `lrn_gemm_bias_act`, dgrad `dy W` (K-major GEMM on W^T), wgrad `dy^T x` (`lrn_gemm_tn`, MN-major operands,
@@ -169,7 +182,7 @@ class LinearBf16Fn(torch.autograd.Function):
         if need_w:
             dw = ops.gemm_tn(dyb, xb)
         if need_b:
-            db = dyb.sum(dim=0, dtype=torch.float32)
+            db = _col_sum(dyb)
         return dx, dw, db
 
 
@@ -211,7 +224,7 @@ class KVProjFn(torch.autograd.Function):
         if need_w:
             dw = ops.gemm_tn(dyb, xb)
         if need_b:
-            db = dyb.sum(dim=0, dtype=torch.float32)
+            db = _col_sum(dyb)
         return dx, dw, db, None, None
 
 
