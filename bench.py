@@ -91,11 +91,11 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(segments: int, points: int, steps: int, warmup: int):
-    """Time the torch-CPU port of the reference encoder on all host threads (segments/s)."""
+def cpu_reference_run(segments: int, points: int, steps: int, warmup: int, threads: int | None = None):
+    """Time the torch-CPU port of the reference encoder on `threads` host threads (default: all) (segments/s)."""
     import torch
     from oracle import synth, torch_port
-    threads = os.cpu_count() or 1
+    threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = synth.to_torch(synth.make_state_dict(0))
     ctx = torch.from_numpy(synth.make_inputs(segments, points, seed=1234)[0]).transpose(2, 1)
@@ -318,6 +318,9 @@ def main():
         cpu_baseline = {"value": v, "unit": "segments/s", "cores": threads, "kind": "port",
                         "sample": f"{seg} segments x {N} points per step, 1 warm-up + 3 timed "
                                   f"(torch-CPU port of the reference encoder, fp32)", "ms_per_step": dt * 1e3}
+        v1, dt1, _ = cpu_reference_run(2, N, 2, 1, threads=1)       # per-core figure
+        cpu_baseline["single_thread"] = {"value": v1, "cores": 1, "sample": f"2 segments x {N} points per step, 1 warm-up + 2 timed"}
+        torch.set_num_threads(os.cpu_count() or 1)
 
     print(json.dumps({
         "metric": "segments_per_sec", "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps,

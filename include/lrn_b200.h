@@ -295,6 +295,10 @@ int lrn_head_update(const float* hidden, const float* w2, const float* b2, int64
  * gradient is bf16 (cols % 64 == 0). */
 int lrn_col_sum_bf16(const void* A, int64_t ld, int64_t rows, int64_t cols, float* out, lrn_stream_t stream);
 
+/* src (B, H, N, 32) bf16 contiguous (the dK / dV of one cross-attention layer) -> column block `layer` of the
+ * (B, N, L, H, 32) gradient buffer that the K / V projection's dgrad and wgrad GEMMs read. */
+int lrn_gather_heads(const void* src, int B, int H, int N, int layer, int L, void* dst, lrn_stream_t stream);
+
 /* ---- training-loop machinery ----
  * One Adam step over a flat fp32 buffer holding every parameter (train.py:40 optim.Adam(model.parameters(), lr);
  * torch.optim.Adam semantics without amsgrad, weight decay added to the gradient); step counts from 1. */

@@ -26,7 +26,7 @@ EXPORTS = [
     "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe", "lrn_train_workspace_bytes",
     "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
     "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden", "lrn_pos_hidden_backward",
-    "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_scene_resample", "lrn_adam_step", "lrn_l1_deep_supervision", "lrn_col_sum_bf16",
+    "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_scene_resample", "lrn_adam_step", "lrn_l1_deep_supervision", "lrn_col_sum_bf16", "lrn_gather_heads",
     "lrn_add_layernorm", "lrn_add_layernorm_backward", "lrn_self_attention32", "lrn_head_update",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
@@ -93,6 +93,8 @@ def _load():
     lib.lrn_self_attention32.argtypes = [vp, vp, vp, ci, vp]
     lib.lrn_head_update.restype = ci
     lib.lrn_head_update.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+    lib.lrn_gather_heads.restype = ci
+    lib.lrn_gather_heads.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp]
     lib.lrn_col_sum_bf16.restype = ci
     lib.lrn_col_sum_bf16.argtypes = [vp, i64, i64, i64, vp, vp]
     lib.lrn_adam_step.restype = ci

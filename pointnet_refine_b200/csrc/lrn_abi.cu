@@ -1356,4 +1356,19 @@ int lrn_col_sum_bf16(const void* A, int64_t ld, int64_t rows, int64_t cols, floa
   return LRN_OK;
 }
 
+int lrn_gather_heads(const void* src, int B, int H, int N, int layer, int L, void* dst, lrn_stream_t stream) {
+  if (!src || !dst) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (B <= 0 || H <= 0 || N <= 0 || L <= 0 || layer < 0 || layer >= L) return fail(LRN_ERR_BAD_SHAPE, "B=%d H=%d N=%d layer=%d L=%d", B, H, N, layer, L);
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) return fail(LRN_ERR_MISALIGNED, "16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const long long groups = static_cast<long long>(B) * H * ((N + 7) / 8);
+  const int grid = int(std::min<long long>((groups + 7) / 8, static_cast<long long>(dev.sms) * 16));
+  gather_heads_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(src), B, H, N, layer, L,
+                                                                                reinterpret_cast<uint4*>(dst));
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
 }  // extern "C"

@@ -448,6 +448,29 @@ __global__ void copy_submatrix_kernel(const float* __restrict__ src, long long l
   }
 }
 
+// Attention gradients back into the projection layout: src (B, H, N, 32) bf16 contiguous (what scaled_dot_product_attention
+// returns for dK / dV of one layer) -> dst[b][n][layer][h][0:32] of a (B, N, L, H, 32) buffer, i.e. the column block of
+// that layer in the (B*N, L*H*32) gradient matrix the dgrad / wgrad GEMMs read.  One warp moves 8 points of one head per
+// step: 512 contiguous bytes in, eight 64-byte pieces out.
+__global__ void __launch_bounds__(256)
+gather_heads_kernel(const uint4* __restrict__ src, int B, int H, int N, int layer, int L, uint4* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long groups = static_cast<long long>(B) * H * ((N + 7) / 8);
+  const int per = (N + 7) / 8;
+  for (long long gidx = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; gidx < groups; gidx += warps) {
+    const int n0 = static_cast<int>(gidx % per) * 8;
+    const long long bh = gidx / per;
+    const int h = static_cast<int>(bh % H);
+    const long long b = bh / H;
+    const int n = n0 + (lane >> 2), piece = lane & 3;   // 4 x 16 bytes = one point's 32 bf16
+    if (n < N) {
+      const uint4 v = src[((b * H + h) * N + n) * 4 + piece];
+      dst[(((b * N + n) * L + layer) * H + h) * 4 + piece] = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Training-loop machinery: Adam over one flat parameter buffer and the L1 deep-supervision loss.
 // ---------------------------------------------------------------------------------------------

@@ -211,9 +211,15 @@ class KVProjFn(torch.autograd.Function):
         xb, wb = ctx.saved_tensors
         B, N, K, L, H, x_dtype = ctx.meta
         dy = torch.empty(B, N, L, H, wb.shape[0] // (L * H), dtype=torch.bfloat16, device=xb.device)
+        hd = dy.shape[-1]
         for i, g in enumerate(grads):
             if g is None:
                 dy[:, :, i].zero_()
+            elif hd == 32 and g.dtype == torch.bfloat16 and g.is_contiguous():
+                with torch.cuda.device(g.device):      # (B,H,N,32) as SDPA returns it -> its column block, one pass
+                    _lib.check(lib.lrn_gather_heads(g.data_ptr(), B, H, N, i, L, dy.data_ptr(), _stream_ptr(g.device)),
+                               "lrn_gather_heads")
+                _lib.launch_counter += 1
             else:
                 dy[:, :, i].copy_(g.transpose(1, 2))
         dyb = dy.view(B * N, -1)
