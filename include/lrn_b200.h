@@ -224,13 +224,13 @@ int lrn_gemm_tn(const void* At, int64_t lda, const void* Bt, int64_t ldb, float*
  * src/model.py:123-128, for the eval path).
  *   qfold (B*256, 256) bf16: row h*32+q = log2(e)/sqrt(32) * (q_h[q] Wk_h), Wk_h = in_proj_weight[256+32h : 256+32h+32]
  *   kp    (B*N, 256)  bf16, row pitch ld_kp: memory + positional embedding     mem (B*N, 256) bf16, row pitch ld_mem: memory
- *   out   (B*splits*256, 256) fp32: softmax(qfold kp^T) mem per split, normalised inside the split
+ *   out   (B*splits*256, 256) fp32, or bf16 with out_bf16 = 1: softmax(qfold kp^T) mem per split, normalised inside the split
  *   lse   (B*splits*256) fp32: log2 of the split's sum of 2^score (to merge splits; splits = 1: final result)
  * The caller applies Wv_h / bv_h to `out` (rows of the softmax sum to one, so the bias passes through).
  * lrn_ctx_attention_splits(B, N) is the split count the library would pick (few segments: several clusters each). */
 int lrn_ctx_attention_splits(int B, int N);
 int lrn_ctx_attention(const void* qfold, const void* kp, int64_t ld_kp, const void* mem, int64_t ld_mem, int B, int N,
-                      int splits, float* out, float* lse, lrn_stream_t stream);
+                      int splits, void* out, int out_bf16, float* lse, lrn_stream_t stream);
 
 /* out[pt][0:256) = bf16(relu(W1 xyz + b1)): first layer of PositionalEncoding (src/model.py:66-75) on the context points
  * (context (P,4) fp32, xyz = first three columns; src/model.py:197).  out rows have a pitch of ld_out bf16 elements, so

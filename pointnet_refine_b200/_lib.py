@@ -77,7 +77,7 @@ def _load():
     lib.lrn_ctx_attention_splits.restype = ci
     lib.lrn_ctx_attention_splits.argtypes = [ci, ci]
     lib.lrn_ctx_attention.restype = ci
-    lib.lrn_ctx_attention.argtypes = [vp, vp, i64, vp, i64, ci, ci, ci, vp, vp, vp]
+    lib.lrn_ctx_attention.argtypes = [vp, vp, i64, vp, i64, ci, ci, ci, vp, ci, vp, vp]
     lib.lrn_scene_resample.restype = ci
     lib.lrn_scene_resample.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.lrn_scene_workspace_bytes.restype = sz

@@ -43,7 +43,8 @@ struct AttnParams {
   int N;          // points per segment
   int splits;     // clusters per segment
   int steps_per_split;
-  float* out;     // (B * splits * 256, 256) fp32: normalised partial attention over memory
+  void* out;      // (B * splits * 256, 256) fp32 (or bf16 if out_bf16): normalised partial attention over memory
+  int out_bf16;
   float* lse;     // (B * splits * 256) fp32: log2-sum-exp2 of the scaled scores of the split
 };
 
@@ -286,8 +287,19 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = __uint_as_float(r[i]) * inv;
           __syncwarp();
+          if (p.out_bf16) {  // two rows per instruction, 16 lanes x bf16 pair = 64 contiguous bytes per row
+            uint32_t* o16 = reinterpret_cast<uint32_t*>(p.out);
+            const int half = lane >> 4, l = lane & 15;
 #pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) p.out[(out_row0 + rr) * 256 + 32 * c + lane] = scratch[rr * 33 + lane];
+            for (int rr = 0; rr < 32; rr += 2) {
+              const float* src = scratch + (rr + half) * 33 + 2 * l;
+              o16[((out_row0 + rr + half) * 256 + 32 * c) / 2 + l] = ptx::pack_bf16x2(src[0], src[1]);
+            }
+          } else {
+            float* o32 = reinterpret_cast<float*>(p.out);
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) o32[(out_row0 + rr) * 256 + 32 * c + lane] = scratch[rr * 33 + lane];
+          }
           __syncwarp();
         }
         p.lse[out_row0 + lane] = m_ref + log2f(l_sum);

@@ -662,7 +662,7 @@ int lrn_ctx_attention_splits(int B, int N) {
 }
 
 int lrn_ctx_attention(const void* qfold, const void* kp, int64_t ld_kp, const void* mem, int64_t ld_mem, int B, int N,
-                      int splits, float* out, float* lse, lrn_stream_t stream) {
+                      int splits, void* out, int out_bf16, float* lse, lrn_stream_t stream) {
   if (!qfold || !kp || !mem || !out || !lse) return fail(LRN_ERR_BAD_ARG, "null pointer");
   if (B <= 0 || N <= 0 || int64_t(B) * N >= (int64_t(1) << 31) - 256) return fail(LRN_ERR_BAD_SHAPE, "B=%d N=%d", B, N);
   if (ld_kp < 256 || ld_mem < 256) return fail(LRN_ERR_BAD_ARG, "row pitch below 256");
@@ -683,6 +683,7 @@ int lrn_ctx_attention(const void* qfold, const void* kp, int64_t ld_kp, const vo
   p.splits = splits;
   p.steps_per_split = per;
   p.out = out;
+  p.out_bf16 = out_bf16 ? 1 : 0;
   p.lse = lse;
   static bool configured = false;
   if (!configured) {

@@ -310,7 +310,7 @@ class LineRefineNet(nn.Module):
                 bqk = scale * torch.einsum("hc,hcd->hd", bq, wk).reshape(H * d)
                 wvo = torch.einsum("ohc,hcd->ohd", wo.view(d, H, hd), wv).reshape(d, H * d)
                 bvo = wo @ bv + bo
-                layers.append(tuple(t.float().contiguous() for t in (wqk, bqk, wvo, bvo)))
+                layers.append(tuple(t.float().contiguous() for t in (wqk, bqk, wvo, bvo)) + (wvo.float().bfloat16().contiguous(),))
             w2 = self.pos_emb.mlp[2].weight.detach()
             wx = torch.cat([torch.eye(d, device=w2.device, dtype=w2.dtype), w2], dim=1).bfloat16().contiguous()
             self._attn_cache = (fp, layers, wx, self.pos_emb.mlp[2].bias.detach().float().contiguous())
@@ -344,7 +344,7 @@ class LineRefineNet(nn.Module):
         current = noisy_line.clone()
         outs = []
         big = rows >= 256     # thousands of rows: every step below is one native kernel; else latency-oriented stock ops
-        for layer, head, (wqk, bqk, wvo, bvo) in zip(self.decoder_layers, self.reg_branches, layers_w):
+        for layer, head, (wqk, bqk, wvo, bvo, wvo16) in zip(self.decoder_layers, self.reg_branches, layers_w):
             qpos = lin(F.relu(pe0(current)), pe2.weight, pe2.bias)
             q = tgt + qpos
             sa = layer.self_attn
@@ -360,8 +360,13 @@ class LineRefineNet(nn.Module):
                 tgt = layer.norm1(tgt + lin(att.transpose(1, 2).reshape(B, -1, d), sa.out_proj.weight, sa.out_proj.bias))
             # folded queries: row q * 8 + h of the segment's 256 (any row order works, rows are independent)
             qf = lin(tgt + qpos, wqk, bqk, out_dtype=torch.bfloat16).view(B, H * 32, d)   # tf32 accumulate, rounded once
-            o = ops.ctx_attention(qf, kp, mem).view(B, 32, H * d)
-            ffn_in = ops.add_layernorm(tgt, lin(o, wvo, bvo), layer.norm2) if big else layer.norm2(tgt + lin(o, wvo, bvo))
+            if big:   # attention output leaves the kernel as bf16, Wv / out_proj (folded) is a bf16 GEMM with fp32 output
+                o = ops.ctx_attention(qf, kp, mem, out_dtype=torch.bfloat16).view(rows, H * d)
+                cross = ops.gemm_bias_act(o, wvo16, bvo, out_dtype=torch.float32).view(B, 32, d)
+                ffn_in = ops.add_layernorm(tgt, cross, layer.norm2)
+            else:
+                o = ops.ctx_attention(qf, kp, mem).view(B, 32, H * d)
+                ffn_in = layer.norm2(tgt + lin(o, wvo, bvo))
             ffn = lin(lin(ffn_in, layer.linear1.weight, layer.linear1.bias, relu=True), layer.linear2.weight, layer.linear2.bias)
             tgt = ops.add_layernorm(ffn_in, ffn, layer.norm3) if big else layer.norm3(ffn_in + ffn)
             if big:

@@ -198,10 +198,12 @@ def gemm_tn(at: torch.Tensor, bt: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def ctx_attention(qfold: torch.Tensor, kp: torch.Tensor, mem: torch.Tensor, splits: int | None = None) -> torch.Tensor:
+def ctx_attention(qfold: torch.Tensor, kp: torch.Tensor, mem: torch.Tensor, splits: int | None = None,
+                  out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """softmax(qfold @ kp^T) @ mem per segment on the tensor cores, K / V never materialised (lrn_ctx_attention).
     qfold (B, 256, 256) bf16 folded queries (scores in log2 units), kp / mem (B, N, 256) bf16 (rows may be strided
-    views of a wider buffer) -> (B, 256, 256) fp32."""
+    views of a wider buffer) -> (B, 256, 256) in out_dtype (fp32, or bf16 written straight from the kernel when a
+    segment is not split)."""
     for t in (qfold, kp, mem):
         if t.dtype != torch.bfloat16 or not t.is_cuda:
             raise TypeError("ctx_attention expects CUDA bfloat16 tensors")
@@ -217,16 +219,18 @@ def ctx_attention(qfold: torch.Tensor, kp: torch.Tensor, mem: torch.Tensor, spli
     (kp, ld_kp), (mem, ld_mem) = rows(kp), rows(mem)
     if splits is None:
         splits = lib.lrn_ctx_attention_splits(B, N)
-    out = torch.empty(B, splits, 256, 256, dtype=torch.float32, device=kp.device)
+    direct_bf16 = out_dtype == torch.bfloat16 and splits == 1
+    out = torch.empty(B, splits, 256, 256, dtype=torch.bfloat16 if direct_bf16 else torch.float32, device=kp.device)
     lse = torch.empty(B, splits, 256, dtype=torch.float32, device=kp.device)
     with torch.cuda.device(kp.device):
         _lib.check(lib.lrn_ctx_attention(qfold.data_ptr(), kp.data_ptr(), ld_kp, mem.data_ptr(), ld_mem, B, N, splits,
-                                         out.data_ptr(), lse.data_ptr(), _stream_ptr(kp.device)), "lrn_ctx_attention")
+                                         out.data_ptr(), int(direct_bf16), lse.data_ptr(), _stream_ptr(kp.device)),
+                   "lrn_ctx_attention")
     _lib.launch_counter += 1
     if splits == 1:
-        return out[:, 0]
+        return out[:, 0] if direct_bf16 else out[:, 0].to(out_dtype)
     w = torch.softmax(lse * 0.6931471805599453, dim=1)  # lse is in log2 units
-    return (out * w.unsqueeze(-1)).sum(1)
+    return (out * w.unsqueeze(-1)).sum(1).to(out_dtype)
 
 
 def pos_hidden(w1: torch.Tensor, b1: torch.Tensor, context: torch.Tensor, out: torch.Tensor) -> torch.Tensor:

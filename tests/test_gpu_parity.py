@@ -165,6 +165,9 @@ def test_ctx_attention_matches_fp64(dev, B, N, splits, ramp):
     wide = torch.empty(B, N, 512, dtype=torch.bfloat16, device=dev)
     wide[:, :, :256] = mem
     assert torch.equal(ops.ctx_attention(qf, kp, wide[:, :, :256], splits), out)
+    # bf16 output: written by the kernel itself when the segment is not split, the fp32 result rounded once otherwise
+    out16 = ops.ctx_attention(qf, kp, mem, splits, out_dtype=torch.bfloat16)
+    assert out16.dtype == torch.bfloat16 and torch.equal(out16, out.bfloat16())
 
 
 def test_pos_hidden_and_bf16_memory(dev):
