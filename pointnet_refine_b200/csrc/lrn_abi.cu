@@ -1210,8 +1210,9 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
     bn_bwd_apply_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, 0, U + uo, kULd, P, 1024, mean + uo,
                                                             rstd + uo, pr->fusion_bn_w, S1 + uo, S2 + uo, dU, 1024);
     LRN_CUDA(cudaGetLastError());
-    col_stats_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, P, g->fusion_b, nullptr);
-    LRN_CUDA(cudaGetLastError());
+    // d(fusion conv bias) = sum_p dU is exactly zero: dU is the output of a batch-statistic BatchNorm backward, whose
+    // columns sum to zero over the batch (the bias only shifts the batch mean).  It stays at the memset above instead of
+    // the bf16 rounding noise a column sum of dU would give; same for conv2..conv5 below.
     // d(operand row) = dUf Wf  (columns >= 1984 of the padded transposed weight are zero)
     if ((st = run_gemm_bf16(dU, 1024, P, 1024, ws + W.wft, 1024, kCat, nullptr, dA, kCat, 0, 0, s))) return st;
     // dWf = dUf^T X   (K = points; MN-major operands straight from the point-major buffers)
@@ -1235,8 +1236,6 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
                                                          rstd + uo, pr->bn_w[i], S1 + uo, S2 + uo, dU, 1024);
     LRN_CUDA(cudaGetLastError());
     if (k == 1) break;
-    col_stats_kernel<<<stats_grid(C, P), 256, 0, s>>>(dU, 1024, P, g->conv_b[i], nullptr);
-    LRN_CUDA(cudaGetLastError());
     const int cin = kChan[k - 1], cin_p = std::max(cin, 128);
     // dW_k = dU_k^T X_{k-1}
     if ((st = lrn_gemm_tn(dU, 1024, X + kCatOff[k - 1], kCat, gW, cin_p, C, cin_p, P, stream))) return st;
@@ -1249,6 +1248,7 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
       reinterpret_cast<const float4*>(context), P, dU, 1024, dHp, 128, X + kFusionK, kCat, g->conv_w[0], g->conv_b[0],
       g->gate0_w, g->gate0_b);
   LRN_CUDA(cudaGetLastError());
+  LRN_CUDA(cudaMemsetAsync(g->conv_b[0], 0, 64 * 4, s));  // in front of bn1: exactly zero as well (see fusion_b above)
   return LRN_OK;
 }
 

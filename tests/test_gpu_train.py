@@ -63,8 +63,9 @@ def test_train_forward_backward_matches_torch(dev, B, N):
         assert torch.isfinite(p.grad).all(), name
         gn, gr = p.grad.flatten().double(), q.grad.flatten().double()
         if name.startswith(("conv", "fusion.0")) and name.endswith("bias"):
-            # a bias in front of a batch-stat BatchNorm has zero gradient; ours is bf16 rounding noise of sum(dU)
-            assert float(gn.abs().max()) <= 0.1, name
+            # a bias in front of a batch-stat BatchNorm has zero gradient (the reference's is fp32 rounding noise of an
+            # analytically vanishing sum); the native backward writes the exact zero
+            assert float(gn.abs().max()) == 0.0, name
             continue
         rel = float((gn - gr).norm() / gr.norm())
         cos = float(torch.dot(gn, gr) / (gn.norm() * gr.norm()))
