@@ -274,6 +274,19 @@ def main():
                           "note": "LineRefineNet.forward -> (6,B,32,3); encoder, context_proj, folded-query cross attention "
                                   "(K/V never materialised), query side (linears, 32x32 self attention, add+LayerNorm, heads) on "
                                   "the sm_100a kernels; point_mlp and the K=3 pos_emb layer are stock PyTorch ops"}
+            if B * N >= 1024 * 1024:   # inference_whole_scene.py's setting: 1024 context points per line
+                ctx_ws = ctx.reshape(-1, 4)[:1024 * 1024].view(1024, 1024, 4)
+                line_ws = torch.randn(1024, 32, 3, device=dev, generator=gen)
+                for _ in range(2):
+                    model(ctx_ws, line_ws)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    model(ctx_ws, line_ws)
+                torch.cuda.synchronize()
+                fw = (time.perf_counter() - t0) / 3
+                full_model["whole_scene_setting"] = {"segments": 1024, "points_per_segment": 1024, "ms_per_forward": fw * 1e3,
+                                                     "segments_per_sec": 1024 / fw}
 
     if rank != 0:
         if world > 1:
