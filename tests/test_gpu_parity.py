@@ -398,15 +398,17 @@ def test_host_pipeline_matches_direct_call(dev):
     assert (got[:, 1024:] - direct[:, 1024:]).abs().max() <= 1e-5
 
 
-def test_cuda_graph_replay_is_bit_identical(dev):
-    """B = 1 whole-scene style call (inference_whole_scene.py:130-139): one graph replay == the eager launches."""
+@pytest.mark.parametrize("B,N", [(1, 1024), (24, 512)])
+def test_cuda_graph_replay_is_bit_identical(dev, B, N):
+    """B = 1 whole-scene style call (inference_whole_scene.py:130-139) and a batch large enough for the native query side:
+    one graph replay == the eager launches."""
     import pointnet_refine_b200 as prb
     sd = synth.make_state_dict(0)
     m = _model(sd, dev, "bf16")
-    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(1, 1024, seed=21))
+    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(B, N, seed=21))
     with torch.no_grad():
         eager = m(ctx, line).clone()
-        runner = prb.GraphedLineRefineNet(m, 1, 1024)
+        runner = prb.GraphedLineRefineNet(m, B, N)
         for _ in range(3):
             out = runner(ctx, line)
         torch.cuda.synchronize()
