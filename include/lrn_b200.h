@@ -122,8 +122,11 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
 /* ---- point loading + first layer, stand-alone (tf32 tier, per-layer path, and bench.py's HBM roofline line) ----
  * Replaces: relu(bn1(conv1(x))) and the gate's Conv1d(1,64)+ReLU, src/model.py:43,33-34, in fp32 FMA on the raw points:
  * reads 16 B/point, writes feat1 -> operand columns [0,64) and the gate hidden block -> [1984,2048) of
- * `operand_rows` ((rows, 2048) in the tier's operand type).  HBM-bound: 16 + 256 B (bf16) / 16 + 512 B (tf32) per point. */
-int lrn_point_embed(const void* packed, int precision, const float* context, int64_t rows, void* operand_rows,
+ * `operand_rows` ((rows, 2048) in the tier's operand type).  HBM-bound: 16 + 256 B (bf16) / 16 + 512 B (tf32) per point.
+ * tiled = 1 (bf16): `operand_rows` is in the tiled layout the default path keeps its operand matrix in,
+ * [row tile of 128][column block of 64][128 rows][64 columns] (rows rounded up to 128): the two blocks a tile of points
+ * writes are contiguous 16 KB pieces instead of 128-byte pieces at the 4 KB row pitch. */
+int lrn_point_embed(const void* packed, int precision, const float* context, int64_t rows, void* operand_rows, int tiled,
                     lrn_stream_t stream);
 
 /* ---- regression head + cumulative-offset bookkeeping ----

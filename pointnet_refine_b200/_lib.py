@@ -71,7 +71,7 @@ def _load():
     lib.lrn_profile_read.restype = ci
     lib.lrn_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     lib.lrn_point_embed.restype = ci
-    lib.lrn_point_embed.argtypes = [vp, ci, vp, i64, vp, vp]
+    lib.lrn_point_embed.argtypes = [vp, ci, vp, i64, vp, ci, vp]
     lib.lrn_gemm_tn.restype = ci
     lib.lrn_gemm_tn.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp]
     lib.lrn_ctx_attention_splits.restype = ci

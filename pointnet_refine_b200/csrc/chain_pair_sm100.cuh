@@ -47,6 +47,7 @@ struct ChainParams {
   const float* b4;    // (512)
   const float* b5;    // (1024), C5 only
   void* cat;          // operand rows (M, 2048) bf16
+  int tiled;          // operand matrix in the tiled layout: tmCat is a 4-D map, every store is one contiguous 16 KB block
   long long* dbg;
 };
 
@@ -217,6 +218,11 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // one [128 rows x 64 columns] activation block -> operand matrix (row0 is a multiple of 128, col of 64)
+  auto store_blk = [&](const void* smem_src, int col, int row0) {
+    if (p.tiled) ptx::tma_store_4d(&tmCat, smem_src, 0, 0, col >> 6, row0 >> 7);
+    else ptx::tma_store_2d(&tmCat, smem_src, col, row0);
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer (both CTAs)
@@ -400,8 +406,8 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       if (lane == 0) ptx::mbar_arrive_cluster(ready_leader0);
       ptx::named_bar_sync(1, 32 * kPairEpiWarps);
       if (issuer) {
-        ptx::tma_store_2d(&tmCat, smem + L::kF1, 0, row0);
-        ptx::tma_store_2d(&tmCat, smem + L::kGH, 1984, row0);
+        store_blk(smem + L::kF1, 0, row0);
+        store_blk(smem + L::kGH, 1984, row0);
         ptx::bulk_commit();
       }
     };
@@ -428,8 +434,8 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       }
       ptx::named_bar_sync(1, 32 * kPairEpiWarps);
       if (issuer) {
-        ptx::tma_store_2d(&tmCat, smem + L::kF2, 64, row0);
-        ptx::tma_store_2d(&tmCat, smem + L::kF2 + kChainBlock, 128, row0);
+        store_blk(smem + L::kF2, 64, row0);
+        store_blk(smem + L::kF2 + kChainBlock, 128, row0);
         ptx::bulk_commit();
       }
       if (stamp) p.dbg[it * 8 + 3] = clock64();  // conv2 drained, F2 stores issued
@@ -449,7 +455,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       ptx::named_bar_sync(1, 32 * kPairEpiWarps);
       if (issuer) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) ptx::tma_store_2d(&tmCat, smem + L::kF3 + b * kChainBlock, 192 + 64 * b, row0);
+        for (int b = 0; b < 4; ++b) store_blk(smem + L::kF3 + b * kChainBlock, 192 + 64 * b, row0);
         ptx::bulk_commit();
       }
       if (stamp) p.dbg[it * 8 + 5] = clock64();  // conv3 drained, F3 stores issued
@@ -481,7 +487,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         if (issuer) {
 #pragma unroll
           for (int b = 0; b < 4; ++b)
-            ptx::tma_store_2d(&tmCat, smem + (c == 0 ? L::kF2 : L::kF3) + b * kChainBlock, 448 + 256 * c + 64 * b, row0);
+            store_blk(smem + (c == 0 ? L::kF2 : L::kF3) + b * kChainBlock, 448 + 256 * c + 64 * b, row0);
           ptx::bulk_commit();
         }
         if (C5) {
@@ -522,7 +528,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
           if (issuer) {
 #pragma unroll
             for (int b = 0; b < 4; ++b)
-              ptx::tma_store_2d(&tmCat, smem + L::kF3 + b * kChainBlock, 960 + 256 * n + 64 * b, row0);
+              store_blk(smem + L::kF3 + b * kChainBlock, 960 + 256 * n + 64 * b, row0);
             ptx::bulk_commit();
           }
           if (stamp5) p.dbg[64 + 40 + n] = clock64();  // drained, stores issued

@@ -44,6 +44,7 @@ struct GemmParams {
   void* out;
   long long ldo;  // elements
   int out_f32;
+  int a_tiled;  // A operand in the tiled layout ([row tile][column block][128 rows][128 B]); tmA is then a 4-D map
   int relu;
   int round_tf32;  // fp32 output is a TF32 operand of the next layer: round to nearest instead of truncating later
   int out_col0;    // pair kernels with staged TMA stores: first output column inside the output tensor map

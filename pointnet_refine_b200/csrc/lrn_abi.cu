@@ -126,6 +126,26 @@ int make_tmap(CUtensorMap* m, int precision, const void* base, int64_t rows, int
   return LRN_OK;
 }
 
+// Tiled operand matrix (bf16): [row tile of 128][column block of 64][128 rows][128 bytes] - every [128 x 64] box that the
+// kernels move is one contiguous 16 KB block in global memory (a row-major matrix scatters it as 128 pieces of 128 bytes
+// at the row pitch, which caps the write bandwidth of the chain kernel at about half of a streaming copy).
+int make_tmap_tiled(CUtensorMap* m, const void* base, int64_t rows, int64_t cols) {
+  EncodeTiledFn enc;
+  int st = get_encode_fn(&enc);
+  if (st) return st;
+  if ((reinterpret_cast<uintptr_t>(base) & 1023) || cols % 64) return fail(LRN_ERR_MISALIGNED, "tiled tensor map base / columns");
+  const cuuint64_t nb = cuuint64_t(cols / 64), nt = cuuint64_t((rows + 127) / 128);
+  cuuint64_t dims[4] = {64, 128, nb, nt};
+  cuuint64_t strides[3] = {128, 16384, nb * 16384};
+  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LRN_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed (%d)", int(r));
+  return LRN_OK;
+}
+
 struct DeviceInfo {
   int device = -1;
   int sms = 0;
@@ -479,6 +499,13 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     static const bool no_chain = [] { const char* e = getenv("LRN_NO_CHAIN"); return e && e[0] == '1'; }();
     static const bool chain5 = [] { const char* e = getenv("LRN_CHAIN5"); return !(e && e[0] == '0'); }();
     const bool fused_chain = !tf32 && plan_f.pair && !no_chain;
+    // default bf16 path (chain kernel with conv5 + fusion kernel): the operand matrix is kept in the tiled layout
+    static const bool no_tiled = [] { const char* e = getenv("LRN_NO_TILED"); return e && e[0] == '1'; }();
+    const bool tiled = fused_chain && chain5 && !no_tiled;
+    if (tiled) {
+      st = make_tmap_tiled(&ta, cat, rows, kCat);
+      if (st) return st;
+    }
     if (fused_chain) {
       static bool configured = false;
       if (!configured) {
@@ -496,6 +523,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       cp.b4 = reinterpret_cast<const float*>(pk + L.b[4]);
       cp.b5 = reinterpret_cast<const float*>(pk + L.b[5]);
       cp.cat = cat;
+      cp.tiled = tiled ? 1 : 0;
       static const int dbg_layer = [] { const char* e = getenv("LRN_DBG_LAYER"); return e ? atoi(e) : 0; }();
       cp.dbg = dbg_layer == 4 ? g_dbg : nullptr;
       // reported as stage "conv5" (with conv5 fused) or "conv4"; the other chain stages then read 0
@@ -546,6 +574,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.kb_main = kFusionK / bk;
       p.kb_gate = kGateK / bk;
       p.a_col0 = 0;
+      p.a_tiled = tiled ? 1 : 0;
       p.bias_f = reinterpret_cast<const float*>(pk + L.bf);
       p.bias_g = reinterpret_cast<const float*>(pk + L.bg);
       p.row0 = r0;
@@ -885,9 +914,10 @@ int lrn_profile_read(float* ms_per_stage, int64_t* launches_per_stage) {
   return LRN_OK;
 }
 
-int lrn_point_embed(const void* packed, int precision, const float* context, int64_t rows, void* operand_rows,
+int lrn_point_embed(const void* packed, int precision, const float* context, int64_t rows, void* operand_rows, int tiled,
                     lrn_stream_t stream) {
   if (bad_precision(precision) || !packed || !context || !operand_rows || rows <= 0) return fail(LRN_ERR_BAD_ARG, "bad argument");
+  if (tiled && precision != LRN_PREC_BF16) return fail(LRN_ERR_BAD_ARG, "the tiled operand layout is the bf16 tier's");
   DeviceInfo dev;
   int st = device_info(&dev);
   if (st) return st;
@@ -900,7 +930,7 @@ int lrn_point_embed(const void* packed, int precision, const float* context, int
   if (precision == LRN_PREC_TF32)
     point_embed_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context), rows, ew, operand_rows, kCat);
   else
-    point_embed_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context), rows, ew, operand_rows, kCat);
+    point_embed_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context), rows, ew, operand_rows, tiled ? 0 : kCat);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

@@ -49,6 +49,8 @@ struct EmbedWeights {
   const float* bg1;  // (64)
 };
 
+// ld > 0: row-major operand rows of pitch ld.  ld == 0 (bf16 only): the tiled layout of the default path,
+// [row tile of 128][column block of 64][128 rows][64 columns] - feat1 is column block 0, the gate hidden block is block 31.
 template <bool TF32>
 __global__ void __launch_bounds__(256) point_embed_kernel(const float4* __restrict__ ctx, long long rows,
                                                           EmbedWeights w, void* __restrict__ cat, int ld) {
@@ -78,9 +80,10 @@ __global__ void __launch_bounds__(256) point_embed_kernel(const float4* __restri
       *reinterpret_cast<float4*>(row + 1984 + 4 * sub) =
           make_float4(ptx::round_tf32(h[0]), ptx::round_tf32(h[1]), ptx::round_tf32(h[2]), ptx::round_tf32(h[3]));
     } else {
-      uint16_t* row = reinterpret_cast<uint16_t*>(cat) + pt * ld;
+      uint16_t* row = reinterpret_cast<uint16_t*>(cat) + (ld ? pt * ld : (pt >> 7) * (32ll * 8192) + (pt & 127) * 64);
+      const long long gate_off = ld ? 1984 : 31ll * 8192;
       *reinterpret_cast<uint2*>(row + 4 * sub) = make_uint2(ptx::pack_bf16x2(f[0], f[1]), ptx::pack_bf16x2(f[2], f[3]));
-      *reinterpret_cast<uint2*>(row + 1984 + 4 * sub) =
+      *reinterpret_cast<uint2*>(row + gate_off + 4 * sub) =
           make_uint2(ptx::pack_bf16x2(h[0], h[1]), ptx::pack_bf16x2(h[2], h[3]));
     }
   };

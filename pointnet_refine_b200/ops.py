@@ -292,15 +292,18 @@ def head_update(hidden: torch.Tensor, w2, b2, current: torch.Tensor, noisy: torc
     return cum
 
 
-def point_embed(folded: FoldedEncoder, context: torch.Tensor) -> torch.Tensor:
+def point_embed(folded: FoldedEncoder, context: torch.Tensor, tiled: bool = False) -> torch.Tensor:
     """Stand-alone first layer (+ gate layer 1): context (P, 4) or (B, N, 4) fp32 -> operand rows (P, 2048) in the
-    tier's operand type with columns [0,64) and [1984,2048) written (the rest is left uninitialised)."""
+    tier's operand type with columns [0,64) and [1984,2048) written (the rest is left uninitialised).
+    tiled (bf16 tier): the result is the tiled operand matrix of the default path instead,
+    (ceil(P/128), 32, 128, 64): [row tile][column block][row][column]; blocks 0 and 31 are written."""
     context = _f32c(context).reshape(-1, 4)
     P = context.shape[0]
     dt = torch.float32 if folded.precision == "tf32" else torch.bfloat16
-    rows = torch.empty(P, 2048, dtype=dt, device=context.device)
+    rows = (torch.empty((P + 127) // 128, 32, 128, 64, dtype=dt, device=context.device) if tiled
+            else torch.empty(P, 2048, dtype=dt, device=context.device))
     with torch.cuda.device(context.device):
-        _lib.check(lib.lrn_point_embed(folded.blob.data_ptr(), folded.prec_id, context.data_ptr(), P, rows.data_ptr(),
+        _lib.check(lib.lrn_point_embed(folded.blob.data_ptr(), folded.prec_id, context.data_ptr(), P, rows.data_ptr(), int(tiled),
                                        _stream_ptr(context.device)), "lrn_point_embed")
     _lib.launch_counter += 1
     return rows

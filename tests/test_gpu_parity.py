@@ -187,6 +187,21 @@ def test_pos_hidden_and_bf16_memory(dev):
         assert torch.equal(memx[:, :, :256], mem32.bfloat16())          # the memory half is left alone
 
 
+def test_point_embed_tiled_layout_equals_row_major(dev):
+    """Stand-alone first layer in the tiled operand layout of the default path == the row-major rows, re-tiled."""
+    from pointnet_refine_b200 import ops
+    sd = synth.make_state_dict(0)
+    m = _model(sd, dev, "bf16")
+    ctx = torch.from_numpy(synth.make_inputs(3, 1000, seed=2)[0]).to(dev)       # 3000 points: a ragged last tile
+    folded = m.context_encoder.folded()
+    rm = ops.point_embed(folded, ctx)                                            # (3000, 2048)
+    tl = ops.point_embed(folded, ctx, tiled=True)                                # (24, 32, 128, 64)
+    assert tl.shape == (24, 32, 128, 64)
+    for blk, c0 in ((0, 0), (31, 1984)):
+        flat = tl[:, blk].reshape(-1, 64)[:3000]
+        assert torch.equal(flat, rm[:, c0:c0 + 64])
+
+
 def test_query_side_kernels_match_torch(dev):
     """add + LayerNorm, the 32 x 32 self attention and the head update against the stock modules."""
     import torch.nn.functional as F
