@@ -265,7 +265,7 @@ def main():
         # ---- informational: the whole LineRefineNet forward (encoder + context_proj + 6 decoder layers + heads)
         full_model = None
         if rank == 0:
-            fb = min(B, 256)
+            fb = min(B, 296)      # 4 x 74 segments x 4096 points = four full encoder waves, 4 attention items per CTA pair
             line = torch.randn(fb, 32, 3, device=dev, generator=gen)
             for _ in range(2):
                 model(ctx[:fb], line)

@@ -443,9 +443,9 @@ class LineRefineNet(nn.Module):
         attn = fast and self.precision == "bf16" and self.ctx_attention and noisy_line.shape[1] == 32
         N = context.shape[1]
         if attn:
-            # ~1M context points per pass, up to 2048 segments: the query-side GEMMs (32 rows per segment) need
+            # ~1.2M context points per pass, up to 2048 segments: the query-side GEMMs (32 rows per segment) need
             # thousands of rows to fill the 74 CTA pairs, and no (B,N,1536) K / V temporaries exist on this path
-            chunk = max(1, min(8 * self.segment_chunk, (1 << 20) // max(N, 1)))
+            chunk = max(1, min(8 * self.segment_chunk, (4 * ops.DEFAULT_CHUNK_ROWS) // max(N, 1)))   # four full encoder waves
         else:
             chunk = max(1, min(self.segment_chunk, (1 << 20) // max(N, 1))) if fast else self.segment_chunk
         outs = []

@@ -15,7 +15,7 @@ from pointnet_refine_b200.shard import segment_shard
 ap = argparse.ArgumentParser()
 ap.add_argument("--segments", type=int, default=1_000_000)
 ap.add_argument("--points", type=int, default=2048)
-ap.add_argument("--chunk", type=int, default=512)
+ap.add_argument("--chunk", type=int, default=1184, help="segments per forward call (1184 x 2048 points = two decoder passes of four full encoder waves)")
 ap.add_argument("--encoder", action="store_true")
 ap.add_argument("--graph", action="store_true", help="replay the chunk forward as a CUDA graph")
 args = ap.parse_args()
