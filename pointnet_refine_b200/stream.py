@@ -6,6 +6,8 @@ from __future__ import annotations
 
 import torch
 
+from .ops import DEFAULT_CHUNK_ROWS
+
 
 class HostEncoderPipeline:
     def __init__(self, encoder, segments_per_chunk: int = 512):
@@ -32,6 +34,9 @@ class HostEncoderPipeline:
         if host_out is None:
             host_out = torch.empty(B, 2048, dtype=torch.float32).pin_memory()
         chunk = min(self.chunk, B)
+        per_wave = DEFAULT_CHUNK_ROWS // N        # segments of one full encoder wave (74 at N = 4096)
+        if per_wave >= 1 and chunk >= per_wave:
+            chunk = chunk // per_wave * per_wave   # whole waves per host chunk: no partially filled launch in the middle
         stage = self._buffers(chunk, N, dev)
         compute = torch.cuda.current_stream(dev)
         copied = [torch.cuda.Event(), torch.cuda.Event()]
