@@ -22,8 +22,11 @@
 // C5 = true appends conv5 (512 -> 1024, src/model.py:47; 75 % of the chain's FLOPs) with its A operand in
 // TENSOR MEMORY: the conv4 epilogue writes feat4 as packed bf16 into TMEM columns [0, 256) (row = lane,
 // two channels per column) besides staging it for the TMA store, and conv5 runs as
-// tcgen05.mma.cta_group::2 [D], [A_tmem], B_desc ("TS" form) over four 256-channel chunks accumulated in
-// columns [256, 512).  Only the weights touch shared memory.  Measured: the TMEM A read costs ~128 cycles
+// tcgen05.mma.cta_group::2 [D], [A_tmem], B_desc ("TS" form) over eight 128-channel chunks that alternate between
+// two accumulators (columns [256, 384) / [384, 512)): the drain of chunk n hides under the MMAs of chunk n + 1
+// (an N = 128 TS MMA takes 77 cycles against 64 of math, tools/mma_probe.cu, but four 256-channel chunks through
+// the single accumulator that fits beside feat4 serialise MMAs and drains: 8.6k instead of 2 x 2.5k cycles per 256
+// channels).  Only the weights touch shared memory.  Measured: the TMEM A read costs ~128 cycles
 // per MMA whatever N is, so N = 256 (128-cycle math) is the shape that runs at the tensor-pipe floor
 // (N = 128 chunks with double-buffered accumulators took 125 cycles per MMA, i.e. half rate); the
 // shared-memory-operand form of the same MMA takes ~194 cycles.  conv5 streams 512 KB of weights per CTA and
@@ -224,56 +227,73 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     else ptx::tma_store_2d(&tmCat, smem_src, col, row0);
   };
 
+  // Producer and MMA issue loops run warp-converged with the TMA / tcgen05 instructions predicated on elect.sync
+  // (uniform-register operands, no per-lane serialisation), and the MMA loop looks at the next weight stage's barrier
+  // while the current k-block is being issued: see gemm_pair_sm100.cuh and tools/mma_probe.cu.
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer (both CTAs)
-    if (lane == 0) {
-      // Two stage sequences share the per-stage barriers: conv2..conv4 cycle over the S dedicated stages (pointer
-      // pa), conv5 over all W stages (pointer pb).  Parities are tracked per stage (bit s of `par`); the MMA warp
-      // walks the identical sequence.
-      int pa = 0, pb = 0, it = 0;
-      uint32_t par = 0;
-      auto load = [&](int st, const CUtensorMap* tm, int kcol, int nrow, uint32_t bytes) {
-        ptx::mbar_wait(&w_empty[st], ((par >> st) & 1) ^ 1);
-        par ^= 1u << st;
-        const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&w_full[st]), 0);
+    // Two stage sequences share the per-stage barriers: conv2..conv4 cycle over the S dedicated stages (pointer
+    // pa), conv5 over all W stages (pointer pb).  Parities are tracked per stage (bit s of `par`); the MMA warp
+    // walks the identical sequence.
+    int pa = 0, pb = 0, it = 0;
+    uint32_t par = 0;
+    const uint32_t full_leader0 = ptx::mapa(ptx::smem_u32(&w_full[0]), 0);
+    auto load = [&](int st, const CUtensorMap* tm, int kcol, int nrow, uint32_t bytes) {
+      ptx::mbar_wait(&w_empty[st], ((par >> st) & 1) ^ 1);
+      par ^= 1u << st;
+      if (ptx::elect_one()) {
         if (leader) ptx::mbar_arrive_expect_tx(&w_full[st], 2 * bytes);
-        ptx::tma_load_2d_pair(stage_ptr(st), tm, full_leader, kcol, nrow);
-      };
-      auto next_a = [&]() { const int st = pa; pa = pa + 1 == S ? 0 : pa + 1; return st; };
-      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
-        load(next_a(), &tmW2, 0, static_cast<int>(rank) * 64, 64 * 128);                                    // conv2: N = 128
-        for (int kb = 0; kb < 2; ++kb) load(next_a(), &tmW3, kb * 64, static_cast<int>(rank) * 128, 128 * 128);  // conv3: N = 256
-        for (int c = 0; c < 2; ++c)                                                                        // conv4: 2 x (N = 256)
-          for (int kb = 0; kb < 4; ++kb) load(next_a(), &tmW4, kb * 64, c * 256 + static_cast<int>(rank) * 128, 128 * 128);
-        if (C5) {                                                                                          // conv5: 4 x (N = 256)
-          bool fz_ok = false;
-          for (int n = 0; n < 4; ++n)
-            for (int kb = 0; kb < 8; ++kb) {
-              const int st = pb;
-              pb = pb + 1 == W ? 0 : pb + 1;
-              if (st >= S && !fz_ok) {  // borrowed block: the feat4 store that staged through it must have drained it
-                ptx::mbar_wait(fz_free, it & 1);
-                fz_ok = true;
-              }
-              load(st, &tmW5, kb * 64, n * 256 + static_cast<int>(rank) * 128, 128 * 128);
+        ptx::tma_load_2d_pair(stage_ptr(st), tm, full_leader0 + 8u * st, kcol, nrow);
+      }
+      __syncwarp();
+    };
+    auto next_a = [&]() { const int st = pa; pa = pa + 1 == S ? 0 : pa + 1; return st; };
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+      load(next_a(), &tmW2, 0, static_cast<int>(rank) * 64, 64 * 128);                                    // conv2: N = 128
+      for (int kb = 0; kb < 2; ++kb) load(next_a(), &tmW3, kb * 64, static_cast<int>(rank) * 128, 128 * 128);  // conv3: N = 256
+      for (int c = 0; c < 2; ++c)                                                                        // conv4: 2 x (N = 256)
+        for (int kb = 0; kb < 4; ++kb) load(next_a(), &tmW4, kb * 64, c * 256 + static_cast<int>(rank) * 128, 128 * 128);
+      if (C5) {                                                                                          // conv5: 8 x (N = 128)
+        bool fz_ok = false;
+        for (int n = 0; n < 8; ++n)
+          for (int kb2 = 0; kb2 < 4; ++kb2) {   // one stage = two 64-wide k-blocks of this CTA's 64 weight rows (2 x 8 KB)
+            const int st = pb;
+            pb = pb + 1 == W ? 0 : pb + 1;
+            if (st >= S && !fz_ok) {  // borrowed block: the feat4 store that staged through it must have drained it
+              ptx::mbar_wait(fz_free, it & 1);
+              fz_ok = true;
             }
-        }
+            ptx::mbar_wait(&w_empty[st], ((par >> st) & 1) ^ 1);
+            par ^= 1u << st;
+            if (ptx::elect_one()) {
+              if (leader) ptx::mbar_arrive_expect_tx(&w_full[st], 2 * kChainBlock);
+              const int nrow = n * 128 + static_cast<int>(rank) * 64;
+              ptx::tma_load_2d_pair(stage_ptr(st), &tmW5, full_leader0 + 8u * st, (2 * kb2) * 64, nrow);
+              ptx::tma_load_2d_pair(stage_ptr(st) + kChainBlock / 2, &tmW5, full_leader0 + 8u * st, (2 * kb2 + 1) * 64, nrow);
+            }
+            __syncwarp();
+          }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA)
     if (leader) {
       int pa = 0, pb = 0, it = 0;
       uint32_t wpar = 0;  // per-stage parity of w_full (same stage sequence as the producer)
+      int peek_st = -1;   // stage whose full barrier was already seen complete while the previous k-block was issued
+      // wait for weight stage `st` (unless the look-ahead has seen it), then look at stage `nx` (the next one of the same sequence)
+      auto wait_stage = [&](int st, int nx) {
+        if (peek_st != st) ptx::mbar_wait(&w_full[st], (wpar >> st) & 1);
+        wpar ^= 1u << st;
+        ptx::tc_fence_after();
+        peek_st = ptx::mbar_test_wait(&w_full[nx], (wpar >> nx) & 1) ? nx : -1;
+      };
       // one weight k-block: A = activation block `a_off` of this CTA (and the peer's at the same offset)
       auto kblock = [&](uint32_t a_off, uint32_t d_tmem, uint32_t idesc, bool first) {
         const int st = pa;
         pa = pa + 1 == S ? 0 : pa + 1;
-        ptx::mbar_wait(&w_full[st], (wpar >> st) & 1);
-        wpar ^= 1u << st;
-        ptx::tc_fence_after();
-        if (lane == 0) {
+        wait_stage(st, pa);
+        if (ptx::elect_one()) {
           const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + a_off));
           const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(stage_ptr(st)));
 #pragma unroll
@@ -284,7 +304,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         __syncwarp();
       };
       auto commit_acc = [&](int buf) {
-        if (lane == 0) ptx::tc_commit_pair(&acc_full[buf], 3);
+        if (ptx::elect_one()) ptx::tc_commit_pair(&acc_full[buf], 3);
         __syncwarp();
       };
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
@@ -305,7 +325,8 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         // conv3: F2 (K = 128) -> buf1
         ptx::mbar_wait(&act_ready[1], par);
         if (C5) {
-          ptx::mbar_wait(&acc5_free[0], 1);  // previous tile's last conv5 chunk drained
+          ptx::mbar_wait(&acc5_free[0], 1);  // previous tile's last two conv5 chunks drained (four completions per
+          ptx::mbar_wait(&acc5_free[1], 1);  // buffer and tile: the phase parity is back to 0)
         } else {
           ptx::mbar_wait(&acc_free[1], 1);
         }
@@ -321,32 +342,36 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
           commit_acc(c);
         }
         if (C5) {
-          // conv5: A = feat4 in TMEM columns [0, 256) (K = 512), four 256-channel chunks -> columns [256, 512)
+          // conv5: A = feat4 in TMEM columns [0, 256) (K = 512); eight 128-channel chunks alternate between two
+          // accumulators (columns [256, 384) and [384, 512)), so chunk n + 1 runs while chunk n is drained.
           ptx::mbar_wait(a4_ready, par);
           ptx::tc_fence_after();
           const bool stamp5 = p.dbg && cluster_id == 0 && lane == 0 && it == 1;
           if (stamp5) p.dbg[64 + 8] = clock64();  // feat4 in TMEM
-          for (int n = 0; n < 4; ++n) {
-            ptx::mbar_wait(&acc5_free[0], (n & 1) ^ 1);  // chunk n - 1 (or the previous tile's chunk 3) drained
+          for (int n = 0; n < 8; ++n) {
+            const int b = n & 1, j = n >> 1;
+            ptx::mbar_wait(&acc5_free[b], (j & 1) ^ 1);  // chunk n - 2 (or the previous tile's chunk 6 / 7) drained
             ptx::tc_fence_after();
             if (stamp5) p.dbg[64 + 16 + n] = clock64();  // accumulator free
-            for (int kb = 0; kb < 8; ++kb) {
+            for (int kb2 = 0; kb2 < 4; ++kb2) {
               const int st = pb;
               pb = pb + 1 == W ? 0 : pb + 1;
-              ptx::mbar_wait(&w_full[st], (wpar >> st) & 1);
-              wpar ^= 1u << st;
-              ptx::tc_fence_after();
-              if (lane == 0) {
-                const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(stage_ptr(st)));
+              wait_stage(st, pb);
+              if (ptx::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc_mma_ts_pair(tmem_base + 256, tmem_base + kb * 32 + k * 8, db + 2 * k, kIdesc256, (kb > 0 || k > 0) ? 1u : 0u);
+                for (int h = 0; h < 2; ++h) {
+                  const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(stage_ptr(st)) + h * (kChainBlock / 2));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    tc_mma_ts_pair(tmem_base + 256 + 128 * b, tmem_base + (2 * kb2 + h) * 32 + k * 8, db + 2 * k, kIdesc128,
+                                   (kb2 > 0 || h > 0 || k > 0) ? 1u : 0u);
+                }
                 ptx::tc_commit_pair(&w_empty[st], 3);
-                if (kb == 7) ptx::tc_commit_pair(&acc5_full[0], 3);
-                if (kb == 7 && stamp5) p.dbg[64 + n] = clock64();  // chunk n issued
+                if (kb2 == 3) ptx::tc_commit_pair(&acc5_full[b], 3);
               }
               __syncwarp();
             }
+            if (stamp5) p.dbg[64 + n] = clock64();  // chunk n issued
           }
         }
         if (stamp) p.dbg[it * 8 + 1] = clock64();
@@ -509,26 +534,30 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         }
       }
       if (C5) {
-        // ---- conv5 epilogues: chunk n = channels [256 n, +256); this warp: columns [128 sub, +128) -> staging blocks
-        //      F3 (F2 / Z hold conv5 weights now) -> operand row columns 960 + 256 n + 64 b
+        // ---- conv5 epilogues: chunk n = channels [128 n, +128) in accumulator n & 1; this warp: columns [64 sub, +64)
+        //      -> staging blocks F3[2 (n & 1) + sub] (F2 / Z hold conv5 weights now) -> operand row columns 960 + 128 n + 64 b
         const uint32_t free5_leader0 = ptx::mapa(ptx::smem_u32(&acc5_free[0]), 0);
-        for (int n = 0; n < 4; ++n) {
-          staging_free(0);  // F3 was last read by the previous store group (feat4 chunk 1 / conv5 chunk n - 1)
+        for (int n = 0; n < 8; ++n) {
+          const int b = n & 1, j = n >> 1;
+          // blocks 2b, 2b + 1 of F3 were last read by the store of feat4 chunk 1 (n < 2) or of conv5 chunk n - 2: everything
+          // but the most recent group (chunk n - 1) must have been read
+          staging_free(n == 0 ? 0 : 1);
           const bool stamp5 = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it == 1;
           if (stamp5) p.dbg[64 + 24 + n] = clock64();  // staging free
-          ptx::mbar_wait(&acc5_full[0], n & 1);
+          ptx::mbar_wait(&acc5_full[b], j & 1);
           ptx::tc_fence_after();
           if (stamp5) p.dbg[64 + 32 + n] = clock64();  // accumulator ready
-          chain_drain<4, true>(t_lane + 256 + 128 * sub, 128 * sub, sconst + L::kB5 + 256 * n, sF3, rr, p.cat, grow, p.M, 0);
+          chain_drain<2, true>(t_lane + 256 + 128 * b + 64 * sub, 64 * sub, sconst + L::kB5 + 128 * n, sF3 + 2 * b * kChainBlock, rr,
+                               p.cat, grow, p.M, 0);
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(free5_leader0);
+          if (lane == 0) ptx::mbar_arrive_cluster(free5_leader0 + 8 * b);
           ptx::named_bar_sync(1, 32 * kPairEpiWarps);
           if (issuer) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-              store_blk(smem + L::kF3 + b * kChainBlock, 960 + 256 * n + 64 * b, row0);
+            for (int bb = 0; bb < 2; ++bb)
+              store_blk(smem + L::kF3 + (2 * b + bb) * kChainBlock, 960 + 128 * n + 64 * bb, row0);
             ptx::bulk_commit();
           }
           if (stamp5) p.dbg[64 + 40 + n] = clock64();  // drained, stores issued

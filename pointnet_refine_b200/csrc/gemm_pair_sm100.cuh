@@ -71,8 +71,8 @@ struct KbSlot {
   bool gate;
   int kb;  // index within its own group (gate / fusion)
 };
-__device__ __forceinline__ KbSlot fusion_slot(int it, int s, int kb_main, int kb_gate) {
-  const int ins = it == 0 ? 0 : kb_main / 3;
+__device__ __forceinline__ int fusion_gate_pos(int it, int kb_main) { return it == 0 ? 0 : kb_main / 3; }
+__device__ __forceinline__ KbSlot fusion_slot(int ins, int s, int kb_gate) {
   if (s < ins) return {false, s};
   if (s < ins + kb_gate) return {true, s - ins};
   return {false, s - kb_gate};
@@ -153,58 +153,62 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Both issue loops below are executed by the WHOLE warp with only the TMA / tcgen05 instructions predicated on
+  // elect.sync: every address and descriptor is then provably warp-uniform and lives in uniform registers.  Issued from
+  // an `if (lane == 0)` region the same instructions are wrapped in per-lane serialisation loops with R2UR moves, and
+  // since the tensor pipe queues only about one MMA ahead, that issue latency (plus the barrier round trip per k-block)
+  // showed up as ~194 instead of 128 cycles per 256x256x16 MMA (tools/mma_probe.cu, profiles/r02_mma_probe*.txt).
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int work = cluster_id; work < num_tiles; work += num_clusters, ++it) {
-        const int tile = work % out_tiles;
-        const int m_blk = tile / p.n_tiles;
-        const int n_blk = tile - m_blk * p.n_tiles;
-        const int kb_total = kb_count(work), kb0 = kb_begin(work);
-        for (int s = 0; s < kb_total; ++s) {
-          int kcol = kb0 + s;
-          if (EPI == EPI_FUSION) {  // the gate k-blocks are the last columns of the operand row
-            const KbSlot slot = fusion_slot(it, s, p.kb_main, p.kb_gate);
-            kcol = slot.gate ? p.kb_main + slot.kb : slot.kb;
-          }
-          ptx::mbar_wait(&bar_empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStage;
-          const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bar_full[stage]), 0);
-          if (EPI == EPI_FUSION && (p.flags & FUSE_DBG_NO_TMA)) {  // tuning experiment: MMA on stale smem
-            if (leader) ptx::mbar_arrive(&bar_full[stage]);
-          } else {
-            if (leader) ptx::mbar_arrive_expect_tx(&bar_full[stage], 2 * L::kStage);
-            if (MN) {  // boxes of 64 k-rows x 64 m/n columns: this CTA's 128 m and BN/2 n
-#pragma unroll
-              for (int b = 0; b < 2; ++b)
-                ptx::tma_load_2d_pair(sa + b * 8192, &tmA, full_leader, m_blk * 2 * BM + static_cast<int>(rank) * BM + 64 * b,
-                                      kcol * BK);
-#pragma unroll
-              for (int b = 0; b < BN / 128; ++b)
-                ptx::tma_load_2d_pair(sa + L::kA + b * 8192, &tmB, full_leader,
-                                      n_blk * BN + static_cast<int>(rank) * (BN / 2) + 64 * b, kcol * BK);
-            } else {
-              if (p.a_tiled)  // one contiguous 16 KB block: (column block, row tile) of the tiled operand matrix
-                ptx::tma_load_4d_pair(sa, &tmA, full_leader, 0, 0, (p.a_col0 + kcol * BK) / BK, m_blk * 2 + static_cast<int>(rank));
-              else
-                ptx::tma_load_2d_pair(sa, &tmA, full_leader, p.a_col0 + kcol * BK, m_blk * 2 * BM + static_cast<int>(rank) * BM);
-              ptx::tma_load_2d_pair(sa + L::kA, &tmB, full_leader, kcol * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
-            }
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    const uint32_t full_leader0 = ptx::mapa(ptx::smem_u32(&bar_full[0]), 0);
+    for (int work = cluster_id; work < num_tiles; work += num_clusters, ++it) {
+      const int tile = work % out_tiles;
+      const int m_blk = tile / p.n_tiles;
+      const int n_blk = tile - m_blk * p.n_tiles;
+      const int kb_total = kb_count(work), kb0 = kb_begin(work);
+      const int ins = fusion_gate_pos(it, p.kb_main);
+      for (int s = 0; s < kb_total; ++s) {
+        int kcol = kb0 + s;
+        if (EPI == EPI_FUSION) {  // the gate k-blocks are the last columns of the operand row
+          const KbSlot slot = fusion_slot(ins, s, p.kb_gate);
+          kcol = slot.gate ? p.kb_main + slot.kb : slot.kb;
         }
+        ptx::mbar_wait(&bar_empty[stage], phase ^ 1);
+        if (ptx::elect_one()) {
+          uint8_t* sa = smem + stage * L::kStage;
+          const uint32_t full_leader = full_leader0 + 8u * stage;
+          if (leader) ptx::mbar_arrive_expect_tx(&bar_full[stage], 2 * L::kStage);
+          if (MN) {  // boxes of 64 k-rows x 64 m/n columns: this CTA's 128 m and BN/2 n
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+              ptx::tma_load_2d_pair(sa + b * 8192, &tmA, full_leader, m_blk * 2 * BM + static_cast<int>(rank) * BM + 64 * b,
+                                    kcol * BK);
+#pragma unroll
+            for (int b = 0; b < BN / 128; ++b)
+              ptx::tma_load_2d_pair(sa + L::kA + b * 8192, &tmB, full_leader,
+                                    n_blk * BN + static_cast<int>(rank) * (BN / 2) + 64 * b, kcol * BK);
+          } else {
+            if (p.a_tiled)  // one contiguous 16 KB block: (column block, row tile) of the tiled operand matrix
+              ptx::tma_load_4d_pair(sa, &tmA, full_leader, 0, 0, (p.a_col0 + kcol * BK) / BK, m_blk * 2 + static_cast<int>(rank));
+            else
+              ptx::tma_load_2d_pair(sa, &tmA, full_leader, p.a_col0 + kcol * BK, m_blk * 2 * BM + static_cast<int>(rank) * BM);
+            ptx::tma_load_2d_pair(sa + L::kA, &tmB, full_leader, kcol * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      bool peeked = false;  // the full barrier of `stage` was already seen complete (looked at one k-block ahead)
       for (int work = cluster_id; work < num_tiles; work += num_clusters, ++it) {
         const int kb_total = kb_count(work);
         const bool stamp = p.dbg && cluster_id == 0 && lane == 0 && it < 16;
@@ -216,37 +220,38 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t par_free = (EPI == EPI_FUSION) ? ((it & 1) ^ 1) : (((it >> 1) & 1) ^ 1);
         const uint32_t acc_main = tmem_base + rf * BN;
         const uint32_t acc_gate = tmem_base + (rf ^ 1) * BN;
+        const int ins = fusion_gate_pos(it, p.kb_main);
+        const int kb_last = (EPI == EPI_FUSION ? p.kb_main : kb_total) - 1;
         for (int s = 0; s < kb_total; ++s) {
           KbSlot slot{false, s};
-          if (EPI == EPI_FUSION) slot = fusion_slot(it, s, p.kb_main, p.kb_gate);
+          if (EPI == EPI_FUSION) slot = fusion_slot(ins, s, p.kb_gate);
           if (slot.kb == 0) {  // first write into this region/stage: wait until the epilogue has drained it
             ptx::mbar_wait(&bar_tempty[slot.gate ? (rf ^ 1) : rf], par_free);
             ptx::tc_fence_after();
           }
-          ptx::mbar_wait(&bar_full[stage], phase);
+          if (!peeked) ptx::mbar_wait(&bar_full[stage], phase);
           ptx::tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = ptx::smem_u32(smem + stage * L::kStage);
+          const int cur = stage;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          // look at the next stage now: the answer arrives while this k-block's MMAs are being issued
+          peeked = ptx::mbar_test_wait(&bar_full[stage], phase);
+          if (ptx::elect_one()) {
+            const uint32_t a_addr = ptx::smem_u32(smem + cur * L::kStage);
             const uint64_t da = MN ? ptx::make_smem_desc_sw128_mn(a_addr, 8192) : ptx::make_smem_desc_sw128(a_addr);
             const uint64_t db = MN ? ptx::make_smem_desc_sw128_mn(a_addr + L::kA, 8192) : ptx::make_smem_desc_sw128(a_addr + L::kA);
             const uint32_t d = slot.gate ? acc_gate : acc_main;
             // K step of one MMA (16 bf16): 32 bytes along a K-major row, or 16 k-rows = 2048 bytes of an MN-major tile
             constexpr int kStep = MN ? (2048 >> 4) : 2;
-            if (!(EPI == EPI_FUSION && (p.flags & FUSE_DBG_NO_MMA))) {
 #pragma unroll
-              for (int k = 0; k < kMmaPerKb; ++k)
-                ptx::tc_mma_ss_pair<TF32>(d, da + kStep * k, db + kStep * k, kIdesc, (slot.kb > 0 || k > 0) ? 1u : 0u);
-            }
-            ptx::tc_commit_pair(&bar_empty[stage], 3);  // frees this smem stage in BOTH CTAs
+            for (int k = 0; k < kMmaPerKb; ++k)
+              ptx::tc_mma_ss_pair<TF32>(d, da + kStep * k, db + kStep * k, kIdesc, (slot.kb > 0 || k > 0) ? 1u : 0u);
+            ptx::tc_commit_pair(&bar_empty[cur], 3);  // frees this smem stage in BOTH CTAs
             if (slot.gate && slot.kb == p.kb_gate - 1) ptx::tc_commit_pair(&bar_tfull[rf ^ 1], 3);  // G_t complete
-            if (!slot.gate && slot.kb == (EPI == EPI_FUSION ? p.kb_main : kb_total) - 1) {
-              ptx::tc_commit_pair(&bar_tfull[rf], 3);                                               // F_t complete
-              if (stamp) p.dbg[it * 8 + 1] = clock64();
-            }
+            if (!slot.gate && slot.kb == kb_last) ptx::tc_commit_pair(&bar_tfull[rf], 3);           // F_t complete
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (stamp) p.dbg[it * 8 + 1] = clock64();  // last MMA of the tile issued
       }
     }
   } else {
@@ -363,7 +368,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (stamp) p.dbg[it * 8 + 2] = clock64();  // G ready
 #pragma unroll
         for (int i = 0; i < kChunks; ++i) {  // both phases hide under the next main loop: no need to pipeline the loads
-          if (p.flags & FUSE_DBG_SKIP_A) { for (int j = 0; j < 16; ++j) gq[16 * i + j] = 0; continue; }
           const int c0 = col_lo + 32 * i;
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(t_lane + (rf ^ 1) * BN + c0, r);
@@ -388,7 +392,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         {
 #pragma unroll
           for (int i = 0; i < kChunks; ++i) {
-            if (p.flags & FUSE_DBG_SKIP_B) continue;
             const int c0 = col_lo + 32 * i;
             uint32_t r[32];
             ptx::tmem_ld_32x32b_x32(t_lane + rf * BN + c0, r);

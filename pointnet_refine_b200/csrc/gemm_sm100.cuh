@@ -29,8 +29,7 @@ constexpr int kGemmThreads = 192;   // 6 warps
 constexpr int kTileRowBytes = 128;  // one swizzle row: 64 bf16 or 32 tf32 along K
 
 enum { EPI_ACT = 0, EPI_FUSION = 1 };
-enum { FUSE_POOL = 1, FUSE_ARGMAX = 2, FUSE_STORE_CN = 4, FUSE_STORE_PM = 8,
-       FUSE_DBG_SKIP_A = 16, FUSE_DBG_SKIP_B = 32, FUSE_DBG_NO_TMA = 64, FUSE_DBG_NO_MMA = 128 };  // tuning experiments only (env LRN_DBG_SKIP, wrong results)
+enum { FUSE_POOL = 1, FUSE_ARGMAX = 2, FUSE_STORE_CN = 4, FUSE_STORE_PM = 8 };
 
 struct GemmParams {
   int M;        // rows (points) covered by this launch

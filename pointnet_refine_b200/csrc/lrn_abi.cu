@@ -470,10 +470,12 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
   }
   const GemmPlan plan_f = plan_gemm(1024, EPI_FUSION), plan_p = plan_gemm(256, EPI_ACT);
   CUtensorMap tw_chain[4];
+  static const bool chain5 = [] { const char* e = getenv("LRN_CHAIN5"); return !(e && e[0] == '0'); }();
   if (!tf32) {
     for (int k = 2; k <= 5; ++k) {
+      // TMA box = the weight rows ONE CTA of the pair stages per k-block: N / 2 (conv2 and conv5 run as N = 128 MMAs)
       st = make_tmap(&tw_chain[k - 2], precision, pk + L.w[k], kChan[k], kChan[k - 1], kChan[k - 1],
-                     k == 2 ? 64 : 128);
+                     (k == 2 || (k == 5 && chain5)) ? 64 : 128);
       if (st) return st;
     }
   }
@@ -497,7 +499,6 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     // bf16 tier: conv1..conv4 + gate layer 1 as ONE fused kernel (activations stay in shared memory);
     // LRN_NO_CHAIN=1 or the tf32 tier run one kernel per layer.
     static const bool no_chain = [] { const char* e = getenv("LRN_NO_CHAIN"); return e && e[0] == '1'; }();
-    static const bool chain5 = [] { const char* e = getenv("LRN_CHAIN5"); return !(e && e[0] == '0'); }();
     const bool fused_chain = !tf32 && plan_f.pair && !no_chain;
     // default bf16 path (chain kernel with conv5 + fusion kernel): the operand matrix is kept in the tiled layout
     static const bool no_tiled = [] { const char* e = getenv("LRN_NO_TILED"); return e && e[0] == '1'; }();
@@ -582,8 +583,6 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.inv_npts = 1.0f / float(N);
       p.flags = ((flags & LRN_OUT_ARGMAX) ? (FUSE_ARGMAX | FUSE_POOL) : (flags & LRN_OUT_POOL) ? FUSE_POOL : 0) |
                 ((flags & LRN_OUT_FUSED) ? FUSE_STORE_CN : 0) | ((flags & LRN_OUT_MEMORY) ? FUSE_STORE_PM : 0);
-      static const int dbg_skip = [] { const char* e = getenv("LRN_DBG_SKIP"); return e ? atoi(e) : 0; }();
-      p.flags |= (dbg_skip & 15) * FUSE_DBG_SKIP_A;  // tuning experiments only
       p.global_feat = global_feat;
       p.pool_key = keys;
       p.fused_cn = fused;

@@ -50,15 +50,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking look at a barrier phase (mbarrier.test_wait never suspends the thread): used by the MMA / TMA issue
+// loops to learn, while the current k-block is being issued, whether the NEXT stage is already there, so that the
+// barrier round trip is off the tensor pipe's critical path (tools/mma_probe: 146 -> 130 cycles per 256x256x16 MMA).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug becomes a trap (error status to the host) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("lrn: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
-             parity);
-      __trap();
-    }
+    if (++spins > (1u << 24)) __trap();
   }
 }
 

@@ -30,7 +30,7 @@ if os.environ.get("LRN_DBG_LAYER") == "4":
     if int(f[64 + 8]) != 0:
         z = int(f[64 + 8])
         print("conv5 of tile 1 (cycles since feat4-in-TMEM): per chunk n: [acc free (MMA), chunk issued (MMA) | staging free, acc ready, drained (epilogue)]")
-        for n in range(4):
+        for n in range(8):
             print(f"  n={n}: {int(f[64+16+n])-z:7d} {int(f[64+n])-z:7d} | {int(f[64+24+n])-z:7d} {int(f[64+32+n])-z:7d} {int(f[64+40+n])-z:7d}")
     sys.exit(0)
 for i in range(16):
