@@ -157,8 +157,6 @@ int lrn_profile_enable(int on);
 /* Tuning aid: while `device_buffer` (>= 128 int64, zeroed by the caller) is non-null, cluster 0 of the
  * fusion kernel records clock64() stamps of its first 16 tiles there (see tools/timeline.py). */
 int lrn_debug_timeline(long long* device_buffer);
-/* Validation aid: out (128,64) fp32 = A (128,64) bf16 * W (64,64)^T bf16 with A fed from tensor memory. */
-int lrn_debug_ts_probe(const void* a_bf16, const void* w_bf16, float* out, lrn_stream_t stream);
 int lrn_profile_read(float* ms_per_stage /*[LRN_STAGE_COUNT]*/, int64_t* launches_per_stage /*[LRN_STAGE_COUNT]*/);
 
 /* ---- train mode: batch-statistic BatchNorm forward + hand-written backward of the context encoder ----

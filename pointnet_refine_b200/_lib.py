@@ -23,7 +23,7 @@ PRECISIONS = {"bf16": PREC_BF16, "tf32": PREC_TF32}
 EXPORTS = [
     "lrn_abi_version", "lrn_status_string", "lrn_last_error", "lrn_device_check",
     "lrn_encoder_packed_bytes", "lrn_encoder_fold", "lrn_encoder_workspace_bytes", "lrn_encoder_forward",
-    "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_debug_ts_probe", "lrn_train_workspace_bytes",
+    "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_train_workspace_bytes",
     "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
     "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden", "lrn_pos_hidden_backward",
     "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_scene_resample", "lrn_adam_step", "lrn_l1_deep_supervision", "lrn_col_sum_bf16", "lrn_gather_heads",
@@ -105,8 +105,6 @@ def _load():
     lib.lrn_pos_hidden_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp]
     lib.lrn_pos_hidden.restype = ci
     lib.lrn_pos_hidden.argtypes = [vp, vp, vp, i64, vp, i64, vp]
-    lib.lrn_debug_ts_probe.restype = ci
-    lib.lrn_debug_ts_probe.argtypes = [vp, vp, vp, vp]
     lib.lrn_debug_timeline.restype = ci
     lib.lrn_debug_timeline.argtypes = [vp]
     if lib.lrn_abi_version() != 1:

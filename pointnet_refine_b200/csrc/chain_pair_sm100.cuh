@@ -19,19 +19,16 @@
 // conv4 chunk 1 -> buf1, so conv4's second chunk runs while the first one is drained, and the next
 // tile's conv1 is computed while conv4's first chunk runs.
 //
-// C5 = true appends conv5 (512 -> 1024, src/model.py:47; 75 % of the chain's FLOPs) with its A operand in
+// conv5 (512 -> 1024, src/model.py:47; 75 % of the chain's FLOPs) runs in the same kernel with its A operand in
 // TENSOR MEMORY: the conv4 epilogue writes feat4 as packed bf16 into TMEM columns [0, 256) (row = lane,
 // two channels per column) besides staging it for the TMA store, and conv5 runs as
 // tcgen05.mma.cta_group::2 [D], [A_tmem], B_desc ("TS" form) over eight 128-channel chunks that alternate between
-// two accumulators (columns [256, 384) / [384, 512)): the drain of chunk n hides under the MMAs of chunk n + 1
-// (an N = 128 TS MMA takes 77 cycles against 64 of math, tools/mma_probe.cu, but four 256-channel chunks through
-// the single accumulator that fits beside feat4 serialise MMAs and drains: 8.6k instead of 2 x 2.5k cycles per 256
-// channels).  Only the weights touch shared memory.  Measured: the TMEM A read costs ~128 cycles
-// per MMA whatever N is, so N = 256 (128-cycle math) is the shape that runs at the tensor-pipe floor
-// (N = 128 chunks with double-buffered accumulators took 125 cycles per MMA, i.e. half rate); the
-// shared-memory-operand form of the same MMA takes ~194 cycles.  conv5 streams 512 KB of weights per CTA and
-// tile; with a TMA latency of ~2.8k cycles the three 16 KB stages are latency-bound (17 B/clk), so while
-// conv5 runs the four F2 / Z blocks (idle then) serve as four more weight stages (7 x 16 KB in flight).
+// two accumulators (columns [256, 384) / [384, 512)): the drain of chunk n hides under the MMAs of chunk n + 1.
+// An N = 128 TS MMA takes 77 cycles against 64 of math (tools/mma_probe.cu), but four 256-channel chunks through
+// the single accumulator that fits beside feat4 serialise MMAs and drains (8.6k instead of 2 x 2.5k cycles per 256
+// channels).  Only the weights touch shared memory: conv5 streams 512 KB of them per CTA and tile, and while it runs
+// the four F2 / Z blocks (idle then) serve as four more 16 KB weight stages (7 in flight; one stage = two 64-wide
+// k-blocks of the CTA's 64 weight rows = 8 MMAs per barrier round trip).
 #pragma once
 #include "gemm_pair_sm100.cuh"
 
@@ -48,9 +45,8 @@ struct ChainParams {
   const float* b2;    // (128) folded biases of conv2..conv4
   const float* b3;    // (256)
   const float* b4;    // (512)
-  const float* b5;    // (1024), C5 only
-  void* cat;          // operand rows (M, 2048) bf16
-  int tiled;          // operand matrix in the tiled layout: tmCat is a 4-D map, every store is one contiguous 16 KB block
+  const float* b5;    // (1024)
+  void* cat;          // operand matrix (M, 2048) bf16 in the tiled layout (tmCat is its 4-D map: one store = one contiguous 16 KB block)
   long long* dbg;
 };
 
@@ -93,9 +89,9 @@ __device__ __forceinline__ void stage_row_chunk(uint32_t blocks, int rr, int c0,
 }
 
 // Drain NCHUNKS x 32 accumulator columns starting at TMEM address `t_addr` (layer column `col_lo`) of this
-// thread's row: bias + ReLU -> bf16 -> either swizzled smem blocks (the next layer's A operand and the
-// TMA-store source) or direct global stores.  TMEM loads are double-buffered.
-// Same, but the packed bf16 pairs are also kept in registers (they become a TMEM-resident A operand).
+// thread's row: bias + ReLU -> bf16 -> swizzled smem blocks (the next layer's A operand and the TMA-store
+// source).  TMEM loads are double-buffered.  chain_drain_keep also keeps the packed bf16 pairs in registers
+// (they become a TMEM-resident A operand).
 template <int NCHUNKS>
 __device__ __forceinline__ void chain_drain_keep(uint32_t t_addr, int col_lo, const float* bias, uint32_t sblocks, int rr,
                                                  uint32_t (&keep)[NCHUNKS * 16]) {
@@ -114,9 +110,8 @@ __device__ __forceinline__ void chain_drain_keep(uint32_t t_addr, int col_lo, co
   }
 }
 
-template <int NCHUNKS, bool TO_SMEM>
-__device__ __forceinline__ void chain_drain(uint32_t t_addr, int col_lo, const float* bias, uint32_t sblocks, int rr,
-                                            void* cat, long long grow, int M, int gcol0) {
+template <int NCHUNKS>
+__device__ __forceinline__ void chain_drain(uint32_t t_addr, int col_lo, const float* bias, uint32_t sblocks, int rr) {
   uint32_t r[2][32];
   ptx::tmem_ld_32x32b_x32(t_addr, r[0]);
 #pragma unroll
@@ -127,11 +122,7 @@ __device__ __forceinline__ void chain_drain(uint32_t t_addr, int col_lo, const f
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[i & 1][j]) + bias[c0 + j], 0.f);
-    if (TO_SMEM) {
-      stage_row_chunk(sblocks, rr, c0, v);
-    } else if (grow < M) {
-      store_row_chunk<false>(cat, grow * 2048 + gcol0 + c0, v, false, false);
-    }
+    stage_row_chunk(sblocks, rr, c0, v);
   }
 }
 
@@ -146,7 +137,6 @@ __device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem,
       : "memory");
 }
 
-template <bool C5>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3,
                   const __grid_constant__ CUtensorMap tmW4, const __grid_constant__ CUtensorMap tmW5,
@@ -184,7 +174,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     ptx::prefetch_tmap(&tmW2);
     ptx::prefetch_tmap(&tmW3);
     ptx::prefetch_tmap(&tmW4);
-    if (C5) ptx::prefetch_tmap(&tmW5);
+    ptx::prefetch_tmap(&tmW5);
     ptx::prefetch_tmap(&tmCat);
     for (int s = 0; s < W; ++s) {
       ptx::mbar_init(&w_full[s], 1);
@@ -204,7 +194,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
   if (warp == 1) ptx::tmem_alloc_pair<512>(tmem_ptr);
   if (warp >= 2) {  // layer constants -> shared memory, once
     const int t = threadIdx.x - 64;
-    for (int i = t; i < (C5 ? L::kNumConst : L::kB5); i += 32 * kPairEpiWarps) {
+    for (int i = t; i < L::kNumConst; i += 32 * kPairEpiWarps) {
       float v;
       if (i < L::kB1) v = p.w1[i];
       else if (i < L::kWg1) v = p.b1[i - L::kB1];
@@ -223,8 +213,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr;
   // one [128 rows x 64 columns] activation block -> operand matrix (row0 is a multiple of 128, col of 64)
   auto store_blk = [&](const void* smem_src, int col, int row0) {
-    if (p.tiled) ptx::tma_store_4d(&tmCat, smem_src, 0, 0, col >> 6, row0 >> 7);
-    else ptx::tma_store_2d(&tmCat, smem_src, col, row0);
+    ptx::tma_store_4d(&tmCat, smem_src, 0, 0, col >> 6, row0 >> 7);
   };
 
   // Producer and MMA issue loops run warp-converged with the TMA / tcgen05 instructions predicated on elect.sync
@@ -253,7 +242,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       for (int kb = 0; kb < 2; ++kb) load(next_a(), &tmW3, kb * 64, static_cast<int>(rank) * 128, 128 * 128);  // conv3: N = 256
       for (int c = 0; c < 2; ++c)                                                                        // conv4: 2 x (N = 256)
         for (int kb = 0; kb < 4; ++kb) load(next_a(), &tmW4, kb * 64, c * 256 + static_cast<int>(rank) * 128, 128 * 128);
-      if (C5) {                                                                                          // conv5: 8 x (N = 128)
+      {                                                                                                  // conv5: 8 x (N = 128)
         bool fz_ok = false;
         for (int n = 0; n < 8; ++n)
           for (int kb2 = 0; kb2 < 4; ++kb2) {   // one stage = two 64-wide k-blocks of this CTA's 64 weight rows (2 x 8 KB)
@@ -311,37 +300,30 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         const uint32_t par = it & 1;
         const bool stamp = p.dbg && cluster_id == 0 && lane == 0 && it < 16;
         if (stamp) p.dbg[it * 8 + 0] = clock64();
-        // Barrier bookkeeping.  Without conv5 each accumulator buffer is drained twice per tile (conv2|conv3 and a
-        // conv4 chunk): waits alternate parity 1 (previous tile's conv4 chunk) / 0.  With conv5 the conv4 chunks are
-        // not handed back (buf0 becomes conv5's A operand, buf1 its accumulators): acc_free completes once per
-        // tile, and the buffers are reusable once the tensor pipe (in order) is past conv5 and acc5_free says
-        // the last conv5 chunks have been drained.
+        // Barrier bookkeeping.  The conv4 chunks are not handed back through acc_free (buf0 becomes conv5's A operand,
+        // buf1 its accumulators): acc_free completes once per tile, and the buffers are reusable once the tensor pipe
+        // (in order) is past conv5 and acc5_free says the last conv5 chunks have been drained.
         // conv2: F1 (K = 64) -> buf0[0:128)
         ptx::mbar_wait(&act_ready[0], par);
-        if (!C5) ptx::mbar_wait(&acc_free[0], 1);
         ptx::tc_fence_after();
         kblock(L::kF1, tmem_base, kIdesc128, true);
         commit_acc(0);
         // conv3: F2 (K = 128) -> buf1
         ptx::mbar_wait(&act_ready[1], par);
-        if (C5) {
-          ptx::mbar_wait(&acc5_free[0], 1);  // previous tile's last two conv5 chunks drained (four completions per
-          ptx::mbar_wait(&acc5_free[1], 1);  // buffer and tile: the phase parity is back to 0)
-        } else {
-          ptx::mbar_wait(&acc_free[1], 1);
-        }
+        ptx::mbar_wait(&acc5_free[0], 1);  // previous tile's last two conv5 chunks drained (four completions per
+        ptx::mbar_wait(&acc5_free[1], 1);  // buffer and tile: the phase parity is back to 0)
         ptx::tc_fence_after();
         for (int kb = 0; kb < 2; ++kb) kblock(L::kF2 + kb * kChainBlock, tmem_base + 256, kIdesc256, kb == 0);
         commit_acc(1);
         // conv4: F3 (K = 256) -> buf0 (channels 0..255), buf1 (channels 256..511)
         ptx::mbar_wait(&act_ready[2], par);
         for (int c = 0; c < 2; ++c) {
-          ptx::mbar_wait(&acc_free[c], C5 ? par : 0);  // this tile's conv2 / conv3 accumulator drained
+          ptx::mbar_wait(&acc_free[c], par);  // this tile's conv2 / conv3 accumulator drained
           ptx::tc_fence_after();
           for (int kb = 0; kb < 4; ++kb) kblock(L::kF3 + kb * kChainBlock, tmem_base + c * 256, kIdesc256, kb == 0);
           commit_acc(c);
         }
-        if (C5) {
+        {
           // conv5: A = feat4 in TMEM columns [0, 256) (K = 512); eight 128-channel chunks alternate between two
           // accumulators (columns [256, 384) and [384, 512)), so chunk n + 1 runs while chunk n is drained.
           ptx::mbar_wait(a4_ready, par);
@@ -441,7 +423,6 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     if (cluster_id < p.num_tiles) embed(cluster_id);
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
       const int row0 = tile * 2 * BM + static_cast<int>(rank) * BM;
-      const long long grow = row0 + rr;
       // ---- conv2 epilogue: buf0[0:128) -> F2 (2 blocks); this warp: columns [64 sub, 64 sub + 64)
       const bool stamp = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it < 16;
       // F2 doubled as staging in the previous tile: feat4 chunk 0 (then only f4c1), or conv5 chunk 2 (then only chunk 3)
@@ -449,7 +430,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       ptx::mbar_wait(&acc_full[0], 0);
       ptx::tc_fence_after();
       if (stamp) p.dbg[it * 8 + 2] = clock64();  // conv2 accumulator ready
-      chain_drain<2, true>(t_lane + 64 * sub, 64 * sub, sconst + L::kB2, sF2, rr, p.cat, grow, p.M, 0);
+      chain_drain<2>(t_lane + 64 * sub, 64 * sub, sconst + L::kB2, sF2, rr);
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
       __syncwarp();
@@ -469,7 +450,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       ptx::mbar_wait(&acc_full[1], 0);
       ptx::tc_fence_after();
       if (stamp) p.dbg[it * 8 + 4] = clock64();  // conv3 accumulator ready
-      chain_drain<4, true>(t_lane + 256 + 128 * sub, 128 * sub, sconst + L::kB3, sF3, rr, p.cat, grow, p.M, 0);
+      chain_drain<4>(t_lane + 256 + 128 * sub, 128 * sub, sconst + L::kB3, sF3, rr);
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
       __syncwarp();
@@ -496,18 +477,11 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         staging_free(has_next ? 2 : 1);
         ptx::mbar_wait(&acc_full[c], 1);
         ptx::tc_fence_after();
-        uint32_t keep[C5 ? 64 : 1];
-        if (C5) {
-          chain_drain_keep<4>(t_lane + 256 * c + 128 * sub, 128 * sub, sconst + L::kB4 + 256 * c, c == 0 ? sF2 : sF3, rr,
-                              reinterpret_cast<uint32_t(&)[64]>(keep));
-        } else {
-          chain_drain<4, true>(t_lane + 256 * c + 128 * sub, 128 * sub, sconst + L::kB4 + 256 * c, c == 0 ? sF2 : sF3, rr,
-                               p.cat, grow, p.M, 0);
-        }
+        uint32_t keep[64];
+        chain_drain_keep<4>(t_lane + 256 * c + 128 * sub, 128 * sub, sconst + L::kB4 + 256 * c, c == 0 ? sF2 : sF3, rr, keep);
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (!C5 && lane == 0) ptx::mbar_arrive_cluster(free_leader0 + 8 * c);
         ptx::named_bar_sync(1, 32 * kPairEpiWarps);  // every warp is done reading this accumulator buffer
         if (issuer) {
 #pragma unroll
@@ -515,12 +489,12 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
             store_blk(smem + (c == 0 ? L::kF2 : L::kF3) + b * kChainBlock, 448 + 256 * c + 64 * b, row0);
           ptx::bulk_commit();
         }
-        if (C5) {
+        {
           // feat4 channels [256 c + 128 sub, +128) as conv5's A operand: packed columns [128 c + 64 sub, +64) of buf0
           // (all reads of buf0 by chunk 0 finished at the barrier above / one iteration earlier)
           ptx::tc_fence_after();
           ptx::tmem_st_32x32b_x32(t_lane + 128 * c + 64 * sub, reinterpret_cast<const uint32_t(&)[32]>(keep[0]));
-          ptx::tmem_st_32x32b_x32(t_lane + 128 * c + 64 * sub + 32, reinterpret_cast<const uint32_t(&)[32]>(keep[C5 ? 32 : 0]));
+          ptx::tmem_st_32x32b_x32(t_lane + 128 * c + 64 * sub + 32, reinterpret_cast<const uint32_t(&)[32]>(keep[32]));
           ptx::tmem_st_wait();
           if (c == 1) {
             ptx::tc_fence_before();
@@ -533,7 +507,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
           }
         }
       }
-      if (C5) {
+      {
         // ---- conv5 epilogues: chunk n = channels [128 n, +128) in accumulator n & 1; this warp: columns [64 sub, +64)
         //      -> staging blocks F3[2 (n & 1) + sub] (F2 / Z hold conv5 weights now) -> operand row columns 960 + 128 n + 64 b
         const uint32_t free5_leader0 = ptx::mapa(ptx::smem_u32(&acc5_free[0]), 0);
@@ -547,8 +521,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
           ptx::mbar_wait(&acc5_full[b], j & 1);
           ptx::tc_fence_after();
           if (stamp5) p.dbg[64 + 32 + n] = clock64();  // accumulator ready
-          chain_drain<2, true>(t_lane + 256 + 128 * b + 64 * sub, 64 * sub, sconst + L::kB5 + 128 * n, sF3 + 2 * b * kChainBlock, rr,
-                               p.cat, grow, p.M, 0);
+          chain_drain<2>(t_lane + 256 + 128 * b + 64 * sub, 64 * sub, sconst + L::kB5 + 128 * n, sF3 + 2 * b * kChainBlock, rr);
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           __syncwarp();

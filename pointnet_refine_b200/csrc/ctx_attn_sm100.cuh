@@ -105,41 +105,54 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_o = tmem_base + 256;
 
+  // TMA and tcgen05 instructions are issued from warp-converged loops under elect.sync (uniform-register operands,
+  // no per-lane serialisation loops): see gemm_pair_sm100.cuh / tools/mma_probe.cu.
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      const uint32_t q_leader = ptx::mapa(ptx::smem_u32(q_full), 0);
-      int g = 0;  // running step counter over all items of this cluster: stage = g & 1, phase = (g >> 1) & 1
-      for (int item = cluster_id; item < p.items; item += num_clusters) {
-        const int seg = item_seg(item), step0 = item_step0(item), steps = item_steps(item);
-        const int64_t seg_row0 = static_cast<int64_t>(seg) * p.N;
-        // the previous item's last S product has finished reading the folded queries
-        if (g >= 1) ptx::mbar_wait(&s_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+    const uint32_t q_leader = ptx::mapa(ptx::smem_u32(q_full), 0);
+    const uint32_t kp_leader0 = ptx::mapa(ptx::smem_u32(&kp_full[0]), 0);
+    const uint32_t v_leader0 = ptx::mapa(ptx::smem_u32(&v_full[0]), 0);
+    int g = 0;  // running step counter over all items of this cluster: stage = g & 1, phase = (g >> 1) & 1
+    for (int item = cluster_id; item < p.items; item += num_clusters) {
+      const int seg = item_seg(item), step0 = item_step0(item), steps = item_steps(item);
+      const int64_t seg_row0 = static_cast<int64_t>(seg) * p.N;
+      // the previous item's last S product has finished reading the folded queries
+      if (g >= 1) ptx::mbar_wait(&s_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+      if (ptx::elect_one()) {
         if (leader) ptx::mbar_arrive_expect_tx(q_full, 2 * 65536);
+#pragma unroll
         for (int kb = 0; kb < 4; ++kb)
           ptx::tma_load_2d_pair(smem + L::kQ + kb * 16384, &tmQ, q_leader, kb * 64, seg * 256 + static_cast<int>(rank) * 128);
-        for (int j = 0; j < steps; ++j, ++g) {
-          const int st = g & 1;
-          const uint32_t prev = ((g - 2) >> 1) & 1;  // parity of the phase that step g - 2 completed
-          const int row = static_cast<int>(seg_row0) + (step0 + j) * kAttnStep;
-          // Kp: this CTA's 64 points of the step (the B operand of S is split by points across the pair)
-          if (g >= 2) ptx::mbar_wait(&s_full[st], prev);
-          const uint32_t kp_leader = ptx::mapa(ptx::smem_u32(&kp_full[st]), 0);
+      }
+      __syncwarp();
+      for (int j = 0; j < steps; ++j, ++g) {
+        const int st = g & 1;
+        const uint32_t prev = ((g - 2) >> 1) & 1;  // parity of the phase that step g - 2 completed
+        const int row = static_cast<int>(seg_row0) + (step0 + j) * kAttnStep;
+        // Kp: this CTA's 64 points of the step (the B operand of S is split by points across the pair)
+        if (g >= 2) ptx::mbar_wait(&s_full[st], prev);
+        if (ptx::elect_one()) {
           if (leader) ptx::mbar_arrive_expect_tx(&kp_full[st], 2 * 32768);
+#pragma unroll
           for (int kb = 0; kb < 4; ++kb)
-            ptx::tma_load_2d_pair(smem + L::kKp + st * 32768 + kb * 8192, &tmKp, kp_leader, kb * 64, row + static_cast<int>(rank) * 64);
-          // Mem: all 128 points, this CTA's 128 of the 256 output dims (the B operand of O is split by dims)
-          if (g >= 2) ptx::mbar_wait(&o_done[st], prev);
-          const uint32_t v_leader = ptx::mapa(ptx::smem_u32(&v_full[st]), 0);
+            ptx::tma_load_2d_pair(smem + L::kKp + st * 32768 + kb * 8192, &tmKp, kp_leader0 + 8u * st, kb * 64,
+                                  row + static_cast<int>(rank) * 64);
+        }
+        __syncwarp();
+        // Mem: all 128 points, this CTA's 128 of the 256 output dims (the B operand of O is split by dims)
+        if (g >= 2) ptx::mbar_wait(&o_done[st], prev);
+        if (ptx::elect_one()) {
           if (leader) ptx::mbar_arrive_expect_tx(&v_full[st], 2 * 32768);
+#pragma unroll
           for (int pb = 0; pb < 2; ++pb)
+#pragma unroll
             for (int db = 0; db < 2; ++db)
-              ptx::tma_load_2d_pair(smem + L::kV + st * 32768 + pb * 16384 + db * 8192, &tmV, v_leader,
+              ptx::tma_load_2d_pair(smem + L::kV + st * 32768 + pb * 16384 + db * 8192, &tmV, v_leader0 + 8u * st,
                                     static_cast<int>(rank) * 128 + db * 64, row + pb * 64);
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA)
     if (leader) {
@@ -147,7 +160,7 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int st = g & 1;
         ptx::mbar_wait(&kp_full[st], (g >> 1) & 1);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        if (ptx::elect_one()) {
           const uint32_t d = tmem_base + st * 128;
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
@@ -173,7 +186,7 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ptx::mbar_wait(&p_ready[st], par);
           ptx::mbar_wait(&v_full[st], par);
           ptx::tc_fence_after();
-          if (lane == 0) {  // O += P_j Mem_j : A = P_j in the first 64 columns of S buffer st (2 points per column)
+          if (ptx::elect_one()) {  // O += P_j Mem_j : A = P_j in the first 64 columns of S buffer st (2 points per column)
 #pragma unroll
             for (int pb = 0; pb < 2; ++pb) {
               const uint64_t db = ptx::make_smem_desc_sw128_mn(ptx::smem_u32(smem + L::kV + st * 32768 + pb * 16384), 8192);

@@ -2,8 +2,7 @@
 // cluster of two CTAs.  Each CTA stages its own 128 rows of A and HALF of the weight tile, the
 // leader CTA's elected thread issues tcgen05.mma.cta_group::2 (M = 256), and each CTA's TMEM holds
 // the accumulator rows of its own 128 points.  Compared with the single-CTA 128x128 tile this
-// halves the shared-memory operand traffic per MMA cycle (64 B/clk instead of 128 B/clk), which is
-// what bounded the first version (profiles/r01_*).
+// halves the operand bytes each SM has to pull through TMA per MMA cycle.
 //
 //   warp 0      : TMA producer (both CTAs; bytes are counted on the LEADER's full barrier)
 //   warp 1      : TMEM allocator (both CTAs) + MMA issuer (leader only)
@@ -20,7 +19,7 @@
 //             the region again, so consecutive main loops run back to back and both epilogue phases hide
 //             under the 31 fusion k-blocks of the next tile.
 #pragma once
-#include "gemm_sm100.cuh"
+#include "gemm_common.cuh"
 
 namespace lrn {
 

@@ -13,12 +13,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
-#include "gemm_sm100.cuh"
+#include "gemm_common.cuh"
 #include "gemm_pair_sm100.cuh"
 #include "chain_pair_sm100.cuh"
-#include "ts_probe.cuh"
 #include "ctx_attn_sm100.cuh"
 #include "scene_kernels.cuh"
 #include "query_kernels.cuh"
@@ -173,20 +173,17 @@ int device_info(DeviceInfo* out) {
 }
 
 // ------------------------------------------------------------------ GEMM launch
-template <int BN, bool TF32, int EPI, int STAGES>
-int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sms, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_kernel<BN, TF32, EPI, STAGES>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
-    configured = true;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: `done` remembers (one bit per device ordinal) where a
+// kernel has been configured, so a process that drives several GPUs configures every one of them.
+template <typename Kern>
+int configure_smem(Kern kern, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  LRN_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = uint64_t(1) << (dev & 63);
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.fetch_or(bit, std::memory_order_release);
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  if (tiles <= 0) return LRN_OK;
-  const int grid = std::min(tiles, sms);
-  kern<<<grid, kGemmThreads, L::kDynamic, stream>>>(ta, tb, p);
-  LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
 
@@ -195,11 +192,9 @@ int launch_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
                   cudaStream_t stream) {
   using L = PairSmem<BN, STAGES, EPI == EPI_FUSION, STAGED>;
   auto kern = gemm_pair_kernel<BN, TF32, EPI, STAGES, GENERAL, STAGED, MN>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    LRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};  // per instantiation
+  int st = configure_smem(kern, L::kDynamic, configured);
+  if (st) return st;
   const int tiles = p.m_tiles * p.n_tiles * std::max(p.k_splits, 1);
   if (tiles <= 0) return LRN_OK;
   const int grid = 2 * std::min(tiles, sms / 2);  // one CTA pair (cluster of 2) per work-item slot
@@ -208,28 +203,18 @@ int launch_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   return LRN_OK;
 }
 
-// How one GEMM is tiled: CTA pairs (cta_group::2, 256-row tiles) by default; LRN_GEMM_V1=1 in the
-// environment selects the single-CTA kernels (kept for A/B measurements).
+// How one GEMM is tiled over CTA pairs (cta_group::2, 256-row tiles).
 struct GemmPlan {
-  bool pair;
   int bn;          // output channels per tile
   int b_box_rows;  // weight rows per TMA box (= rows one CTA stages)
   int m_rows;      // points per tile
 };
 
 GemmPlan plan_gemm(int64_t N, int epi) {
-  static const bool v1 = [] { const char* e = getenv("LRN_GEMM_V1"); return e && e[0] == '1'; }();
   GemmPlan g{};
-  g.pair = !v1;
-  if (g.pair) {
-    g.bn = (epi == EPI_FUSION || N % 256 == 0) ? 256 : 128;
-    g.b_box_rows = g.bn / 2;
-    g.m_rows = 2 * BM;
-  } else {
-    g.bn = (epi == EPI_FUSION) ? 128 : (N % 256 == 0 ? 256 : 128);
-    g.b_box_rows = g.bn;
-    g.m_rows = BM;
-  }
+  g.bn = (epi == EPI_FUSION || N % 256 == 0) ? 256 : 128;
+  g.b_box_rows = g.bn / 2;
+  g.m_rows = 2 * BM;
   return g;
 }
 
@@ -237,36 +222,24 @@ GemmPlan plan_gemm(int64_t N, int epi) {
 int launch_gemm(int precision, const GemmPlan& g, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
                 const GemmParams& p, int sms, cudaStream_t stream, const CUtensorMap* tout = nullptr) {
   const bool tf32 = precision == LRN_PREC_TF32;
-  static const bool no_staged = [] { const char* e = getenv("LRN_NO_STAGED"); return e && e[0] == '1'; }();
-  if (g.pair && epi == EPI_ACT && !tf32 && !p.out_f32 && tout && !no_staged) {
+  if (epi == EPI_ACT && !tf32 && !p.out_f32 && tout) {  // bf16 output: staged TMA stores
     return g.bn == 128 ? launch_pair_t<128, false, EPI_ACT, 6, true, true>(ta, tb, *tout, p, sms, stream)
                        : launch_pair_t<256, false, EPI_ACT, 4, true, true>(ta, tb, *tout, p, sms, stream);
   }
-  if (g.pair) {
-    if (epi == EPI_FUSION) {
-      // fast variant: no argmax and every warp's 32 points are valid and inside one segment
-      const bool fast = !(p.flags & FUSE_ARGMAX) && p.npts % 32 == 0 && p.M % 32 == 0 && p.row0 % 32 == 0;
-      if (fast)
-        return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, false>(ta, tb, ta, p, sms, stream)
-                    : launch_pair_t<256, false, EPI_FUSION, 5, false>(ta, tb, ta, p, sms, stream);
-      return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, true>(ta, tb, ta, p, sms, stream)
-                  : launch_pair_t<256, false, EPI_FUSION, 5, true>(ta, tb, ta, p, sms, stream);
-    }
-    if (g.bn == 128)
-      return tf32 ? launch_pair_t<128, true, EPI_ACT, 8>(ta, tb, ta, p, sms, stream)
-                  : launch_pair_t<128, false, EPI_ACT, 8>(ta, tb, ta, p, sms, stream);
-    return tf32 ? launch_pair_t<256, true, EPI_ACT, 6>(ta, tb, ta, p, sms, stream)
-                : launch_pair_t<256, false, EPI_ACT, 6>(ta, tb, ta, p, sms, stream);
-  }
   if (epi == EPI_FUSION) {
-    return tf32 ? launch_gemm_t<128, true, EPI_FUSION, 6>(ta, tb, p, sms, stream)
-                : launch_gemm_t<128, false, EPI_FUSION, 6>(ta, tb, p, sms, stream);
+    // fast variant: no argmax and every warp's 32 points are valid and inside one segment
+    const bool fast = !(p.flags & FUSE_ARGMAX) && p.npts % 32 == 0 && p.M % 32 == 0 && p.row0 % 32 == 0;
+    if (fast)
+      return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, false>(ta, tb, ta, p, sms, stream)
+                  : launch_pair_t<256, false, EPI_FUSION, 5, false>(ta, tb, ta, p, sms, stream);
+    return tf32 ? launch_pair_t<256, true, EPI_FUSION, 5, true>(ta, tb, ta, p, sms, stream)
+                : launch_pair_t<256, false, EPI_FUSION, 5, true>(ta, tb, ta, p, sms, stream);
   }
   if (g.bn == 128)
-    return tf32 ? launch_gemm_t<128, true, EPI_ACT, 6>(ta, tb, p, sms, stream)
-                : launch_gemm_t<128, false, EPI_ACT, 6>(ta, tb, p, sms, stream);
-  return tf32 ? launch_gemm_t<256, true, EPI_ACT, 4>(ta, tb, p, sms, stream)
-              : launch_gemm_t<256, false, EPI_ACT, 4>(ta, tb, p, sms, stream);
+    return tf32 ? launch_pair_t<128, true, EPI_ACT, 8>(ta, tb, ta, p, sms, stream)
+                : launch_pair_t<128, false, EPI_ACT, 8>(ta, tb, ta, p, sms, stream);
+  return tf32 ? launch_pair_t<256, true, EPI_ACT, 6>(ta, tb, ta, p, sms, stream)
+              : launch_pair_t<256, false, EPI_ACT, 6>(ta, tb, ta, p, sms, stream);
 }
 
 int fold_one(int precision, const float* w, const float* b, const float* g, const float* beta, const float* mean,
@@ -470,12 +443,11 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
   }
   const GemmPlan plan_f = plan_gemm(1024, EPI_FUSION), plan_p = plan_gemm(256, EPI_ACT);
   CUtensorMap tw_chain[4];
-  static const bool chain5 = [] { const char* e = getenv("LRN_CHAIN5"); return !(e && e[0] == '0'); }();
   if (!tf32) {
     for (int k = 2; k <= 5; ++k) {
       // TMA box = the weight rows ONE CTA of the pair stages per k-block: N / 2 (conv2 and conv5 run as N = 128 MMAs)
       st = make_tmap(&tw_chain[k - 2], precision, pk + L.w[k], kChan[k], kChan[k - 1], kChan[k - 1],
-                     (k == 2 || (k == 5 && chain5)) ? 64 : 128);
+                     (k == 2 || k == 5) ? 64 : 128);
       if (st) return st;
     }
   }
@@ -496,24 +468,17 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     st = make_tmap(&ta, precision, cat, rows, kCat, kCat, BM);
     if (st) return st;
 
-    // bf16 tier: conv1..conv4 + gate layer 1 as ONE fused kernel (activations stay in shared memory);
-    // LRN_NO_CHAIN=1 or the tf32 tier run one kernel per layer.
-    static const bool no_chain = [] { const char* e = getenv("LRN_NO_CHAIN"); return e && e[0] == '1'; }();
-    const bool fused_chain = !tf32 && plan_f.pair && !no_chain;
-    // default bf16 path (chain kernel with conv5 + fusion kernel): the operand matrix is kept in the tiled layout
-    static const bool no_tiled = [] { const char* e = getenv("LRN_NO_TILED"); return e && e[0] == '1'; }();
-    const bool tiled = fused_chain && chain5 && !no_tiled;
+    // bf16 tier: conv1..conv5 + gate layer 1 as ONE fused kernel (activations stay on the SM, the operand matrix is kept
+    // in the tiled layout); the tf32 tier runs one kernel per layer on row-major operand rows.
+    const bool fused_chain = !tf32;
+    const bool tiled = fused_chain;
     if (tiled) {
       st = make_tmap_tiled(&ta, cat, rows, kCat);
       if (st) return st;
     }
     if (fused_chain) {
-      static bool configured = false;
-      if (!configured) {
-        LRN_CUDA(cudaFuncSetAttribute(chain_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kDynamic));
-        LRN_CUDA(cudaFuncSetAttribute(chain_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kDynamic));
-        configured = true;
-      }
+      static std::atomic<uint64_t> configured{0};
+      if ((st = configure_smem(chain_pair_kernel, ChainSmem::kDynamic, configured))) return st;
       ChainParams cp{};
       cp.M = int(rows);
       cp.num_tiles = int((rows + 2 * BM - 1) / (2 * BM));
@@ -524,18 +489,11 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       cp.b4 = reinterpret_cast<const float*>(pk + L.b[4]);
       cp.b5 = reinterpret_cast<const float*>(pk + L.b[5]);
       cp.cat = cat;
-      cp.tiled = tiled ? 1 : 0;
       static const int dbg_layer = [] { const char* e = getenv("LRN_DBG_LAYER"); return e ? atoi(e) : 0; }();
       cp.dbg = dbg_layer == 4 ? g_dbg : nullptr;
-      // reported as stage "conv5" (with conv5 fused) or "conv4"; the other chain stages then read 0
-      StageTimer timer(chain5 ? LRN_STAGE_CONV5 : LRN_STAGE_CONV4, s);
+      StageTimer timer(LRN_STAGE_CONV5, s);  // reported as stage "conv5"; the other chain stages then read 0
       const int grid = 2 * std::min(cp.num_tiles, dev.sms / 2);
-      if (chain5)
-        chain_pair_kernel<true><<<grid, kPairThreads, ChainSmem::kDynamic, s>>>(tw_chain[0], tw_chain[1], tw_chain[2],
-                                                                                tw_chain[3], ta, cp);
-      else
-        chain_pair_kernel<false><<<grid, kPairThreads, ChainSmem::kDynamic, s>>>(tw_chain[0], tw_chain[1], tw_chain[2],
-                                                                                 tw_chain[3], ta, cp);
+      chain_pair_kernel<<<grid, kPairThreads, ChainSmem::kDynamic, s>>>(tw_chain[0], tw_chain[1], tw_chain[2], tw_chain[3], ta, cp);
       LRN_CUDA(cudaGetLastError());
     } else {  // layer 1 (+ gate layer 1): raw points -> operand columns
       StageTimer timer(LRN_STAGE_EMBED, s);
@@ -546,7 +504,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
         point_embed_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context) + r0, rows, ew, cat, kCat);
       LRN_CUDA(cudaGetLastError());
     }
-    for (int k = fused_chain ? (chain5 ? 6 : 5) : 2; k <= 5; ++k) {  // conv2..conv5, each writes its own column block of the operand row
+    for (int k = fused_chain ? 6 : 2; k <= 5; ++k) {  // tf32 tier: conv2..conv5, each writes its own column block of the operand row
       GemmParams p{};
       p.M = int(rows);
       p.m_tiles = m_tiles_of(plan[k]);
@@ -713,11 +671,8 @@ int lrn_ctx_attention(const void* qfold, const void* kp, int64_t ld_kp, const vo
   p.out = out;
   p.out_bf16 = out_bf16 ? 1 : 0;
   p.lse = lse;
-  static bool configured = false;
-  if (!configured) {
-    LRN_CUDA(cudaFuncSetAttribute(ctx_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kDynamic));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  if ((st = configure_smem(ctx_attn_kernel, int(AttnSmem::kDynamic), configured))) return st;
   const int clusters = std::min(B * splits, dev.sms / 2);  // persistent: one cluster per SM pair walks the items
   ctx_attn_kernel<<<2 * clusters, kAttnThreads, AttnSmem::kDynamic, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   LRN_CUDA(cudaGetLastError());
@@ -861,26 +816,10 @@ int lrn_scene_segments(const float* scene_pts, int64_t S, const float* scene_sor
   LRN_CUDA(cudaGetLastError());
   const int cap = scene_cap(N);
   const size_t smem = size_t(cap) * 12;
-  static size_t configured = 0;
-  if (smem > configured) {
-    LRN_CUDA(cudaFuncSetAttribute(scene::select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = smem;
-  }
+  // the opt-in above 48 KB is per device and the size depends on N: set it on every call (a host-side attribute write)
+  LRN_CUDA(cudaFuncSetAttribute(scene::select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   scene::select_kernel<<<L, 256, smem, s>>>(pts, centers, count, offset, N, cap, seed, stat, cand, keys, context,
                                             reinterpret_cast<long long*>(indices), counts);
-  LRN_CUDA(cudaGetLastError());
-  return LRN_OK;
-}
-
-int lrn_debug_ts_probe(const void* a_bf16 /* (128,64) */, const void* w_bf16 /* (64,64) */, float* out /* (128,64) */,
-                       lrn_stream_t stream) {
-  DeviceInfo dev;
-  int st = device_info(&dev);
-  if (st) return st;
-  CUtensorMap tw;
-  st = make_tmap(&tw, LRN_PREC_BF16, w_bf16, 64, 64, 64, 64);
-  if (st) return st;
-  ts_probe_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tw, static_cast<const uint32_t*>(a_bf16), out);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
@@ -980,7 +919,7 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt,
   // Weight gradients: few output tiles, K = all points.  Split K over the idle CTA pairs; the splits add their
   // partial products atomically into the zeroed fp32 output.
   const int out_tiles = p.m_tiles * p.n_tiles, slots = dev.sms / 2;
-  if (g.pair && out_f32 && !relu && precision == LRN_PREC_BF16 && out_tiles < slots && p.kb_main >= 64) {
+  if (out_f32 && !relu && precision == LRN_PREC_BF16 && out_tiles < slots && p.kb_main >= 64) {
     const int want = std::min((2 * slots + out_tiles - 1) / out_tiles, p.kb_main / 16);
     if (want > 1) {
       p.kb_per_split = (p.kb_main + want - 1) / want;
@@ -1352,11 +1291,8 @@ int lrn_self_attention32(const float* qk, const float* v, float* out, int B, lrn
   DeviceInfo dev;
   int st = device_info(&dev);
   if (st) return st;
-  static bool configured = false;
-  if (!configured) {
-    LRN_CUDA(cudaFuncSetAttribute(self_attn32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelfAttnSmem));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  if ((st = configure_smem(self_attn32_kernel, int(kSelfAttnSmem), configured))) return st;
   self_attn32_kernel<<<std::min(B, dev.sms * 2), 256, kSelfAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(qk, v, out, B);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;

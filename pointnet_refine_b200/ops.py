@@ -126,13 +126,10 @@ def encoder_forward(folded: FoldedEncoder, context: torch.Tensor, *, pool=True, 
 def encoder_launches(P: int, flags: int, chunk_rows: int = 0, precision: str = "bf16") -> int:
     """Kernels lrn_encoder_forward enqueues for P points (mirrors the chunk loop in csrc/lrn_abi.cu):
     bf16 tier = fused conv1..conv5 kernel + fusion kernel; tf32 tier = one kernel per layer."""
-    import os
     al = lambda v: (v + 127) // 128 * 128
     chunk = min(al(max(chunk_rows or DEFAULT_CHUNK_ROWS, 128)), al(P))
     chunks = (P + chunk - 1) // chunk
-    fused_chain = precision == "bf16" and os.environ.get("LRN_NO_CHAIN") != "1" and os.environ.get("LRN_GEMM_V1") != "1"
-    chain5 = os.environ.get("LRN_CHAIN5") != "0"
-    per_chunk = ((2 if chain5 else 3) if fused_chain else 6) + (1 if flags & OUT_MEMORY else 0)
+    per_chunk = (2 if precision == "bf16" else 6) + (1 if flags & OUT_MEMORY else 0)
     return chunks * per_chunk + (1 if flags & OUT_ARGMAX else 0)
 
 

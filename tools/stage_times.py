@@ -30,5 +30,5 @@ P = B * N
 flop = {"conv2": 2*64*128, "conv3": 2*128*256, "conv4": 2*256*512, "conv5": 2*512*1024, "fusion": 2*2048*1024}
 out = {k: round(v[0] / 3, 3) for k, v in prof.items()}
 tf = {k: round(flop[k] * P / (v[0] / 3 * 1e-3) / 1e12, 1) for k, v in prof.items() if k in flop and v[0] > 0}
-print(json.dumps({"v1": os.environ.get("LRN_GEMM_V1", "0"), "prec": prec, "B": B, "N": N, "chunk": chunk, "ms_step": round(ms, 2),
+print(json.dumps({"prec": prec, "B": B, "N": N, "chunk": chunk, "ms_step": round(ms, 2),
                   "Mpts_s": round(P / ms / 1e3, 1), "stage_ms": out, "stage_tflops": tf}))
