@@ -15,9 +15,18 @@ own shard, no data-path collective (segments are independent) -> weak scaling.
                D2H read of global_feat, every step
   roofline   : fusion GEMM kernel (72.7 % of the FLOPs): algorithmic FLOP per launch / mean launch
                duration from CUDA events recorded around each launch (lrn_profile_*), against the
-               sustained bf16 peak of MEASURED_PEAKS.json
-  cpu_baseline / --impl reference : the torch-CPU port of the reference (oracle/torch_port.py; the
-               reference itself cannot travel to the GPU box) on the host cores, bounded sample.
+               sustained bf16 peak of MEASURED_PEAKS.json; `chain_kernel` is the same for the fused conv1..conv5 kernel
+  cpu_baseline / --impl reference : the reference's OWN module (oracle/_ref/src/model.py, staged by oracle/make_ref.py
+               from /root/reference in the build container; kind "reference") on the host cores, bounded sample;
+               the op-for-op port oracle/torch_port.py (kind "port") only if the staged copy is absent.
+
+Extra keys, measured on rank 0 / all ranks after the timed region (bounded, a few seconds in total):
+  full_model     : whole LineRefineNet.forward at the configs[1] shape (4096 x 4096, chunked inside the module)
+  config5        : BASELINE configs[4], 256 segments x 65,536 points, encoder + pooling, with property spot checks
+  config3_sample : BASELINE configs[2] (1M segments x 2048 points, strong-scaled over the ranks): every rank runs a
+                   sample of its shard through the whole forward; seconds for the full 1M sweep extrapolated linearly
+  train_step     : BASELINE configs[3], 1024 segments x 1024 points per GPU: forward + L1 deep-supervision loss +
+                   backward + Adam on the native train path (DistributedDataParallel over NCCL when N > 1)
 """
 from __future__ import annotations
 
@@ -35,7 +44,9 @@ sys.path.insert(0, ROOT)
 FLOP_PER_POINT_ENCODER = 5_587_584
 FLOP_PER_POINT_FUSION_KERNEL = 2 * (1984 + 64) * 1024   # fusion conv + gate layer 2 = 4,194,304
 FLOP_PER_POINT_CHAIN_KERNEL = 2 * (64 * 128 + 128 * 256 + 256 * 512 + 512 * 1024)   # conv2..conv5 = 1,392,640
+FLOP_PER_POINT_FORWARD = 8_013_952      # whole LineRefineNet.forward per context point (+ 0.399 GFLOP per segment)
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+TRAIN_BOUND_MS = {"burst": 16.2, "sustained": 19.3}   # 26.4 TFLOP per 1024 x 1024 step / measured peaks
 
 
 def load_peaks():
@@ -44,6 +55,16 @@ def load_peaks():
             return json.load(f), "measured"
     except Exception:
         return dict(FALLBACK_PEAKS), "fallback"
+
+
+def tf32_peak(peaks):
+    """Sustained cuBLAS tf32 8192^3 figure measured on this pool with the MEASURED_PEAKS.json method
+    (tools/cublas_peak.py -> profiles/r02_cublas_peak.json); half the bf16 figure if that file is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_cublas_peak.json")) as f:
+            return float(json.load(f)["tf32"]["sustained_tflops"]), "profiles/r02_cublas_peak.json tf32 sustained (cuBLAS 8192^3)"
+    except Exception:
+        return 0.5 * float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])), "0.5 x bf16_tflops_sustained (no tf32 measurement)"
 
 
 class ClockSampler:
@@ -73,40 +94,64 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
             except ValueError:
                 continue
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        sm.sort()
+        sm.sort(); pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w": pw[len(pw) // 2] if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(segments: int, points: int, steps: int, warmup: int, threads: int | None = None):
-    """Time the torch-CPU port of the reference encoder on `threads` host threads (default: all) (segments/s)."""
+# ---------------------------------------------------------------------------------------------- CPU arm
+def _reference_callables():
+    """(kind, encoder(ctx_bcn) -> (gf, fused), forward(ctx, line) -> out): the staged reference module if present,
+    else the torch-CPU port."""
     import torch
-    from oracle import synth, torch_port
+    from oracle import make_ref, synth, torch_port
+    sd = synth.to_torch(synth.make_state_dict(0))
+    ref = make_ref.load()
+    if ref is not None:
+        m = ref.LineRefineNet()
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        return "reference", m.context_encoder, m
+    return "port", (lambda x: torch_port.encoder_forward(sd, x)), (lambda c, l: torch_port.line_refine_forward(sd, c, l))
+
+
+def cpu_reference_run(segments: int, points: int, steps: int, warmup: int, threads: int | None = None, full_forward: bool = False):
+    """Time the reference's encoder (or whole forward) on `threads` host threads (default: all) -> segments/s."""
+    import torch
+    from oracle import synth
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd = synth.to_torch(synth.make_state_dict(0))
-    ctx = torch.from_numpy(synth.make_inputs(segments, points, seed=1234)[0]).transpose(2, 1)
+    kind, encoder, forward = _reference_callables()
+    ctx_np, line_np = synth.make_inputs(segments, points, seed=1234)
+    ctx, line = torch.from_numpy(ctx_np), torch.from_numpy(line_np)
+    ctx_t = ctx.transpose(2, 1)
+    fn = (lambda: forward(ctx, line)) if full_forward else (lambda: encoder(ctx_t))
     with torch.no_grad():
         for _ in range(warmup):
-            torch_port.encoder_forward(sd, ctx)
+            fn()
         t0 = time.perf_counter()
         for _ in range(steps):
-            torch_port.encoder_forward(sd, ctx)
+            fn()
         dt = (time.perf_counter() - t0) / steps
-    return segments / dt, dt, torch.get_num_threads()
+    return segments / dt, dt, torch.get_num_threads(), kind
+
+
+def kind_text(kind):
+    return ("the reference's own src/model.py (staged copy, oracle/_ref)" if kind == "reference"
+            else "torch-CPU port of the reference (oracle/torch_port.py)")
 
 
 def main():
@@ -120,6 +165,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--cpu-sample-segments", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip full_model / config5 / config3_sample / train_step")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -136,14 +182,18 @@ def main():
         if rank != 0:
             return
         seg = args.cpu_sample_segments
-        v, dt, threads = cpu_reference_run(seg, args.points, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
-        sample = f"{seg} segments x {args.points} points per step (torch-CPU port of the reference encoder, fp32)"
+        steps, warm = max(5, min(args.steps, 8)), max(1, min(args.warmup, 2))
+        v, dt, threads, kind = cpu_reference_run(seg, args.points, steps, warm)
+        vf, dtf, _, _ = cpu_reference_run(max(1, seg // 2), args.points, 3, 1, full_forward=True)
+        sample = f"{seg} segments x {args.points} points per step, {warm} warm-up + {steps} timed ({kind_text(kind)}, encoder, fp32)"
         print(json.dumps({
             "impl": "reference", "metric": "segments_per_sec", "value": v, "unit": "segments/s", "n_gpus": args.gpus,
-            "steps": max(1, min(args.steps, 3)), "warmup": max(1, min(args.warmup, 1)), "ms_per_step": dt * 1e3,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "points_per_sec": v * args.points, "config": config,
-            "cpu_baseline": {"value": v, "unit": "segments/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "segments/s", "cores": threads, "kind": kind, "sample": sample,
+                             "full_forward": {"value": vf, "unit": "segments/s", "ms_per_step": dtf * 1e3,
+                                              "sample": f"{max(1, seg // 2)} segments x {args.points} points, 1 warm-up + 3 timed, LineRefineNet.forward"}},
             "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -165,6 +215,13 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     torch.manual_seed(0)                            # random-init weights of the reference architecture (PyTorch default
     model = prb.LineRefineNet()                     # init), BatchNorm affine / running statistics randomised so that the
     with torch.no_grad():                           # folding is not the identity
@@ -184,6 +241,7 @@ def main():
     def step():
         return enc.run_native(ctx, pool=True)["global_feat"]
 
+    extras = {}
     with torch.no_grad():
         for _ in range(args.warmup):
             step()
@@ -200,38 +258,37 @@ def main():
         barrier()
         launches = _lib.launch_counter - launches0
         clocks = sampler.stop() if rank == 0 else None
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        ms_per_step = ms / args.steps
+        ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         value = world * B / (ms_per_step * 1e-3)
 
         # ---- per-kernel timing for the roofline (same workload, events around every launch)
+        prof_steps = min(args.steps, 3)
         ops.profile_enable(True)
-        for _ in range(min(args.steps, 3)):
+        for _ in range(prof_steps):
             step()
         prof = ops.profile_read()
         ops.profile_enable(False)
 
         # ---- HBM roofline of the stand-alone point loader + first layer (north_star evidence item; the bf16 tier's
-        #      default path has this stage inside the fused chain kernel): 16 B in + 256 B out per point
+        #      default path has this stage inside the fused chain kernel): 16 B in + 256 B out per point.  The output
+        #      buffer is allocated once and 20 launches are timed back to back; 4M points = 1.1 GB per launch (> L2).
         rows_hbm = min(B * N, 4 * 1024 * 1024)
         folded = enc.folded()
         pts = ctx.reshape(-1, 4)[:rows_hbm]
+
         def time_embed(tiled):
+            out = ops.point_embed(folded, pts, tiled=tiled)
             for _ in range(2):
-                ops.point_embed(folded, pts, tiled=tiled)
+                ops.point_embed(folded, pts, tiled=tiled, out=out)
             h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             h0.record()
-            for _ in range(5):
-                ops.point_embed(folded, pts, tiled=tiled)
+            for _ in range(20):
+                ops.point_embed(folded, pts, tiled=tiled, out=out)
             h1.record()
             torch.cuda.synchronize()
-            return h0.elapsed_time(h1) / 5
+            return h0.elapsed_time(h1) / 20
         # bf16 tier: the operand matrix of the default path is tiled (contiguous 16 KB blocks); the row-major figure
-        # (128-byte pieces at the 4 KB row pitch, the layout of the per-layer / tf32 paths) is reported next to it
+        # (128-byte pieces at the 4 KB row pitch, the layout of the tf32 tier) is reported next to it
         embed_ms_rowmajor = time_embed(False)
         embed_ms = time_embed(True) if args.precision == "bf16" else embed_ms_rowmajor
         embed_bytes = rows_hbm * (16 + 2 * 64 * (2 if args.precision == "bf16" else 4))
@@ -255,43 +312,106 @@ def main():
         for _ in range(e2e_steps):
             e2e_step()
         torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3
-        if world > 1:
-            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e_value = world * B / (e2e_ms / e2e_steps * 1e-3)
+        del host_ctx, pipe
 
-        # ---- informational: the whole LineRefineNet forward (encoder + context_proj + 6 decoder layers + heads)
-        full_model = None
-        if rank == 0:
-            fb = min(B, 296)      # 4 x 74 segments x 4096 points = four full encoder waves, 4 attention items per CTA pair
-            line = torch.randn(fb, 32, 3, device=dev, generator=gen)
-            for _ in range(2):
-                model(ctx[:fb], line)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                model(ctx[:fb], line)
-            torch.cuda.synchronize()
-            fm = (time.perf_counter() - t0) / 3
-            full_model = {"segments_per_sec": fb / fm, "ms_per_forward": fm * 1e3, "segments": fb, "points_per_segment": N,
-                          "note": "LineRefineNet.forward -> (6,B,32,3); encoder, context_proj, folded-query cross attention "
-                                  "(K/V never materialised), query side (linears, 32x32 self attention, add+LayerNorm, heads) on "
-                                  "the sm_100a kernels; point_mlp and the K=3 pos_emb layer are stock PyTorch ops"}
-            if B * N >= 1024 * 1024:   # inference_whole_scene.py's setting: 1024 context points per line
-                ctx_ws = ctx.reshape(-1, 4)[:1024 * 1024].view(1024, 1024, 4)
-                line_ws = torch.randn(1024, 32, 3, device=dev, generator=gen)
-                for _ in range(2):
-                    model(ctx_ws, line_ws)
+        if not args.no_extras and args.precision == "bf16":
+            # ---- the whole LineRefineNet forward at the configs[1] shape (encoder + context_proj + 6 decoder layers + heads);
+            #      the module walks the batch in passes of four encoder waves
+            if rank == 0:
+                line = torch.randn(B, 32, 3, device=dev, generator=gen)
+                model(ctx[:min(B, 592)], line[:min(B, 592)])
                 torch.cuda.synchronize()
-                t0 = time.perf_counter()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                out_full = model(ctx, line)
+                f1.record()
+                torch.cuda.synchronize()
+                fm = f0.elapsed_time(f1) * 1e-3
+                extras["full_model"] = {
+                    "segments_per_sec": B / fm, "points_per_sec": B * N / fm, "ms_per_forward": fm * 1e3, "segments": B,
+                    "points_per_segment": N, "finite": bool(torch.isfinite(out_full).all()),
+                    "tflops": (FLOP_PER_POINT_FORWARD * B * N + 0.399e9 * B) / fm / 1e12,
+                    "note": "LineRefineNet.forward -> (6,B,32,3) over the whole configs[1] batch (one call, chunked inside the module): "
+                            "encoder, context_proj, folded-query cross attention (K/V never materialised) and the query side on the "
+                            "sm_100a kernels"}
+                del out_full
+                if B * N >= 1024 * 1024:   # inference_whole_scene.py's setting: 1024 context points per line
+                    ctx_ws = ctx.reshape(-1, 4)[:1024 * 1024].view(1024, 1024, 4)
+                    for _ in range(2):
+                        model(ctx_ws, line[:1024])
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        model(ctx_ws, line[:1024])
+                    torch.cuda.synchronize()
+                    fw = (time.perf_counter() - t0) / 3
+                    extras["full_model"]["whole_scene_setting"] = {"segments": 1024, "points_per_segment": 1024, "ms_per_forward": fw * 1e3,
+                                                                   "segments_per_sec": 1024 / fw}
+                del line
+
+            # ---- BASELINE configs[4]: 256 segments x 65,536 points (same point count as configs[1]; every segment spans 256
+            #      tiles and 55 of a wave's CTA pairs, the pooling reduces across tiles, CTAs and waves through atomics)
+            if rank == 0 and B * N >= 256 * 65536:
+                c5 = ctx.reshape(-1, 4)[:256 * 65536].view(256, 65536, 4)
+                enc.run_native(c5, pool=True)
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
                 for _ in range(3):
-                    model(ctx_ws, line_ws)
+                    g5 = enc.run_native(c5, pool=True)["global_feat"]
+                f1.record()
                 torch.cuda.synchronize()
-                fw = (time.perf_counter() - t0) / 3
-                full_model["whole_scene_setting"] = {"segments": 1024, "points_per_segment": 1024, "ms_per_forward": fw * 1e3,
-                                                     "segments_per_sec": 1024 / fw}
+                t5 = f0.elapsed_time(f1) / 3 * 1e-3
+                # property spot checks (no oracle in the native arm): max >= mean >= 0, a segment computed alone gives the same
+                # maxima bit for bit, and the means agree to the atomics' summation order
+                alone = enc.run_native(c5[7:8].contiguous(), pool=True)["global_feat"]
+                extras["config5"] = {
+                    "workload": "256 segments x 65,536 points, encoder + max/mean pooling (BASELINE.json configs[4])",
+                    "segments_per_sec": 256 / t5, "points_per_sec": 256 * 65536 / t5, "ms_per_pass": t5 * 1e3,
+                    "checks": {"finite": bool(torch.isfinite(g5).all()), "max_ge_mean": bool((g5[:, :1024] >= g5[:, 1024:]).all()),
+                               "segment_alone_max_bit_equal": bool(torch.equal(alone[0, :1024], g5[7, :1024])),
+                               "segment_alone_mean_abs_diff": float((alone[0, 1024:] - g5[7, 1024:]).abs().max())}}
+                del c5, g5
+
+            # ---- BASELINE configs[2]: 1M segments x 2048 points over the ranks (strong scaling): every rank pushes a sample of
+            #      its shard through the whole forward; inputs are generated on the device chunk by chunk
+            total_seg, pts3 = 1_000_000, 2048
+            shard_seg = -(-total_seg // world)
+            sample_seg = min(shard_seg, 16 * 1184)                      # 16 calls of 1184 segments (two decoder passes each)
+            chunk3 = 1184
+            ctx3 = torch.randn(chunk3, pts3, 4, device=dev, generator=gen)
+            line3 = torch.randn(chunk3, 32, 3, device=dev, generator=gen)
+            acc = torch.zeros((), device=dev, dtype=torch.float64)
+            model(ctx3, line3)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            done = 0
+            while done < sample_seg:
+                n = min(chunk3, sample_seg - done)
+                acc.add_(model(ctx3[:n], line3[:n])[-1].double().sum())
+                done += n
+            f1.record()
+            barrier()
+            t3 = max_over_ranks(f0.elapsed_time(f1) * 1e-3)
+            extras["config3_sample"] = {
+                "workload": "inference_whole_scene-style sweep, 1,000,000 segments x 2048 points, LineRefineNet.forward, contiguous segment "
+                            "shards over the ranks, no collective (BASELINE.json configs[2])",
+                "sample_segments_per_gpu": sample_seg, "shard_segments_per_gpu": shard_seg, "sample_seconds": t3,
+                "segments_per_sec": world * sample_seg / t3, "extrapolated_seconds_1M": t3 * shard_seg / sample_seg,
+                "finite": bool(torch.isfinite(acc))}
+            del ctx3, line3
+
+    # ---- BASELINE configs[3]: training step, 1024 segments x 1024 points per GPU (native train path; DDP over NCCL if N > 1)
+    if not args.no_extras and args.precision == "bf16":
+        del ctx
+        torch.cuda.empty_cache()
+        try:
+            extras["train_step"] = train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, max_over_ranks)
+        except torch.cuda.OutOfMemoryError:
+            extras["train_step"] = {"error": "out of memory"}
 
     if rank != 0:
         if world > 1:
@@ -301,46 +421,51 @@ def main():
     peaks, peak_kind = load_peaks()
     f_ms, f_n = prof["fusion"]
     total_ms = sum(v[0] for v in prof.values())
-    points_per_launch = B * N * min(args.steps, 3) / max(f_n, 1)
+    points_per_launch = B * N * prof_steps / max(f_n, 1)
     achieved = FLOP_PER_POINT_FUSION_KERNEL * points_per_launch / (f_ms / max(f_n, 1) * 1e-3) / 1e12 if f_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    peak_src = f"{peak_kind} bf16_tflops_sustained (cuBLAS 8192^3 back to back under the power cap)"
     if args.precision == "tf32":
-        peak *= 0.5    # no TF32 peak is measured; half the bf16 figure
-    roofline = {"bound": "tensor", "kernel": "gemm_pair_kernel<256,EPI_FUSION> (fusion conv + gate + pooling, cta_group::2)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": f"{peak_kind} bf16_tflops_sustained" + (" x 0.5 (tf32)" if args.precision == "tf32" else ""),
-                "traffic": None,
-                "kernel_ms_per_launch": f_ms / max(f_n, 1), "kernel_share_of_step": f_ms / total_ms if total_ms else None,
-                "stage_ms_per_step": {k: v[0] / min(args.steps, 3) for k, v in prof.items()},
-                "whole_encoder_tflops": FLOP_PER_POINT_ENCODER * B * N / (ms_per_step * 1e-3) / 1e12}
+        peak, peak_src = tf32_peak(peaks)
+    traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roofline["traffic"] = json.load(f).get("fusion_dram_bytes_per_launch")
+            traffic = json.load(f)
     except Exception:
         pass
+    roofline = {"bound": "tensor", "kernel": "gemm_pair_kernel<256,EPI_FUSION> (fusion conv + gate + pooling, cta_group::2)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": traffic.get("fusion_dram_bytes_per_launch") if args.precision == "bf16" else None,
+                "kernel_ms_per_launch": f_ms / max(f_n, 1), "kernel_share_of_step": f_ms / total_ms if total_ms else None,
+                "stage_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()},
+                "whole_encoder_tflops": FLOP_PER_POINT_ENCODER * B * N / (ms_per_step * 1e-3) / 1e12,
+                "whole_encoder_frac": FLOP_PER_POINT_ENCODER * B * N / (ms_per_step * 1e-3) / 1e12 / peak}
     # second tensor-bound kernel: the fused conv1..conv5 chain (its tensor-core work = conv2..conv5; contains the
-    # widest shared-MLP layer, conv5 512 -> 1024).  Only when the chain kernel is the path taken (bf16 tier, defaults).
+    # widest shared-MLP layer, conv5 512 -> 1024).  bf16 tier only (the tf32 tier runs one kernel per layer).
     c_ms, c_n = prof["conv5"]
-    chain_path = args.precision == "bf16" and all(prof[k][1] == 0 for k in ("conv2", "conv3", "conv4")) and c_n > 0
-    if chain_path and c_ms > 0:
-        c_ach = FLOP_PER_POINT_CHAIN_KERNEL * B * N * min(args.steps, 3) / (c_ms * 1e-3) / 1e12
-        roofline["chain_kernel"] = {"kernel": "chain_pair_kernel<true> (conv1 FMA + conv2..conv5 on tcgen05, conv5 with A in TMEM)",
+    if args.precision == "bf16" and c_n > 0 and c_ms > 0:
+        c_ach = FLOP_PER_POINT_CHAIN_KERNEL * B * N * prof_steps / (c_ms * 1e-3) / 1e12
+        roofline["chain_kernel"] = {"kernel": "chain_pair_kernel (conv1 FMA + conv2..conv5 on tcgen05, conv5 with A in TMEM)",
                                     "achieved": c_ach, "peak": peak, "unit": "TFLOP/s", "frac": c_ach / peak,
                                     "kernel_ms_per_launch": c_ms / c_n, "kernel_share_of_step": c_ms / total_ms if total_ms else None,
-                                    "algorithmic_flop_per_point": FLOP_PER_POINT_CHAIN_KERNEL}
+                                    "algorithmic_flop_per_point": FLOP_PER_POINT_CHAIN_KERNEL,
+                                    "traffic": traffic.get("chain_dram_bytes_per_launch")}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         seg = args.cpu_sample_segments
-        v, dt, threads = cpu_reference_run(seg, N, 3, 1)
-        cpu_baseline = {"value": v, "unit": "segments/s", "cores": threads, "kind": "port",
-                        "sample": f"{seg} segments x {N} points per step, 1 warm-up + 3 timed "
-                                  f"(torch-CPU port of the reference encoder, fp32)", "ms_per_step": dt * 1e3}
-        v1, dt1, _ = cpu_reference_run(2, N, 2, 1, threads=1)       # per-core figure
+        v, dt, threads, kind = cpu_reference_run(seg, N, 5, 1)
+        cpu_baseline = {"value": v, "unit": "segments/s", "cores": threads, "kind": kind,
+                        "sample": f"{seg} segments x {N} points per step, 1 warm-up + 5 timed ({kind_text(kind)}, encoder, fp32)",
+                        "ms_per_step": dt * 1e3}
+        v1, dt1, _, _ = cpu_reference_run(2, N, 2, 1, threads=1)       # per-core figure
         cpu_baseline["single_thread"] = {"value": v1, "cores": 1, "sample": f"2 segments x {N} points per step, 1 warm-up + 2 timed"}
+        vf, dtf, _, _ = cpu_reference_run(max(1, seg // 2), N, 2, 1, full_forward=True)
+        cpu_baseline["full_forward"] = {"value": vf, "unit": "segments/s", "ms_per_step": dtf * 1e3,
+                                        "sample": f"{max(1, seg // 2)} segments x {N} points, 1 warm-up + 2 timed, LineRefineNet.forward"}
         torch.set_num_threads(os.cpu_count() or 1)
 
-    print(json.dumps({
+    line_out = {
         "metric": "segments_per_sec", "value": value, "unit": "segments/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "points_per_sec": value * N,
@@ -350,16 +475,75 @@ def main():
         "roofline": roofline,
         "roofline_hbm": {"bound": "hbm", "kernel": "point_embed_kernel (point loading + conv1 + gate layer 1, stand-alone)",
                          "achieved": embed_bytes / (embed_ms * 1e-3) / 1e9, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
-                         "frac": embed_bytes / (embed_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]), "traffic": None,
+                         "frac": embed_bytes / (embed_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]),
+                         "traffic": traffic.get("point_embed_dram_bytes_per_launch"),
+                         "traffic_points": traffic.get("point_embed_points_per_launch"),
                          "points": rows_hbm, "algorithmic_bytes_per_point": embed_bytes // rows_hbm,
                          "layout": "tiled operand matrix (default bf16 path)" if args.precision == "bf16" else "row-major operand rows",
                          "row_major_achieved": embed_bytes / (embed_ms_rowmajor * 1e-3) / 1e9,
-                         "note": "torch allocation of the operand rows is outside the events' kernel time but inside "
-                                 "the loop; the default bf16 path runs this stage inside chain_pair_kernel"},
-        "cpu_baseline": cpu_baseline, "full_model": full_model,
-    }))
+                         "note": "20 launches into one preallocated buffer, events around the loop; the default bf16 path runs this "
+                                 "stage inside chain_pair_kernel"},
+        "cpu_baseline": cpu_baseline,
+    }
+    line_out.update(extras)
+    print(json.dumps(line_out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, max_over_ranks):
+    """Forward + L1 deep-supervision loss (train.py:63-69) + backward + Adam at 1024 segments x 1024 points per GPU."""
+    from pointnet_refine_b200 import optim as lrn_optim
+    Bt, Nt = 1024, 1024
+    torch.manual_seed(0)
+    m = prb.LineRefineNet().to(dev).train()
+    m.context_encoder.native_training = True
+    net = m
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(m, device_ids=[local_rank], find_unused_parameters=True)   # train_dist.py:147
+    opt = lrn_optim.FlatAdam(m.parameters(), lr=1e-3)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    ctx = torch.randn(Bt, Nt, 4, device=dev, generator=g)
+    line = torch.randn(Bt, 32, 3, device=dev, generator=g)
+    tgt = 0.1 * torch.randn(Bt, 32, 3, device=dev, generator=g)
+
+    def one():
+        opt.zero_grad()
+        loss = lrn_optim.deep_supervision_l1(net(ctx, line), tgt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps = 5
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    allreduce_ms = None
+    if world > 1:      # the gradient all-reduce alone: 9,695,954 fp32 = 38.8 MB (what DDP moves per step, train_dist.py:188)
+        flat = torch.zeros(9_695_954, device=dev)
+        for _ in range(2):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            dist.all_reduce(flat)
+        a1.record()
+        torch.cuda.synchronize()
+        allreduce_ms = max_over_ranks(a0.elapsed_time(a1) / 5)
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    return {"workload": "1024 segments x 1024 points per GPU, LineRefineNet train step: forward + L1 deep supervision + backward + Adam "
+                        "(BASELINE.json configs[3]); DistributedDataParallel over NCCL when n_gpus > 1",
+            "ms_per_step": ms, "segments_per_sec": world * Bt / (ms * 1e-3), "n_gpus": world, "allreduce_ms": allreduce_ms,
+            "loss": float(loss.detach()), "finite": bool(torch.isfinite(loss.detach())),
+            "bound_ms": TRAIN_BOUND_MS, "frac_of_bound_sustained": TRAIN_BOUND_MS["sustained"] / ms, "peak_mem_gb": peak_gb}
 
 
 if __name__ == "__main__":

@@ -1072,9 +1072,9 @@ int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running
     const int C = kUW[i], uo = kUOff[i];
     const float* gamma = i < 5 ? pr->bn_w[i] : pr->fusion_bn_w;
     const float* beta = i < 5 ? pr->bn_b[i] : pr->fusion_bn_b;
-    col_stats_kernel<<<stats_grid(C, P), 256, 0, s>>>(U + uo, kULd, P, sum + uo, sumsq + uo);
+    col_stats_kernel<<<stats_grid(C, P), 256, 0, s>>>(U + uo, kULd, P, sum + uo, sumsq + uo, 1);
     LRN_CUDA(cudaGetLastError());
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum + uo, sumsq + uo, P, C, gamma, beta, pr->bn_eps, momentum,
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum + uo, sumsq + uo, U + uo, P, C, gamma, beta, pr->bn_eps, momentum,
                                                        running ? running->mean[i] : nullptr,
                                                        running ? running->var[i] : nullptr, mean + uo, rstd + uo,
                                                        scale + uo, shift + uo);
@@ -1166,7 +1166,7 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
                                                   scale + kUOff[5], shift + kUOff[5], dU, dZ, 1024);
     }
     LRN_CUDA(cudaGetLastError());
-    col_stats_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dZ, 1024, P, Sz, nullptr);  // d(gate layer 2 bias)
+    col_stats_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dZ, 1024, P, Sz, nullptr, 0);  // d(gate layer 2 bias)
     LRN_CUDA(cudaGetLastError());
     LRN_CUDA(d2d(g->gate2_b, Sz, 1024));
     const int uo = kUOff[5];
@@ -1317,7 +1317,7 @@ int lrn_col_sum_bf16(const void* A, int64_t ld, int64_t rows, int64_t cols, floa
   if (rows <= 0 || cols <= 0 || cols % 64 || ld < cols || ld % 2) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld cols=%lld ld=%lld (cols %% 64 == 0)", (long long)rows, (long long)cols, (long long)ld);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   LRN_CUDA(cudaMemsetAsync(out, 0, size_t(cols) * 4, s));
-  col_stats_kernel<<<stats_grid(int(cols), rows), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(A), ld, rows, out, nullptr);
+  col_stats_kernel<<<stats_grid(int(cols), rows), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(A), ld, rows, out, nullptr, 0);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

@@ -55,12 +55,17 @@ train_embed_kernel(const float4* __restrict__ ctx, long long rows, const float* 
 }
 
 // Per-column sum and sum of squares of a bf16 (rows x C) matrix -> fp32 atomics into sum[C], sumsq[C].
+// `shifted`: the sums are taken of (x - K_c) with the pivot K_c = A[0][c] (row 0 of the same column), so that the
+// variance E[(x-K)^2] - E[x-K]^2 formed from them does not cancel when |mean| >> std (the naive E[x^2] - mean^2 in
+// fp32 loses all digits there); bn_finalize_kernel adds the pivot back.
 // Block = 64 columns (32 bf16 pairs) x 8 row lanes, 4 independent loads in flight per thread; grid = (C / 64, row slabs).
 __global__ void __launch_bounds__(256)
 col_stats_kernel(const __nv_bfloat16* __restrict__ A, long long ld, long long rows, float* __restrict__ sum,
-                 float* __restrict__ sumsq) {
+                 float* __restrict__ sumsq, int shifted) {
   const int cp = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + 2 * cp;
+  float2 piv = make_float2(0.f, 0.f);
+  if (shifted) piv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(A + c));
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
   const long long stride = gridDim.y * 8ll;
   long long r = blockIdx.y * 8ll + lane_r;
@@ -70,13 +75,15 @@ col_stats_kernel(const __nv_bfloat16* __restrict__ A, long long ld, long long ro
     for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const __nv_bfloat162*>(A + (r + k * stride) * ld + c);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 f = __bfloat1622float2(v[k]);
+      float2 f = __bfloat1622float2(v[k]);
+      f.x -= piv.x; f.y -= piv.y;
       s0 += f.x; s1 += f.y;
       q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
     }
   }
   for (; r < rows; r += stride) {
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(A + r * ld + c));
+    float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(A + r * ld + c));
+    f.x -= piv.x; f.y -= piv.y;
     s0 += f.x; s1 += f.y;
     q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
   }
@@ -93,7 +100,9 @@ col_stats_kernel(const __nv_bfloat16* __restrict__ A, long long ld, long long ro
 }
 
 // Batch statistics -> mean / rstd, the fused scale/shift of the normalisation, and the running-stat update.
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, long long rows, int C,
+// sum / sumsq are the pivot-shifted sums of col_stats_kernel (pivot_row = row 0 of the matrix they were taken of).
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq,
+                                   const __nv_bfloat16* __restrict__ pivot_row, long long rows, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
@@ -101,8 +110,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float n = static_cast<float>(rows);
-  const float m = sum[c] / n;
-  const float var = fmaxf(sumsq[c] / n - m * m, 0.f);  // biased
+  const float d = sum[c] / n;                          // mean of (x - pivot)
+  const float m = bf2f(pivot_row[c]) + d;
+  const float var = fmaxf(sumsq[c] / n - d * d, 0.f);  // biased; shift-invariant
   const float r = rsqrtf(var + eps);
   mean[c] = m;
   rstd[c] = r;

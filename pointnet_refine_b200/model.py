@@ -9,10 +9,11 @@ What runs where
   * eval mode, CUDA tensors: the context encoder (+ pooling, + context_proj) and the regression
     heads run in the hand-written sm_100a library through the C ABI (ops.py).  The DETR decoder,
     point_mlp and pos_emb (SURVEY.md section 8f "next" rows) use stock PyTorch CUDA ops.
-  * train mode (batch-statistic BatchNorm, autograd): the context encoder runs natively too (train_ops.py:
-    batch-stat BN forward and a hand-written backward on the tcgen05 GEMMs, bf16 tier); the decoder and
-    context_proj are stock PyTorch ops.  `native_training = False` / LRN_NATIVE_TRAIN=0 or the tf32 tier use
-    the stock PyTorch formulation of the encoder instead.
+  * train mode (batch-statistic BatchNorm, autograd): by default the stock PyTorch fp32 formulation, i.e. exactly
+    the reference's numerics (a bf16 forward flips the ReLU mask of a few per mille of the activations, which is
+    within tolerance for inference but changes gradients -- the caller decides).  `native_training = True` /
+    LRN_NATIVE_TRAIN=1 (bf16 tier) switches the encoder, context_proj and the decoder's linears to the sm_100a
+    train path (train_ops.py: batch-stat BN forward and a hand-written backward on the tcgen05 GEMMs).
   * CPU tensors: not supported -- there is no CPU path in the product (the oracle lives in oracle/).
 """
 from __future__ import annotations
@@ -76,7 +77,7 @@ class MultiScalePointNetEncoder(nn.Module):
         self.intensity_gate = nn.Sequential(nn.Conv1d(1, 64, 1), nn.ReLU(), nn.Conv1d(64, out_dim, 1), nn.Sigmoid())
         self.precision = _DEFAULT_PRECISION     # "bf16" | "tf32" (tensor-core operand tier)
         self.chunk_rows = 0                     # 0 = library default
-        self.native_training = os.environ.get("LRN_NATIVE_TRAIN", "1") != "0"   # train mode on the sm_100a kernels
+        self.native_training = os.environ.get("LRN_NATIVE_TRAIN", "0") == "1"   # opt-in: train mode on the sm_100a kernels (bf16)
         self._folded = None                     # (fingerprint, FoldedEncoder); never in the state_dict
         self._proj = None                       # optional nn.Linear(1024,256) folded alongside (set by LineRefineNet)
 
@@ -117,8 +118,9 @@ class MultiScalePointNetEncoder(nn.Module):
     def forward(self, x):
         _require_cuda(x, "MultiScalePointNetEncoder")
         if self.training and self.native_training and self.precision == "bf16":
-            from .train_ops import encoder_train_forward   # batch-stat BN forward + hand-written backward
-            return encoder_train_forward(self, x.transpose(2, 1))
+            from .train_ops import encoder_train_forward, native_train_supported   # batch-stat BN forward + hand-written backward
+            if native_train_supported(self):
+                return encoder_train_forward(self, x.transpose(2, 1))
         if not _use_native(self, x):
             return self._forward_torch(x)
         out = self.run_native(x.transpose(2, 1), pool=True, fused=True)
@@ -432,7 +434,9 @@ class LineRefineNet(nn.Module):
     def forward(self, context, noisy_line):
         _require_cuda(context, "LineRefineNet")
         if not _use_native(self, context, noisy_line):
-            if self.training and self.fast_decoder and self.precision == "bf16" and self.context_encoder.native_training:
+            from .train_ops import native_train_supported
+            if (self.training and self.fast_decoder and self.precision == "bf16" and self.context_encoder.native_training
+                    and native_train_supported(self.context_encoder)):
                 from .train_ops import encoder_train_forward
                 _, fused_pm = encoder_train_forward(self.context_encoder, context, point_major=True)
                 return self._refine_fast_train(context, noisy_line, fused_pm)

@@ -289,18 +289,22 @@ def head_update(hidden: torch.Tensor, w2, b2, current: torch.Tensor, noisy: torc
     return cum
 
 
-def point_embed(folded: FoldedEncoder, context: torch.Tensor, tiled: bool = False) -> torch.Tensor:
+def point_embed(folded: FoldedEncoder, context: torch.Tensor, tiled: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
     """Stand-alone first layer (+ gate layer 1): context (P, 4) or (B, N, 4) fp32 -> operand rows (P, 2048) in the
     tier's operand type with columns [0,64) and [1984,2048) written (the rest is left uninitialised).
     tiled (bf16 tier): the result is the tiled operand matrix of the default path instead,
-    (ceil(P/128), 32, 128, 64): [row tile][column block][row][column]; blocks 0 and 31 are written."""
+    (ceil(P/128), 32, 128, 64): [row tile][column block][row][column]; blocks 0 and 31 are written.
+    `out`: a buffer returned by an earlier call with the same arguments, to be reused."""
     context = _f32c(context).reshape(-1, 4)
     P = context.shape[0]
     dt = torch.float32 if folded.precision == "tf32" else torch.bfloat16
-    rows = (torch.empty((P + 127) // 128, 32, 128, 64, dtype=dt, device=context.device) if tiled
-            else torch.empty(P, 2048, dtype=dt, device=context.device))
+    shape = ((P + 127) // 128, 32, 128, 64) if tiled else (P, 2048)
+    if out is None:
+        out = torch.empty(shape, dtype=dt, device=context.device)
+    elif tuple(out.shape) != shape or out.dtype != dt or not out.is_contiguous():
+        raise ValueError("point_embed: `out` does not match the requested layout")
     with torch.cuda.device(context.device):
-        _lib.check(lib.lrn_point_embed(folded.blob.data_ptr(), folded.prec_id, context.data_ptr(), P, rows.data_ptr(), int(tiled),
+        _lib.check(lib.lrn_point_embed(folded.blob.data_ptr(), folded.prec_id, context.data_ptr(), P, out.data_ptr(), int(tiled),
                                        _stream_ptr(context.device)), "lrn_point_embed")
     _lib.launch_counter += 1
-    return rows
+    return out

@@ -22,6 +22,8 @@ class FlatAdam(torch.optim.Optimizer):
         if any((not p.is_cuda) or p.dtype != torch.float32 for p in params):
             raise TypeError("FlatAdam expects CUDA float32 parameters (no CPU fallback)")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatAdam keeps ONE flat buffer: pass a plain parameter list, not several parameter groups")
         dev = params[0].device
         pad = lambda n: (n + 63) // 64 * 64         # every parameter starts 256-byte aligned (TMA / float4 consumers)
         total = sum(pad(p.numel()) for p in params)
@@ -29,28 +31,54 @@ class FlatAdam(torch.optim.Optimizer):
         self._grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self._m = torch.zeros(total, dtype=torch.float32, device=dev)
         self._v = torch.zeros(total, dtype=torch.float32, device=dev)
-        self._views = []
+        views = []
         off = 0
         with torch.no_grad():
             for p in params:
                 n = p.numel()
                 self._flat[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self._flat[off:off + n].view(p.shape)          # the module keeps its Parameter objects
-                self._views.append((p, self._grad[off:off + n].view(p.shape)))
+                views.append((p, self._grad[off:off + n].view(p.shape)))
                 off += pad(n)
+        self._views = views
         self._step = 0
         self._attach()
 
-    def _attach(self):
+    def _attach(self, keep_foreign: bool = True):
+        """Make every parameter's .grad the view of the flat gradient buffer.  A gradient some other code bound to
+        .grad meanwhile (e.g. DistributedDataParallel(gradient_as_bucket_view=True), set_to_none) is copied in when
+        `keep_foreign` -- i.e. in step(), where it is THIS step's gradient -- and dropped in zero_grad()."""
         for p, g in self._views:
             if p.grad is not g:
-                if p.grad is not None:
-                    g.copy_(p.grad)            # a gradient that arrived while .grad was detached
+                if p.grad is not None and keep_foreign:
+                    g.copy_(p.grad)
                 p.grad = g
 
+    def add_param_group(self, param_group):
+        if getattr(self, "_views", None) is not None:
+            raise ValueError("FlatAdam: parameter groups cannot be added after construction (one flat buffer)")
+        super().add_param_group(param_group)
+
     def zero_grad(self, set_to_none: bool = False):
+        self._attach(keep_foreign=False)     # rebind first: a stale foreign .grad must not be copied into the zeroed buffer
         self._grad.zero_()
-        self._attach()
+
+    def state_dict(self):
+        """Adam moments and the step count live in the flat buffers, not in `self.state`: add them to the checkpoint."""
+        sd = super().state_dict()
+        sd["flat_adam"] = {"exp_avg": self._m.clone(), "exp_avg_sq": self._v.clone(), "step": self._step}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop("flat_adam", None)
+        super().load_state_dict(state_dict)
+        if flat is not None:
+            if flat["exp_avg"].numel() != self._m.numel():
+                raise ValueError("FlatAdam.load_state_dict: checkpoint belongs to a different parameter list")
+            self._m.copy_(flat["exp_avg"])
+            self._v.copy_(flat["exp_avg_sq"])
+            self._step = int(flat["step"])
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -43,21 +43,21 @@ PARAM_NAMES = ([f"conv{k}.weight" for k in range(1, 6)] + [f"conv{k}.bias" for k
                   "intensity_gate.0.weight", "intensity_gate.0.bias", "intensity_gate.2.weight", "intensity_gate.2.bias"])
 
 
-def _params_struct(t):
-    """t: list of contiguous fp32 CUDA tensors in PARAM_NAMES order."""
+def _params_struct(t, eps=1e-5):
+    """t: list of contiguous fp32 CUDA tensors in PARAM_NAMES order; eps: the BatchNorm layers' eps."""
     p = _lib.EncoderParams()
     for k in range(5):
         p.conv_w[k], p.conv_b[k] = t[k].data_ptr(), t[5 + k].data_ptr()
         p.bn_w[k], p.bn_b[k] = t[10 + k].data_ptr(), t[15 + k].data_ptr()
     p.fusion_w, p.fusion_b, p.fusion_bn_w, p.fusion_bn_b = (x.data_ptr() for x in t[20:24])
     p.gate0_w, p.gate0_b, p.gate2_w, p.gate2_b = (x.data_ptr() for x in t[24:28])
-    p.bn_eps = 1e-5
+    p.bn_eps = float(eps)
     return p
 
 
 class EncoderTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, context, running, momentum, point_major, *params):
+    def forward(ctx, context, running, momentum, eps, point_major, *params):
         """context (B,N,4) fp32 CUDA; running = list of 12 buffers (6 running_mean, 6 running_var) updated in
         place, or None; params in PARAM_NAMES order.  Returns (global_feat (B,2048), fused (B,1024,N)) fp32, or with
         point_major the (B,N,1024) bf16 tensor context_proj consumes (LineRefineNet never uses global_feat)."""
@@ -65,7 +65,7 @@ class EncoderTrainFn(torch.autograd.Function):
         B, N, _ = context.shape
         dev = context.device
         t = [_f32c(p.detach()) for p in params]
-        ps = _params_struct(t)
+        ps = _params_struct(t, eps)
         nbytes = lib.lrn_train_workspace_bytes(B, N)
         ws = _aligned_bytes(nbytes, dev)           # owned by this node until its backward has run
         fused = (torch.empty(B, N, 1024, dtype=torch.bfloat16, device=dev) if point_major
@@ -88,7 +88,7 @@ class EncoderTrainFn(torch.autograd.Function):
                        "lrn_encoder_train_forward")
         _lib.launch_counter += 12 + 1 + 6 * 2 + 5 + 6 + 1 + (0 if point_major else 1)
         ctx.save_for_backward(context, *t)
-        ctx.ws, ctx.shape, ctx.point_major, ctx.argmax = ws, (B, N), bool(point_major), am
+        ctx.ws, ctx.shape, ctx.point_major, ctx.argmax, ctx.eps = ws, (B, N), bool(point_major), am, float(eps)
         if point_major:
             return fused
         ctx.mark_non_differentiable(am)
@@ -99,6 +99,10 @@ class EncoderTrainFn(torch.autograd.Function):
         context, *t = ctx.saved_tensors
         B, N = ctx.shape
         dev = context.device
+        if ctx.ws is None:
+            raise RuntimeError("pointnet_refine_b200: the native encoder's saved activations (12 KB per point) are released "
+                               "by its first backward; a second backward through the same forward (retain_graph=True) is "
+                               "not supported -- run the forward again")
         if ctx.point_major:
             d_gf, d_fused = None, douts[0].to(torch.bfloat16).contiguous()
         else:
@@ -111,7 +115,7 @@ class EncoderTrainFn(torch.autograd.Function):
             g.bn_w[k], g.bn_b[k] = grads[10 + k].data_ptr(), grads[15 + k].data_ptr()
         g.fusion_w, g.fusion_b, g.fusion_bn_w, g.fusion_bn_b = (x.data_ptr() for x in grads[20:24])
         g.gate0_w, g.gate0_b, g.gate2_w, g.gate2_b = (x.data_ptr() for x in grads[24:28])
-        ps = _params_struct(t)
+        ps = _params_struct(t, ctx.eps)
         with torch.cuda.device(dev):
             _lib.check(lib.lrn_encoder_train_backward(C.byref(ps), context.data_ptr(), B, N,
                                                       d_fused.data_ptr() if d_fused is not None else None, int(ctx.point_major),
@@ -121,7 +125,20 @@ class EncoderTrainFn(torch.autograd.Function):
                                                       _stream_ptr(dev)), "lrn_encoder_train_backward")
         _lib.launch_counter += 60
         ctx.ws = None
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
+
+
+def _encoder_bns(module):
+    return [module.bn1, module.bn2, module.bn3, module.bn4, module.bn5, module.fusion[1]]
+
+
+def native_train_supported(module) -> bool:
+    """The native train path implements torch.nn.BatchNorm1d's default training behaviour: every BatchNorm of the encoder
+    in training mode with running statistics, an exponential momentum and one common eps.  Anything else (frozen /
+    .eval()'d BatchNorm layers, momentum=None cumulative averaging, track_running_stats=False) runs the stock ops."""
+    bns = _encoder_bns(module)
+    return all(b.training and b.track_running_stats and b.momentum is not None and b.affine and b.eps == bns[0].eps
+               and b.momentum == bns[0].momentum for b in bns)
 
 
 def encoder_train_forward(module, context, point_major=False):
@@ -130,9 +147,9 @@ def encoder_train_forward(module, context, point_major=False):
     point_major=True returns (None, fused_pm (B,N,1024) bf16) for LineRefineNet, which never uses global_feat."""
     sd = dict(module.named_parameters())
     params = [sd[n] for n in PARAM_NAMES]
-    bns = [module.bn1, module.bn2, module.bn3, module.bn4, module.bn5, module.fusion[1]]
+    bns = _encoder_bns(module)
     running = [b.running_mean for b in bns] + [b.running_var for b in bns]
-    out = EncoderTrainFn.apply(context, running, float(bns[0].momentum), point_major, *params)
+    out = EncoderTrainFn.apply(context, running, float(bns[0].momentum), float(bns[0].eps), point_major, *params)
     with torch.no_grad():
         for b in bns:
             b.num_batches_tracked += 1

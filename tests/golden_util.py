@@ -18,3 +18,13 @@ def load_case(name):
     sd = synth.make_state_dict(wseed, bool(rbn))
     ctx, line = synth.make_inputs(B, N, seed=iseed, dist=dist)
     return g, sd, ctx, line, (sub_c, sub_n)
+
+
+def report(**kv):
+    """Append one measured-error record to gpurun_out/parity_report.jsonl (created on GPU runs; ignored elsewhere):
+    the numbers behind the assertions, for DESIGN.md / profiles/."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(kv) + "\n")

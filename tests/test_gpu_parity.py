@@ -2,9 +2,15 @@
 (pointnet_refine_b200.ops -> liblrn_b200.so); the numpy oracle and the committed golden fixtures
 (generated from the unmodified reference, oracle/make_golden.py) are the checkers.
 
-Tolerances (north_star): TF32 tier max-abs 1e-3; bf16 tier 1e-2 relative to the output range.
-argmax is compared where the reference's top-2 gap exceeds the tier's value tolerance (bit-exact
-argmax is not attainable with reduced-precision operands)."""
+Tolerances (north_star), for the global feature AND the refined offsets: TF32 tier max-abs 1e-3; bf16 tier 1e-2
+relative to the output range.  argmax: bit-exact wherever the reference's top-2 gap exceeds twice the tier's value
+tolerance; over ALL untied (segment, channel) pairs the agreement rate is measured, reported
+(gpurun_out/parity_report.jsonl) and held above a floor per tier (reduced-precision operands cannot reproduce an
+argmax whose top-2 gap is below their rounding error).
+
+Accepted argmax deviation, spelled out: north_star asks for bit-exact indices "where the reference has no ties".
+Exact equality is asserted only on the gap-filtered subset; on the remaining untied pairs (gap > 0 but within
+2x tolerance) indices may differ from the reference, bounded by the agreement floors below."""
 import numpy as np
 import pytest
 import torch
@@ -13,9 +19,19 @@ pytestmark = pytest.mark.gpu
 
 from oracle import lrn_oracle as orc  # noqa: E402
 from oracle import synth  # noqa: E402
-from tests.golden_util import EVAL_CASES, load_case  # noqa: E402
+from tests.golden_util import EVAL_CASES, load_case, report  # noqa: E402
 
 TIERS = {"bf16": 1e-2, "tf32": 1e-3}
+# floor of the argmax agreement with the fp32 reference over ALL untied (segment, channel) pairs.  Measured on the
+# B200 (gpurun_out/parity_report.jsonl -> profiles/r02_parity_report.jsonl): bf16 98.9-99.3 % on the N(0,1) fixtures and
+# 95.3 % on the realistic one (x up to +-25 m, value range 10), tf32 99.86-100 %; SURVEY.md section 7.3 predicted
+# 98.1-98.9 % / 99.7-99.9 % from a CPU emulation of the operand rounding.  The "exact" tier asserts 100 % (below).
+ARGMAX_FLOOR = {"bf16": 0.94, "tf32": 0.995}
+
+
+def _offset_tol(prec, ref_out):
+    """north_star: refined offsets within 1e-2 of their range (bf16 tier) / 1e-3 max-abs (tf32 tier)."""
+    return 1e-2 * max(1.0, float(np.abs(ref_out).max())) if prec == "bf16" else 1e-3
 
 
 @pytest.fixture(scope="module")
@@ -100,6 +116,12 @@ def test_encoder_matches_reference_golden(dev, name, prec):
     safe = g["gap"] > 2 * tol                                        # reference argmax where it is unambiguous
     if safe.any():
         assert np.array_equal(arg[safe], g["argmax"][safe])
+    untied = g["gap"] > 0                                            # every pair the reference decides without a tie
+    rate = float((arg[untied] == g["argmax"][untied]).mean()) if untied.any() else 1.0
+    report(test="encoder_golden", case=name, tier=prec, gf_err=float(np.abs(gf - g["global_feat"]).max()), range=rng,
+           argmax_agreement_untied=rate, untied_pairs=int(untied.sum()), exact_subset_pairs=int(safe.sum()))
+    if N >= 256:                                                     # (tiny segments: a handful of pairs, rate is noise)
+        assert rate >= ARGMAX_FLOOR[prec], (name, prec, rate)
 
 
 @pytest.mark.parametrize("prec", list(TIERS))
@@ -110,8 +132,9 @@ def test_full_forward_matches_reference_golden(dev, name, prec):
     with torch.no_grad():
         out = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev)).cpu().numpy()
     assert out.shape == g["out"].shape == (6, ctx.shape[0], 32, 3)
-    rng = max(1.0, float(np.abs(g["out"]).max()))
-    assert np.abs(out - g["out"]).max() <= (5e-2 if prec == "bf16" else 5e-3) * rng
+    err = float(np.abs(out - g["out"]).max())
+    report(test="full_forward_golden", case=name, tier=prec, offsets_err=err, range=float(np.abs(g["out"]).max()))
+    assert err <= _offset_tol(prec, g["out"]), (name, prec, err)
 
 
 def test_module_encoder_interface(dev):
@@ -245,16 +268,20 @@ def test_full_forward_batched_vs_live_oracle(dev, B, N):
         out_kv = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
         m.fast_decoder = False
         out_stock = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
-    for o in (out, out_kv, out_stock):
-        assert np.abs(o.cpu().numpy() - ref).max() <= 5e-2 * rng
+    for tag, o in (("attn", out), ("kv", out_kv), ("stock", out_stock)):
+        err = float(np.abs(o.cpu().numpy() - ref).max())
+        report(test="full_forward_live", B=B, N=N, tier="bf16", path=tag, offsets_err=err, range=rng)
+        assert err <= _offset_tol("bf16", ref), (tag, err)
     # tf32 tier: K / V GEMMs + SDPA in fp32 with RNA-rounded TF32 operands (fast) vs the stock decoder
     m32 = _model(sd, dev, "tf32")
     with torch.no_grad():
         fast32 = m32(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
         m32.fast_decoder = False
         stock32 = m32(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
-    assert np.abs(fast32.cpu().numpy() - ref).max() <= 2e-3 * rng
-    assert np.abs(stock32.cpu().numpy() - ref).max() <= 2e-3 * rng
+    for tag, o in (("fast", fast32), ("stock", stock32)):
+        err = float(np.abs(o.cpu().numpy() - ref).max())
+        report(test="full_forward_live", B=B, N=N, tier="tf32", path=tag, offsets_err=err, range=rng)
+        assert err <= _offset_tol("tf32", ref), (tag, err)
 
 
 def test_full_forward_chunking_and_segment_independence_at_scale(dev):
@@ -428,3 +455,44 @@ def test_cuda_graph_replay_is_bit_identical(dev, B, N):
             out = runner(ctx, line)
         torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+def test_compat_shim_runs_reference_smoke(dev):
+    """The body of the reference's own smoke test (src/model.py:236-246: default-constructed model, randn(2,1024,4) /
+    randn(2,32,3), expects (6,2,32,3) and prints the parameter count) through `from src.model import LineRefineNet` with
+    <repo>/compat first on sys.path -- on the GPU, in the module's default train mode and in eval mode -- plus the
+    checkpoint round trip of inference_whole_scene.py:202-204."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import os, sys, tempfile
+root = sys.argv[1]
+sys.path[:0] = [os.path.join(root, "compat"), root]
+import torch
+from src.model import LineRefineNet
+device = torch.device("cuda")
+model = LineRefineNet().to(device)
+ctx = torch.randn(2, 1024, 4, device=device)
+line = torch.randn(2, 32, 3, device=device)
+out = model(ctx, line)                                     # train mode, like `python src/model.py`
+print(out.shape)
+assert tuple(out.shape) == (6, 2, 32, 3) and torch.isfinite(out).all()
+print(f"Model Parameters: {sum(p.numel() for p in model.parameters())}")
+with tempfile.TemporaryDirectory() as d:
+    path = os.path.join(d, "best_model.pth")
+    torch.save(model.state_dict(), path)
+    m2 = LineRefineNet().to(device)
+    m2.load_state_dict(torch.load(path, map_location=device))
+m2.eval()
+model.eval()
+with torch.no_grad():
+    a = model(ctx, line)[-1]                               # inference_whole_scene.py:137-139
+    b = m2(ctx, line)[-1]
+assert tuple(a.shape) == (2, 32, 3) and torch.equal(a, b)
+print("compat smoke ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code, root], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "compat smoke ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "Model Parameters: 9695954" in r.stdout

@@ -1,10 +1,14 @@
 """Train-mode path on the GPU (BASELINE.json configs[3] class): batch-statistic BatchNorm forward and the
-hand-written backward through the C ABI, against the stock-PyTorch formulation of the same module in fp32.
+hand-written backward through the C ABI (opt-in: `native_training = True`).
 
-bf16 tier: forward within 2e-2 of the range.  Gradients are compared in relative L2 / cosine: a reduced-precision
-forward flips the ReLU mask of a few per mille of the activations that sit at zero (measured 0.4 %), and every
-flipped element moves its whole gradient, so element-wise max-abs parity is not meaningful -- the native
-arithmetic itself matches a bf16 emulation of it to 2e-3 (tools/train_debug.py)."""
+Two references:
+  * the PARITY reference is the stock-PyTorch fp32 module evaluated on a forward whose tensor-core operands are
+    rounded to bf16 at exactly the points where the native path rounds them (`_emulated_encoder`): same ReLU masks,
+    same batch statistics, autograd in fp32.  Gradients must agree to 2e-2 relative L2 per parameter.
+  * against the un-rounded fp32 module the forward is within 2e-2 of the range; gradients are only required to point
+    the same way (cosine), because a bf16 forward flips the ReLU mask of a few per mille of the activations that sit
+    at zero (measured 0.4 %) and every flipped element moves its whole gradient.  That is why the native train path
+    is opt-in: the default train mode is the reference's fp32 arithmetic."""
 import copy
 
 import numpy as np
@@ -30,8 +34,121 @@ def _pair(dev, seed=7):
     m.load_state_dict(synth.to_torch(synth.make_state_dict(seed)), strict=True)
     enc = m.context_encoder.train()
     ref = copy.deepcopy(enc).train()
+    enc.native_training = True             # opt-in: sm_100a train path
     ref.native_training = False            # stock PyTorch ops, fp32
     return enc, ref
+
+
+def _rb(t):
+    """round to bf16, keep fp32 storage; autograd passes the gradient through unchanged"""
+    return t.bfloat16().float()
+
+
+def _saved_activations(node, P):
+    """The bf16 activations the native forward kept for its backward (workspace layout of csrc/lrn_abi.cu:train_layout):
+    X (P, 2048) = [feat1..feat5 | gate hidden], U (P, 3008) = pre-BatchNorm values of conv1..conv5 and the fusion conv,
+    Z (P, 1024) = gate layer 2 pre-activation."""
+    ws = node.ws
+    Pp = (P + 255) // 256 * 256
+    al = lambda v: (v + 1023) // 1024 * 1024
+    o_x, o_u = 0, al(Pp * 2048 * 2)
+    o_z = o_u + al(Pp * 3008 * 2)
+    take = lambda off, cols: ws[off: off + Pp * cols * 2].view(torch.bfloat16).view(Pp, cols)[:P].float()
+    return take(o_x, 2048), take(o_u, 3008), take(o_z, 1024)
+
+
+def _emulated_encoder(ref, ctx, saved=None):
+    """Stock fp32 math of MultiScalePointNetEncoder.forward in train mode (src/model.py:39-62) with the operands of every
+    tensor-core GEMM and every stored activation rounded to bf16 where csrc/lrn_abi.cu:lrn_encoder_train_forward rounds
+    them: U_k (pre-BatchNorm, statistics are taken of the rounded values), X_k, the gate hidden layer, bf16 weights for
+    conv2..conv5 / fusion / gate layer 2; conv1 and gate layer 1 consume raw fp32 points.
+    `saved` = (X, U, Z) of the native forward: every rounded tensor then takes the native VALUE (which differs from this
+    restatement by a bf16 ulp wherever the fp32 accumulation order moved a sum across a rounding boundary) while autograd
+    still differentiates the restatement -- identical ReLU masks and batch statistics, fp32 backward."""
+    B, N, _ = ctx.shape
+    P = B * N
+    x = ctx.reshape(P, 4)
+    sd = dict(ref.named_parameters())
+    w = lambda n: sd[n].squeeze(-1)
+    u_off = [0, 64, 192, 448, 960, 1984]
+    x_off = [0, 64, 192, 448, 960]
+
+    def pin(t, native):          # value of `native`, gradient of `t`
+        return t if native is None else t + (native - t).detach()
+
+    def bn(u, name):
+        mu, var = u.mean(0), u.var(0, unbiased=False)
+        scale = sd[name + ".weight"] * torch.rsqrt(var + 1e-5)
+        return u * scale + (sd[name + ".bias"] - mu * scale)
+
+    X, U, Z = saved if saved is not None else (None, None, None)
+    cols = lambda M, o, c: None if M is None else M[:, o:o + c]
+    chan = [64, 128, 256, 512, 1024]
+    feats = []
+    u = pin(_rb(x @ w("conv1.weight").T + sd["conv1.bias"]), cols(U, 0, 64))
+    for k in range(1, 6):
+        xk = pin(_rb(torch.relu(bn(u, f"bn{k}"))), cols(X, x_off[k - 1], chan[k - 1]))
+        feats.append(xk)
+        if k < 5:
+            u = pin(_rb(xk @ _rb(w(f"conv{k + 1}.weight")).T + sd[f"conv{k + 1}.bias"]), cols(U, u_off[k], chan[k]))
+    h = pin(_rb(torch.relu(x[:, 3:4] @ w("intensity_gate.0.weight").T + sd["intensity_gate.0.bias"])), cols(X, 1984, 64))
+    uf = pin(_rb(torch.cat(feats, 1) @ _rb(w("fusion.0.weight")).T + sd["fusion.0.bias"]), cols(U, 1984, 1024))
+    z = pin(_rb(h @ _rb(w("intensity_gate.2.weight")).T + sd["intensity_gate.2.bias"]), Z)
+    fused = torch.relu(bn(uf, "fusion.1")) * (0.5 + 0.5 * torch.sigmoid(z))
+    fused = fused.view(B, N, 1024).permute(0, 2, 1)
+    return torch.cat([fused.max(dim=2)[0], fused.mean(dim=2)], dim=1), fused
+
+
+@pytest.mark.parametrize("B,N", [(4, 600), (2, 1024), (8, 2048)])
+def test_train_gradients_match_bf16_emulation(dev, B, N):
+    """Gradient PARITY of the hand-written backward: fp32 autograd through the restated forward pinned to the native
+    forward's own bf16 activations (same masks, same statistics).  What is left is the bf16 rounding of the backward's
+    GEMM operands (dY, dU, d feat)."""
+    enc, ref = _pair(dev)
+    ctx = torch.from_numpy(synth.make_inputs(B, N, seed=1241)[0]).to(dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    R = torch.randn(B, 1024, N, device=dev, generator=g)
+    R2 = torch.randn(B, 2048, device=dev, generator=g)
+    gf_n, fz_n = enc(ctx.transpose(2, 1))
+    saved = _saved_activations(fz_n.grad_fn, B * N)
+    ((fz_n * R).sum() / (B * N) + (gf_n * R2).sum() / B).backward()
+    # 1. the restatement on its own reproduces the native forward to a few bf16 ulps of the range
+    with torch.no_grad():
+        _, fz_free = _emulated_encoder(ref, ctx)
+    rng = float(fz_free.abs().max())
+    assert float((fz_n.detach() - fz_free).abs().max()) <= 1e-2 * rng
+    # 2. pinned to the native activations the fused output agrees to fp32 rounding, and so must the gradients up to
+    #    the backward's own bf16 operand rounding
+    gf_e, fz_e = _emulated_encoder(ref, ctx, saved)
+    assert float((fz_n - fz_e).detach().abs().max()) <= 1e-4 * rng
+    ((fz_e * R).sum() / (B * N) + (gf_e * R2).sum() / B).backward()
+    worst = {}
+    for (name, p), (_, q) in zip(enc.named_parameters(), ref.named_parameters()):
+        if name.startswith(("conv", "fusion.0")) and name.endswith("bias"):
+            continue                                                        # analytically zero (asserted elsewhere)
+        gn, gr = p.grad.flatten().double(), q.grad.flatten().double()
+        worst[name] = float((gn - gr).norm() / gr.norm())
+    print("train gradient rel-L2 vs fp32 autograd on the native forward state:",
+          {k: round(v, 4) for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:8]})
+    bad = {k: v for k, v in worst.items() if v > 2e-2}
+    assert not bad, bad
+
+
+def test_train_statistics_survive_large_means(dev):
+    """|mean| >> std in a pre-BatchNorm channel: the statistics are pivot-shifted sums (E[x^2] - mean^2 in fp32 cancels as
+    mean^2 / var grows).  conv1's bias is pushed to +-16 while its outputs vary by ~1 (beyond that the bf16 storage of the
+    pre-activations, not the statistics, is what limits the batch variance)."""
+    enc, ref = _pair(dev)
+    with torch.no_grad():
+        for e in (enc, ref):
+            e.conv1.bias.add_(16.0 * torch.sign(e.conv1.bias))
+    ctx = torch.from_numpy(synth.make_inputs(2, 1024, seed=5)[0]).to(dev)
+    with torch.no_grad():
+        enc(ctx.transpose(2, 1))
+        ref(ctx.transpose(2, 1))
+    # running_var after one step = 0.9 * old + 0.1 * unbiased batch variance: compare the batch part
+    vn, vr = enc.bn1.running_var, ref.bn1.running_var
+    assert float(((vn - vr).abs() / vr.abs()).max()) <= 5e-2, float(((vn - vr).abs() / vr.abs()).max())
 
 
 @pytest.mark.parametrize("B,N", [(4, 600), (2, 1024), (3, 37)])
@@ -67,9 +184,8 @@ def test_train_forward_backward_matches_torch(dev, B, N):
             # analytically vanishing sum); the native backward writes the exact zero
             assert float(gn.abs().max()) == 0.0, name
             continue
-        rel = float((gn - gr).norm() / gr.norm())
         cos = float(torch.dot(gn, gr) / (gn.norm() * gr.norm()))
-        assert rel <= 0.3 and cos >= 0.95, (name, rel, cos)   # worst: conv1 (end of the chain), rel 0.23 / cos 0.974
+        assert cos >= 0.95, (name, cos)   # direction only: ReLU-mask flips of the bf16 forward (see the module docstring)
 
 
 def test_train_pooled_loss_uses_native_argmax_scatter(dev):
@@ -100,6 +216,7 @@ def test_train_matches_reference_golden(dev):
     m = prb.LineRefineNet().to(dev)
     m.load_state_dict(synth.to_torch(sd), strict=True)
     enc = m.context_encoder.train()
+    enc.native_training = True
     with torch.no_grad():
         gf, fused = enc(torch.from_numpy(ctx).to(dev).transpose(2, 1))
     rng = max(1.0, float(np.abs(g["global_feat"]).max()))
@@ -116,6 +233,7 @@ def test_full_model_train_step_decreases_loss(dev):
     import pointnet_refine_b200 as prb
     torch.manual_seed(0)
     m = prb.LineRefineNet().to(dev).train()
+    m.context_encoder.native_training = True
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
     ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(8, 512, seed=5))
     tgt = 0.1 * torch.randn(8, 32, 3, device=dev)
@@ -133,6 +251,26 @@ def test_full_model_train_step_decreases_loss(dev):
     m.eval()
     with torch.no_grad():                       # the eval path re-folds the updated weights and running stats
         assert torch.isfinite(m(ctx, line)).all()
+
+
+def test_default_train_mode_is_reference_arithmetic(dev):
+    """Without the opt-in, model.train() runs the stock fp32 formulation (the reference's numerics); with it, a frozen
+    (eval-mode) BatchNorm layer or momentum=None falls back to the stock ops instead of being silently ignored."""
+    import pointnet_refine_b200 as prb
+    from pointnet_refine_b200.train_ops import native_train_supported
+    m = prb.LineRefineNet().to(dev).train()
+    assert m.context_encoder.native_training is False
+    m.context_encoder.native_training = True
+    assert native_train_supported(m.context_encoder)
+    m.context_encoder.bn3.eval()
+    assert not native_train_supported(m.context_encoder)
+    m.context_encoder.bn3.train()
+    m.context_encoder.bn2.momentum = None
+    assert not native_train_supported(m.context_encoder)
+    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(2, 256, seed=5))
+    out = m(ctx, line)                                  # cumulative-average BatchNorm: stock path, still trains
+    out.sum().backward()
+    assert all(p.grad is not None for p in m.parameters())
 
 
 def test_ddp_step_two_ranks():
@@ -174,6 +312,7 @@ def test_train_fast_decoder_close_to_stock(dev, B):
     m = prb.LineRefineNet().to(dev)
     m.load_state_dict(synth.to_torch(synth.make_state_dict(2)), strict=True)
     m.train()
+    m.context_encoder.native_training = True
     for mod in m.modules():                       # switch every dropout off, keep batch-stat BatchNorm
         if isinstance(mod, torch.nn.Dropout):
             mod.p = 0.0
@@ -235,6 +374,7 @@ def test_flat_adam_trains_line_refine_net(dev):
     from pointnet_refine_b200.optim import FlatAdam, deep_supervision_l1
     torch.manual_seed(0)
     m = prb.LineRefineNet().to(dev).train()
+    m.context_encoder.native_training = True
     opt = FlatAdam(m.parameters(), lr=1e-3)
     ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(8, 512, seed=5))
     tgt = 0.1 * torch.randn(8, 32, 3, device=dev)

@@ -114,3 +114,36 @@ def test_scene_host_resampling_equals_oracle():
             pts[nv // 2] = pts[nv // 2 - 1]                  # a zero-length segment
         for n in (32, 200):
             np.testing.assert_array_equal(sc.resample_polyline(pts, n), so.resample_polyline(pts, n))
+
+
+def test_compat_shim_resolves_reference_import():
+    """`from src.model import LineRefineNet` (reference train.py:7, inference_whole_scene.py:13) resolves to the B200-native
+    module when <repo>/compat is ahead on sys.path; the reference's checkpoint round trip
+    (torch.save(model.state_dict()) -> load_state_dict(torch.load(..., map_location)), train.py:106 /
+    inference_whole_scene.py:203-204) works strictly."""
+    import subprocess
+    import sys
+    code = r"""
+import os, sys, tempfile
+root = sys.argv[1]
+sys.path[:0] = [os.path.join(root, "compat"), root]
+import torch
+from src.model import LineRefineNet, MultiScalePointNetEncoder, PositionalEncoding, DetrTransformerDecoderLayer
+import pointnet_refine_b200 as prb
+assert LineRefineNet is prb.LineRefineNet and MultiScalePointNetEncoder is prb.MultiScalePointNetEncoder
+model = LineRefineNet()                                   # default-constructed, as every reference script does
+assert sum(p.numel() for p in model.parameters()) == 9695954      # the count src/model.py:245 prints
+with tempfile.TemporaryDirectory() as d:
+    path = os.path.join(d, "best_model.pth")
+    torch.save(model.state_dict(), path)
+    other = LineRefineNet()
+    missing = other.load_state_dict(torch.load(path, map_location="cpu"))      # strict=True is the default
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for (k, a), (_, b) in zip(model.state_dict().items(), other.state_dict().items()):
+        assert torch.equal(a, b), k
+enc = MultiScalePointNetEncoder(in_channel=4, out_dim=1024)
+assert len(enc.state_dict()) == 46
+print("compat ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "compat ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

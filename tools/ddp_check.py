@@ -16,6 +16,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 torch.manual_seed(0)
 model = prb.LineRefineNet().to(dev).train()
+model.context_encoder.native_training = True            # opt-in: sm_100a train path
 ddp = DDP(model, device_ids=[local], find_unused_parameters=True)          # as train_dist.py:147
 opt = torch.optim.Adam(ddp.parameters(), lr=1e-3)
 g = torch.Generator(device=dev).manual_seed(100 + rank)                    # different shard per rank

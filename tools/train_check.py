@@ -12,6 +12,7 @@ B, N = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (4, 600)
 m = prb.LineRefineNet().to(dev)
 m.load_state_dict(synth.to_torch(synth.make_state_dict(7)))
 enc = m.context_encoder.train()
+enc.native_training = True
 ref = copy.deepcopy(enc).train()
 ref.native_training = False
 ctx = torch.from_numpy(synth.make_inputs(B, N, seed=1241)[0]).to(dev)

@@ -11,6 +11,7 @@ B, N = 4, 600
 P = B * N; Pp = (P + 255) // 256 * 256
 m = prb.LineRefineNet().to(dev); m.load_state_dict(synth.to_torch(synth.make_state_dict(7)))
 enc = m.context_encoder.train()
+enc.native_training = True
 ctx = torch.from_numpy(synth.make_inputs(B, N, seed=1241)[0]).to(dev)
 R = torch.randn(B, 1024, N, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
 # ---- native

@@ -9,6 +9,7 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 m = prb.LineRefineNet().to(dev).train()
+m.context_encoder.native_training = True
 opt = torch.optim.Adam(m.parameters(), lr=1e-3)
 ctx = torch.randn(B, N, 4, device=dev); line = torch.randn(B, 32, 3, device=dev); tgt = torch.randn(B, 32, 3, device=dev)
 def step():

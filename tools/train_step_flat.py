@@ -11,6 +11,7 @@ res = {}
 for flat in (True, False):
     torch.manual_seed(0)
     m = prb.LineRefineNet().to(dev).train()
+    m.context_encoder.native_training = True
     opt = FlatAdam(m.parameters(), lr=1e-3) if flat else torch.optim.Adam(m.parameters(), lr=1e-3)
     ctx = torch.randn(B, N, 4, device=dev); line = torch.randn(B, 32, 3, device=dev); tgt = torch.randn(B, 32, 3, device=dev)
     def step():
