@@ -292,6 +292,27 @@ int lrn_self_attention32(const float* qk, const float* v, float* out, int B, lrn
 int lrn_head_update(const float* hidden, const float* w2, const float* b2, int64_t rows, float* current, const float* noisy,
                     float* cum, lrn_stream_t stream);
 
+/* ---- query side for FEW polyline rows (B = 1 whole-scene calls, inference_whole_scene.py:130-139): one nn.Linear per launch,
+ * fp32 FMA, the layer's weights read once and spread over N/8 blocks (a 256-row tensor-core tile would be mostly padding).
+ *   out[M,N] = act(x'[M,K] w[N,K]^T + bias),  out fp32 or bf16 (out_bf16 = 1), relu optional, row pitches in elements.
+ *   x' = x                      (x2 = NULL, mlp3_w1 = NULL)
+ *   x' = x + x2                 (with_pos_embed: tgt + query_pos, src/model.py:101-102,113,124)
+ *   x' = relu(mlp3_w1 c + mlp3_b1) with x = c (M,3): the K = 3 first layer of PositionalEncoding (src/model.py:68-72, called at
+ *        :212) or of point_mlp (:151-153, BatchNorm folded by the caller) fused into the load of the second layer's operand.
+ * Replaces the nn.Linear calls of DetrTransformerDecoderLayer.forward (src/model.py:104-135), pos_emb (:64-75) and
+ * point_mlp (:150-159, 200-201) for query batches below 256 rows.  N % 8 == 0, K % 32 == 0. */
+int lrn_rows_linear(const float* x, int64_t ldx, const float* x2, int64_t ldx2, const float* mlp3_w1, const float* mlp3_b1,
+                    const float* w, const float* bias, void* out, int64_t ldo, int out_bf16, int relu, int64_t M, int64_t N,
+                    int64_t K, lrn_stream_t stream);
+/* out (rows,256) fp32 = relu(W1 current + b1): first layer of pos_emb on the current polyline points (src/model.py:212) when
+ * its second layer runs as a tensor-core GEMM (thousands of rows). */
+int lrn_query_pos_hidden(const float* w1, const float* b1, const float* current, int64_t rows, float* out, lrn_stream_t stream);
+/* out = a + b over n fp32 elements (n % 4 == 0): with_pos_embed ahead of a tensor-core linear. */
+int lrn_add(const float* a, const float* b, float* out, int64_t n, lrn_stream_t stream);
+/* Merge the splits of lrn_ctx_attention: part (B, splits, 256, 256) fp32, lse (B, splits, 256) -> out (B, 256, 256) fp32 or
+ * bf16, out[b][q] = sum_s 2^(lse_s - max) part_s / sum_s 2^(lse_s - max). */
+int lrn_ctx_attention_merge(const float* part, const float* lse, int B, int splits, void* out, int out_bf16, lrn_stream_t stream);
+
 /* out[c] = sum over rows of the bf16 matrix A (rows, cols), row pitch ld: the bias gradient of a linear layer whose output
  * gradient is bf16 (cols % 64 == 0). */
 int lrn_col_sum_bf16(const void* A, int64_t ld, int64_t rows, int64_t cols, float* out, lrn_stream_t stream);

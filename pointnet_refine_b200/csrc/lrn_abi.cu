@@ -22,6 +22,7 @@
 #include "ctx_attn_sm100.cuh"
 #include "scene_kernels.cuh"
 #include "query_kernels.cuh"
+#include "query_small.cuh"
 #include "pointwise.cuh"
 
 namespace {
@@ -1308,6 +1309,82 @@ int lrn_head_update(const float* hidden, const float* w2, const float* b2, int64
   if (st) return st;
   const int grid = int(std::min<int64_t>((rows + 7) / 8, int64_t(dev.sms) * 8));
   head_update_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hidden, w2, b2, rows, current, noisy, cum);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_rows_linear(const float* x, int64_t ldx, const float* x2, int64_t ldx2, const float* mlp3_w1, const float* mlp3_b1,
+                    const float* w, const float* bias, void* out, int64_t ldo, int out_bf16, int relu, int64_t M, int64_t N,
+                    int64_t K, lrn_stream_t stream) {
+  if (!x || !w || !out || (mlp3_w1 && (!mlp3_b1 || x2))) return fail(LRN_ERR_BAD_ARG, "null pointer or both x2 and mlp3_w1 given");
+  if (M <= 0 || M > (int64_t(1) << 24) || N <= 0 || N % 8 || K <= 0 || K % 32 || K > (1 << 20))
+    return fail(LRN_ERR_BAD_SHAPE, "M=%lld N=%lld K=%lld (N %% 8 == 0, K %% 32 == 0)", (long long)M, (long long)N, (long long)K);
+  if ((reinterpret_cast<uintptr_t>(w) & 15)) return fail(LRN_ERR_MISALIGNED, "w needs 16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  RowsLinearArgs a{};
+  a.x = x; a.x2 = x2; a.w1 = mlp3_w1; a.b1 = mlp3_b1; a.w = w; a.bias = bias; a.out = out;
+  a.ldx = ldx; a.ldx2 = ldx2; a.ldo = ldo;
+  a.M = int(M); a.N = int(N); a.K = int(K);
+  a.relu = relu ? 1 : 0;
+  a.out_bf16 = out_bf16 ? 1 : 0;
+  const unsigned row_tiles = unsigned((M + 31) / 32);
+  if (row_tiles > 65535) return fail(LRN_ERR_BAD_SHAPE, "M=%lld: more than 65535 row tiles", (long long)M);
+  const bool nb4 = (N / 8) * row_tiles < unsigned(dev.sms);  // few blocks: halve the columns per block
+  const dim3 grid(unsigned(N / (nb4 ? 4 : 8)), row_tiles);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (nb4) {
+    if (mlp3_w1) rows_linear_kernel<ROWS_IN_MLP3, 4><<<grid, 256, 0, s>>>(a);
+    else if (x2) rows_linear_kernel<ROWS_IN_SUM, 4><<<grid, 256, 0, s>>>(a);
+    else rows_linear_kernel<ROWS_IN_PLAIN, 4><<<grid, 256, 0, s>>>(a);
+  } else {
+    if (mlp3_w1) rows_linear_kernel<ROWS_IN_MLP3, 8><<<grid, 256, 0, s>>>(a);
+    else if (x2) rows_linear_kernel<ROWS_IN_SUM, 8><<<grid, 256, 0, s>>>(a);
+    else rows_linear_kernel<ROWS_IN_PLAIN, 8><<<grid, 256, 0, s>>>(a);
+  }
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_query_pos_hidden(const float* w1, const float* b1, const float* current, int64_t rows, float* out, lrn_stream_t stream) {
+  if (!w1 || !b1 || !current || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (rows <= 0) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld", (long long)rows);
+  if (reinterpret_cast<uintptr_t>(out) & 15) return fail(LRN_ERR_MISALIGNED, "out needs 16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const int grid = int(std::min<int64_t>((rows + 7) / 8, int64_t(dev.sms) * 8));
+  query_pos_hidden_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(current, rows, w1, b1, out);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_add(const float* a, const float* b, float* out, int64_t n, lrn_stream_t stream) {
+  if (!a || !b || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (n <= 0 || n % 4) return fail(LRN_ERR_BAD_SHAPE, "n=%lld (a positive multiple of 4)", (long long)n);
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return fail(LRN_ERR_MISALIGNED, "16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const int grid = int(std::min<int64_t>((n / 4 + 255) / 256, int64_t(dev.sms) * 8));
+  add_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+                                                                       reinterpret_cast<float4*>(out), n / 4);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_ctx_attention_merge(const float* part, const float* lse, int B, int splits, void* out, int out_bf16, lrn_stream_t stream) {
+  if (!part || !lse || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (B <= 0 || splits <= 0 || int64_t(B) * 256 >= (int64_t(1) << 31)) return fail(LRN_ERR_BAD_SHAPE, "B=%d splits=%d", B, splits);
+  if ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out)) & 15) return fail(LRN_ERR_MISALIGNED, "16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  const int rows = B * 256;
+  const int grid = std::min((rows + 7) / 8, dev.sms * 8);
+  ctx_merge_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, lse, rows, splits, out, out_bf16 ? 1 : 0);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

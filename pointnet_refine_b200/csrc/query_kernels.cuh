@@ -127,11 +127,21 @@ self_attn32_kernel(const float* __restrict__ qk, const float* __restrict__ v, fl
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const long long row0 = static_cast<long long>(b) * 32;
     __syncwarp();
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) {  // coalesced 128-byte rows
-      qs[j * 33 + lane] = qk[(row0 + j) * 512 + h * 32 + lane];
-      ks[j * 33 + lane] = qk[(row0 + j) * 512 + 256 + h * 32 + lane];
-      vs[j * 33 + lane] = v[(row0 + j) * 256 + h * 32 + lane];
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 8) {  // coalesced 128-byte rows, 24 loads in flight per lane (one segment per block: latency-bound)
+      float tq[8], tk[8], tv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        tq[j] = qk[(row0 + j0 + j) * 512 + h * 32 + lane];
+        tk[j] = qk[(row0 + j0 + j) * 512 + 256 + h * 32 + lane];
+        tv[j] = v[(row0 + j0 + j) * 256 + h * 32 + lane];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        qs[(j0 + j) * 33 + lane] = tq[j];
+        ks[(j0 + j) * 33 + lane] = tk[j];
+        vs[(j0 + j) * 33 + lane] = tv[j];
+      }
     }
     __syncwarp();
     float q[32], s[32];

@@ -1,6 +1,11 @@
 """CUDA-graph replay of the whole eval forward for a fixed (B, N): the reference's whole-scene loop runs the
 model once per lane line with B = 1 (inference_whole_scene.py:130-139), where ~100 small launches, not the GPU,
-set the latency.  Capture happens once; every call copies the inputs into static buffers and replays."""
+set the latency.  Capture happens once; every call copies the inputs into static buffers and replays.
+
+The captured launches hold raw pointers: the encoder's scratch buffer, the BN-folded operand blob and the folded decoder
+weights.  The wrapper keeps all of them alive (warm-up and capture run on the same side stream, so the scratch buffer the
+warm-up sized is the one the graph uses), and a replay after a parameter change would silently use the old weights: call
+`recapture()` after load_state_dict / an optimizer step."""
 from __future__ import annotations
 
 import torch
@@ -14,15 +19,24 @@ class GraphedLineRefineNet:
         self.model = model
         self.ctx = torch.zeros(B, N, 4, dtype=torch.float32, device=dev)
         self.line = torch.zeros(B, M, 3, dtype=torch.float32, device=dev)
-        side = torch.cuda.Stream(device=dev)
+        self._side = torch.cuda.Stream(device=dev)
+        self.recapture()
+
+    def recapture(self):
+        from . import ops
+        model, dev = self.model, self.ctx.device
+        side = self._side
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.no_grad(), torch.cuda.stream(side):      # warm-up: folds weights, sizes workspaces, sets kernel attributes
             for _ in range(3):
                 model(self.ctx, self.line)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        with torch.no_grad(), torch.cuda.graph(self.graph, stream=side):
             self.out = model(self.ctx, self.line)
+        # everything the captured kernels point at that the graph's own memory pool does not own
+        self._keep = (ops.workspaces_of(dev), model.context_encoder._folded, getattr(model, "_attn_cache", None),
+                      getattr(model, "_pm_cache", None), getattr(model, "_kv_cache", None))
 
     @torch.no_grad()
     def __call__(self, context: torch.Tensor, noisy_line: torch.Tensor) -> torch.Tensor:

@@ -292,7 +292,8 @@ class LineRefineNet(nn.Module):
         (csrc/ctx_attn_sm100.cuh):  Wqk (2048,256), bqk: (tgt+qpos) -> 8 heads x 256 folded query (scores come out
         in log2 units, 1/sqrt(32) included);  Wvo (256,2048), bvo: 8 heads x (softmax . memory) -> out_proj output.
         Plus [I | pos_emb.mlp.2.weight] (256,512) bf16, so that one GEMM over [memory | pos hidden] rows gives
-        memory + pos.  Re-made when a parameter changes."""
+        memory + pos.  Weight preparation, not data path: computed on the host in float64 once per parameter change
+        (like lrn_encoder_fold, it must be redone when a parameter changes) and uploaded."""
         ps = [self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias]
         for l in self.decoder_layers:
             ps += [l.cross_attn.in_proj_weight, l.cross_attn.in_proj_bias, l.cross_attn.out_proj.weight, l.cross_attn.out_proj.bias]
@@ -300,83 +301,96 @@ class LineRefineNet(nn.Module):
         if getattr(self, "_attn_cache", None) is None or self._attn_cache[0] != fp:
             d, H = self.d_model, 8
             hd = d // H
+            dev = ps[0].device
             scale = math.log2(math.e) / math.sqrt(hd)
+            host = lambda t: t.detach().cpu().double()
+            up = lambda t, dt=torch.float32: t.to(dt).contiguous().to(dev)
             layers = []
             for l in self.decoder_layers:
                 ca = l.cross_attn
-                w, b = ca.in_proj_weight.detach().double(), ca.in_proj_bias.detach().double()
+                w, b = host(ca.in_proj_weight), host(ca.in_proj_bias)
                 wq, wk, wv = w[:d].view(H, hd, d), w[d:2 * d].view(H, hd, d), w[2 * d:].view(H, hd, d)
                 bq, bv = b[:d].view(H, hd), b[2 * d:]
-                wo, bo = ca.out_proj.weight.detach().double(), ca.out_proj.bias.detach().double()
+                wo, bo = host(ca.out_proj.weight), host(ca.out_proj.bias)
                 wqk = scale * torch.einsum("hcd,hce->hde", wk, wq).reshape(H * d, d)          # row h*256+j: folded dim j of head h
                 bqk = scale * torch.einsum("hc,hcd->hd", bq, wk).reshape(H * d)
                 wvo = torch.einsum("ohc,hcd->ohd", wo.view(d, H, hd), wv).reshape(d, H * d)
                 bvo = wo @ bv + bo
-                layers.append(tuple(t.float().contiguous() for t in (wqk, bqk, wvo, bvo)) + (wvo.float().bfloat16().contiguous(),))
-            w2 = self.pos_emb.mlp[2].weight.detach()
-            wx = torch.cat([torch.eye(d, device=w2.device, dtype=w2.dtype), w2], dim=1).bfloat16().contiguous()
-            self._attn_cache = (fp, layers, wx, self.pos_emb.mlp[2].bias.detach().float().contiguous())
+                layers.append((up(wqk), up(bqk), up(wvo), up(bvo), up(wvo.float(), torch.bfloat16)))
+            w2 = host(self.pos_emb.mlp[2].weight)
+            wx = up(torch.cat([torch.eye(d, dtype=w2.dtype), w2], dim=1).float(), torch.bfloat16)
+            self._attn_cache = (fp, layers, wx, up(host(self.pos_emb.mlp[2].bias)))
         return self._attn_cache[1:]
 
-    def _refine_attn(self, context, noisy_line, memx):
-        """Eval-mode decoder, bf16 tier, M = 32: per layer the cross attention is ONE lrn_ctx_attention launch over
-        kp = memory + pos and memory (bf16), with Wk / Wv folded into the 32 x 8 queries and into out_proj - K and V
-        of nn.MultiheadAttention (src/model.py:123-128) are never formed.  `memx` (B,N,512) bf16 is the encoder's
-        LRN_OUT_MEMORY_BF16 buffer: [memory | room for the positional hidden layer].  The linears of the query side
-        (self-attention projections, FFN, pos_emb layer 2, the folded query / output maps) run on the tcgen05 GEMM
-        in its tf32 tier; the 32 x 32 self attention, LayerNorms and residual adds are stock PyTorch ops.
-        Same parameters and math as DetrTransformerDecoderLayer.forward (src/model.py:104-135) in eval mode."""
+    def _point_mlp_weights(self):
+        """point_mlp (src/model.py:150-159) with its three eval-mode BatchNorms folded into the 1x1 convs:
+        [(W1 (64,3), b1), (W2 (128,64), b2), (W3 (256,128), b3)] fp32.  Host-side weight preparation, cached like _attn_weights."""
+        ts = list(self.point_mlp.parameters()) + list(self.point_mlp.buffers())
+        fp = tuple((t.data_ptr(), t._version) for t in ts)
+        if getattr(self, "_pm_cache", None) is None or self._pm_cache[0] != fp:
+            dev = ts[0].device
+            out = []
+            for ci, bi in ((0, 1), (3, 4), (6, 7)):
+                conv, bn = self.point_mlp[ci], self.point_mlp[bi]
+                s = bn.weight.detach().cpu().double() / torch.sqrt(bn.running_var.detach().cpu().double() + bn.eps)
+                w = conv.weight.detach().cpu().double().squeeze(-1) * s[:, None]
+                b = (conv.bias.detach().cpu().double() - bn.running_mean.detach().cpu().double()) * s + bn.bias.detach().cpu().double()
+                out.append((w.float().contiguous().to(dev), b.float().contiguous().to(dev)))
+            self._pm_cache = (fp, out)
+        return self._pm_cache[1]
+
+    def _refine_attn(self, context, noisy_line, memx, out):
+        """Eval-mode decoder, bf16 tier, M = 32, every step on this library's kernels: per layer the cross attention is ONE
+        lrn_ctx_attention launch over kp = memory + pos and memory (bf16), with Wk / Wv folded into the 32 x 8 queries and
+        into out_proj - K and V of nn.MultiheadAttention (src/model.py:123-128) are never formed.  `memx` (B,N,512) bf16 is
+        the encoder's LRN_OUT_MEMORY_BF16 buffer: [memory | room for the positional hidden layer].  The linears of the
+        query side (point_mlp, pos_emb, self-attention projections, FFN, the folded query / output maps) run on the tcgen05
+        GEMM in its tf32 tier when the batch has >= 256 polyline rows, and as fp32 rows_linear launches below that (B < 8:
+        the whole-scene loop's B = 1, inference_whole_scene.py:130-139); self attention, residual + LayerNorm, heads and
+        the cumulative offsets are the kernels of csrc/query_kernels.cuh.  The six cumulative offsets are written straight
+        into `out` (6,B,32,3).  Same parameters and math as DetrTransformerDecoderLayer.forward (src/model.py:104-135)."""
         B, N, _ = context.shape
         d, H = self.d_model, 8
         layers_w, wx, b2 = self._attn_weights()
+        (pw1, pb1), (pw2, pb2), (pw3, pb3) = self._point_mlp_weights()
         ops.pos_hidden(self.pos_emb.mlp[0].weight.detach(), self.pos_emb.mlp[0].bias.detach(), context, memx[:, :, d:])
         kp = ops.gemm_bias_act(memx.view(B * N, 2 * d), wx, b2, out_dtype=torch.bfloat16).view(B, N, d)
         mem = memx[:, :, :d]
         rows = B * noisy_line.shape[1]
+        big = rows >= 256     # thousands of rows: tensor-core linears; else one fp32 rows_linear launch per nn.Linear
 
-        def lin(x, w, b, relu=False, out_dtype=None):   # (B,32,K) fp32 -> (B,32,N) fp32 (or out_dtype)
-            if rows < 256:
-                y = F.linear(x, w, b)
-                y = F.relu(y) if relu else y
-                return y if out_dtype is None else y.to(out_dtype)
+        def lin(x, w, b, relu=False, out_dtype=None, add=None):   # (B,32,K) fp32 [+ add] -> (B,32,N) fp32 (or out_dtype)
+            if not big:
+                return ops.rows_linear(x, w, b, add=add, relu=relu, out_dtype=out_dtype or torch.float32)
+            if add is not None:
+                x = ops.add(x, add)
             return ops.gemm_bias_act(x.reshape(rows, -1), w.detach(), b.detach(), relu=relu, out_dtype=out_dtype).view(B, -1, w.shape[0])
 
         pe0, pe2 = self.pos_emb.mlp[0], self.pos_emb.mlp[2]
-        tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
+        tgt = ops.rows_linear(ops.rows_linear(noisy_line, pw2, pb2, mlp3=(pw1, pb1), relu=True), pw3, pb3)   # point_mlp
         current = noisy_line.clone()
-        outs = []
-        big = rows >= 256     # thousands of rows: every step below is one native kernel; else latency-oriented stock ops
-        for layer, head, (wqk, bqk, wvo, bvo, wvo16) in zip(self.decoder_layers, self.reg_branches, layers_w):
-            qpos = lin(F.relu(pe0(current)), pe2.weight, pe2.bias)
-            q = tgt + qpos
-            sa = layer.self_attn
-            qk = lin(q, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d])
-            v = lin(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:])
+        for i, (layer, head, (wqk, bqk, wvo, bvo, wvo16)) in enumerate(zip(self.decoder_layers, self.reg_branches, layers_w)):
             if big:
-                att = ops.self_attention32(qk, v)
-                tgt = ops.add_layernorm(tgt, lin(att, sa.out_proj.weight, sa.out_proj.bias), layer.norm1)
+                qpos = lin(ops.query_pos_hidden(pe0.weight, pe0.bias, current), pe2.weight, pe2.bias)
             else:
-                qk5 = qk.view(B, -1, 2, H, d // H)
-                att = F.scaled_dot_product_attention(qk5[:, :, 0].transpose(1, 2), qk5[:, :, 1].transpose(1, 2),
-                                                     v.view(B, -1, H, d // H).transpose(1, 2))
-                tgt = layer.norm1(tgt + lin(att.transpose(1, 2).reshape(B, -1, d), sa.out_proj.weight, sa.out_proj.bias))
+                qpos = ops.rows_linear(current, pe2.weight, pe2.bias, mlp3=(pe0.weight, pe0.bias))
+            sa = layer.self_attn
+            qk = lin(tgt, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d], add=qpos)
+            v = lin(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:])
+            att = ops.self_attention32(qk, v)
+            tgt = ops.add_layernorm(tgt, lin(att, sa.out_proj.weight, sa.out_proj.bias), layer.norm1)
             # folded queries: row q * 8 + h of the segment's 256 (any row order works, rows are independent)
-            qf = lin(tgt + qpos, wqk, bqk, out_dtype=torch.bfloat16).view(B, H * 32, d)   # tf32 accumulate, rounded once
+            qf = lin(tgt, wqk, bqk, out_dtype=torch.bfloat16, add=qpos).view(B, H * 32, d)   # fp32 / tf32 accumulate, rounded once
             if big:   # attention output leaves the kernel as bf16, Wv / out_proj (folded) is a bf16 GEMM with fp32 output
                 o = ops.ctx_attention(qf, kp, mem, out_dtype=torch.bfloat16).view(rows, H * d)
                 cross = ops.gemm_bias_act(o, wvo16, bvo, out_dtype=torch.float32).view(B, 32, d)
-                ffn_in = ops.add_layernorm(tgt, cross, layer.norm2)
             else:
-                o = ops.ctx_attention(qf, kp, mem).view(B, 32, H * d)
-                ffn_in = layer.norm2(tgt + lin(o, wvo, bvo))
+                cross = ops.rows_linear(ops.ctx_attention(qf, kp, mem).view(B, 32, H * d), wvo, bvo)
+            ffn_in = ops.add_layernorm(tgt, cross, layer.norm2)
             ffn = lin(lin(ffn_in, layer.linear1.weight, layer.linear1.bias, relu=True), layer.linear2.weight, layer.linear2.bias)
-            tgt = ops.add_layernorm(ffn_in, ffn, layer.norm3) if big else layer.norm3(ffn_in + ffn)
-            if big:
-                hid = lin(tgt, head[0].weight, head[0].bias, relu=True)
-                outs.append(ops.head_update(hid, head[2].weight, head[2].bias, current, noisy_line))
-            else:
-                outs.append(ops.head_forward(head[0].weight, head[0].bias, head[2].weight, head[2].bias, tgt, current, noisy_line))
-        return torch.stack(outs)
+            tgt = ops.add_layernorm(ffn_in, ffn, layer.norm3)
+            hid = lin(tgt, head[0].weight, head[0].bias, relu=True)
+            ops.head_update(hid, head[2].weight, head[2].bias, current, noisy_line, out=out[i])
 
     def _refine_fast_train(self, context, noisy_line, fused_pm):
         """Autograd-capable twin of _refine_fast for model.train(): context_proj, the memory positional embedding
@@ -452,14 +466,17 @@ class LineRefineNet(nn.Module):
             chunk = max(1, min(8 * self.segment_chunk, (4 * ops.DEFAULT_CHUNK_ROWS) // max(N, 1)))   # four full encoder waves
         else:
             chunk = max(1, min(self.segment_chunk, (1 << 20) // max(N, 1))) if fast else self.segment_chunk
+        if attn:
+            result = torch.empty(self.num_decoder_layers, context.shape[0], 32, 3, dtype=torch.float32, device=context.device)
+            for s in range(0, context.shape[0], chunk):
+                ctx = context[s:s + chunk].contiguous()
+                memx = self.context_encoder.run_native(ctx, pool=False, memory=True, memory_bf16=True)["memory"]
+                self._refine_attn(ctx, noisy_line[s:s + chunk].contiguous(), memx, result[:, s:s + chunk])
+            return result
         outs = []
         for s in range(0, context.shape[0], chunk):
             ctx = context[s:s + chunk].contiguous()
             line = noisy_line[s:s + chunk].contiguous()
-            if attn:
-                memx = self.context_encoder.run_native(ctx, pool=False, memory=True, memory_bf16=True)["memory"]
-                outs.append(self._refine_attn(ctx, line, memx))
-                continue
             memory = self.context_encoder.run_native(ctx, pool=False, memory=True)["memory"]
             outs.append(self._refine_fast(ctx, line, memory) if fast else self._refine(ctx, line, memory, native_heads=True))
         return torch.cat(outs, dim=1)

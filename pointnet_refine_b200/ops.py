@@ -77,11 +77,18 @@ _workspaces: dict = {}
 
 
 def _workspace(nbytes: int, device):
-    key = (device.type, device.index)
+    """Grow-only scratch buffer per (device, stream): calls on different streams never share one, and a buffer that has
+    been replaced by a larger one stays alive for whoever still holds it (graph.py keeps the one its capture baked in)."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         _workspaces[key] = ws = _aligned_bytes(nbytes, device)
     return ws
+
+
+def workspaces_of(device) -> list:
+    """The scratch buffers currently cached for `device` (a CUDA graph must keep the ones it captured alive)."""
+    return [ws for key, ws in _workspaces.items() if key[:2] == (device.type, device.index)]
 
 
 def encoder_forward(folded: FoldedEncoder, context: torch.Tensor, *, pool=True, argmax=False, fused=False,
@@ -133,12 +140,20 @@ def encoder_launches(P: int, flags: int, chunk_rows: int = 0, precision: str = "
     return chunks * per_chunk + (1 if flags & OUT_ARGMAX else 0)
 
 
-def head_forward(w1, b1, w2, b2, tgt, current, noisy):
+def _cum_out(out, current):
+    if out is None:
+        return torch.empty_like(current)
+    if out.shape != current.shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 tensor of current's shape")
+    return out
+
+
+def head_forward(w1, b1, w2, b2, tgt, current, noisy, out=None):
     """reg_branches[i] + cumulative-offset update (lrn_head_forward).  `current` (B,M,3) is updated
-    in place; returns the cumulative offset (B,M,3)."""
+    in place; returns the cumulative offset (B,M,3) (written into `out` when given)."""
     tgt = _f32c(tgt)
     rows = tgt.numel() // 256
-    cum = torch.empty_like(current)
+    cum = _cum_out(out, current)
     dev = tgt.device
     with torch.cuda.device(dev):
         _lib.check(lib.lrn_head_forward(_f32c(w1).data_ptr(), _f32c(b1).data_ptr(), _f32c(w2).data_ptr(),
@@ -224,10 +239,14 @@ def ctx_attention(qfold: torch.Tensor, kp: torch.Tensor, mem: torch.Tensor, spli
                                          out.data_ptr(), int(direct_bf16), lse.data_ptr(), _stream_ptr(kp.device)),
                    "lrn_ctx_attention")
     _lib.launch_counter += 1
-    if splits == 1:
-        return out[:, 0] if direct_bf16 else out[:, 0].to(out_dtype)
-    w = torch.softmax(lse * 0.6931471805599453, dim=1)  # lse is in log2 units
-    return (out * w.unsqueeze(-1)).sum(1).to(out_dtype)
+    if splits == 1 and (direct_bf16 or out_dtype == torch.float32):
+        return out[:, 0]
+    merged = torch.empty(B, 256, 256, dtype=out_dtype, device=kp.device)     # merge the splits by their log-sum-exp
+    with torch.cuda.device(kp.device):
+        _lib.check(lib.lrn_ctx_attention_merge(out.data_ptr(), lse.data_ptr(), B, splits, merged.data_ptr(),
+                                               int(out_dtype == torch.bfloat16), _stream_ptr(kp.device)), "lrn_ctx_attention_merge")
+    _lib.launch_counter += 1
+    return merged
 
 
 def pos_hidden(w1: torch.Tensor, b1: torch.Tensor, context: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
@@ -275,18 +294,76 @@ def self_attention32(qk: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def head_update(hidden: torch.Tensor, w2, b2, current: torch.Tensor, noisy: torch.Tensor) -> torch.Tensor:
+def head_update(hidden: torch.Tensor, w2, b2, current: torch.Tensor, noisy: torch.Tensor, out=None) -> torch.Tensor:
     """Second head layer + cumulative-offset update (lrn_head_update): `current` (B,M,3) is updated in place; returns the
-    cumulative offset (B,M,3)."""
+    cumulative offset (B,M,3) (written into `out` when given)."""
     hidden = _f32c(hidden)
     rows = hidden.numel() // 128
-    cum = torch.empty_like(current)
+    cum = _cum_out(out, current)
     with torch.cuda.device(hidden.device):
         _lib.check(lib.lrn_head_update(hidden.data_ptr(), _f32c(w2.detach()).data_ptr(), _f32c(b2.detach()).data_ptr(), rows,
                                        current.data_ptr(), _f32c(noisy).data_ptr(), cum.data_ptr(), _stream_ptr(hidden.device)),
                    "lrn_head_update")
     _lib.launch_counter += 1
     return cum
+
+
+def rows_linear(x: torch.Tensor, w: torch.Tensor, bias, *, add: torch.Tensor | None = None, mlp3=None, relu=False,
+                out_dtype=torch.float32) -> torch.Tensor:
+    """nn.Linear for FEW rows in fp32 FMA (lrn_rows_linear): out (M, N) = act(x' @ w.T + bias), w (N, K) fp32.
+    x' = x (M, K), or x + add, or relu(c @ w1.T + b1) with x = c (M, 3) and mlp3 = (w1 (K,3), b1 (K)): the K = 3 first
+    layer of pos_emb / point_mlp fused into the operand load.  Leading dimensions of x are flattened."""
+    w = _f32c(w.detach())
+    N, K = w.shape
+    lead = x.shape[:-1]
+    x = _f32c(x).reshape(-1, x.shape[-1])
+    M = x.shape[0]
+    if mlp3 is not None:
+        if x.shape[1] != 3 or add is not None:
+            raise ValueError("rows_linear: mlp3 takes (M, 3) coordinates and no addend")
+        w1, b1 = _f32c(mlp3[0].detach()).reshape(-1, 3), _f32c(mlp3[1].detach())
+        if w1.shape[0] != K or b1.numel() != K:
+            raise ValueError("rows_linear: mlp3 first layer must have K outputs")
+    elif x.shape[1] != K:
+        raise ValueError(f"rows_linear: x has {x.shape[1]} columns, w expects {K}")
+    x2 = None
+    if add is not None:
+        x2 = _f32c(add).reshape(-1, K)
+        if x2.shape[0] != M:
+            raise ValueError("rows_linear: addend shape")
+    b = _f32c(bias.detach()) if bias is not None else None
+    out = torch.empty(M, N, dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lrn_rows_linear(x.data_ptr(), x.stride(0), x2.data_ptr() if x2 is not None else None, K,
+                                       w1.data_ptr() if mlp3 is not None else None, b1.data_ptr() if mlp3 is not None else None,
+                                       w.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), N,
+                                       int(out_dtype == torch.bfloat16), int(relu), M, N, K, _stream_ptr(x.device)), "lrn_rows_linear")
+    _lib.launch_counter += 1
+    return out.view(*lead, N)
+
+
+def query_pos_hidden(w1: torch.Tensor, b1: torch.Tensor, current: torch.Tensor) -> torch.Tensor:
+    """relu(current @ w1.T + b1): (..., 3) -> (..., 256) fp32 (lrn_query_pos_hidden), first layer of pos_emb on the polyline."""
+    current = _f32c(current)
+    rows = current.numel() // 3
+    out = torch.empty(*current.shape[:-1], 256, dtype=torch.float32, device=current.device)
+    with torch.cuda.device(current.device):
+        _lib.check(lib.lrn_query_pos_hidden(_f32c(w1.detach()).data_ptr(), _f32c(b1.detach()).data_ptr(), current.data_ptr(), rows,
+                                            out.data_ptr(), _stream_ptr(current.device)), "lrn_query_pos_hidden")
+    _lib.launch_counter += 1
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a + b for fp32 tensors of equal shape (lrn_add)."""
+    a, b = _f32c(a), _f32c(b)
+    if a.shape != b.shape or a.numel() % 4:
+        raise ValueError("add: equal shapes with a multiple of 4 elements expected")
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.lrn_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream_ptr(a.device)), "lrn_add")
+    _lib.launch_counter += 1
+    return out
 
 
 def point_embed(folded: FoldedEncoder, context: torch.Tensor, tiled: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
