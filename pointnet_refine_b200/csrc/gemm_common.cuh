@@ -44,6 +44,13 @@ struct GemmParams {
   int k_splits;    // pair EPI_ACT kernels, fp32 output: > 1 = split-K, every split atomically adds its partial
                    // product into the (zeroed) output; 0 / 1 = one pass over K
   int kb_per_split;
+  // fp32x3 tier (3 x TF32 split, "exact" argmax tier): every fp32 operand is stored as hi = rna_tf32(v) and
+  // lo = rna_tf32(v - hi), `*_lo_off` elements further along the row, and the k-loop runs three passes
+  // A_hi B_hi + A_lo B_hi + A_hi B_lo into the same accumulator (kb_main / kb_gate count all three passes).
+  int split3;
+  int a_lo_off, b_lo_off;  // elements
+  long long out_lo_off;    // EPI_ACT with round_tf32 / FUSE_STORE_PM: where the lo half of an output row goes
+  int exact_gate;          // EPI_FUSION: keep G in tensor memory until F is complete and evaluate the gate in full fp32
   // EPI_FUSION
   const float* bias_f;
   const float* bias_g;
@@ -109,6 +116,23 @@ __device__ __forceinline__ void pool_chunk(const float (&v)[32], bool mask, long
   }
   warp_transpose_reduce(s, lane, OpAddF());
   if (s[0] > 0.f) atomicAdd(p.global_feat + seg * 2048 + 1024 + ch0 + lane, s[0] * p.inv_npts);
+}
+
+// fp32 values as pairs of TF32 operands (fp32x3 tier): hi = rna_tf32(v) at `elem_off`, lo = rna_tf32(v - hi) `lo_off` further
+__device__ __forceinline__ void store_row_chunk_split(float* out, long long elem_off, long long lo_off, const float (&v)[32]) {
+  float4* dh = reinterpret_cast<float4*>(out + elem_off);
+  float4* dl = reinterpret_cast<float4*>(out + elem_off + lo_off);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = ptx::round_tf32(v[4 * q + j]);
+      l[j] = ptx::round_tf32(v[4 * q + j] - h[j]);
+    }
+    dh[q] = make_float4(h[0], h[1], h[2], h[3]);
+    dl[q] = make_float4(l[0], l[1], l[2], l[3]);
+  }
 }
 
 template <bool TF32>

@@ -175,6 +175,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const KbSlot slot = fusion_slot(ins, s, p.kb_gate);
           kcol = slot.gate ? p.kb_main + slot.kb : slot.kb;
         }
+        int a_extra = 0, b_extra = 0;
+        if (TF32 && p.split3) {  // three passes over the same k-blocks: A_hi B_hi, A_lo B_hi, A_hi B_lo
+          KbSlot slot{false, s};
+          if (EPI == EPI_FUSION) slot = fusion_slot(ins, s, p.kb_gate);
+          const int n1 = (slot.gate ? p.kb_gate : p.kb_main) / 3;
+          const int pass = slot.kb / n1;
+          kcol = (slot.gate ? p.kb_main / 3 : 0) + slot.kb - pass * n1;
+          a_extra = pass == 1 ? p.a_lo_off : 0;
+          b_extra = pass == 2 ? p.b_lo_off : 0;
+        }
         ptx::mbar_wait(&bar_empty[stage], phase ^ 1);
         if (ptx::elect_one()) {
           uint8_t* sa = smem + stage * L::kStage;
@@ -193,8 +203,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.a_tiled)  // one contiguous 16 KB block: (column block, row tile) of the tiled operand matrix
               ptx::tma_load_4d_pair(sa, &tmA, full_leader, 0, 0, (p.a_col0 + kcol * BK) / BK, m_blk * 2 + static_cast<int>(rank));
             else
-              ptx::tma_load_2d_pair(sa, &tmA, full_leader, p.a_col0 + kcol * BK, m_blk * 2 * BM + static_cast<int>(rank) * BM);
-            ptx::tma_load_2d_pair(sa + L::kA, &tmB, full_leader, kcol * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+              ptx::tma_load_2d_pair(sa, &tmA, full_leader, p.a_col0 + kcol * BK + a_extra, m_blk * 2 * BM + static_cast<int>(rank) * BM);
+            ptx::tma_load_2d_pair(sa + L::kA, &tmB, full_leader, kcol * BK + b_extra, n_blk * BN + static_cast<int>(rank) * (BN / 2));
           }
         }
         __syncwarp();
@@ -324,6 +334,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n_blk * BN + c0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+          } else if (valid && TF32 && p.split3 && p.round_tf32) {  // fp32x3 tier: the next layer's operand as hi / lo TF32 halves
+            store_row_chunk_split(reinterpret_cast<float*>(p.out), static_cast<long long>(row) * p.ldo + n_blk * BN + c0, p.out_lo_off, v);
           } else if (valid) {
             store_row_chunk<TF32>(p.out, static_cast<long long>(row) * p.ldo + n_blk * BN + c0, v, p.out_f32 != 0,
                                   p.round_tf32 != 0);
@@ -362,11 +374,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
         // ---- phase A: G_t -> gamma = 0.5 + 0.5 * sigmoid(G + bg), kept in registers (16-bit fixed point)
         uint32_t gq[kHalfCols / 2];
+        const bool exact = TF32 && p.exact_gate;  // fp32x3 tier: G stays in tensor memory until phase B (no 16-bit gamma)
         ptx::mbar_wait(&bar_tfull[rf ^ 1], it & 1);
         ptx::tc_fence_after();
         if (stamp) p.dbg[it * 8 + 2] = clock64();  // G ready
 #pragma unroll
-        for (int i = 0; i < kChunks; ++i) {  // both phases hide under the next main loop: no need to pipeline the loads
+        for (int i = 0; i < (exact ? 0 : kChunks); ++i) {  // both phases hide under the next main loop: no need to pipeline the loads
           const int c0 = col_lo + 32 * i;
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(t_lane + (rf ^ 1) * BN + c0, r);
@@ -381,7 +394,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[rf ^ 1]), 0));  // G region drained
+        if (lane == 0 && !exact) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[rf ^ 1]), 0));  // G region drained
         if (stamp) p.dbg[it * 8 + 3] = clock64();  // phase A done
 
         // ---- phase B: v = relu(F_t + bf) * gamma, stores, pooling
@@ -396,13 +409,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tmem_ld_32x32b_x32(t_lane + rf * BN + c0, r);
             ptx::tmem_ld_wait();
             float v[32];
+            if (exact) {  // gate in full fp32: 0.5 + 0.5 / (1 + exp(-z)), src/model.py:54-55
+              uint32_t rg[32];
+              ptx::tmem_ld_32x32b_x32(t_lane + (rf ^ 1) * BN + c0, rg);
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float f0 = fmaxf(__uint_as_float(r[j]) + sb[c0 + j], 0.f);
-              const float f1 = fmaxf(__uint_as_float(r[j + 1]) + sb[c0 + j + 1], 0.f);
-              const uint32_t g = gq[16 * i + j / 2];
-              v[j] = valid ? f0 * gamma_lo(g) : 0.f;
-              v[j + 1] = valid ? f1 * gamma_hi(g) : 0.f;
+              for (int j = 0; j < 32; ++j) {
+                const float f = fmaxf(__uint_as_float(r[j]) + sb[c0 + j], 0.f);
+                const float z = __uint_as_float(rg[j]) + sb[BN + c0 + j];
+                v[j] = valid ? f * (0.5f + __fdiv_rn(0.5f, 1.f + expf(-z))) : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float f0 = fmaxf(__uint_as_float(r[j]) + sb[c0 + j], 0.f);
+                const float f1 = fmaxf(__uint_as_float(r[j + 1]) + sb[c0 + j + 1], 0.f);
+                const uint32_t g = gq[16 * i + j / 2];
+                v[j] = valid ? f0 * gamma_lo(g) : 0.f;
+                v[j + 1] = valid ? f1 * gamma_hi(g) : 0.f;
+              }
             }
             const int ch0 = n_blk * BN + c0;
             if ((p.flags & FUSE_STORE_CN) && valid) {
@@ -410,8 +435,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.npts] = v[j];
             }
-            if ((p.flags & FUSE_STORE_PM) && valid)
-              store_row_chunk<TF32>(p.fused_pm, static_cast<long long>(row) * 1024 + ch0, v, TF32, TF32);
+            if ((p.flags & FUSE_STORE_PM) && valid) {
+              if (TF32 && p.split3)
+                store_row_chunk_split(reinterpret_cast<float*>(p.fused_pm), static_cast<long long>(row) * 2048 + ch0, 1024, v);
+              else
+                store_row_chunk<TF32>(p.fused_pm, static_cast<long long>(row) * 1024 + ch0, v, TF32, TF32);
+            }
             if (p.flags & (FUSE_POOL | FUSE_ARGMAX)) {
               if (!GENERAL || (uniform && !(p.flags & FUSE_ARGMAX))) {
                 float mx, sm;
@@ -431,7 +460,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tc_fence_before();
         __syncwarp();
         if (stamp) p.dbg[it * 8 + 5] = clock64();  // phase B done
-        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[rf]), 0));  // F region drained
+        if (lane == 0) {
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[rf]), 0));  // F region drained
+          if (exact) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[rf ^ 1]), 0));  // ... and G with it
+        }
       }
     }
   }

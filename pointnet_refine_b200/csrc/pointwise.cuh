@@ -16,7 +16,7 @@ __global__ void fold_linear_kernel(const float* __restrict__ w, const float* __r
                                    const float* __restrict__ g, const float* __restrict__ beta,
                                    const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout,
                                    int cin, OutT* __restrict__ out_w, long long ld, int col0,
-                                   float* __restrict__ out_b, int rna_tf32) {
+                                   float* __restrict__ out_b, int rna_tf32, long long lo_off = 0) {
   const long long total = static_cast<long long>(cout) * cin;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -26,6 +26,10 @@ __global__ void fold_linear_kernel(const float* __restrict__ w, const float* __r
     const float v = w[i] * s;
     if constexpr (sizeof(OutT) == 2) {
       out_w[co * ld + col0 + ci] = __float2bfloat16_rn(v);
+    } else if (lo_off) {  // fp32x3 tier: hi / lo TF32 halves of the folded weight
+      const float h = ptx::round_tf32(v);
+      out_w[co * ld + col0 + ci] = h;
+      out_w[co * ld + lo_off + col0 + ci] = ptx::round_tf32(v - h);
     } else {
       out_w[co * ld + col0 + ci] = rna_tf32 ? ptx::round_tf32(v) : v;
     }
@@ -53,7 +57,7 @@ struct EmbedWeights {
 // [row tile of 128][column block of 64][128 rows][64 columns] - feat1 is column block 0, the gate hidden block is block 31.
 template <bool TF32>
 __global__ void __launch_bounds__(256) point_embed_kernel(const float4* __restrict__ ctx, long long rows,
-                                                          EmbedWeights w, void* __restrict__ cat, int ld) {
+                                                          EmbedWeights w, void* __restrict__ cat, int ld, int lo_off = 0) {
   const int sub = threadIdx.x & 15;  // channel group: channels [4*sub, 4*sub + 4)
   float4 wr[4];
   float br[4], gw[4], gb[4];
@@ -75,6 +79,16 @@ __global__ void __launch_bounds__(256) point_embed_kernel(const float4* __restri
     }
     if constexpr (TF32) {
       float* row = reinterpret_cast<float*>(cat) + pt * ld;
+      if (lo_off) {  // fp32x3 tier: lo = rna_tf32(v - hi) in the second half of the operand row
+        float fl[4], hl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          fl[j] = ptx::round_tf32(f[j] - ptx::round_tf32(f[j]));
+          hl[j] = ptx::round_tf32(h[j] - ptx::round_tf32(h[j]));
+        }
+        *reinterpret_cast<float4*>(row + lo_off + 4 * sub) = make_float4(fl[0], fl[1], fl[2], fl[3]);
+        *reinterpret_cast<float4*>(row + lo_off + 1984 + 4 * sub) = make_float4(hl[0], hl[1], hl[2], hl[3]);
+      }
       *reinterpret_cast<float4*>(row + 4 * sub) =
           make_float4(ptx::round_tf32(f[0]), ptx::round_tf32(f[1]), ptx::round_tf32(f[2]), ptx::round_tf32(f[3]));
       *reinterpret_cast<float4*>(row + 1984 + 4 * sub) =

@@ -307,7 +307,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float(r & 0xFFFFE000u);  // low 13 bits cleared explicitly: the fp32x3 tier computes v - round_tf32(v)
 }
 
 }  // namespace ptx
