@@ -47,8 +47,11 @@ enum lrn_status {
 /* Arithmetic tier of the tensor-core layers (conv2..conv5, fusion, gate layer 2,
  * context_proj).  conv1 and gate layer 1 always run in fp32 FMA on raw fp32 xyz/intensity.
  *   BF16: operands rounded to bfloat16, fp32 accumulate  (tolerance 1e-2 of range)
- *   TF32: operands fp32 read as TF32, fp32 accumulate    (tolerance 1e-3 max-abs) */
-enum lrn_precision { LRN_PREC_BF16 = 0, LRN_PREC_TF32 = 1 };
+ *   TF32: operands fp32 read as TF32, fp32 accumulate    (tolerance 1e-3 max-abs)
+ *   FP32X3: every operand as two TF32 halves (hi + lo), three tensor-core passes per k-block (hi*hi + lo*hi + hi*lo), fp32
+ *         accumulate, gate evaluated in full fp32: fp32-class products (relative error ~2^-21 per product) for callers that
+ *         need the max-pool ARGMAX of the fp32 reference (src/model.py:58); about a third of the TF32 tier's throughput. */
+enum lrn_precision { LRN_PREC_BF16 = 0, LRN_PREC_TF32 = 1, LRN_PREC_FP32X3 = 2 };
 
 /* Output selection for lrn_encoder_forward (bitwise or). */
 enum lrn_encoder_flags {

@@ -16,9 +16,9 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "lrn_b200.h")
 
 # enums of include/lrn_b200.h
 LRN_OK = 0
-PREC_BF16, PREC_TF32 = 0, 1
+PREC_BF16, PREC_TF32, PREC_FP32X3 = 0, 1, 2
 OUT_POOL, OUT_ARGMAX, OUT_FUSED, OUT_MEMORY, OUT_MEMORY_BF16 = 1, 2, 4, 8, 16
-PRECISIONS = {"bf16": PREC_BF16, "tf32": PREC_TF32}
+PRECISIONS = {"bf16": PREC_BF16, "tf32": PREC_TF32, "fp32x3": PREC_FP32X3}
 
 EXPORTS = [
     "lrn_abi_version", "lrn_status_string", "lrn_last_error", "lrn_device_check",

@@ -53,7 +53,9 @@ constexpr int64_t kDefaultChunkRows = 148 * 128 * 16;  // 303,104 points per wav
 const int kChan[6] = {4, 64, 128, 256, 512, 1024};
 const int kCatOff[6] = {0, 0, 64, 192, 448, 960};  // column of feat_k inside the operand row
 
-size_t elem_size(int precision) { return precision == LRN_PREC_TF32 ? 4 : 2; }
+size_t elem_size(int precision) { return precision == LRN_PREC_BF16 ? 2 : 4; }
+// fp32x3 tier: every tensor-core operand row is stored twice as wide, [hi | lo] TF32 halves of the fp32 value
+int op_mul(int precision) { return precision == LRN_PREC_FP32X3 ? 2 : 1; }
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ------------------------------------------------------------------ packed weight blob
@@ -80,9 +82,10 @@ PackedLayout packed_layout(int precision) {
   L.b1 = take(64 * 4);
   L.wg1 = take(64 * 4);
   L.bg1 = take(64 * 4);
-  for (int k = 2; k <= 5; ++k) L.w[k] = take(size_t(kChan[k]) * kChan[k - 1] * es);
-  L.wfg = take(size_t(1024) * kCat * es);
-  L.wp = take(size_t(256) * 1024 * es);
+  const size_t wm = size_t(op_mul(precision));
+  for (int k = 2; k <= 5; ++k) L.w[k] = take(size_t(kChan[k]) * kChan[k - 1] * es * wm);
+  L.wfg = take(size_t(1024) * kCat * es * wm);
+  L.wp = take(size_t(256) * 1024 * es * wm);
   for (int k = 2; k <= 5; ++k) L.b[k] = take(size_t(kChan[k]) * 4);
   L.bf = take(1024 * 4);
   L.bg = take(1024 * 4);
@@ -120,7 +123,7 @@ int make_tmap(CUtensorMap* m, int precision, const void* base, int64_t rows, int
   cuuint64_t strides[1] = {cuuint64_t(ld * es)};
   cuuint32_t box[2] = {cuuint32_t(128 / es), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, precision == LRN_PREC_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r = enc(m, precision != LRN_PREC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LRN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
@@ -222,7 +225,7 @@ GemmPlan plan_gemm(int64_t N, int epi) {
 // `tout`: tensor map of the bf16 output (box 64 x 128, 128B swizzle) or nullptr -> direct stores.
 int launch_gemm(int precision, const GemmPlan& g, int epi, const CUtensorMap& ta, const CUtensorMap& tb,
                 const GemmParams& p, int sms, cudaStream_t stream, const CUtensorMap* tout = nullptr) {
-  const bool tf32 = precision == LRN_PREC_TF32;
+  const bool tf32 = precision != LRN_PREC_BF16;
   if (epi == EPI_ACT && !tf32 && !p.out_f32 && tout) {  // bf16 output: staged TMA stores
     return g.bn == 128 ? launch_pair_t<128, false, EPI_ACT, 6, true, true>(ta, tb, *tout, p, sms, stream)
                        : launch_pair_t<256, false, EPI_ACT, 4, true, true>(ta, tb, *tout, p, sms, stream);
@@ -245,12 +248,13 @@ int launch_gemm(int precision, const GemmPlan& g, int epi, const CUtensorMap& ta
 
 int fold_one(int precision, const float* w, const float* b, const float* g, const float* beta, const float* mean,
              const float* var, float eps, int cout, int cin, void* out_w, int64_t ld, int col0, float* out_b,
-             cudaStream_t stream, bool operand = true) {
+             cudaStream_t stream, bool operand = true, int64_t lo_off = 0) {
   const long long total = static_cast<long long>(cout) * cin;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
-  if (precision == LRN_PREC_TF32)
+  if (precision != LRN_PREC_BF16)
     fold_linear_kernel<float><<<grid, 256, 0, stream>>>(w, b, g, beta, mean, var, eps, cout, cin,
-                                                        static_cast<float*>(out_w), ld, col0, out_b, operand ? 1 : 0);
+                                                        static_cast<float*>(out_w), ld, col0, out_b, operand ? 1 : 0,
+                                                        precision == LRN_PREC_FP32X3 && operand ? lo_off : 0);
   else
     fold_linear_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, b, g, beta, mean, var, eps, cout, cin,
                                                                 static_cast<__nv_bfloat16*>(out_w), ld, col0, out_b, 0);
@@ -288,7 +292,7 @@ struct StageTimer {  // RAII: brackets the kernels of one stage with events when
 
 long long* g_dbg = nullptr;  // lrn_debug_timeline: device buffer for clock64() stamps of the fusion kernel
 
-bool bad_precision(int p) { return p != LRN_PREC_BF16 && p != LRN_PREC_TF32; }
+bool bad_precision(int p) { return p != LRN_PREC_BF16 && p != LRN_PREC_TF32 && p != LRN_PREC_FP32X3; }
 
 struct WorkspaceLayout {
   int64_t chunk;
@@ -304,9 +308,9 @@ WorkspaceLayout workspace_layout(int64_t B, int64_t N, int precision, int flags,
   W.chunk = chunk;
   size_t off = 0;
   W.cat = off;
-  off = align_up(off + size_t(chunk) * kCat * es, 1024);
+  off = align_up(off + size_t(chunk) * kCat * es * op_mul(precision), 1024);
   W.fused_pm = off;
-  if (flags & LRN_OUT_MEMORY) off = align_up(off + size_t(chunk) * 1024 * es, 1024);
+  if (flags & LRN_OUT_MEMORY) off = align_up(off + size_t(chunk) * 1024 * es * op_mul(precision), 1024);
   W.keys = off;
   if (flags & LRN_OUT_ARGMAX) off = align_up(off + size_t(B) * 1024 * 8, 1024);
   W.total = off;
@@ -362,6 +366,7 @@ int lrn_encoder_fold(const lrn_encoder_params* pr, int precision, void* packed, 
     return fail(LRN_ERR_BAD_ARG, "null fusion/gate parameter");
   uint8_t* base = static_cast<uint8_t*>(packed);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int wm = op_mul(precision);
   // conv1 stays fp32 (FMA kernel); gate layer 1 is copied as is
   st = fold_one(LRN_PREC_TF32, pr->conv_w[0], pr->conv_b[0], pr->bn_w[0], pr->bn_b[0], pr->bn_mean[0], pr->bn_var[0],
                 pr->bn_eps, 64, 4, base + L.w1, 4, 0, reinterpret_cast<float*>(base + L.b1), s, /*operand=*/false);
@@ -370,20 +375,20 @@ int lrn_encoder_fold(const lrn_encoder_params* pr, int precision, void* packed, 
   LRN_CUDA(cudaMemcpyAsync(base + L.bg1, pr->gate0_b, 64 * 4, cudaMemcpyDeviceToDevice, s));
   for (int k = 2; k <= 5; ++k) {
     st = fold_one(precision, pr->conv_w[k - 1], pr->conv_b[k - 1], pr->bn_w[k - 1], pr->bn_b[k - 1], pr->bn_mean[k - 1],
-                  pr->bn_var[k - 1], pr->bn_eps, kChan[k], kChan[k - 1], base + L.w[k], kChan[k - 1], 0,
-                  reinterpret_cast<float*>(base + L.b[k]), s);
+                  pr->bn_var[k - 1], pr->bn_eps, kChan[k], kChan[k - 1], base + L.w[k], kChan[k - 1] * wm, 0,
+                  reinterpret_cast<float*>(base + L.b[k]), s, true, kChan[k - 1]);
     if (st) return st;
   }
   st = fold_one(precision, pr->fusion_w, pr->fusion_b, pr->fusion_bn_w, pr->fusion_bn_b, pr->fusion_bn_mean,
-                pr->fusion_bn_var, pr->bn_eps, 1024, kFusionK, base + L.wfg, kCat, 0,
-                reinterpret_cast<float*>(base + L.bf), s);
+                pr->fusion_bn_var, pr->bn_eps, 1024, kFusionK, base + L.wfg, kCat * wm, 0,
+                reinterpret_cast<float*>(base + L.bf), s, true, kCat);
   if (st) return st;
   st = fold_one(precision, pr->gate2_w, pr->gate2_b, nullptr, nullptr, nullptr, nullptr, 0.f, 1024, kGateK,
-                base + L.wfg, kCat, kFusionK, reinterpret_cast<float*>(base + L.bg), s);
+                base + L.wfg, kCat * wm, kFusionK, reinterpret_cast<float*>(base + L.bg), s, true, kCat);
   if (st) return st;
   if (pr->proj_w && pr->proj_b) {
     st = fold_one(precision, pr->proj_w, pr->proj_b, nullptr, nullptr, nullptr, nullptr, 0.f, 256, 1024, base + L.wp,
-                  1024, 0, reinterpret_cast<float*>(base + L.bp), s);
+                  1024 * wm, 0, reinterpret_cast<float*>(base + L.bp), s, true, 1024);
     if (st) return st;
   }
   return LRN_OK;
@@ -417,7 +422,9 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
   int st = device_info(&dev);
   if (st) return st;
 
-  const bool tf32 = precision == LRN_PREC_TF32;
+  const bool tf32 = precision != LRN_PREC_BF16;      // fp32 operands on the kind::tf32 tensor-core path
+  const bool x3 = precision == LRN_PREC_FP32X3;      // ... as hi / lo halves, three passes per k-block (fp32-class products)
+  const int wm = op_mul(precision), kpass = x3 ? 3 : 1;
   const size_t es = elem_size(precision);
   const int bk = int(128 / es);
   const PackedLayout L = packed_layout(precision);
@@ -439,7 +446,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
   GemmPlan plan[6];
   for (int k = 2; k <= 5; ++k) {
     plan[k] = plan_gemm(kChan[k], EPI_ACT);
-    st = make_tmap(&tw[k], precision, pk + L.w[k], kChan[k], kChan[k - 1], kChan[k - 1], plan[k].b_box_rows);
+    st = make_tmap(&tw[k], precision, pk + L.w[k], kChan[k], kChan[k - 1] * wm, kChan[k - 1] * wm, plan[k].b_box_rows);
     if (st) return st;
   }
   const GemmPlan plan_f = plan_gemm(1024, EPI_FUSION), plan_p = plan_gemm(256, EPI_ACT);
@@ -452,10 +459,10 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       if (st) return st;
     }
   }
-  st = make_tmap(&twfg, precision, pk + L.wfg, 1024, kCat, kCat, plan_f.b_box_rows);
+  st = make_tmap(&twfg, precision, pk + L.wfg, 1024, kCat * wm, kCat * wm, plan_f.b_box_rows);
   if (st) return st;
   if (flags & LRN_OUT_MEMORY) {
-    st = make_tmap(&twp, precision, pk + L.wp, 256, 1024, 1024, plan_p.b_box_rows);
+    st = make_tmap(&twp, precision, pk + L.wp, 256, 1024 * wm, 1024 * wm, plan_p.b_box_rows);
     if (st) return st;
   }
 
@@ -466,7 +473,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
     const int64_t rows = std::min<int64_t>(W.chunk, P - r0);
     auto m_tiles_of = [&](const GemmPlan& g) { return int((rows + g.m_rows - 1) / g.m_rows); };
     CUtensorMap ta, tpm;
-    st = make_tmap(&ta, precision, cat, rows, kCat, kCat, BM);
+    st = make_tmap(&ta, precision, cat, rows, kCat * wm, kCat * wm, BM);
     if (st) return st;
 
     // bf16 tier: conv1..conv5 + gate layer 1 as ONE fused kernel (activations stay on the SM, the operand matrix is kept
@@ -500,7 +507,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       StageTimer timer(LRN_STAGE_EMBED, s);
       const int grid = int(std::min<int64_t>((rows + 15) / 16, int64_t(dev.sms) * 16));
       if (tf32)
-        point_embed_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context) + r0, rows, ew, cat, kCat);
+        point_embed_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context) + r0, rows, ew, cat, kCat * wm, x3 ? kCat : 0);
       else
         point_embed_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(context) + r0, rows, ew, cat, kCat);
       LRN_CUDA(cudaGetLastError());
@@ -510,12 +517,16 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.M = int(rows);
       p.m_tiles = m_tiles_of(plan[k]);
       p.n_tiles = kChan[k] / plan[k].bn;
-      p.kb_main = kChan[k - 1] / bk;
+      p.kb_main = kpass * (kChan[k - 1] / bk);
       p.kb_gate = 0;
+      p.split3 = x3 ? 1 : 0;
+      p.a_lo_off = kCat;
+      p.b_lo_off = kChan[k - 1];
+      p.out_lo_off = kCat;
       p.a_col0 = kCatOff[k - 1];
       p.bias = reinterpret_cast<const float*>(pk + L.b[k]);
       p.out = static_cast<uint8_t*>(cat) + size_t(kCatOff[k]) * es;
-      p.ldo = kCat;
+      p.ldo = kCat * wm;
       p.out_f32 = tf32 ? 1 : 0;
       p.relu = 1;
       p.round_tf32 = tf32 ? 1 : 0;
@@ -531,8 +542,12 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.M = int(rows);
       p.m_tiles = m_tiles_of(plan_f);
       p.n_tiles = 1024 / plan_f.bn;
-      p.kb_main = kFusionK / bk;
-      p.kb_gate = kGateK / bk;
+      p.kb_main = kpass * (kFusionK / bk);
+      p.kb_gate = kpass * (kGateK / bk);
+      p.split3 = x3 ? 1 : 0;
+      p.exact_gate = x3 ? 1 : 0;
+      p.a_lo_off = kCat;
+      p.b_lo_off = kCat;
       p.a_col0 = 0;
       p.a_tiled = tiled ? 1 : 0;
       p.bias_f = reinterpret_cast<const float*>(pk + L.bf);
@@ -552,13 +567,16 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       if (st) return st;
     }
     if (flags & LRN_OUT_MEMORY) {  // memory = fused * Wp^T + bp
-      st = make_tmap(&tpm, precision, fused_pm, rows, 1024, 1024, BM);
+      st = make_tmap(&tpm, precision, fused_pm, rows, 1024 * wm, 1024 * wm, BM);
       if (st) return st;
       GemmParams p{};
       p.M = int(rows);
       p.m_tiles = m_tiles_of(plan_p);
       p.n_tiles = 256 / plan_p.bn;
-      p.kb_main = 1024 / bk;
+      p.kb_main = kpass * (1024 / bk);
+      p.split3 = x3 ? 1 : 0;
+      p.a_lo_off = 1024;
+      p.b_lo_off = 1024;
       p.a_col0 = 0;
       p.bias = reinterpret_cast<const float*>(pk + L.bp);
       p.relu = 0;
@@ -855,7 +873,8 @@ int lrn_profile_read(float* ms_per_stage, int64_t* launches_per_stage) {
 
 int lrn_point_embed(const void* packed, int precision, const float* context, int64_t rows, void* operand_rows, int tiled,
                     lrn_stream_t stream) {
-  if (bad_precision(precision) || !packed || !context || !operand_rows || rows <= 0) return fail(LRN_ERR_BAD_ARG, "bad argument");
+  if ((precision != LRN_PREC_BF16 && precision != LRN_PREC_TF32) || !packed || !context || !operand_rows || rows <= 0)
+    return fail(LRN_ERR_BAD_ARG, "bad argument");
   if (tiled && precision != LRN_PREC_BF16) return fail(LRN_ERR_BAD_ARG, "the tiled operand layout is the bf16 tier's");
   DeviceInfo dev;
   int st = device_info(&dev);
@@ -893,7 +912,7 @@ int lrn_head_forward(const float* w1, const float* b1, const float* w2, const fl
 int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias,
                       void* out, int64_t ldo, int out_f32, int relu, int64_t M, int64_t N, int64_t K,
                       lrn_stream_t stream) {
-  if (bad_precision(precision) || !A || !Wt || !out) return fail(LRN_ERR_BAD_ARG, "null pointer or bad precision");
+  if ((precision != LRN_PREC_BF16 && precision != LRN_PREC_TF32) || !A || !Wt || !out) return fail(LRN_ERR_BAD_ARG, "null pointer or bad precision");
   const size_t es = elem_size(precision);
   const int bk = int(128 / es);
   if (M <= 0 || N <= 0 || K <= 0 || K % bk || N % 128 || M >= (int64_t(1) << 31))

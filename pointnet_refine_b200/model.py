@@ -75,7 +75,7 @@ class MultiScalePointNetEncoder(nn.Module):
             setattr(self, f"bn{k}", nn.BatchNorm1d(widths[k]))
         self.fusion = nn.Sequential(nn.Conv1d(sum(widths[1:]), out_dim, 1), nn.BatchNorm1d(out_dim), nn.ReLU())
         self.intensity_gate = nn.Sequential(nn.Conv1d(1, 64, 1), nn.ReLU(), nn.Conv1d(64, out_dim, 1), nn.Sigmoid())
-        self.precision = _DEFAULT_PRECISION     # "bf16" | "tf32" (tensor-core operand tier)
+        self.precision = _DEFAULT_PRECISION     # "bf16" | "tf32" | "fp32x3" (tensor-core operand tier; fp32x3 = 3 x TF32 split, fp32-class)
         self.chunk_rows = 0                     # 0 = library default
         self.native_training = os.environ.get("LRN_NATIVE_TRAIN", "0") == "1"   # opt-in: train mode on the sm_100a kernels (bf16)
         self._folded = None                     # (fingerprint, FoldedEncoder); never in the state_dict
@@ -204,7 +204,11 @@ class LineRefineNet(nn.Module):
 
     def _refine(self, context, noisy_line, memory, native_heads):
         pos_mem = self.pos_emb(context[:, :, :3])
-        tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
+        if native_heads:   # eval: point_mlp with its BatchNorms folded, fp32 FMA (cuDNN would run the 1x1 convs in TF32 by default)
+            (pw1, pb1), (pw2, pb2), (pw3, pb3) = self._point_mlp_weights()
+            tgt = ops.rows_linear(ops.rows_linear(noisy_line, pw2, pb2, mlp3=(pw1, pb1), relu=True), pw3, pb3)
+        else:
+            tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)
         current = noisy_line.clone()
         outs = []
         for layer, head in zip(self.decoder_layers, self.reg_branches):
@@ -457,7 +461,8 @@ class LineRefineNet(nn.Module):
             _, fused = self.context_encoder(context.transpose(2, 1))   # train mode: native fwd/bwd (bf16 tier)
             memory = self.context_proj(fused.transpose(2, 1))
             return self._refine(context, noisy_line, memory, native_heads=False)
-        fast = self.fast_decoder            # both tiers; the folded-query attention kernel below is bf16 only
+        fast = self.fast_decoder and self.precision != "fp32x3"   # bf16 / tf32 tiers; the folded-query attention kernel below is bf16 only;
+        # the fp32x3 tier keeps the whole decoder in fp32 (stock attention / linears, native point_mlp and heads)
         attn = fast and self.precision == "bf16" and self.ctx_attention and noisy_line.shape[1] == 32
         N = context.shape[1]
         if attn:

@@ -9,8 +9,9 @@ tolerance; over ALL untied (segment, channel) pairs the agreement rate is measur
 argmax whose top-2 gap is below their rounding error).
 
 Accepted argmax deviation, spelled out: north_star asks for bit-exact indices "where the reference has no ties".
-Exact equality is asserted only on the gap-filtered subset; on the remaining untied pairs (gap > 0 but within
-2x tolerance) indices may differ from the reference, bounded by the agreement floors below."""
+bf16 / tf32 tiers: exact equality is asserted only on the gap-filtered subset; on the remaining untied pairs (gap > 0
+but within 2x tolerance) indices may differ from the reference, bounded by the agreement floors below.  fp32x3 tier
+(LRN_PREC_FP32X3, `model.precision = "fp32x3"`): exact equality on ALL untied pairs, i.e. what north_star states."""
 import numpy as np
 import pytest
 import torch
@@ -21,17 +22,18 @@ from oracle import lrn_oracle as orc  # noqa: E402
 from oracle import synth  # noqa: E402
 from tests.golden_util import EVAL_CASES, load_case, report  # noqa: E402
 
-TIERS = {"bf16": 1e-2, "tf32": 1e-3}
+TIERS = {"bf16": 1e-2, "tf32": 1e-3, "fp32x3": 1e-4}      # fp32x3: 3 x TF32 split (fp32-class products)
 # floor of the argmax agreement with the fp32 reference over ALL untied (segment, channel) pairs.  Measured on the
 # B200 (gpurun_out/parity_report.jsonl -> profiles/r02_parity_report.jsonl): bf16 98.9-99.3 % on the N(0,1) fixtures and
 # 95.3 % on the realistic one (x up to +-25 m, value range 10), tf32 99.86-100 %; SURVEY.md section 7.3 predicted
-# 98.1-98.9 % / 99.7-99.9 % from a CPU emulation of the operand rounding.  The "exact" tier asserts 100 % (below).
-ARGMAX_FLOOR = {"bf16": 0.94, "tf32": 0.995}
+# 98.1-98.9 % / 99.7-99.9 % from a CPU emulation of the operand rounding.  The opt-in fp32x3 tier (3 x TF32 split, gate in
+# full fp32) reproduces the reference's argmax on EVERY untied pair of every fixture (13-14k pairs), which is asserted.
+ARGMAX_FLOOR = {"bf16": 0.94, "tf32": 0.995, "fp32x3": 1.0}   # fp32x3: every untied pair of every fixture (measured 100 %)
 
 
 def _offset_tol(prec, ref_out):
-    """north_star: refined offsets within 1e-2 of their range (bf16 tier) / 1e-3 max-abs (tf32 tier)."""
-    return 1e-2 * max(1.0, float(np.abs(ref_out).max())) if prec == "bf16" else 1e-3
+    """north_star: refined offsets within 1e-2 of their range (bf16 tier) / 1e-3 max-abs (tf32 tier); fp32x3: 1e-4."""
+    return {"bf16": 1e-2 * max(1.0, float(np.abs(ref_out).max())), "tf32": 1e-3, "fp32x3": 1e-4}[prec]
 
 
 @pytest.fixture(scope="module")
