@@ -26,7 +26,7 @@ Extra keys, measured on rank 0 / all ranks after the timed region (bounded, a fe
   config3_sample : BASELINE configs[2] (1M segments x 2048 points, strong-scaled over the ranks): every rank runs a
                    sample of its shard through the whole forward; seconds for the full 1M sweep extrapolated linearly
   train_step     : BASELINE configs[3], 1024 segments x 1024 points per GPU: forward + L1 deep-supervision loss +
-                   backward + Adam on the native train path (DistributedDataParallel over NCCL when N > 1)
+                   backward + Adam on the native train path (FlatDataParallel: flat gradient buffer + NCCL all-reduce when N > 1)
 """
 from __future__ import annotations
 
@@ -499,8 +499,8 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
     m = prb.LineRefineNet().to(dev).train()
     m.context_encoder.native_training = True
     net = m
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(m, device_ids=[local_rank], find_unused_parameters=True)   # train_dist.py:147
+    if world > 1:     # where train_dist.py:147 wraps the model in DistributedDataParallel: one flat gradient buffer, two
+        net = prb.FlatDataParallel(m)   # all-reduce slices over NCCL, the first overlapped with the encoder's backward
     opt = lrn_optim.FlatAdam(m.parameters(), lr=1e-3)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     ctx = torch.randn(Bt, Nt, 4, device=dev, generator=g)
@@ -540,7 +540,7 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
         allreduce_ms = max_over_ranks(a0.elapsed_time(a1) / 5)
     peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     return {"workload": "1024 segments x 1024 points per GPU, LineRefineNet train step: forward + L1 deep supervision + backward + Adam "
-                        "(BASELINE.json configs[3]); DistributedDataParallel over NCCL when n_gpus > 1",
+                        "(BASELINE.json configs[3]); FlatDataParallel (flat gradient buffer, NCCL all-reduce) when n_gpus > 1",
             "ms_per_step": ms, "segments_per_sec": world * Bt / (ms * 1e-3), "n_gpus": world, "allreduce_ms": allreduce_ms,
             "loss": float(loss.detach()), "finite": bool(torch.isfinite(loss.detach())),
             "bound_ms": TRAIN_BOUND_MS, "frac_of_bound_sustained": TRAIN_BOUND_MS["sustained"] / ms, "peak_mem_gb": peak_gb}

@@ -9,6 +9,7 @@ from .model import (DetrTransformerDecoderLayer, LineRefineNet, MultiScalePointN
                     PositionalEncoding)
 
 from .graph import GraphedLineRefineNet  # noqa: F401,E402
+from .ddp import FlatDataParallel  # noqa: F401,E402  (flat-gradient data parallelism for train_dist.py-style loops)
 from . import scene  # noqa: F401,E402  (whole-scene front end: build_segments, refine_scene)
 
-__all__ = ["GraphedLineRefineNet", "LineRefineNet", "MultiScalePointNetEncoder", "PositionalEncoding", "DetrTransformerDecoderLayer", "ops", "scene"]
+__all__ = ["FlatDataParallel", "GraphedLineRefineNet", "LineRefineNet", "MultiScalePointNetEncoder", "PositionalEncoding", "DetrTransformerDecoderLayer", "ops", "scene"]

@@ -11,6 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import lib
+from .flat import FlatParams
 from .ops import _stream_ptr
 
 
@@ -24,35 +25,18 @@ class FlatAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         if len(self.param_groups) != 1:
             raise ValueError("FlatAdam keeps ONE flat buffer: pass a plain parameter list, not several parameter groups")
-        dev = params[0].device
-        pad = lambda n: (n + 63) // 64 * 64         # every parameter starts 256-byte aligned (TMA / float4 consumers)
-        total = sum(pad(p.numel()) for p in params)
-        self._flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self._grad = torch.zeros(total, dtype=torch.float32, device=dev)
-        self._m = torch.zeros(total, dtype=torch.float32, device=dev)
-        self._v = torch.zeros(total, dtype=torch.float32, device=dev)
-        views = []
-        off = 0
-        with torch.no_grad():
-            for p in params:
-                n = p.numel()
-                self._flat[off:off + n].copy_(p.detach().reshape(-1))
-                p.data = self._flat[off:off + n].view(p.shape)          # the module keeps its Parameter objects
-                views.append((p, self._grad[off:off + n].view(p.shape)))
-                off += pad(n)
-        self._views = views
+        self._fp = FlatParams.of(params) or FlatParams(params)     # shared with ddp.FlatDataParallel when it wrapped the model first
+        self._flat, self._grad = self._fp.flat, self._fp.grad
+        self._m = torch.zeros_like(self._flat)
+        self._v = torch.zeros_like(self._flat)
+        self._views = list(zip(self._fp.params, self._fp.grad_views))
         self._step = 0
-        self._attach()
 
     def _attach(self, keep_foreign: bool = True):
         """Make every parameter's .grad the view of the flat gradient buffer.  A gradient some other code bound to
         .grad meanwhile (e.g. DistributedDataParallel(gradient_as_bucket_view=True), set_to_none) is copied in when
         `keep_foreign` -- i.e. in step(), where it is THIS step's gradient -- and dropped in zero_grad()."""
-        for p, g in self._views:
-            if p.grad is not g:
-                if p.grad is not None and keep_foreign:
-                    g.copy_(p.grad)
-                p.grad = g
+        self._fp.attach(keep_foreign)
 
     def add_param_group(self, param_group):
         if getattr(self, "_views", None) is not None:

@@ -147,3 +147,76 @@ print("compat ok")
 """
     r = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "compat ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ------------------------------------------------------------------ flat-gradient data parallelism (host logic, gloo)
+def _tiny_model():
+    import torch.nn as nn
+
+    class Tiny(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.context_encoder = nn.Sequential(nn.Linear(4, 8), nn.BatchNorm1d(8), nn.ReLU())
+            self.head = nn.Linear(8, 2)
+
+        def forward(self, x):
+            return self.head(self.context_encoder(x))
+    torch.manual_seed(7)
+    return Tiny()
+
+
+def _fdp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from pointnet_refine_b200.ddp import FlatDataParallel
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    m = _tiny_model()
+    if rank == 1:                                   # replicas must be re-synchronised from rank 0 at wrap time
+        with torch.no_grad():
+            for p in m.parameters():
+                p.add_(1.0)
+    net = FlatDataParallel(m)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    x = torch.randn(16, 4, generator=torch.Generator().manual_seed(100 + rank))
+    grads = None
+    for step in range(2):
+        opt.zero_grad()                             # set_to_none: autograd binds fresh .grad tensors, the hooks re-home them
+        net(x).square().mean().backward()
+        if step == 0:
+            grads = [p.grad.clone() for p in m.parameters()]
+            assert all(p.grad.data_ptr() == g.data_ptr() for p, g in zip(net.flat.params, net.flat.grad_views))
+        opt.step()
+    q.put((rank, [g.numpy() for g in grads], [p.detach().numpy().copy() for p in m.parameters()],
+           m.context_encoder[1].running_mean.numpy().copy(), net.allreduce_calls))
+    dist.destroy_process_group()
+
+
+def test_flat_data_parallel_two_ranks_gloo():
+    """One flat gradient buffer, reduced in two slices (decoder side first, encoder slice at the end of backward):
+    gradients equal the mean of the per-rank gradients, replicas stay identical, buffers follow rank 0."""
+    import torch.multiprocessing as mp
+    world, port = 2, 29547
+    ctx_mp = mp.get_context("spawn")
+    q = ctx_mp.Queue()
+    procs = [ctx_mp.Process(target=_fdp_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = dict()
+    for _ in range(world):
+        r, grads, params, rm, calls = q.get(timeout=180)
+        res[r] = (grads, params, rm, calls)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    # single-process reference: both ranks start from rank 0's weights; gradient = mean over ranks
+    want = None
+    for rank in range(world):
+        m = _tiny_model()
+        x = torch.randn(16, 4, generator=torch.Generator().manual_seed(100 + rank))
+        m(x).square().mean().backward()
+        g = [p.grad.clone() for p in m.parameters()]
+        want = g if want is None else [a + b for a, b in zip(want, g)]
+    want = [w / world for w in want]
+    for rank in range(world):
+        for got, w in zip(res[rank][0], want):
+            np.testing.assert_allclose(got, w.numpy(), rtol=1e-5, atol=1e-7)
+        assert res[rank][3] == 4                    # two slices per step, two steps
+    for a, b in zip(res[0][1], res[1][1]):
+        assert np.array_equal(a, b)                 # parameters identical after two optimizer steps
