@@ -307,11 +307,21 @@ int lrn_head_update(const float* hidden, const float* w2, const float* b2, int64
 int lrn_rows_linear(const float* x, int64_t ldx, const float* x2, int64_t ldx2, const float* mlp3_w1, const float* mlp3_b1,
                     const float* w, const float* bias, void* out, int64_t ldo, int out_bf16, int relu, int64_t M, int64_t N,
                     int64_t K, lrn_stream_t stream);
-/* out (rows,256) fp32 = relu(W1 current + b1): first layer of pos_emb on the current polyline points (src/model.py:212) when
- * its second layer runs as a tensor-core GEMM (thousands of rows). */
-int lrn_query_pos_hidden(const float* w1, const float* b1, const float* current, int64_t rows, float* out, lrn_stream_t stream);
-/* out = a + b over n fp32 elements (n % 4 == 0): with_pos_embed ahead of a tensor-core linear. */
-int lrn_add(const float* a, const float* b, float* out, int64_t n, lrn_stream_t stream);
+/* out (rows,256) fp32 = relu(W1 c + b1): first layer of pos_emb (src/model.py:68-72) on the current polyline points (:212,
+ * coords (rows,3), ld = 3) or on the context points (:197, coords = context (rows,4), ld = 4; tf32 tier) when the second
+ * layer runs as a tensor-core GEMM.  round_tf32 = 1 rounds the result to the nearest TF32 value (a tf32-tier GEMM operand;
+ * the tensor core would otherwise truncate it). */
+int lrn_query_pos_hidden(const float* w1, const float* b1, const float* coords, int64_t ld, int64_t rows, float* out,
+                         int round_tf32, lrn_stream_t stream);
+/* out = a + b over n fp32 elements (n % 4 == 0): with_pos_embed ahead of a tensor-core linear.  b may be NULL (copy);
+ * round_tf32 = 1 rounds the result to the nearest TF32 value. */
+int lrn_add(const float* a, const float* b, float* out, int64_t n, int round_tf32, lrn_stream_t stream);
+/* fp32 cross attention of the 32 polyline queries of each of B segments over its N context points, 8 heads x 32
+ * (nn.MultiheadAttention cross_attn in eval mode, src/model.py:123-128; the tf32 tier, where K / V of all layers come from
+ * hoisted TF32 GEMMs): q (B*32, 256) in-projected queries; k / v: point (b*N + n) at k + (b*N + n) * ld_kv (head h at
+ * + 32 h), so a layer's K is a column block of the (B*N, L*256) GEMM result; out (B*32, 256) heads concatenated. */
+int lrn_cross_attention32(const float* q, const float* k, const float* v, int64_t ld_kv, int B, int N, float* out,
+                          lrn_stream_t stream);
 /* Merge the splits of lrn_ctx_attention: part (B, splits, 256, 256) fp32, lse (B, splits, 256) -> out (B, 256, 256) fp32 or
  * bf16, out[b][q] = sum_s 2^(lse_s - max) part_s / sum_s 2^(lse_s - max). */
 int lrn_ctx_attention_merge(const float* part, const float* lse, int B, int splits, void* out, int out_bf16, lrn_stream_t stream);

@@ -1366,21 +1366,22 @@ int lrn_rows_linear(const float* x, int64_t ldx, const float* x2, int64_t ldx2, 
   return LRN_OK;
 }
 
-int lrn_query_pos_hidden(const float* w1, const float* b1, const float* current, int64_t rows, float* out, lrn_stream_t stream) {
-  if (!w1 || !b1 || !current || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
-  if (rows <= 0) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld", (long long)rows);
+int lrn_query_pos_hidden(const float* w1, const float* b1, const float* coords, int64_t ld, int64_t rows, float* out,
+                         int round_tf32, lrn_stream_t stream) {
+  if (!w1 || !b1 || !coords || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (rows <= 0 || ld < 3) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld ld=%lld", (long long)rows, (long long)ld);
   if (reinterpret_cast<uintptr_t>(out) & 15) return fail(LRN_ERR_MISALIGNED, "out needs 16-byte alignment");
   DeviceInfo dev;
   int st = device_info(&dev);
   if (st) return st;
   const int grid = int(std::min<int64_t>((rows + 7) / 8, int64_t(dev.sms) * 8));
-  query_pos_hidden_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(current, rows, w1, b1, out);
+  query_pos_hidden_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(coords, ld, rows, w1, b1, out, round_tf32 ? 1 : 0);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
 
-int lrn_add(const float* a, const float* b, float* out, int64_t n, lrn_stream_t stream) {
-  if (!a || !b || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+int lrn_add(const float* a, const float* b, float* out, int64_t n, int round_tf32, lrn_stream_t stream) {
+  if (!a || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
   if (n <= 0 || n % 4) return fail(LRN_ERR_BAD_SHAPE, "n=%lld (a positive multiple of 4)", (long long)n);
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15)
     return fail(LRN_ERR_MISALIGNED, "16-byte alignment");
@@ -1389,7 +1390,22 @@ int lrn_add(const float* a, const float* b, float* out, int64_t n, lrn_stream_t 
   if (st) return st;
   const int grid = int(std::min<int64_t>((n / 4 + 255) / 256, int64_t(dev.sms) * 8));
   add_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
-                                                                       reinterpret_cast<float4*>(out), n / 4);
+                                                                       reinterpret_cast<float4*>(out), n / 4, round_tf32 ? 1 : 0);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_cross_attention32(const float* q, const float* k, const float* v, int64_t ld_kv, int B, int N, float* out,
+                          lrn_stream_t stream) {
+  if (!q || !k || !v || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (B <= 0 || N <= 0 || ld_kv < 256 || int64_t(B) * 8 >= (int64_t(1) << 31)) return fail(LRN_ERR_BAD_SHAPE, "B=%d N=%d ld=%lld", B, N, (long long)ld_kv);
+  if (reinterpret_cast<uintptr_t>(q) & 15) return fail(LRN_ERR_MISALIGNED, "q needs 16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  static std::atomic<uint64_t> configured{0};
+  if ((st = configure_smem(cross_attn32_kernel, int(kCrossAttnSmem), configured))) return st;
+  cross_attn32_kernel<<<B * 8, 256, kCrossAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(q, k, v, ld_kv, N, out);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

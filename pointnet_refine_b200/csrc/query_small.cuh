@@ -126,12 +126,12 @@ __global__ void __launch_bounds__(256) rows_linear_kernel(const RowsLinearArgs a
   }
 }
 
-// out[r][0:256) = relu(W1 c_r + b1) in fp32: first layer of PositionalEncoding on the current polyline points
-// (src/model.py:68-72 at :212) for batches large enough that its second layer runs on the tensor cores.
-// One warp per row, lane = 8 consecutive channels.
-__global__ void __launch_bounds__(256) query_pos_hidden_kernel(const float* __restrict__ cur /* (rows,3) */, long long rows,
+// out[r][0:256) = [rna_tf32](relu(W1 c_r + b1)) in fp32: first layer of PositionalEncoding (src/model.py:68-72) on the current
+// polyline points (:212; rows of 3 floats) or on the context points (:197; rows of 4 floats, tf32 tier) when its second
+// layer runs on the tensor cores.  One warp per row, lane = 8 consecutive channels; `ld` = floats per coordinate row.
+__global__ void __launch_bounds__(256) query_pos_hidden_kernel(const float* __restrict__ cur, long long ld, long long rows,
                                                                const float* __restrict__ w1 /* (256,3) */,
-                                                               const float* __restrict__ b1, float* __restrict__ out) {
+                                                               const float* __restrict__ b1, float* __restrict__ out, int rna) {
   const int lane = threadIdx.x & 31;
   float wx[8], wy[8], wz[8], bb[8];
 #pragma unroll
@@ -144,23 +144,130 @@ __global__ void __launch_bounds__(256) query_pos_hidden_kernel(const float* __re
   }
   const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
-    const float px = cur[3 * r], py = cur[3 * r + 1], pz = cur[3 * r + 2];
+    const float px = cur[ld * r], py = cur[ld * r + 1], pz = cur[ld * r + 2];
     float h[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) h[j] = fmaxf(fmaf(wx[j], px, fmaf(wy[j], py, fmaf(wz[j], pz, bb[j]))), 0.f);
+    for (int j = 0; j < 8; ++j) {
+      h[j] = fmaxf(fmaf(wx[j], px, fmaf(wy[j], py, fmaf(wz[j], pz, bb[j]))), 0.f);
+      if (rna) h[j] = ptx::round_tf32(h[j]);
+    }
     float4* o = reinterpret_cast<float4*>(out + r * 256 + 8 * lane);
     o[0] = make_float4(h[0], h[1], h[2], h[3]);
     o[1] = make_float4(h[4], h[5], h[6], h[7]);
   }
 }
 
-// out = a + b over n4 float4 elements (with_pos_embed ahead of a tensor-core linear).
+// out = [rna_tf32](a + b) over n4 float4 elements (with_pos_embed ahead of a tensor-core linear); b may be null
+// (then: a copy rounded to the nearest TF32 value, the operand form of the tf32 tier's GEMMs).
 __global__ void __launch_bounds__(256) add_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
-                                                  float4* __restrict__ out, long long n4) {
+                                                  float4* __restrict__ out, long long n4, int rna) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float4 u = a[i], v = b[i];
-    out[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    float4 u = a[i];
+    if (b) {
+      const float4 v = b[i];
+      u = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    }
+    if (rna) u = make_float4(ptx::round_tf32(u.x), ptx::round_tf32(u.y), ptx::round_tf32(u.z), ptx::round_tf32(u.w));
+    out[i] = u;
+  }
+}
+
+// Cross attention of the 32 polyline queries of a segment over its N context points in fp32 (tf32 tier: K / V come from
+// the hoisted TF32 GEMMs; nn.MultiheadAttention cross_attn in eval mode, src/model.py:123-128).  Block = (segment, head);
+// lane = query; the eight warps take the key blocks of 32 round-robin, each with its own running (max, sum, 32 outputs),
+// merged through shared memory at the end.  K / V rows of a block are parked in shared memory and read as broadcasts.
+//   q (B*32, 256) fp32 in-projected queries; k, v: row (b*N + n) at k + (b*N + n) * ld, head h at + 32 h; out (B*32, 256).
+constexpr int kCrossAttnSmem = 8 * 2 * 32 * 33 * 4;
+__global__ void __launch_bounds__(256) cross_attn32_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                           const float* __restrict__ v, long long ld, int N,
+                                                           float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x >> 3, h = blockIdx.x & 7;
+  float* ks = sm + w * 2 * 32 * 33;
+  float* vs = ks + 32 * 33;
+  float qr[32], acc[32];
+  {
+    const float* qp = q + (static_cast<long long>(b) * 32 + lane) * 256 + h * 32;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(qp + c);
+      qr[c] = t.x * 0.17677669529663688f; qr[c + 1] = t.y * 0.17677669529663688f;   // 1 / sqrt(32)
+      qr[c + 2] = t.z * 0.17677669529663688f; qr[c + 3] = t.w * 0.17677669529663688f;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  const float* kb = k + static_cast<long long>(b) * N * ld + h * 32 + lane;
+  const float* vb = v + static_cast<long long>(b) * N * ld + h * 32 + lane;
+  for (int n0 = w * 32; n0 < N; n0 += 8 * 32) {
+    const int cnt = min(32, N - n0);
+    __syncwarp();
+#pragma unroll
+    for (int j0 = 0; j0 < 32; j0 += 8) {
+      float tk[8], tv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool in = j0 + j < cnt;
+        tk[j] = in ? kb[static_cast<long long>(n0 + j0 + j) * ld] : 0.f;
+        tv[j] = in ? vb[static_cast<long long>(n0 + j0 + j) * ld] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ks[(j0 + j) * 33 + lane] = tk[j];
+        vs[(j0 + j) * 33 + lane] = tv[j];
+      }
+    }
+    __syncwarp();
+    float s[32], bm = m;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        a0 = fmaf(qr[c], ks[j * 33 + c], a0);
+        a1 = fmaf(qr[c + 1], ks[j * 33 + c + 1], a1);
+      }
+      s[j] = j < cnt ? a0 + a1 : -INFINITY;
+      bm = fmaxf(bm, s[j]);
+    }
+    const float scale = __expf(m - bm);  // 0 for the first block (m = -inf)
+    l *= scale;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] *= scale;
+    m = bm;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float pj = __expf(s[j] - m);  // exp(-inf) = 0 for the padded keys
+      l += pj;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = fmaf(pj, vs[j * 33 + c], acc[c]);
+    }
+  }
+  __syncthreads();
+  // merge the eight warps: red[w][34][32 lanes] = (m, l, acc[32])
+  float* red = sm;
+  red[(w * 34 + 0) * 32 + lane] = m;
+  red[(w * 34 + 1) * 32 + lane] = l;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) red[(w * 34 + 2 + c) * 32 + lane] = acc[c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+    const int qi = i >> 5, c = i & 31;
+    float M = -INFINITY;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) M = fmaxf(M, red[(ww * 34) * 32 + qi]);
+    float L = 0.f, o = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {
+      const float mw = red[(ww * 34) * 32 + qi];
+      const float f = mw == -INFINITY ? 0.f : __expf(mw - M);
+      L = fmaf(red[(ww * 34 + 1) * 32 + qi], f, L);
+      o = fmaf(red[(ww * 34 + 2 + c) * 32 + qi], f, o);
+    }
+    out[(static_cast<long long>(b) * 32 + qi) * 256 + h * 32 + c] = o / L;
   }
 }
 

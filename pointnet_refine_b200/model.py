@@ -229,23 +229,82 @@ class LineRefineNet(nn.Module):
         return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
 
     def _kv_weights(self, op):
-        """Copies in the operand type `op` (bf16 or fp32 for the tf32 tier) of pos_emb.mlp.2 and of the K / V rows of
-        all six cross-attention in_proj matrices ([Wq; Wk; Wv] packing of nn.MultiheadAttention), re-made when a
-        parameter changes."""
+        """Copies in the operand type `op` (bf16, or fp32 rounded to the nearest TF32 value for the tf32 tier) of
+        pos_emb.mlp.2 and of the K / V rows of all six cross-attention in_proj matrices ([Wq; Wk; Wv] packing of
+        nn.MultiheadAttention), re-made when a parameter changes.  Host-side weight preparation (like _attn_weights)."""
         ps = [self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias]
         for l in self.decoder_layers:
             ps += [l.cross_attn.in_proj_weight, l.cross_attn.in_proj_bias]
         fp = (op,) + tuple((t.data_ptr(), t._version) for t in ps)
         if getattr(self, "_kv_cache", None) is None or self._kv_cache[0] != fp:
             d = self.d_model
-            wk = torch.cat([l.cross_attn.in_proj_weight[d:2 * d] for l in self.decoder_layers]).detach()
-            wv = torch.cat([l.cross_attn.in_proj_weight[2 * d:] for l in self.decoder_layers]).detach()
-            bk = torch.cat([l.cross_attn.in_proj_bias[d:2 * d] for l in self.decoder_layers]).detach()
-            bv = torch.cat([l.cross_attn.in_proj_bias[2 * d:] for l in self.decoder_layers]).detach()
-            cast = (lambda t: t.bfloat16().contiguous()) if op == torch.bfloat16 else (lambda t: self._rna_tf32(t.float()))
-            self._kv_cache = (fp, cast(wk), bk.float().contiguous(), cast(wv), bv.float().contiguous(),
-                              cast(self.pos_emb.mlp[2].weight.detach()))
+            dev = ps[0].device
+            host = lambda t: t.detach().cpu().float()
+            wk = torch.cat([host(l.cross_attn.in_proj_weight)[d:2 * d] for l in self.decoder_layers])
+            wv = torch.cat([host(l.cross_attn.in_proj_weight)[2 * d:] for l in self.decoder_layers])
+            bk = torch.cat([host(l.cross_attn.in_proj_bias)[d:2 * d] for l in self.decoder_layers])
+            bv = torch.cat([host(l.cross_attn.in_proj_bias)[2 * d:] for l in self.decoder_layers])
+            cast = (lambda t: t.bfloat16().contiguous().to(dev)) if op == torch.bfloat16 else (lambda t: self._rna_tf32(t).to(dev))
+            self._kv_cache = (fp, cast(wk), bk.contiguous().to(dev), cast(wv), bv.contiguous().to(dev),
+                              cast(host(self.pos_emb.mlp[2].weight)))
         return self._kv_cache[1:]
+
+    def _tf32_weight(self, w):
+        """fp32 weight (or a row slice of one) rounded to the nearest TF32 value, cached until the parameter changes:
+        the operand form of the tf32 tier's tensor-core linears (native rounding kernel, once per parameter update)."""
+        cache = self.__dict__.setdefault("_w32_cache", {})
+        key = (w.data_ptr(), tuple(w.shape))
+        hit = cache.get(key)
+        if hit is None or hit[0] != w._version:
+            cache[key] = hit = (w._version, ops.add(w.detach(), None, round_tf32=True))
+        return hit[1]
+
+    def _refine_tf32(self, context, noisy_line, memory, out):
+        """Eval-mode decoder of the tf32 tier, every step on this library's kernels.  The context-side work is hoisted out
+        of the layer loop: the memory positional embedding and the K / V projections of ALL six cross-attention layers
+        are three TF32 tensor-core GEMMs over the points (they do not depend on the decoder state, src/model.py:123-126;
+        operands rounded to the nearest TF32 value where they are produced - the tensor core would truncate, a bias that
+        adds up over K), and every layer's cross attention is one fp32 lrn_cross_attention32 launch on its column block
+        of those K / V.  Query side as in _refine_attn: tensor-core linears from 256 polyline rows on, fp32 rows_linear
+        below.  Same parameters and math as DetrTransformerDecoderLayer.forward (src/model.py:104-135) in eval mode."""
+        B, N, _ = context.shape
+        d = self.d_model
+        wk, bk, wv, bv, w2 = self._kv_weights(torch.float32)
+        (pw1, pb1), (pw2, pb2), (pw3, pb3) = self._point_mlp_weights()
+        pe0, pe2 = self.pos_emb.mlp[0], self.pos_emb.mlp[2]
+        mem = memory.reshape(B * N, d)
+        h = ops.query_pos_hidden(pe0.weight, pe0.bias, context, round_tf32=True).view(B * N, d)
+        posm = ops.gemm_bias_act(h, w2, pe2.bias.detach())
+        k_all = ops.gemm_bias_act(ops.add(mem, posm, round_tf32=True), wk, bk).view(B, N, 6 * d)
+        v_all = ops.gemm_bias_act(ops.add(mem, None, round_tf32=True), wv, bv).view(B, N, 6 * d)
+        del h, posm
+        rows = B * noisy_line.shape[1]
+        big = rows >= 256
+
+        def lin(x, w, b, relu=False, add=None):
+            if not big:
+                return ops.rows_linear(x, w, b, add=add, relu=relu)
+            x = ops.add(x, add, round_tf32=True)
+            return ops.gemm_bias_act(x.reshape(rows, -1), self._tf32_weight(w), b.detach(), relu=relu).view(B, -1, w.shape[0])
+
+        tgt = ops.rows_linear(ops.rows_linear(noisy_line, pw2, pb2, mlp3=(pw1, pb1), relu=True), pw3, pb3)   # point_mlp
+        current = noisy_line.clone()
+        for i, (layer, head) in enumerate(zip(self.decoder_layers, self.reg_branches)):
+            if big:
+                qpos = lin(ops.query_pos_hidden(pe0.weight, pe0.bias, current), pe2.weight, pe2.bias)
+            else:
+                qpos = ops.rows_linear(current, pe2.weight, pe2.bias, mlp3=(pe0.weight, pe0.bias))
+            sa, ca = layer.self_attn, layer.cross_attn
+            qk = lin(tgt, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d], add=qpos)
+            v = lin(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:])
+            tgt = ops.add_layernorm(tgt, lin(ops.self_attention32(qk, v), sa.out_proj.weight, sa.out_proj.bias), layer.norm1)
+            qh = lin(tgt, ca.in_proj_weight[:d], ca.in_proj_bias[:d], add=qpos)
+            att = ops.cross_attention32(qh, k_all[:, :, i * d:(i + 1) * d], v_all[:, :, i * d:(i + 1) * d])
+            tgt = ops.add_layernorm(tgt, lin(att, ca.out_proj.weight, ca.out_proj.bias), layer.norm2)
+            ffn = lin(lin(tgt, layer.linear1.weight, layer.linear1.bias, relu=True), layer.linear2.weight, layer.linear2.bias)
+            tgt = ops.add_layernorm(tgt, ffn, layer.norm3)
+            hid = lin(tgt, head[0].weight, head[0].bias, relu=True)
+            ops.head_update(hid, head[2].weight, head[2].bias, current, noisy_line, out=out[i])
 
     def _refine_fast(self, context, noisy_line, memory):
         """Eval-mode decoder with the context-side work hoisted out of the layer loop: the memory positional
@@ -471,12 +530,18 @@ class LineRefineNet(nn.Module):
             chunk = max(1, min(8 * self.segment_chunk, (4 * ops.DEFAULT_CHUNK_ROWS) // max(N, 1)))   # four full encoder waves
         else:
             chunk = max(1, min(self.segment_chunk, (1 << 20) // max(N, 1))) if fast else self.segment_chunk
-        if attn:
+        native_tf32 = fast and self.precision == "tf32" and noisy_line.shape[1] == 32
+        if attn or native_tf32:
             result = torch.empty(self.num_decoder_layers, context.shape[0], 32, 3, dtype=torch.float32, device=context.device)
             for s in range(0, context.shape[0], chunk):
                 ctx = context[s:s + chunk].contiguous()
-                memx = self.context_encoder.run_native(ctx, pool=False, memory=True, memory_bf16=True)["memory"]
-                self._refine_attn(ctx, noisy_line[s:s + chunk].contiguous(), memx, result[:, s:s + chunk])
+                line = noisy_line[s:s + chunk].contiguous()
+                if attn:
+                    memx = self.context_encoder.run_native(ctx, pool=False, memory=True, memory_bf16=True)["memory"]
+                    self._refine_attn(ctx, line, memx, result[:, s:s + chunk])
+                else:
+                    memory = self.context_encoder.run_native(ctx, pool=False, memory=True)["memory"]
+                    self._refine_tf32(ctx, line, memory, result[:, s:s + chunk])
             return result
         outs = []
         for s in range(0, context.shape[0], chunk):

@@ -342,26 +342,51 @@ def rows_linear(x: torch.Tensor, w: torch.Tensor, bias, *, add: torch.Tensor | N
     return out.view(*lead, N)
 
 
-def query_pos_hidden(w1: torch.Tensor, b1: torch.Tensor, current: torch.Tensor) -> torch.Tensor:
-    """relu(current @ w1.T + b1): (..., 3) -> (..., 256) fp32 (lrn_query_pos_hidden), first layer of pos_emb on the polyline."""
-    current = _f32c(current)
-    rows = current.numel() // 3
-    out = torch.empty(*current.shape[:-1], 256, dtype=torch.float32, device=current.device)
-    with torch.cuda.device(current.device):
-        _lib.check(lib.lrn_query_pos_hidden(_f32c(w1.detach()).data_ptr(), _f32c(b1.detach()).data_ptr(), current.data_ptr(), rows,
-                                            out.data_ptr(), _stream_ptr(current.device)), "lrn_query_pos_hidden")
+def query_pos_hidden(w1: torch.Tensor, b1: torch.Tensor, coords: torch.Tensor, round_tf32: bool = False) -> torch.Tensor:
+    """relu(coords[..., :3] @ w1.T + b1): (..., 3 or 4) -> (..., 256) fp32 (lrn_query_pos_hidden), first layer of pos_emb on the
+    polyline points (rows of 3) or the context points (rows of 4); optionally rounded to the nearest TF32 value."""
+    coords = _f32c(coords)
+    ld = coords.shape[-1]
+    rows = coords.numel() // ld
+    out = torch.empty(*coords.shape[:-1], 256, dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        _lib.check(lib.lrn_query_pos_hidden(_f32c(w1.detach()).data_ptr(), _f32c(b1.detach()).data_ptr(), coords.data_ptr(), ld, rows,
+                                            out.data_ptr(), int(round_tf32), _stream_ptr(coords.device)), "lrn_query_pos_hidden")
     _lib.launch_counter += 1
     return out
 
 
-def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a + b for fp32 tensors of equal shape (lrn_add)."""
-    a, b = _f32c(a), _f32c(b)
-    if a.shape != b.shape or a.numel() % 4:
+def add(a: torch.Tensor, b: torch.Tensor | None, round_tf32: bool = False) -> torch.Tensor:
+    """a + b for fp32 tensors of equal shape (lrn_add); b = None copies; round_tf32 rounds to the nearest TF32 value."""
+    a = _f32c(a)
+    b = _f32c(b) if b is not None else None
+    if (b is not None and a.shape != b.shape) or a.numel() % 4:
         raise ValueError("add: equal shapes with a multiple of 4 elements expected")
     out = torch.empty_like(a)
     with torch.cuda.device(a.device):
-        _lib.check(lib.lrn_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream_ptr(a.device)), "lrn_add")
+        _lib.check(lib.lrn_add(a.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), a.numel(), int(round_tf32),
+                               _stream_ptr(a.device)), "lrn_add")
+    _lib.launch_counter += 1
+    return out
+
+
+def cross_attention32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """fp32 cross attention of 32 queries per segment over N points, 8 heads x 32 (lrn_cross_attention32):
+    q (B, 32, 256); k, v (B, N, 256) views with unit column stride whose rows may be strided (a layer's column block of
+    the hoisted (B, N, L*256) projections) -> (B, 32, 256)."""
+    q = _f32c(q)
+    B, N, d = k.shape
+    if tuple(q.shape) != (B, 32, 256) or d != 256 or v.shape != k.shape:
+        raise ValueError(f"cross_attention32 shapes {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
+    for t in (k, v):
+        if t.dtype != torch.float32 or t.stride(2) != 1 or (B > 1 and t.stride(0) != N * t.stride(1)):
+            raise ValueError("cross_attention32: k / v must be fp32 (B, N, 256) views with segments back to back")
+    if k.stride(1) != v.stride(1):
+        raise ValueError("cross_attention32: k and v must share their row pitch")
+    out = torch.empty(B, 32, 256, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.lrn_cross_attention32(q.data_ptr(), k.data_ptr(), v.data_ptr(), k.stride(1), B, N, out.data_ptr(),
+                                             _stream_ptr(q.device)), "lrn_cross_attention32")
     _lib.launch_counter += 1
     return out
 

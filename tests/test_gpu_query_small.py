@@ -18,6 +18,11 @@ def dev():
     return torch.device("cuda:0")
 
 
+def _rna_tf32(t):
+    """fp32 tensor -> nearest TF32 value (ties away from zero), the rounding of cvt.rna.tf32.f32"""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 @pytest.mark.parametrize("M,N,K", [(1, 8, 32), (32, 256, 256), (33, 512, 256), (224, 2048, 256), (32, 256, 2048), (96, 256, 1024),
                                    (32, 128, 64), (65, 256, 128)])
 def test_rows_linear_matches_fp64(dev, M, N, K):
@@ -54,8 +59,14 @@ def test_query_pos_hidden_and_add(dev):
         cur, w1, b1 = r(rows, 3) * 5, r(256, 3), r(256)
         ref = (cur.double() @ w1.double().T + b1.double()).clamp_min(0)
         assert float((ops.query_pos_hidden(w1, b1, cur).double() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+        ctx4 = torch.cat([cur, r(rows, 1)], dim=1)                       # context rows [x, y, z, intensity]
+        got4 = ops.query_pos_hidden(w1, b1, ctx4, round_tf32=True)
+        assert float((got4.double() - ref).abs().max()) <= 2.0 ** -11 * max(1.0, float(ref.abs().max()))
+        assert int((got4.view(torch.int32) & 0x1FFF).abs().max()) == 0   # TF32-exact values
         a, b = r(rows, 256), r(rows, 256)
         assert torch.equal(ops.add(a, b), a + b)
+        rounded = ops.add(a, None, round_tf32=True)
+        assert torch.equal(rounded, _rna_tf32(a))
 
 
 @pytest.mark.parametrize("B,N,splits", [(1, 1024, None), (2, 700, 3), (1, 65, 1)])
@@ -76,31 +87,53 @@ def test_ctx_attention_split_merge(dev, B, N, splits):
     assert got16.dtype == torch.bfloat16 and float((got16.float() - got).abs().max()) <= 2.0 ** -7 * max(1.0, float(got.abs().max()))
 
 
-@pytest.mark.parametrize("B,N", [(1, 1024), (2, 300), (7, 513)])
-def test_small_batch_forward_vs_live_oracle(dev, B, N):
-    """B < 8 (fewer than 256 polyline rows): rows_linear query side, attention split over clusters and merged natively."""
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+@pytest.mark.parametrize("B,N", [(1, 1024), (2, 300), (7, 513), (9, 300)])
+def test_small_batch_forward_vs_live_oracle(dev, B, N, prec):
+    """B < 8 (fewer than 256 polyline rows): rows_linear query side, attention split over clusters and merged natively
+    (bf16 tier) / fp32 cross attention on hoisted TF32 K / V (tf32 tier); B = 9 takes the tensor-core query side."""
     import pointnet_refine_b200 as prb
     sd = synth.make_state_dict(13)
     ctx, line = synth.make_inputs(B, N, seed=77)
     ref = orc.line_refine_forward(sd, ctx, line)
     m = prb.LineRefineNet().to(dev).eval()
     m.load_state_dict(synth.to_torch(sd), strict=True)
+    m.precision = prec
     with torch.no_grad():
         out = m(torch.from_numpy(ctx).to(dev), torch.from_numpy(line).to(dev))
     err = float(np.abs(out.cpu().numpy() - ref).max())
     assert out.shape == (6, B, 32, 3)
-    assert err <= 1e-2 * max(1.0, float(np.abs(ref).max())), err
+    assert err <= (1e-2 * max(1.0, float(np.abs(ref).max())) if prec == "bf16" else 1e-3), err
 
 
+@pytest.mark.parametrize("B,N,splits", [(1, 200, 0), (3, 1000, 0), (2, 129, 0)])
+def test_cross_attention32_matches_torch(dev, B, N, splits):
+    """fp32 cross attention of the tf32 tier on a column block of a wider (B, N, 6*256) projection buffer."""
+    import torch.nn.functional as F
+    from pointnet_refine_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(N)
+    q = torch.randn(B, 32, 256, device=dev, generator=g)
+    kall = torch.randn(B, N, 6 * 256, device=dev, generator=g)
+    vall = torch.randn(B, N, 6 * 256, device=dev, generator=g)
+    for layer in (0, 5):
+        k, v = kall[:, :, layer * 256:(layer + 1) * 256], vall[:, :, layer * 256:(layer + 1) * 256]
+        got = ops.cross_attention32(q, k, v)
+        heads = lambda t: t.reshape(B, -1, 8, 32).transpose(1, 2).double()
+        ref = F.scaled_dot_product_attention(heads(q), heads(k), heads(v)).transpose(1, 2).reshape(B, 32, 256)
+        assert float((got.double() - ref).abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
 @pytest.mark.parametrize("B,N", [(1, 1024), (16, 512)])
-def test_forward_launches_only_library_kernels(dev, B, N):
-    """Eval forward of the default (bf16) tier, B = 1 whole-scene call and a batch on the tensor-core query side: every
+def test_forward_launches_only_library_kernels(dev, B, N, prec):
+    """Eval forward of the bf16 and tf32 tiers, B = 1 whole-scene call and a batch on the tensor-core query side: every
     kernel on the device timeline belongs to this library (lrn:: / scene::); memcpy / memset nodes are allowed."""
     import pointnet_refine_b200 as prb
     from torch.profiler import ProfilerActivity, profile
     sd = synth.make_state_dict(0)
     m = prb.LineRefineNet().to(dev).eval()
     m.load_state_dict(synth.to_torch(sd), strict=True)
+    m.precision = prec
     ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(B, N, seed=3))
     with torch.no_grad():
         m(ctx, line)                      # weight preparation (host-side folds + uploads) happens on the first call
