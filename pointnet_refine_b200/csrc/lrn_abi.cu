@@ -967,6 +967,7 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt,
 // Every GEMM (forward, dgrad, wgrad) is the tcgen05 pair kernel; csrc/train_kernels.cuh holds the glue.
 // =====================================================================================================
 #include "train_kernels.cuh"
+#include "train_attn.cuh"
 
 namespace {
 
@@ -1420,6 +1421,61 @@ int lrn_ctx_attention_merge(const float* part, const float* lse, int B, int spli
   const int rows = B * 256;
   const int grid = std::min((rows + 7) / 8, dev.sms * 8);
   ctx_merge_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part, lse, rows, splits, out, out_bf16 ? 1 : 0);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+static int train_attn_args(TrainAttnParams* p, const float* q, const void* k, const void* v, int64_t ld_kv, int B, int N, float* out,
+                           float* lse, float p_drop, uint64_t seed) {
+  if (!q || !k || !v || !out || !lse) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (B <= 0 || N <= 0 || ld_kv < 32 || ld_kv % 8 || int64_t(B) * 8 >= (int64_t(1) << 31))
+    return fail(LRN_ERR_BAD_SHAPE, "B=%d N=%d ld=%lld", B, N, (long long)ld_kv);
+  if (!(p_drop >= 0.f && p_drop < 1.f)) return fail(LRN_ERR_BAD_ARG, "dropout probability %f", p_drop);
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return fail(LRN_ERR_MISALIGNED, "16-byte alignment");
+  p->q = q;
+  p->k = static_cast<const __nv_bfloat16*>(k);
+  p->v = static_cast<const __nv_bfloat16*>(v);
+  p->ld = ld_kv;
+  p->B = B;
+  p->N = N;
+  p->out = out;
+  p->lse = lse;
+  p->p_drop = p_drop;
+  p->seed = seed;
+  return LRN_OK;
+}
+
+int lrn_train_cross_attention_forward(const float* q, const void* k, const void* v, int64_t ld_kv, int B, int N, float* out,
+                                      float* lse, float p_drop, uint64_t seed, lrn_stream_t stream) {
+  TrainAttnParams p{};
+  int st = train_attn_args(&p, q, k, v, ld_kv, B, N, out, lse, p_drop, seed);
+  if (st) return st;
+  DeviceInfo dev;
+  if ((st = device_info(&dev))) return st;
+  train_attn_fwd_kernel<<<B * 8, 128, kTaFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_train_cross_attention_backward(const float* q, const void* k, const void* v, int64_t ld_kv, int B, int N, const float* out,
+                                       const float* lse, const float* dout, float* dq, void* dk, void* dv, int64_t ld_grad,
+                                       float p_drop, uint64_t seed, lrn_stream_t stream) {
+  TrainAttnParams p{};
+  int st = train_attn_args(&p, q, k, v, ld_kv, B, N, const_cast<float*>(out), const_cast<float*>(lse), p_drop, seed);
+  if (st) return st;
+  if (!dout || !dq || !dk || !dv) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (ld_grad < 32 || ld_grad % 2 || (reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dq)) & 15 ||
+      (reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 3)
+    return fail(LRN_ERR_MISALIGNED, "dout / dq need 16-byte, dk / dv 4-byte alignment; ld_grad even and >= 32");
+  p.dout = dout;
+  p.dq = dq;
+  p.dk = static_cast<__nv_bfloat16*>(dk);
+  p.dv = static_cast<__nv_bfloat16*>(dv);
+  p.ldg = ld_grad;
+  DeviceInfo dev;
+  if ((st = device_info(&dev))) return st;
+  train_attn_bwd_kernel<<<B * 8, 128, kTaBwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

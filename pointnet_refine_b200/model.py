@@ -465,7 +465,7 @@ class LineRefineNet(nn.Module):
         >= 256 query rows; the 32 x 32 self attention, LayerNorms, dropouts and heads are stock ops.  Same parameters
         as DetrTransformerDecoderLayer; dropout draws differ from the reference's RNG stream (they would from run to
         run there, too)."""
-        from .train_ops import add_layernorm, kv_proj, linear_bf16, pos_hidden_train
+        from .train_ops import KVGradShare, add_layernorm, cross_attention_train, kv_proj, linear_bf16, pos_hidden_train
         B, N, _ = context.shape
         d, H = self.d_model, 8
         wk = torch.cat([l.cross_attn.in_proj_weight[d:2 * d] for l in self.decoder_layers])
@@ -475,8 +475,10 @@ class LineRefineNet(nn.Module):
         mem = linear_bf16(fused_pm, self.context_proj.weight, self.context_proj.bias)      # (B,N,256) bf16
         h = pos_hidden_train(context, self.pos_emb.mlp[0].weight, self.pos_emb.mlp[0].bias)    # (B,N,256) bf16
         posm = linear_bf16(h, self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias)
-        k_l = kv_proj(mem + posm, wk, bk, 6, H)     # six (B, H, N, 32) views of one (B, N, 6, H, 32) GEMM result
-        v_l = kv_proj(mem, wv, bv, 6, H)
+        share = KVGradShare()                           # the attention backward writes dK / dV of all layers in place
+        k_l = kv_proj(mem + posm, wk, bk, 6, H, share)  # six (B, H, N, 32) views of one (B, N, 6, H, 32) GEMM result
+        v_l = kv_proj(mem, wv, bv, 6, H, share)
+        native_ca = noisy_line.shape[1] == 32           # 32 queries per segment: lrn_train_cross_attention_* (else SDPA)
         rows = B * noisy_line.shape[1]
         tc = rows >= 256 and rows % 64 == 0   # query-side linears on the bf16 tensor-core path (fwd, dgrad, wgrad)
 
@@ -498,9 +500,13 @@ class LineRefineNet(nn.Module):
             att = lin(att.transpose(1, 2).reshape(B, -1, d), sa.out_proj.weight, sa.out_proj.bias)
             tgt = add_layernorm(tgt, layer.dropout1(att), layer.norm1)
             ca = layer.cross_attn
-            qh = lin(tgt + qpos, ca.in_proj_weight[:d], ca.in_proj_bias[:d]).view(B, -1, H, d // H).transpose(1, 2)
-            att = F.scaled_dot_product_attention(qh.bfloat16(), k_l[i], v_l[i], dropout_p=ca.dropout if self.training else 0.0)
-            att = att.transpose(1, 2).reshape(B, -1, d).float()
+            qh = lin(tgt + qpos, ca.in_proj_weight[:d], ca.in_proj_bias[:d])
+            if native_ca:
+                att = cross_attention_train(qh, k_l[i], v_l[i], ca.dropout if self.training else 0.0, share, i)
+            else:
+                att = F.scaled_dot_product_attention(qh.view(B, -1, H, d // H).transpose(1, 2).bfloat16(), k_l[i], v_l[i],
+                                                     dropout_p=ca.dropout if self.training else 0.0)
+                att = att.transpose(1, 2).reshape(B, -1, d).float()
             tgt = add_layernorm(tgt, layer.dropout2(lin(att, ca.out_proj.weight, ca.out_proj.bias)), layer.norm2)
             ffn = lin(layer.dropout(F.relu(lin(tgt, layer.linear1.weight, layer.linear1.bias))), layer.linear2.weight, layer.linear2.bias)
             tgt = add_layernorm(tgt, layer.dropout3(ffn), layer.norm3)

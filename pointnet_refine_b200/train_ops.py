@@ -203,15 +203,29 @@ class LinearBf16Fn(torch.autograd.Function):
         return dx, dw, db
 
 
+class KVGradShare:
+    """One per training forward: the two (B, N, L, H, 32) bf16 buffers into which every layer's cross-attention backward
+    (CrossAttnTrainFn) writes dK / dV in place; the K / V projections' backward then reads them as they are."""
+
+    def __init__(self):
+        self.dk = self.dv = None
+
+    def buffers(self, B, N, L, device):
+        if self.dk is None:
+            self.dk = torch.empty(B, N, L, 8, 32, dtype=torch.bfloat16, device=device)
+            self.dv = torch.empty_like(self.dk)
+        return self.dk, self.dv
+
+
 class KVProjFn(torch.autograd.Function):
     """K (or V) projections of all L cross-attention layers as ONE bf16 tensor-core linear over the context points,
-    handed to scaled_dot_product_attention as L views (B, H, N, hd) of the (B, N, L, H, hd) result.  The backward
-    gathers the L attention gradients straight into that layout (one strided copy each) instead of autograd's
-    stack + contiguous round trip over the 3 KB/point gradient, then runs dgrad / wgrad like LinearBf16Fn.
-    x (B, N, K) bf16 or fp32, weight (L*H*hd, K) fp32, bias fp32."""
+    handed to the attention as L views (B, H, N, hd) of the (B, N, L, H, hd) result.  The backward takes the L attention
+    gradients in that same layout: when they are the views of a KVGradShare buffer that CrossAttnTrainFn filled in place
+    there is nothing to move; otherwise each is gathered into its column block (one strided copy), then dgrad / wgrad run
+    like LinearBf16Fn.  x (B, N, K) bf16 or fp32, weight (L*H*hd, K) fp32, bias fp32."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, L, H):
+    def forward(ctx, x, weight, bias, L, H, share):
         from . import ops
         B, N, K = x.shape
         xb = x.detach().to(torch.bfloat16).contiguous().view(B * N, K)
@@ -219,6 +233,7 @@ class KVProjFn(torch.autograd.Function):
         ctx.save_for_backward(xb, wb)
         ctx.needs = (x.requires_grad, weight.requires_grad, bias.requires_grad)
         ctx.meta = (B, N, K, L, H, x.dtype)
+        ctx.share = share
         y = ops.gemm_bias_act(xb, wb, bias.detach(), out_dtype=torch.bfloat16).view(B, N, L, H, -1)
         return tuple(y[:, :, i].transpose(1, 2) for i in range(L))
 
@@ -227,18 +242,25 @@ class KVProjFn(torch.autograd.Function):
         from . import ops
         xb, wb = ctx.saved_tensors
         B, N, K, L, H, x_dtype = ctx.meta
-        dy = torch.empty(B, N, L, H, wb.shape[0] // (L * H), dtype=torch.bfloat16, device=xb.device)
-        hd = dy.shape[-1]
-        for i, g in enumerate(grads):
-            if g is None:
-                dy[:, :, i].zero_()
-            elif hd == 32 and g.dtype == torch.bfloat16 and g.is_contiguous():
-                with torch.cuda.device(g.device):      # (B,H,N,32) as SDPA returns it -> its column block, one pass
-                    _lib.check(lib.lrn_gather_heads(g.data_ptr(), B, H, N, i, L, dy.data_ptr(), _stream_ptr(g.device)),
-                               "lrn_gather_heads")
-                _lib.launch_counter += 1
-            else:
-                dy[:, :, i].copy_(g.transpose(1, 2))
+        hd = wb.shape[0] // (L * H)
+        dy = None
+        if ctx.share is not None and ctx.share.dk is not None and all(g is not None for g in grads):
+            for base in (ctx.share.dk, ctx.share.dv):      # every gradient is the layer's column block of ONE shared buffer
+                if all(g.dtype == torch.bfloat16 and g.data_ptr() == base.data_ptr() + 2 * i * H * hd
+                       and tuple(g.stride()) == (N * L * H * hd, hd, L * H * hd, 1) for i, g in enumerate(grads)):
+                    dy = base
+        if dy is None:
+            dy = torch.empty(B, N, L, H, hd, dtype=torch.bfloat16, device=xb.device)
+            for i, g in enumerate(grads):
+                if g is None:
+                    dy[:, :, i].zero_()
+                elif hd == 32 and g.dtype == torch.bfloat16 and g.is_contiguous():
+                    with torch.cuda.device(g.device):      # (B,H,N,32) as SDPA returns it -> its column block, one pass
+                        _lib.check(lib.lrn_gather_heads(g.data_ptr(), B, H, N, i, L, dy.data_ptr(), _stream_ptr(g.device)),
+                                   "lrn_gather_heads")
+                    _lib.launch_counter += 1
+                else:
+                    dy[:, :, i].copy_(g.transpose(1, 2))
         dyb = dy.view(B * N, -1)
         need_x, need_w, need_b = ctx.needs
         dx = dw = db = None
@@ -248,12 +270,66 @@ class KVProjFn(torch.autograd.Function):
             dw = ops.gemm_tn(dyb, xb)
         if need_b:
             db = _col_sum(dyb)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
-def kv_proj(x, weight, bias, layers: int, heads: int):
+def kv_proj(x, weight, bias, layers: int, heads: int, share: KVGradShare | None = None):
     """(B, N, K) -> tuple of `layers` tensors (B, heads, N, hd), see KVProjFn."""
-    return KVProjFn.apply(x, weight, bias, layers, heads)
+    return KVProjFn.apply(x, weight, bias, layers, heads, share)
+
+
+class CrossAttnTrainFn(torch.autograd.Function):
+    """Cross attention of the 32 polyline queries over the context points in train mode (8 heads x 32, dropout on the
+    attention weights), forward and backward on lrn_train_cross_attention_*: K / V are read straight from the K / V
+    projection's (B, N, L, H, 32) buffer and dK / dV are written into the matching KVGradShare buffers in place.
+    q (B, 32, 256) fp32; k, v: the layer's (B, H, N, 32) views handed out by kv_proj."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, p_drop, share, layer):
+        q = _f32c(q.detach())
+        B, H, N, hd = k.shape
+        ld = k.stride(2)
+        if (H, hd) != (8, 32) or tuple(q.shape) != (B, 32, 256) or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16 or \
+                tuple(k.stride()) != (N * ld, 32, ld, 1) or tuple(v.stride()) != tuple(k.stride()):
+            raise ValueError("CrossAttnTrainFn: expected q (B,32,256) and (B,8,N,32) bf16 views of a (B,N,L,8,32) buffer")
+        out = torch.empty_like(q)
+        lse = torch.empty(B, 8, 32, dtype=torch.float32, device=q.device)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0     # host generator: follows torch.manual_seed
+        with torch.cuda.device(q.device):
+            _lib.check(lib.lrn_train_cross_attention_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, B, N, out.data_ptr(),
+                                                             lse.data_ptr(), float(p_drop), seed, _stream_ptr(q.device)),
+                       "lrn_train_cross_attention_forward")
+        _lib.launch_counter += 1
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.cfg = (float(p_drop), seed, share, int(layer))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        p_drop, seed, share, layer = ctx.cfg
+        B, H, N, hd = k.shape
+        dout = _f32c(dout)
+        dq = torch.empty_like(q)
+        L = k.stride(2) // (H * hd)                   # k is the layer's column block of a (B, N, L, H, hd) buffer
+        if share is not None and k.stride(2) == L * H * hd and layer < L:
+            dk_all, dv_all = share.buffers(B, N, L, q.device)
+            gk, gv = dk_all[:, :, layer].transpose(1, 2), dv_all[:, :, layer].transpose(1, 2)
+        else:
+            gk = torch.empty(B, N, H, hd, dtype=torch.bfloat16, device=q.device).transpose(1, 2)
+            gv = torch.empty(B, N, H, hd, dtype=torch.bfloat16, device=q.device).transpose(1, 2)
+        with torch.cuda.device(q.device):
+            _lib.check(lib.lrn_train_cross_attention_backward(q.data_ptr(), k.data_ptr(), v.data_ptr(), k.stride(2), B, N,
+                                                              out.data_ptr(), lse.data_ptr(), dout.data_ptr(), dq.data_ptr(),
+                                                              gk.data_ptr(), gv.data_ptr(), gk.stride(2), p_drop, seed,
+                                                              _stream_ptr(q.device)), "lrn_train_cross_attention_backward")
+        _lib.launch_counter += 1
+        return dq, gk, gv, None, None, None
+
+
+def cross_attention_train(q, k, v, p_drop: float, share: KVGradShare | None, layer: int):
+    """(B, 32, 256) fp32 attention output (heads concatenated, before out_proj); see CrossAttnTrainFn."""
+    return CrossAttnTrainFn.apply(q, k, v, p_drop, share, layer)
 
 
 class PosHiddenFn(torch.autograd.Function):

@@ -429,3 +429,52 @@ def test_add_layernorm_and_pos_hidden_autograd(dev):
     assert float((h.float() - href).detach().abs().max()) <= 2 ** -8 * max(1.0, float(href.detach().abs().max()))
     for a, b in ((gw, lin.weight.grad), (gb, lin.bias.grad)):
         assert float((a - b).norm() / b.norm()) <= 1e-2
+
+
+# ------------------------------------------------------------------ train-mode cross attention (mma.sync kernels)
+def _ta_keep_mask(seed, B, N, p, dev):
+    """Host mirror of ta_keep_scale (csrc/train_attn.cuh): keep / (1 - p) for element (b*8 + h, query, key)."""
+    M32 = 0xFFFFFFFF
+    idx = torch.arange(B * 8 * 32 * N, dtype=torch.int64, device=dev)
+    mul = lambda x, c: (x * c) & M32                       # 32-bit wrap-around product (operands < 2^32: fits int64)
+    x = (idx & M32) ^ mul(idx >> 32, 0x85EBCA77) ^ (seed & M32) ^ ((((seed >> 32) & M32) * 0xC2B2AE3D) & M32)
+    x = x ^ (x >> 16); x = mul(x, 0x21F0AAAD)
+    x = x ^ (x >> 15); x = mul(x, 0x735A2D97)
+    x = x ^ (x >> 15)
+    keep = (x & 0xFFFFFF) >= int(p * 16777216.0)
+    return keep.view(B, 8, 32, N).float() / (1.0 - p)
+
+
+@pytest.mark.parametrize("B,N,p", [(2, 1024, 0.0), (3, 333, 0.0), (2, 40, 0.1), (2, 1000, 0.1)])
+def test_train_cross_attention_matches_torch(dev, B, N, p):
+    """lrn_train_cross_attention_forward / _backward against the same attention in fp64 on the bf16-rounded operands,
+    with the dropout mask regenerated on the host from the kernel's hash; dK / dV land in the shared (B,N,L,H,32) buffers."""
+    from pointnet_refine_b200.train_ops import CrossAttnTrainFn, KVGradShare
+    g = torch.Generator(device=dev).manual_seed(N)
+    L, layer = 6, 4
+    q = torch.randn(B, 32, 256, device=dev, generator=g, requires_grad=True)
+    kall = torch.randn(B, N, L, 8, 32, device=dev, generator=g).bfloat16().requires_grad_()
+    vall = torch.randn(B, N, L, 8, 32, device=dev, generator=g).bfloat16().requires_grad_()
+    r = torch.randn(B, 32, 256, device=dev, generator=g)
+    share = KVGradShare()
+    torch.manual_seed(11)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0      # what the Function will draw
+    torch.manual_seed(11)
+    out = CrossAttnTrainFn.apply(q, kall[:, :, layer].transpose(1, 2), vall[:, :, layer].transpose(1, 2), p, share, layer)
+    (out * r).sum().backward()
+    # reference in fp64 on the operands the kernel sees (q' and P are rounded to bf16 inside: tolerance covers that)
+    qd = q.detach().double().view(B, 32, 8, 32).transpose(1, 2).requires_grad_()
+    kd = kall.detach().double()[:, :, layer].transpose(1, 2).requires_grad_()
+    vd = vall.detach().double()[:, :, layer].transpose(1, 2).requires_grad_()
+    P = torch.softmax(qd @ kd.transpose(2, 3) / 32 ** 0.5, dim=-1)
+    if p > 0:
+        P = P * _ta_keep_mask(seed, B, N, p, dev).double()
+    ref = (P @ vd).transpose(1, 2).reshape(B, 32, 256)
+    (ref * r.double()).sum().backward()
+    rel = lambda a, b: float((a.double() - b).norm() / b.norm())
+    assert rel(out, ref) <= 1e-2, rel(out, ref)
+    assert rel(q.grad, qd.grad.transpose(1, 2).reshape(B, 32, 256)) <= 2e-2
+    assert rel(share.dk[:, :, layer], kd.grad.transpose(1, 2)) <= 2e-2
+    assert rel(share.dv[:, :, layer], vd.grad.transpose(1, 2)) <= 2e-2
+    assert kall.grad is not None and kall.grad.data_ptr() != 0
+    assert rel(kall.grad[:, :, layer], kd.grad.transpose(1, 2)) <= 2e-2
