@@ -326,18 +326,19 @@ int lrn_cross_attention32(const float* q, const float* k, const float* v, int64_
  * bf16, out[b][q] = sum_s 2^(lse_s - max) part_s / sum_s 2^(lse_s - max). */
 int lrn_ctx_attention_merge(const float* part, const float* lse, int B, int splits, void* out, int out_bf16, lrn_stream_t stream);
 
-/* ---- train-mode cross attention (nn.MultiheadAttention cross_attn under model.train(), src/model.py:84,123-128: 8 heads x 32,
- * dropout on the attention weights) for 32 queries per segment, reading K / V straight from the K / V projection's
- * (B, N, layers, 8, 32) bf16 buffer: key n of segment b at k + (b*N + n) * ld_kv, head h at + 32 h (pass the layer's column
- * block as the base pointer).  q, out, dout, dq: (B, 32, 256) fp32, heads concatenated; lse (B, 8, 32) fp32 is written by
- * the forward and read by the backward.  The backward writes dk / dv for every key in the same addressing (row pitch
- * ld_grad), complete for this layer: no per-head gradient tensors, no gathers.  Dropout: counter-based hash of (seed,
- * segment, head, query, key), regenerated by the backward; pass a fresh seed per call and the same one to its backward. */
-int lrn_train_cross_attention_forward(const float* q, const void* k, const void* v, int64_t ld_kv, int B, int N, float* out,
-                                      float* lse, float p_drop, uint64_t seed, lrn_stream_t stream);
-int lrn_train_cross_attention_backward(const float* q, const void* k, const void* v, int64_t ld_kv, int B, int N, const float* out,
-                                       const float* lse, const float* dout, float* dq, void* dk, void* dv, int64_t ld_grad,
-                                       float p_drop, uint64_t seed, lrn_stream_t stream);
+/* ---- train-mode attention for 32 queries per segment (nn.MultiheadAttention under model.train(): cross_attn over the N
+ * context points, src/model.py:84,123-128, and self_attn over the 32 polyline points, :113-117; 8 heads x 32, dropout on the
+ * attention weights).  K / V are read where the projections left them: key n of segment b at k + (b*N + n) * ld_k, head h at
+ * + 32 h (for the cross attention pass a layer's column block of the (B, N, layers, 8, 32) bf16 projection buffer; ld_v
+ * likewise).  q, out, dout, dq: (B, 32, 256) fp32, heads concatenated; lse (B, 8, 32) fp32 is written by the forward and
+ * read by the backward.  The backward writes dk / dv for every key in the same addressing (row pitches ld_dk / ld_dv),
+ * complete for this call: no per-head gradient tensors, no gathers.  Dropout: counter-based hash of (seed, segment, head,
+ * query, key), regenerated by the backward; pass a fresh seed per call and the same one to its backward. */
+int lrn_train_attention_forward(const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N, float* out,
+                                float* lse, float p_drop, uint64_t seed, lrn_stream_t stream);
+int lrn_train_attention_backward(const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N,
+                                 const float* out, const float* lse, const float* dout, float* dq, void* dk, int64_t ld_dk, void* dv,
+                                 int64_t ld_dv, float p_drop, uint64_t seed, lrn_stream_t stream);
 
 /* out[c] = sum over rows of the bf16 matrix A (rows, cols), row pitch ld: the bias gradient of a linear layer whose output
  * gradient is bf16 (cols % 64 == 0). */

@@ -28,7 +28,7 @@ EXPORTS = [
     "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden", "lrn_pos_hidden_backward",
     "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_scene_resample", "lrn_adam_step", "lrn_l1_deep_supervision", "lrn_col_sum_bf16", "lrn_gather_heads",
     "lrn_add_layernorm", "lrn_add_layernorm_backward", "lrn_self_attention32", "lrn_head_update",
-    "lrn_rows_linear", "lrn_query_pos_hidden", "lrn_add", "lrn_ctx_attention_merge", "lrn_cross_attention32", "lrn_train_cross_attention_forward", "lrn_train_cross_attention_backward",
+    "lrn_rows_linear", "lrn_query_pos_hidden", "lrn_add", "lrn_ctx_attention_merge", "lrn_cross_attention32", "lrn_train_attention_forward", "lrn_train_attention_backward",
 ]
 STAGES = ["embed", "conv2", "conv3", "conv4", "conv5", "fusion", "proj"]
 
@@ -112,10 +112,10 @@ def _load():
     lib.lrn_query_pos_hidden.argtypes = [vp, vp, vp, i64, i64, vp, ci, vp]
     lib.lrn_add.restype = ci
     lib.lrn_add.argtypes = [vp, vp, vp, i64, ci, vp]
-    lib.lrn_train_cross_attention_forward.restype = ci
-    lib.lrn_train_cross_attention_forward.argtypes = [vp, vp, vp, i64, ci, ci, vp, vp, C.c_float, C.c_uint64, vp]
-    lib.lrn_train_cross_attention_backward.restype = ci
-    lib.lrn_train_cross_attention_backward.argtypes = [vp, vp, vp, i64, ci, ci, vp, vp, vp, vp, vp, vp, i64, C.c_float, C.c_uint64, vp]
+    lib.lrn_train_attention_forward.restype = ci
+    lib.lrn_train_attention_forward.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp, vp, C.c_float, C.c_uint64, vp]
+    lib.lrn_train_attention_backward.restype = ci
+    lib.lrn_train_attention_backward.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp, vp, vp, vp, vp, i64, vp, i64, C.c_float, C.c_uint64, vp]
     lib.lrn_cross_attention32.restype = ci
     lib.lrn_cross_attention32.argtypes = [vp, vp, vp, i64, ci, ci, vp, vp]
     lib.lrn_ctx_attention_merge.restype = ci

@@ -1425,18 +1425,19 @@ int lrn_ctx_attention_merge(const float* part, const float* lse, int B, int spli
   return LRN_OK;
 }
 
-static int train_attn_args(TrainAttnParams* p, const float* q, const void* k, const void* v, int64_t ld_kv, int B, int N, float* out,
-                           float* lse, float p_drop, uint64_t seed) {
+static int train_attn_args(TrainAttnParams* p, const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N,
+                           float* out, float* lse, float p_drop, uint64_t seed) {
   if (!q || !k || !v || !out || !lse) return fail(LRN_ERR_BAD_ARG, "null pointer");
-  if (B <= 0 || N <= 0 || ld_kv < 32 || ld_kv % 8 || int64_t(B) * 8 >= (int64_t(1) << 31))
-    return fail(LRN_ERR_BAD_SHAPE, "B=%d N=%d ld=%lld", B, N, (long long)ld_kv);
+  if (B <= 0 || N <= 0 || ld_k < 32 || ld_k % 8 || ld_v < 32 || ld_v % 8 || int64_t(B) * 8 >= (int64_t(1) << 31))
+    return fail(LRN_ERR_BAD_SHAPE, "B=%d N=%d ld_k=%lld ld_v=%lld", B, N, (long long)ld_k, (long long)ld_v);
   if (!(p_drop >= 0.f && p_drop < 1.f)) return fail(LRN_ERR_BAD_ARG, "dropout probability %f", p_drop);
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15)
     return fail(LRN_ERR_MISALIGNED, "16-byte alignment");
   p->q = q;
   p->k = static_cast<const __nv_bfloat16*>(k);
   p->v = static_cast<const __nv_bfloat16*>(v);
-  p->ld = ld_kv;
+  p->ld = ld_k;
+  p->ldv = ld_v;
   p->B = B;
   p->N = N;
   p->out = out;
@@ -1446,10 +1447,10 @@ static int train_attn_args(TrainAttnParams* p, const float* q, const void* k, co
   return LRN_OK;
 }
 
-int lrn_train_cross_attention_forward(const float* q, const void* k, const void* v, int64_t ld_kv, int B, int N, float* out,
-                                      float* lse, float p_drop, uint64_t seed, lrn_stream_t stream) {
+int lrn_train_attention_forward(const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N, float* out,
+                                float* lse, float p_drop, uint64_t seed, lrn_stream_t stream) {
   TrainAttnParams p{};
-  int st = train_attn_args(&p, q, k, v, ld_kv, B, N, out, lse, p_drop, seed);
+  int st = train_attn_args(&p, q, k, ld_k, v, ld_v, B, N, out, lse, p_drop, seed);
   if (st) return st;
   DeviceInfo dev;
   if ((st = device_info(&dev))) return st;
@@ -1458,21 +1459,22 @@ int lrn_train_cross_attention_forward(const float* q, const void* k, const void*
   return LRN_OK;
 }
 
-int lrn_train_cross_attention_backward(const float* q, const void* k, const void* v, int64_t ld_kv, int B, int N, const float* out,
-                                       const float* lse, const float* dout, float* dq, void* dk, void* dv, int64_t ld_grad,
-                                       float p_drop, uint64_t seed, lrn_stream_t stream) {
+int lrn_train_attention_backward(const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N,
+                                 const float* out, const float* lse, const float* dout, float* dq, void* dk, int64_t ld_dk, void* dv,
+                                 int64_t ld_dv, float p_drop, uint64_t seed, lrn_stream_t stream) {
   TrainAttnParams p{};
-  int st = train_attn_args(&p, q, k, v, ld_kv, B, N, const_cast<float*>(out), const_cast<float*>(lse), p_drop, seed);
+  int st = train_attn_args(&p, q, k, ld_k, v, ld_v, B, N, const_cast<float*>(out), const_cast<float*>(lse), p_drop, seed);
   if (st) return st;
   if (!dout || !dq || !dk || !dv) return fail(LRN_ERR_BAD_ARG, "null pointer");
-  if (ld_grad < 32 || ld_grad % 2 || (reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dq)) & 15 ||
+  if (ld_dk < 32 || ld_dk % 2 || ld_dv < 32 || ld_dv % 2 || (reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dq)) & 15 ||
       (reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 3)
-    return fail(LRN_ERR_MISALIGNED, "dout / dq need 16-byte, dk / dv 4-byte alignment; ld_grad even and >= 32");
+    return fail(LRN_ERR_MISALIGNED, "dout / dq need 16-byte, dk / dv 4-byte alignment; gradient row pitches even and >= 32");
   p.dout = dout;
   p.dq = dq;
   p.dk = static_cast<__nv_bfloat16*>(dk);
   p.dv = static_cast<__nv_bfloat16*>(dv);
-  p.ldg = ld_grad;
+  p.ldg = ld_dk;
+  p.ldgv = ld_dv;
   DeviceInfo dev;
   if ((st = device_info(&dev))) return st;
   train_attn_bwd_kernel<<<B * 8, 128, kTaBwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(p);

@@ -12,7 +12,8 @@
 // Scores are kept in log2 units: q' = q * log2(e) / sqrt(32).
 //
 // Dropout is a counter-based hash of (seed, segment, head, query, key): forward and backward regenerate the same mask, no
-// mask tensor exists.  keep = hash & 0xFFFFFF >= p * 2^24, kept weights are scaled by 1 / (1 - p).
+// mask tensor exists.  One 32-bit hash serves two adjacent keys (16 bits each against p * 2^16); kept weights are scaled by
+// 1 / (1 - p).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -26,7 +27,7 @@ struct TrainAttnParams {
   const float* q;            // (B, 32, 256) fp32: in-projected queries (bias included), head h = columns [32h, 32h + 32)
   const __nv_bfloat16* k;    // key n of segment b: k + (b * N + n) * ld + 32 h   (a layer's column block of the K buffer)
   const __nv_bfloat16* v;
-  long long ld;              // elements between consecutive points (6 * 256 for the six-layer buffer)
+  long long ld, ldv;         // elements between consecutive keys of k / of v (6 * 256 for the six-layer buffers)
   int B, N;
   float* out;                // (B, 32, 256) fp32, heads concatenated (input of out_proj)
   float* lse;                // (B, 8, 32): log2 of the softmax denominator (+ running maximum), for the backward
@@ -37,7 +38,7 @@ struct TrainAttnParams {
   float* dq;                 // (B, 32, 256)
   __nv_bfloat16* dk;         // same addressing as k / v (its own row pitch)
   __nv_bfloat16* dv;
-  long long ldg;
+  long long ldg, ldgv;       // row pitch of dk / of dv
 };
 
 constexpr int kTaPitch = 40;                 // bf16 elements per shared-memory row (32 + 8: conflict-free ldmatrix)
@@ -72,14 +73,18 @@ __device__ __forceinline__ void frag_b_kn(uint32_t (&r)[4], uint32_t t, int k0, 
   ldsm_x4_t(r, t + ((k0 + (mi & 1) * 8 + row) * kTaPitch + n0 + (mi >> 1) * 8) * 2);
 }
 
-__device__ __forceinline__ float ta_keep_scale(unsigned long long seed, unsigned long long idx, uint32_t thresh, float inv_keep) {
+// One 32-bit hash decides TWO adjacent keys (its low / high 16 bits against p * 2^16): `idx` is the element index of the
+// even key of the pair.  Returns the keep / (1 - p) factors of (even key, odd key).
+__device__ __forceinline__ void ta_keep_pair(unsigned long long seed, unsigned long long idx, uint32_t thresh16, float inv_keep,
+                                             float& k0, float& k1) {
   // 32-bit mix of the 64-bit element index and the seed, then two multiply-xorshift rounds ("lowbias32")
   uint32_t x = static_cast<uint32_t>(idx) ^ (static_cast<uint32_t>(idx >> 32) * 0x85EBCA77u) ^ static_cast<uint32_t>(seed) ^
                (static_cast<uint32_t>(seed >> 32) * 0xC2B2AE3Du);
   x ^= x >> 16; x *= 0x21F0AAADu;
   x ^= x >> 15; x *= 0x735A2D97u;
   x ^= x >> 15;
-  return (x & 0xFFFFFFu) >= thresh ? inv_keep : 0.f;
+  k0 = (x & 0xFFFFu) >= thresh16 ? inv_keep : 0.f;
+  k1 = (x >> 16) >= thresh16 ? inv_keep : 0.f;
 }
 
 // 32 keys x 32 channels of K and V (one head): global -> registers (rows past N are zero), registers -> this warp's
@@ -87,14 +92,14 @@ __device__ __forceinline__ float ta_keep_scale(unsigned long long seed, unsigned
 struct TaKvRegs {
   uint4 k[4], v[4];
 };
-__device__ __forceinline__ void ta_fetch_kv(TaKvRegs& r, const __nv_bfloat16* k, const __nv_bfloat16* v, long long ld, int key0, int N,
-                                            int lane) {
+__device__ __forceinline__ void ta_fetch_kv(TaKvRegs& r, const __nv_bfloat16* k, const __nv_bfloat16* v, long long ld, long long ldv,
+                                            int key0, int N, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int id = lane + 32 * i, row = id >> 2, c = id & 3;
     const bool in = key0 + row < N;
     r.k[i] = in ? *reinterpret_cast<const uint4*>(k + static_cast<long long>(key0 + row) * ld + 8 * c) : make_uint4(0, 0, 0, 0);
-    r.v[i] = in ? *reinterpret_cast<const uint4*>(v + static_cast<long long>(key0 + row) * ld + 8 * c) : make_uint4(0, 0, 0, 0);
+    r.v[i] = in ? *reinterpret_cast<const uint4*>(v + static_cast<long long>(key0 + row) * ldv + 8 * c) : make_uint4(0, 0, 0, 0);
   }
 }
 __device__ __forceinline__ void ta_park_kv(const TaKvRegs& r, uint8_t* sk, uint8_t* sv, int lane) {
@@ -141,8 +146,8 @@ __global__ void __launch_bounds__(128) train_attn_fwd_kernel(const TrainAttnPara
     for (int ks = 0; ks < 2; ++ks) frag_a(qa[mt][ks], ptx::smem_u32(sq), 16 * mt, 16 * ks, lane);
 
   const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.N * p.ld + h * 32;
-  const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.N * p.ld + h * 32;
-  const uint32_t thresh = static_cast<uint32_t>(p.p_drop * 16777216.f);
+  const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.N * p.ldv + h * 32;
+  const uint32_t thresh = static_cast<uint32_t>(p.p_drop * 65536.f);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   float o[2][4][4], mrun[2][2], lrun[2][2];
 #pragma unroll
@@ -156,13 +161,13 @@ __global__ void __launch_bounds__(128) train_attn_fwd_kernel(const TrainAttnPara
   }
   const int nblk = (p.N + 31) >> 5;
   TaKvRegs kv;
-  if (w < nblk) ta_fetch_kv(kv, kb, vb, p.ld, w << 5, p.N, lane);
+  if (w < nblk) ta_fetch_kv(kv, kb, vb, p.ld, p.ldv, w << 5, p.N, lane);
   for (int blk = w; blk < nblk; blk += 4) {
     const int key0 = blk << 5;
     __syncwarp();
     ta_park_kv(kv, sk, sv, lane);
     __syncwarp();
-    if (blk + 4 < nblk) ta_fetch_kv(kv, kb, vb, p.ld, (blk + 4) << 5, p.N, lane);
+    if (blk + 4 < nblk) ta_fetch_kv(kv, kb, vb, p.ld, p.ldv, (blk + 4) << 5, p.N, lane);
     float s[2][4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
@@ -205,15 +210,16 @@ __global__ void __launch_bounds__(128) train_attn_fwd_kernel(const TrainAttnPara
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float pe = exp2f(s[mt][nt][e] - bm[e >> 1]);
-          ls[e >> 1] += pe;
-          float keep = 1.f;
+        for (int hi = 0; hi < 2; ++hi) {
+          const float p0 = exp2f(s[mt][nt][2 * hi] - bm[hi]), p1 = exp2f(s[mt][nt][2 * hi + 1] - bm[hi]);
+          ls[hi] += p0 + p1;
+          float k0 = 1.f, k1 = 1.f;
           if (thresh) {
-            const int qi = 16 * mt + g + 8 * (e >> 1), key = key0 + 8 * nt + 2 * t + (e & 1);
-            keep = ta_keep_scale(p.seed, (static_cast<unsigned long long>(blockIdx.x) * 32 + qi) * p.N + key, thresh, inv_keep);
+            const int qi = 16 * mt + g + 8 * hi, key = key0 + 8 * nt + 2 * t;
+            ta_keep_pair(p.seed, (static_cast<unsigned long long>(blockIdx.x) * 32 + qi) * p.N + key, thresh, inv_keep, k0, k1);
           }
-          s[mt][nt][e] = pe * keep;
+          s[mt][nt][2 * hi] = p0 * k0;
+          s[mt][nt][2 * hi + 1] = p1 * k1;
         }
       lrun[mt][0] += ls[0];
       lrun[mt][1] += ls[1];
@@ -349,10 +355,10 @@ __global__ void __launch_bounds__(128) train_attn_bwd_kernel(const TrainAttnPara
       del_r[mt][hi] = sdelta[16 * mt + g + 8 * hi];
     }
   const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.N * p.ld + h * 32;
-  const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.N * p.ld + h * 32;
+  const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.N * p.ldv + h * 32;
   __nv_bfloat16* dkb = p.dk + static_cast<long long>(b) * p.N * p.ldg + h * 32;
-  __nv_bfloat16* dvb = p.dv + static_cast<long long>(b) * p.N * p.ldg + h * 32;
-  const uint32_t thresh = static_cast<uint32_t>(p.p_drop * 16777216.f);
+  __nv_bfloat16* dvb = p.dv + static_cast<long long>(b) * p.N * p.ldgv + h * 32;
+  const uint32_t thresh = static_cast<uint32_t>(p.p_drop * 65536.f);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const unsigned long long idx0 = static_cast<unsigned long long>(blockIdx.x) * 32;
   float dq[2][4][4];
@@ -365,13 +371,13 @@ __global__ void __launch_bounds__(128) train_attn_bwd_kernel(const TrainAttnPara
 
   const int nblk = (p.N + 31) >> 5;
   TaKvRegs kv;
-  if (w < nblk) ta_fetch_kv(kv, kb, vb, p.ld, w << 5, p.N, lane);
+  if (w < nblk) ta_fetch_kv(kv, kb, vb, p.ld, p.ldv, w << 5, p.N, lane);
   for (int blk = w; blk < nblk; blk += 4) {
     const int key0 = blk << 5;
     __syncwarp();
     ta_park_kv(kv, sk, sv, lane);
     __syncwarp();
-    if (blk + 4 < nblk) ta_fetch_kv(kv, kb, vb, p.ld, (blk + 4) << 5, p.N, lane);
+    if (blk + 4 < nblk) ta_fetch_kv(kv, kb, vb, p.ld, p.ldv, (blk + 4) << 5, p.N, lane);
     // ---- S = q' K^T, dPd = dO V^T as [query x key]; G and Pd
     uint32_t ga[2][2][4];
     {
@@ -396,12 +402,17 @@ __global__ void __launch_bounds__(128) train_attn_bwd_kernel(const TrainAttnPara
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int qi = 16 * mt + g + 8 * (e >> 1), key = key0 + 8 * nt + 2 * t + (e & 1);
-            const float pe = key < p.N ? exp2f(s[mt][nt][e] - lse_r[mt][e >> 1]) : 0.f;
-            const float keep = thresh ? ta_keep_scale(p.seed, (idx0 + qi) * p.N + key, thresh, inv_keep) : 1.f;
-            s[mt][nt][e] = pe * (keep * dp[mt][nt][e] - del_r[mt][e >> 1]);  // G
-            dp[mt][nt][e] = pe * keep;                                        // Pd
+          for (int hi = 0; hi < 2; ++hi) {
+            const int qi = 16 * mt + g + 8 * hi, key = key0 + 8 * nt + 2 * t;
+            float keep[2] = {1.f, 1.f};
+            if (thresh) ta_keep_pair(p.seed, (idx0 + qi) * p.N + key, thresh, inv_keep, keep[0], keep[1]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int e = 2 * hi + j;
+              const float pe = key + j < p.N ? exp2f(s[mt][nt][e] - lse_r[mt][hi]) : 0.f;
+              s[mt][nt][e] = pe * (keep[j] * dp[mt][nt][e] - del_r[mt][hi]);  // G
+              dp[mt][nt][e] = pe * keep[j];                                    // Pd
+            }
           }
           // park both as bf16 tiles [query][key]: element pairs (e = 0, 1) and (e = 2, 3) are adjacent keys of rows g, g + 8
           const int col = 8 * nt + 2 * t;
@@ -475,7 +486,7 @@ __global__ void __launch_bounds__(128) train_attn_bwd_kernel(const TrainAttnPara
             for (int nt = 0; nt < 4; ++nt) {
               *reinterpret_cast<uint32_t*>(dkb + static_cast<long long>(key) * p.ldg + 8 * nt + 2 * t) =
                   ptx::pack_bf16x2(dkc[mt][nt][2 * hi] * 0.6931471805599453f, dkc[mt][nt][2 * hi + 1] * 0.6931471805599453f);
-              *reinterpret_cast<uint32_t*>(dvb + static_cast<long long>(key) * p.ldg + 8 * nt + 2 * t) =
+              *reinterpret_cast<uint32_t*>(dvb + static_cast<long long>(key) * p.ldgv + 8 * nt + 2 * t) =
                   ptx::pack_bf16x2(dvc[mt][nt][2 * hi], dvc[mt][nt][2 * hi + 1]);
             }
           }

@@ -465,7 +465,8 @@ class LineRefineNet(nn.Module):
         >= 256 query rows; the 32 x 32 self attention, LayerNorms, dropouts and heads are stock ops.  Same parameters
         as DetrTransformerDecoderLayer; dropout draws differ from the reference's RNG stream (they would from run to
         run there, too)."""
-        from .train_ops import KVGradShare, add_layernorm, cross_attention_train, kv_proj, linear_bf16, pos_hidden_train
+        from .train_ops import (KVGradShare, add_layernorm, cross_attention_train, kv_proj, linear_bf16, pos_hidden_train,
+                                self_attention_train)
         B, N, _ = context.shape
         d, H = self.d_model, 8
         wk = torch.cat([l.cross_attn.in_proj_weight[d:2 * d] for l in self.decoder_layers])
@@ -478,7 +479,7 @@ class LineRefineNet(nn.Module):
         share = KVGradShare()                           # the attention backward writes dK / dV of all layers in place
         k_l = kv_proj(mem + posm, wk, bk, 6, H, share)  # six (B, H, N, 32) views of one (B, N, 6, H, 32) GEMM result
         v_l = kv_proj(mem, wv, bv, 6, H, share)
-        native_ca = noisy_line.shape[1] == 32           # 32 queries per segment: lrn_train_cross_attention_* (else SDPA)
+        native_ca = noisy_line.shape[1] == 32           # 32 queries per segment: lrn_train_attention_* (else SDPA)
         rows = B * noisy_line.shape[1]
         tc = rows >= 256 and rows % 64 == 0   # query-side linears on the bf16 tensor-core path (fwd, dgrad, wgrad)
 
@@ -493,11 +494,18 @@ class LineRefineNet(nn.Module):
             qpos = lin(F.relu(pe0(current)), pe2.weight, pe2.bias)
             q = tgt + qpos
             sa = layer.self_attn
-            qk = lin(q, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d]).view(B, -1, 2, H, d // H)
-            v = lin(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:]).view(B, -1, H, d // H)
-            att = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2),
-                                                 dropout_p=sa.dropout if self.training else 0.0)
-            att = lin(att.transpose(1, 2).reshape(B, -1, d), sa.out_proj.weight, sa.out_proj.bias)
+            if native_ca:     # [q | k] and v stay bf16 where the tensor-core linear produced them; attention on lrn_train_attention_*
+                lin16 = linear_bf16 if tc else F.linear
+                att = self_attention_train(lin16(q, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d]),
+                                           lin16(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:]),
+                                           sa.dropout if self.training else 0.0)
+            else:
+                qk = lin(q, sa.in_proj_weight[:2 * d], sa.in_proj_bias[:2 * d]).view(B, -1, 2, H, d // H)
+                v = lin(tgt, sa.in_proj_weight[2 * d:], sa.in_proj_bias[2 * d:]).view(B, -1, H, d // H)
+                att = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2),
+                                                     dropout_p=sa.dropout if self.training else 0.0)
+                att = att.transpose(1, 2).reshape(B, -1, d)
+            att = lin(att, sa.out_proj.weight, sa.out_proj.bias)
             tgt = add_layernorm(tgt, layer.dropout1(att), layer.norm1)
             ca = layer.cross_attn
             qh = lin(tgt + qpos, ca.in_proj_weight[:d], ca.in_proj_bias[:d])

@@ -279,26 +279,26 @@ def kv_proj(x, weight, bias, layers: int, heads: int, share: KVGradShare | None 
 
 
 class CrossAttnTrainFn(torch.autograd.Function):
-    """Cross attention of the 32 polyline queries over the context points in train mode (8 heads x 32, dropout on the
-    attention weights), forward and backward on lrn_train_cross_attention_*: K / V are read straight from the K / V
-    projection's (B, N, L, H, 32) buffer and dK / dV are written into the matching KVGradShare buffers in place.
-    q (B, 32, 256) fp32; k, v: the layer's (B, H, N, 32) views handed out by kv_proj."""
+    """Attention of the 32 polyline queries of a segment in train mode (8 heads x 32, dropout on the attention weights),
+    forward and backward on lrn_train_attention_*.  Cross attention: K / V are read straight from the K / V projection's
+    (B, N, L, H, 32) buffer and dK / dV are written into the matching KVGradShare buffers in place.  Self attention:
+    N = 32 keys, any row pitch.  q (B, 32, 256) fp32; k, v: (B, H, N, 32) bf16 views whose heads are 32 elements apart."""
 
     @staticmethod
     def forward(ctx, q, k, v, p_drop, share, layer):
         q = _f32c(q.detach())
         B, H, N, hd = k.shape
-        ld = k.stride(2)
+        ldk, ldv = k.stride(2), v.stride(2)
         if (H, hd) != (8, 32) or tuple(q.shape) != (B, 32, 256) or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16 or \
-                tuple(k.stride()) != (N * ld, 32, ld, 1) or tuple(v.stride()) != tuple(k.stride()):
-            raise ValueError("CrossAttnTrainFn: expected q (B,32,256) and (B,8,N,32) bf16 views of a (B,N,L,8,32) buffer")
+                tuple(k.stride()) != (N * ldk, 32, ldk, 1) or tuple(v.stride()) != (N * ldv, 32, ldv, 1) or v.shape != k.shape:
+            raise ValueError("CrossAttnTrainFn: expected q (B,32,256) and (B,8,N,32) bf16 views with heads 32 elements apart")
         out = torch.empty_like(q)
         lse = torch.empty(B, 8, 32, dtype=torch.float32, device=q.device)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0     # host generator: follows torch.manual_seed
         with torch.cuda.device(q.device):
-            _lib.check(lib.lrn_train_cross_attention_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, B, N, out.data_ptr(),
-                                                             lse.data_ptr(), float(p_drop), seed, _stream_ptr(q.device)),
-                       "lrn_train_cross_attention_forward")
+            _lib.check(lib.lrn_train_attention_forward(q.data_ptr(), k.data_ptr(), ldk, v.data_ptr(), ldv, B, N, out.data_ptr(),
+                                                       lse.data_ptr(), float(p_drop), seed, _stream_ptr(q.device)),
+                       "lrn_train_attention_forward")
         _lib.launch_counter += 1
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.cfg = (float(p_drop), seed, share, int(layer))
@@ -311,18 +311,18 @@ class CrossAttnTrainFn(torch.autograd.Function):
         B, H, N, hd = k.shape
         dout = _f32c(dout)
         dq = torch.empty_like(q)
-        L = k.stride(2) // (H * hd)                   # k is the layer's column block of a (B, N, L, H, hd) buffer
-        if share is not None and k.stride(2) == L * H * hd and layer < L:
+        L = k.stride(2) // (H * hd)                   # cross attention: k is the layer's column block of a (B, N, L, H, hd) buffer
+        if share is not None and k.stride(2) == L * H * hd and v.stride(2) == k.stride(2) and layer < L:
             dk_all, dv_all = share.buffers(B, N, L, q.device)
             gk, gv = dk_all[:, :, layer].transpose(1, 2), dv_all[:, :, layer].transpose(1, 2)
         else:
             gk = torch.empty(B, N, H, hd, dtype=torch.bfloat16, device=q.device).transpose(1, 2)
             gv = torch.empty(B, N, H, hd, dtype=torch.bfloat16, device=q.device).transpose(1, 2)
         with torch.cuda.device(q.device):
-            _lib.check(lib.lrn_train_cross_attention_backward(q.data_ptr(), k.data_ptr(), v.data_ptr(), k.stride(2), B, N,
-                                                              out.data_ptr(), lse.data_ptr(), dout.data_ptr(), dq.data_ptr(),
-                                                              gk.data_ptr(), gv.data_ptr(), gk.stride(2), p_drop, seed,
-                                                              _stream_ptr(q.device)), "lrn_train_cross_attention_backward")
+            _lib.check(lib.lrn_train_attention_backward(q.data_ptr(), k.data_ptr(), k.stride(2), v.data_ptr(), v.stride(2), B, N,
+                                                        out.data_ptr(), lse.data_ptr(), dout.data_ptr(), dq.data_ptr(),
+                                                        gk.data_ptr(), gk.stride(2), gv.data_ptr(), gv.stride(2), p_drop, seed,
+                                                        _stream_ptr(q.device)), "lrn_train_attention_backward")
         _lib.launch_counter += 1
         return dq, gk, gv, None, None, None
 
@@ -330,6 +330,16 @@ class CrossAttnTrainFn(torch.autograd.Function):
 def cross_attention_train(q, k, v, p_drop: float, share: KVGradShare | None, layer: int):
     """(B, 32, 256) fp32 attention output (heads concatenated, before out_proj); see CrossAttnTrainFn."""
     return CrossAttnTrainFn.apply(q, k, v, p_drop, share, layer)
+
+
+def self_attention_train(qk, v, p_drop: float):
+    """Self attention among the 32 polyline points of every segment in train mode (src/model.py:113-117) on the same
+    kernels: qk (B, 32, 512) = [q | k] in-projections, v (B, 32, 256) (any float dtype; bf16 is used as is) ->
+    (B, 32, 256) fp32, heads concatenated."""
+    B = qk.shape[0]
+    qkb, vb = qk.to(torch.bfloat16), v.to(torch.bfloat16)
+    heads = lambda t: t.unflatten(-1, (8, 32)).transpose(1, 2)          # (B, 32, 256) view -> (B, 8, 32, 32), heads 32 apart
+    return CrossAttnTrainFn.apply(qk[..., :256].float(), heads(qkb[..., 256:]), heads(vb), p_drop, None, 0)
 
 
 class PosHiddenFn(torch.autograd.Function):

@@ -433,21 +433,25 @@ def test_add_layernorm_and_pos_hidden_autograd(dev):
 
 # ------------------------------------------------------------------ train-mode cross attention (mma.sync kernels)
 def _ta_keep_mask(seed, B, N, p, dev):
-    """Host mirror of ta_keep_scale (csrc/train_attn.cuh): keep / (1 - p) for element (b*8 + h, query, key)."""
+    """Host mirror of ta_keep_pair (csrc/train_attn.cuh): keep / (1 - p) for element (b*8 + h, query, key); one 32-bit hash
+    of the even key's element index decides the even key (low 16 bits) and the odd key (high 16 bits)."""
     M32 = 0xFFFFFFFF
-    idx = torch.arange(B * 8 * 32 * N, dtype=torch.int64, device=dev)
+    rows = torch.arange(B * 8 * 32, dtype=torch.int64, device=dev).view(-1, 1)
+    keys = torch.arange(N, dtype=torch.int64, device=dev).view(1, -1)
+    idx = rows * N + (keys & ~1)
     mul = lambda x, c: (x * c) & M32                       # 32-bit wrap-around product (operands < 2^32: fits int64)
     x = (idx & M32) ^ mul(idx >> 32, 0x85EBCA77) ^ (seed & M32) ^ ((((seed >> 32) & M32) * 0xC2B2AE3D) & M32)
     x = x ^ (x >> 16); x = mul(x, 0x21F0AAAD)
     x = x ^ (x >> 15); x = mul(x, 0x735A2D97)
     x = x ^ (x >> 15)
-    keep = (x & 0xFFFFFF) >= int(p * 16777216.0)
+    bits = torch.where((keys & 1) == 0, x & 0xFFFF, x >> 16)
+    keep = bits >= int(p * 65536.0)
     return keep.view(B, 8, 32, N).float() / (1.0 - p)
 
 
-@pytest.mark.parametrize("B,N,p", [(2, 1024, 0.0), (3, 333, 0.0), (2, 40, 0.1), (2, 1000, 0.1)])
+@pytest.mark.parametrize("B,N,p", [(2, 1024, 0.0), (3, 333, 0.0), (2, 40, 0.1), (2, 1000, 0.1), (2, 333, 0.25)])
 def test_train_cross_attention_matches_torch(dev, B, N, p):
-    """lrn_train_cross_attention_forward / _backward against the same attention in fp64 on the bf16-rounded operands,
+    """lrn_train_attention_forward / _backward against the same attention in fp64 on the bf16-rounded operands,
     with the dropout mask regenerated on the host from the kernel's hash; dK / dV land in the shared (B,N,L,H,32) buffers."""
     from pointnet_refine_b200.train_ops import CrossAttnTrainFn, KVGradShare
     g = torch.Generator(device=dev).manual_seed(N)
@@ -471,10 +475,31 @@ def test_train_cross_attention_matches_torch(dev, B, N, p):
         P = P * _ta_keep_mask(seed, B, N, p, dev).double()
     ref = (P @ vd).transpose(1, 2).reshape(B, 32, 256)
     (ref * r.double()).sum().backward()
-    rel = lambda a, b: float((a.double() - b).norm() / b.norm())
+    rel = lambda a, b: float((a.detach().double() - b.detach()).norm() / b.detach().norm())
     assert rel(out, ref) <= 1e-2, rel(out, ref)
     assert rel(q.grad, qd.grad.transpose(1, 2).reshape(B, 32, 256)) <= 2e-2
     assert rel(share.dk[:, :, layer], kd.grad.transpose(1, 2)) <= 2e-2
     assert rel(share.dv[:, :, layer], vd.grad.transpose(1, 2)) <= 2e-2
     assert kall.grad is not None and kall.grad.data_ptr() != 0
     assert rel(kall.grad[:, :, layer], kd.grad.transpose(1, 2)) <= 2e-2
+
+
+def test_train_self_attention_matches_torch(dev):
+    """Self attention of the 32 polyline points (N = 32 keys, [q | k] and v with different row pitches) on the same kernels."""
+    from pointnet_refine_b200.train_ops import self_attention_train
+    g = torch.Generator(device=dev).manual_seed(3)
+    B = 5
+    qk = torch.randn(B, 32, 512, device=dev, generator=g).bfloat16().requires_grad_()
+    v = torch.randn(B, 32, 256, device=dev, generator=g).bfloat16().requires_grad_()
+    r = torch.randn(B, 32, 256, device=dev, generator=g)
+    out = self_attention_train(qk, v, 0.0)
+    (out * r).sum().backward()
+    qd = qk.detach().double().requires_grad_()
+    vd = v.detach().double().requires_grad_()
+    heads = lambda t: t.unflatten(-1, (8, 32)).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(heads(qd[..., :256]), heads(qd[..., 256:]), heads(vd))
+    ref = ref.transpose(1, 2).reshape(B, 32, 256)
+    (ref * r.double()).sum().backward()
+    rel = lambda a, b: float((a.detach().double() - b.detach()).norm() / b.detach().norm())
+    assert rel(out, ref) <= 1e-2
+    assert rel(qk.grad, qd.grad) <= 2e-2 and rel(v.grad, vd.grad) <= 2e-2
