@@ -168,6 +168,15 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip full_model / config5 / config3_sample / train_step")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line, the result: anything libraries print to fd 1 meanwhile (NCCL's version banner,
+    # warnings) goes to stderr
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,7 +195,7 @@ def main():
         v, dt, threads, kind = cpu_reference_run(seg, args.points, steps, warm)
         vf, dtf, _, _ = cpu_reference_run(max(1, seg // 2), args.points, 3, 1, full_forward=True)
         sample = f"{seg} segments x {args.points} points per step, {warm} warm-up + {steps} timed ({kind_text(kind)}, encoder, fp32)"
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "segments_per_sec", "value": v, "unit": "segments/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -268,6 +277,17 @@ def main():
             step()
         prof = ops.profile_read()
         ops.profile_enable(False)
+
+        # ---- BASELINE configs[3]: training step, 1024 segments x 1024 points per GPU (native train path; FlatDataParallel over
+        #      NCCL if N > 1).  Runs ahead of the other extra legs: measured after them, the same step is host-bound on a
+        #      multi-rank box (88-190 ms wall for 72 ms of device work), which says nothing about the step itself.
+        if not args.no_extras and args.precision == "bf16":
+            try:
+                with torch.enable_grad():
+                    extras["train_step"] = train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, max_over_ranks)
+            except torch.cuda.OutOfMemoryError:
+                extras["train_step"] = {"error": "out of memory"}
+            torch.cuda.empty_cache()
 
         # ---- HBM roofline of the stand-alone point loader + first layer (north_star evidence item; the bf16 tier's
         #      default path has this stage inside the fused chain kernel): 16 B in + 256 B out per point.  The output
@@ -405,15 +425,6 @@ def main():
                 "finite": bool(torch.isfinite(acc))}
             del ctx3, line3
 
-    # ---- BASELINE configs[3]: training step, 1024 segments x 1024 points per GPU (native train path; DDP over NCCL if N > 1)
-    if not args.no_extras and args.precision == "bf16":
-        del ctx
-        torch.cuda.empty_cache()
-        try:
-            extras["train_step"] = train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, max_over_ranks)
-        except torch.cuda.OutOfMemoryError:
-            extras["train_step"] = {"error": "out of memory"}
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -487,7 +498,7 @@ def main():
         "cpu_baseline": cpu_baseline,
     }
     line_out.update(extras)
-    print(json.dumps(line_out))
+    emit(line_out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -501,7 +512,7 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
     m.context_encoder.native_training = True
     net = m
     if world > 1:     # where train_dist.py:147 wraps the model in DistributedDataParallel: one flat gradient buffer, two
-        net = prb.FlatDataParallel(m)   # all-reduce slices over NCCL, the first overlapped with the encoder's backward
+        net = prb.FlatDataParallel(m, overlap=os.environ.get("LRN_FDP_OVERLAP", "1") != "0")   # all-reduce slices over NCCL, the first overlapped with the encoder's backward
     opt = lrn_optim.FlatAdam(m.parameters(), lr=1e-3)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     ctx = torch.randn(Bt, Nt, 4, device=dev, generator=g)
@@ -515,16 +526,22 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
         opt.step()
         return loss
 
-    for _ in range(2):
+    for _ in range(4):     # the caching allocator settles within a few steps (a training loop's steady state)
         one()
     barrier()
+    stats0 = torch.cuda.memory_stats(dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    steps = 5
+    steps = 8
     for _ in range(steps):
         loss = one()
     e1.record()
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    stats1 = torch.cuda.memory_stats(dev)
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
     allreduce_ms = None
     if world > 1:      # the gradient all-reduce alone: 9,695,954 fp32 = 38.8 MB (what DDP moves per step, train_dist.py:188)
@@ -539,12 +556,38 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
         a1.record()
         torch.cuda.synchronize()
         allreduce_ms = max_over_ranks(a0.elapsed_time(a1) / 5)
+    diag = None
+    if os.environ.get("LRN_BENCH_DIAG") == "1":     # where one more step's time goes (device busy vs collectives vs gaps)
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        per = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            one()
+            th = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            per.append((round(th * 1e3, 1), round((time.perf_counter() - t0) * 1e3, 1)))
+        print("train_step diag: rank", rank, "(host enqueue ms, step wall ms) x3:", per, file=sys.stderr, flush=True)
+        t0 = time.perf_counter()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            one()
+            torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ev = prof.key_averages()
+        top = sorted(ev, key=lambda e: -e.device_time_total)[:6]
+        diag = {"rank": rank, "wall_ms": wall * 1e3, "device_busy_ms": sum(e.device_time_total for e in ev) / 1e3,
+                "nccl_ms": sum(e.device_time_total for e in ev if "nccl" in e.key.lower()) / 1e3,
+                "top": [(e.key[:60], round(e.device_time_total / 1e3, 2), e.count) for e in top]}
+        print("train_step diag:", json.dumps(diag), file=sys.stderr, flush=True)
     peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     return {"workload": "1024 segments x 1024 points per GPU, LineRefineNet train step: forward + L1 deep supervision + backward + Adam "
                         "(BASELINE.json configs[3]); FlatDataParallel (flat gradient buffer, NCCL all-reduce) when n_gpus > 1",
             "ms_per_step": ms, "segments_per_sec": world * Bt / (ms * 1e-3), "n_gpus": world, "allreduce_ms": allreduce_ms,
             "loss": float(loss.detach()), "finite": bool(torch.isfinite(loss.detach())),
-            "bound_ms": TRAIN_BOUND_MS, "frac_of_bound_sustained": TRAIN_BOUND_MS["sustained"] / ms, "peak_mem_gb": peak_gb}
+            "bound_ms": TRAIN_BOUND_MS, "frac_of_bound_sustained": TRAIN_BOUND_MS["sustained"] / ms, "peak_mem_gb": peak_gb,
+            "steps": steps, "clocks": clocks,
+            "device_mallocs_in_timed_region": int(stats1.get("num_device_alloc", 0) - stats0.get("num_device_alloc", 0))}
 
 
 if __name__ == "__main__":
