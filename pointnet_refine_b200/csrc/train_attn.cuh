@@ -129,7 +129,7 @@ constexpr float kTaQScale = 0.17677669529663688f * 1.4426950408889634f;  // log2
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kTaFwdSmem = kTaTile + 4 * 2 * kTaTile + 4 * 34 * 32 * 4;
 
-__global__ void __launch_bounds__(128) train_attn_fwd_kernel(const TrainAttnParams p) {
+__global__ void __launch_bounds__(128, 3) train_attn_fwd_kernel(const TrainAttnParams p) {
   extern __shared__ __align__(16) uint8_t ta_smem[];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.x >> 3, h = blockIdx.x & 7;
