@@ -341,7 +341,7 @@ int lrn_train_attention_backward(const float* q, const void* k, int64_t ld_k, co
                                  int64_t ld_dv, float p_drop, uint64_t seed, lrn_stream_t stream);
 
 /* out[c] = sum over rows of the bf16 matrix A (rows, cols), row pitch ld: the bias gradient of a linear layer whose output
- * gradient is bf16 (cols % 64 == 0). */
+ * gradient is bf16 (cols % 64 == 0, ld % 8 == 0, A 16-byte aligned). */
 int lrn_col_sum_bf16(const void* A, int64_t ld, int64_t rows, int64_t cols, float* out, lrn_stream_t stream);
 
 /* src (B, H, N, 32) bf16 contiguous (the dK / dV of one cross-attention layer) -> column block `layer` of the

@@ -1035,7 +1035,7 @@ int pack_w(const float* src, int rows, int cols, void* dst, int64_t ld, bool tra
 
 // (column blocks of 64 channels, row slabs): enough blocks to fill the chip (~8 per SM) whatever C is
 dim3 stats_grid(int C, int64_t rows) {
-  const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (148 * 8) / (C / 64) + 1));
+  const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (148 * 8) / (C / 64) + 1));  // blocks walk 32 (or 8) rows per step
   return dim3(C / 64, unsigned(slabs));
 }
 
@@ -1484,7 +1484,8 @@ int lrn_train_attention_backward(const float* q, const void* k, int64_t ld_k, co
 
 int lrn_col_sum_bf16(const void* A, int64_t ld, int64_t rows, int64_t cols, float* out, lrn_stream_t stream) {
   if (!A || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
-  if (rows <= 0 || cols <= 0 || cols % 64 || ld < cols || ld % 2) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld cols=%lld ld=%lld (cols %% 64 == 0)", (long long)rows, (long long)cols, (long long)ld);
+  if (rows <= 0 || cols <= 0 || cols % 64 || ld < cols || ld % 8) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld cols=%lld ld=%lld (cols %% 64 == 0, ld %% 8 == 0)", (long long)rows, (long long)cols, (long long)ld);
+  if (reinterpret_cast<uintptr_t>(A) & 15) return fail(LRN_ERR_MISALIGNED, "A needs 16-byte alignment");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   LRN_CUDA(cudaMemsetAsync(out, 0, size_t(cols) * 4, s));
   col_stats_kernel<<<stats_grid(int(cols), rows), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(A), ld, rows, out, nullptr, 0);

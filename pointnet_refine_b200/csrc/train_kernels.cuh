@@ -58,44 +58,57 @@ train_embed_kernel(const float4* __restrict__ ctx, long long rows, const float* 
 // `shifted`: the sums are taken of (x - K_c) with the pivot K_c = A[0][c] (row 0 of the same column), so that the
 // variance E[(x-K)^2] - E[x-K]^2 formed from them does not cancel when |mean| >> std (the naive E[x^2] - mean^2 in
 // fp32 loses all digits there); bn_finalize_kernel adds the pivot back.
-// Block = 64 columns (32 bf16 pairs) x 8 row lanes, 4 independent loads in flight per thread; grid = (C / 64, row slabs).
+// Block = 64 columns as 8 channel groups of 8 (one 16-byte load per thread and row: 8 threads cover 128 contiguous bytes)
+// x 32 row lanes, two independent loads in flight per thread; grid = (C / 64, row slabs).  Requires a 16-byte aligned base
+// and a row pitch that is a multiple of 8 elements.
 __global__ void __launch_bounds__(256)
 col_stats_kernel(const __nv_bfloat16* __restrict__ A, long long ld, long long rows, float* __restrict__ sum,
                  float* __restrict__ sumsq, int shifted) {
-  const int cp = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
-  const int c = blockIdx.x * 64 + 2 * cp;
-  float2 piv = make_float2(0.f, 0.f);
-  if (shifted) piv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(A + c));
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  const long long stride = gridDim.y * 8ll;
-  long long r = blockIdx.y * 8ll + lane_r;
-  for (; r + 3 * stride < rows; r += 4 * stride) {
-    __nv_bfloat162 v[4];
+  const int cg = threadIdx.x & 7, lane_r = threadIdx.x >> 3;
+  const int c = blockIdx.x * 64 + 8 * cg;
+  float piv[8], s[8], q[8];
+  {
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (shifted) raw = *reinterpret_cast<const uint4*>(A + c);
+    const __nv_bfloat16* pv = reinterpret_cast<const __nv_bfloat16*>(&raw);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const __nv_bfloat162*>(A + (r + k * stride) * ld + c);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float2 f = __bfloat1622float2(v[k]);
-      f.x -= piv.x; f.y -= piv.y;
-      s0 += f.x; s1 += f.y;
-      q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+    for (int j = 0; j < 8; ++j) {
+      piv[j] = bf2f(pv[j]);
+      s[j] = q[j] = 0.f;
     }
   }
-  for (; r < rows; r += stride) {
-    float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(A + r * ld + c));
-    f.x -= piv.x; f.y -= piv.y;
-    s0 += f.x; s1 += f.y;
-    q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
-  }
-  __shared__ float sh[4][8][32];
-  sh[0][lane_r][cp] = s0; sh[1][lane_r][cp] = s1; sh[2][lane_r][cp] = q0; sh[3][lane_r][cp] = q1;
-  __syncthreads();
-  if (lane_r < 4) {  // warp w reduces quantity w over the 8 row lanes
-    float t = 0.f;
+  auto acc = [&](const uint4& raw) {
+    const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(&raw);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sh[lane_r][k][cp];
-    if (lane_r < 2) atomicAdd(sum + c + lane_r, t);
-    else if (sumsq) atomicAdd(sumsq + c + (lane_r - 2), t);
+    for (int j = 0; j < 8; ++j) {
+      const float f = bf2f(v[j]) - piv[j];
+      s[j] += f;
+      q[j] = fmaf(f, f, q[j]);
+    }
+  };
+  const long long stride = gridDim.y * 32ll;
+  long long r = blockIdx.y * 32ll + lane_r;
+  for (; r + stride < rows; r += 2 * stride) {
+    const uint4 v0 = *reinterpret_cast<const uint4*>(A + r * ld + c);
+    const uint4 v1 = *reinterpret_cast<const uint4*>(A + (r + stride) * ld + c);
+    acc(v0);
+    acc(v1);
+  }
+  if (r < rows) acc(*reinterpret_cast<const uint4*>(A + r * ld + c));
+  __shared__ float sh[2][32][65];   // [sum | sumsq][row lane][column of the block]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sh[0][lane_r][8 * cg + j] = s[j];
+    sh[1][lane_r][8 * cg + j] = q[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {  // threads 0..63: sums of the 64 columns, 64..127: sums of squares
+    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) t += sh[which][k][col];
+    if (which == 0) atomicAdd(sum + blockIdx.x * 64 + col, t);
+    else if (sumsq) atomicAdd(sumsq + blockIdx.x * 64 + col, t);
   }
 }
 

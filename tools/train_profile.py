@@ -24,5 +24,5 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 ev = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
 tot = sum(e.device_time_total for e in ev)
 print(f"total device time {tot/1e3:.1f} ms for {B}x{N}")
-for e in ev[:28]:
+for e in ev[:60]:
     print(f"{e.device_time_total/1e3:8.2f} ms {100*e.device_time_total/tot:5.1f}% x{e.count:<4d} {e.key[:100]}")
