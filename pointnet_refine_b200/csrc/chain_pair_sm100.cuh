@@ -329,12 +329,12 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
           ptx::mbar_wait(a4_ready, par);
           ptx::tc_fence_after();
           const bool stamp5 = p.dbg && cluster_id == 0 && lane == 0 && it == 1;
-          if (stamp5) p.dbg[64 + 8] = clock64();  // feat4 in TMEM
+          if (stamp5) p.dbg[128 + 8] = clock64();  // feat4 in TMEM
           for (int n = 0; n < 8; ++n) {
             const int b = n & 1, j = n >> 1;
             ptx::mbar_wait(&acc5_free[b], (j & 1) ^ 1);  // chunk n - 2 (or the previous tile's chunk 6 / 7) drained
             ptx::tc_fence_after();
-            if (stamp5) p.dbg[64 + 16 + n] = clock64();  // accumulator free
+            if (stamp5) p.dbg[128 + 16 + n] = clock64();  // accumulator free
             for (int kb2 = 0; kb2 < 4; ++kb2) {
               const int st = pb;
               pb = pb + 1 == W ? 0 : pb + 1;
@@ -353,7 +353,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
               }
               __syncwarp();
             }
-            if (stamp5) p.dbg[64 + n] = clock64();  // chunk n issued
+            if (stamp5) p.dbg[128 + n] = clock64();  // chunk n issued
           }
         }
         if (stamp) p.dbg[it * 8 + 1] = clock64();
@@ -478,7 +478,22 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         ptx::mbar_wait(&acc_full[c], 1);
         ptx::tc_fence_after();
         uint32_t keep[64];
-        chain_drain_keep<4>(t_lane + 256 * c + 128 * sub, 128 * sub, sconst + L::kB4 + 256 * c, c == 0 ? sF2 : sF3, rr, keep);
+        if (c == 0) {
+          chain_drain_keep<4>(t_lane + 128 * sub, 128 * sub, sconst + L::kB4, sF2, rr, keep);
+        } else {
+          // Drain in two halves: in between, feat4 chunk 0's store (staged in F2 + Z, committed at the end of the c = 0
+          // pass) has long been read, so the issuer can hand those four blocks to the weight producer NOW - conv5's
+          // borrowed weight stages are then in flight ~1.5k cycles before feat4 is complete instead of after it (the
+          // first conv5 chunk used to wait ~2.9k cycles for its fourth weight stage).
+          uint32_t (&lo)[32] = reinterpret_cast<uint32_t(&)[32]>(keep[0]);
+          uint32_t (&hi)[32] = reinterpret_cast<uint32_t(&)[32]>(keep[32]);
+          chain_drain_keep<2>(t_lane + 256 + 128 * sub, 128 * sub, sconst + L::kB4 + 256, sF3, rr, lo);
+          if (issuer) {
+            ptx::bulk_wait_read_all();
+            ptx::mbar_arrive(fz_free);
+          }
+          chain_drain_keep<2>(t_lane + 256 + 128 * sub + 64, 128 * sub + 64, sconst + L::kB4 + 256, sF3, rr, hi);
+        }
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         __syncwarp();
@@ -500,10 +515,6 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(a4_ready), 0));
-            if (issuer) {  // feat4 chunk 0's store (staged in F2 + Z) has been read: the blocks may take conv5 weights
-              ptx::bulk_wait_read_keep<1>();
-              ptx::mbar_arrive(fz_free);
-            }
           }
         }
       }
@@ -517,10 +528,10 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
           // but the most recent group (chunk n - 1) must have been read
           staging_free(n == 0 ? 0 : 1);
           const bool stamp5 = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it == 1;
-          if (stamp5) p.dbg[64 + 24 + n] = clock64();  // staging free
+          if (stamp5) p.dbg[128 + 24 + n] = clock64();  // staging free
           ptx::mbar_wait(&acc5_full[b], j & 1);
           ptx::tc_fence_after();
-          if (stamp5) p.dbg[64 + 32 + n] = clock64();  // accumulator ready
+          if (stamp5) p.dbg[128 + 32 + n] = clock64();  // accumulator ready
           chain_drain<2>(t_lane + 256 + 128 * b + 64 * sub, 64 * sub, sconst + L::kB5 + 128 * n, sF3 + 2 * b * kChainBlock, rr);
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
@@ -533,7 +544,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
               store_blk(smem + L::kF3 + (2 * b + bb) * kChainBlock, 960 + 128 * n + 64 * bb, row0);
             ptx::bulk_commit();
           }
-          if (stamp5) p.dbg[64 + 40 + n] = clock64();  // drained, stores issued
+          if (stamp5) p.dbg[128 + 40 + n] = clock64();  // drained, stores issued
         }
       }
       if (stamp) p.dbg[it * 8 + 7] = clock64();  // conv4 drained
