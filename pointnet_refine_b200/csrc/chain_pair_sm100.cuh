@@ -81,10 +81,11 @@ __device__ __forceinline__ void stage_packed_chunk(uint32_t blocks, int rr, int 
   for (int t = 0; t < 4; ++t)
     ptx::st_shared_v4(blk + (((cbase + t) ^ (rr & 7)) << 4), pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
 }
-__device__ __forceinline__ void stage_row_chunk(uint32_t blocks, int rr, int c0, const float (&v)[32]) {
+// ... of relu(v): the clamp is part of the conversion (cvt.rn.relu.bf16x2)
+__device__ __forceinline__ void stage_row_chunk_relu(uint32_t blocks, int rr, int c0, const float (&v)[32]) {
   uint32_t pk[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
   stage_packed_chunk(blocks, rr, c0, pk);
 }
 
@@ -104,8 +105,8 @@ __device__ __forceinline__ void chain_drain_keep(uint32_t t_addr, int col_lo, co
     if (i + 1 < NCHUNKS) ptx::tmem_ld_32x32b_x32(t_addr + 32 * (i + 1), r[(i + 1) & 1]);
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      keep[16 * i + j] = ptx::pack_bf16x2(fmaxf(__uint_as_float(r[i & 1][2 * j]) + bias[c0 + 2 * j], 0.f),
-                                          fmaxf(__uint_as_float(r[i & 1][2 * j + 1]) + bias[c0 + 2 * j + 1], 0.f));
+      keep[16 * i + j] = ptx::pack_bf16x2_relu(__uint_as_float(r[i & 1][2 * j]) + bias[c0 + 2 * j],
+                                               __uint_as_float(r[i & 1][2 * j + 1]) + bias[c0 + 2 * j + 1]);
     stage_packed_chunk(sblocks, rr, c0, &keep[16 * i]);
   }
 }
@@ -119,10 +120,11 @@ __device__ __forceinline__ void chain_drain(uint32_t t_addr, int col_lo, const f
     const int c0 = col_lo + 32 * i;
     ptx::tmem_ld_wait();
     if (i + 1 < NCHUNKS) ptx::tmem_ld_32x32b_x32(t_addr + 32 * (i + 1), r[(i + 1) & 1]);
-    float v[32];
+    uint32_t pk[16];   // bias + ReLU + bf16 rounding: one FADD per value, one cvt.rn.relu.bf16x2 per pair
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[i & 1][j]) + bias[c0 + j], 0.f);
-    stage_row_chunk(sblocks, rr, c0, v);
+    for (int j = 0; j < 16; ++j)
+      pk[j] = ptx::pack_bf16x2_relu(__uint_as_float(r[i & 1][2 * j]) + bias[c0 + 2 * j], __uint_as_float(r[i & 1][2 * j + 1]) + bias[c0 + 2 * j + 1]);
+    stage_packed_chunk(sblocks, rr, c0, pk);
   }
 }
 
@@ -385,28 +387,30 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       }
       ptx::named_bar_sync(1, 32 * kPairEpiWarps);
     };
-    // conv1 (sub 0) / gate layer 1 (sub 1) for one tile: raw point -> 64 bf16 channels of block F1 / GH
-    auto embed = [&](int tile) {
+    // conv1 and gate layer 1 for one tile: raw point -> 64 + 64 bf16 channels of blocks F1 / GH (each warp group: half of both)
+    // this thread's raw point of a tile (requested a whole tile ahead: a DRAM round trip is ~1k cycles)
+    auto load_point = [&](int tile) {
+      const int grow = tile * 2 * BM + static_cast<int>(rank) * BM + rr;
+      return tile < p.num_tiles && grow < p.M ? __ldg(p.ctx + grow) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto embed = [&](int tile, const float4 x) {
       const int row0 = tile * 2 * BM + static_cast<int>(rank) * BM;
       staging_free(4);  // F1GH(t) was followed by f4c0(t-1) f4c1(t-1) F2(t) F3(t)
-      const int grow = row0 + rr;
-      const float4 x = grow < p.M ? __ldg(p.ctx + grow) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      {
+        // both warp groups do half of each: channels [32 sub, 32 sub + 32) of conv1 (4 FMA per channel) and of the gate's
+        // first layer (1 FMA per channel) - conv1 on one group and the gate on the other left the conv1 warps 4x longer
+        const int h = sub;
         float v[32];
-        if (sub == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float4 w = reinterpret_cast<const float4*>(sconst + L::kW1)[32 * h + j];
-            v[j] = fmaxf(fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, sconst[L::kB1 + 32 * h + j])))), 0.f);
-          }
-          stage_row_chunk(sF1, rr, 32 * h, v);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = fmaxf(fmaf(sconst[L::kWg1 + 32 * h + j], x.w, sconst[L::kBg1 + 32 * h + j]), 0.f);
-          stage_row_chunk(sGH, rr, 32 * h, v);
+        for (int j = 0; j < 32; ++j) {
+          const float4 w = reinterpret_cast<const float4*>(sconst + L::kW1)[32 * h + j];
+          v[j] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, sconst[L::kB1 + 32 * h + j]))));
         }
+        stage_row_chunk_relu(sF1, rr, 32 * h, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = fmaf(sconst[L::kWg1 + 32 * h + j], x.w, sconst[L::kBg1 + 32 * h + j]);
+        stage_row_chunk_relu(sGH, rr, 32 * h, v);
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
@@ -420,9 +424,10 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     };
 
     int it = 0;
-    if (cluster_id < p.num_tiles) embed(cluster_id);
+    if (cluster_id < p.num_tiles) embed(cluster_id, load_point(cluster_id));
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
       const int row0 = tile * 2 * BM + static_cast<int>(rank) * BM;
+      const float4 x_next = load_point(tile + num_clusters);
       // ---- conv2 epilogue: buf0[0:128) -> F2 (2 blocks); this warp: columns [64 sub, 64 sub + 64)
       const bool stamp = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it < 16;
       // F2 doubled as staging in the previous tile: feat4 chunk 0 (then only f4c1), or conv5 chunk 2 (then only chunk 3)
@@ -467,7 +472,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       if (stamp) p.dbg[it * 8 + 5] = clock64();  // conv3 drained, F3 stores issued
       // ---- next tile's conv1 while conv4 chunk 0 runs (F1 / GH are free: conv2 of this tile has completed)
       const bool has_next = tile + num_clusters < p.num_tiles;
-      if (has_next) embed(tile + num_clusters);
+      if (has_next) embed(tile + num_clusters, x_next);
       if (stamp) p.dbg[it * 8 + 6] = clock64();  // next tile's conv1 done
       // ---- conv4 epilogues: feat4 channels [256 c + 128 sub, +128) -> staging blocks -> operand row columns 448 + ...
       //      chunk 0 is staged in F2 + Z (conv3 of this tile is done with F2), chunk 1 in F3 (all of conv4 has

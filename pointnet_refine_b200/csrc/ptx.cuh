@@ -303,6 +303,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// max(x, 0) and the bf16 rounding of two values in ONE instruction (ReLU epilogues: saves the two FMNMX)
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // fp32 -> TF32 with round-to-nearest (the tensor core itself just drops the low 13 mantissa bits).
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
