@@ -396,6 +396,37 @@ def main():
                                "segment_alone_mean_abs_diff": float((alone[0, 1024:] - g5[7, 1024:]).abs().max())}}
                 del c5, g5
 
+            # ---- the other arithmetic tiers on a slice of the same batch (rank 0): tf32 (1e-3 max-abs) and fp32x3 (3 x TF32
+            #      split, reproduces the reference's max-pool argmax); roofline against the measured cuBLAS tf32 peak
+            if rank == 0:
+                peaks_t, _ = load_peaks()
+                tf32_pk, tf32_src = tf32_peak(peaks_t)
+                tiers = {}
+                bt = min(B, 592)
+                for tier, passes in (("tf32", 1), ("fp32x3", 3)):
+                    model.precision = tier
+                    enc.run_native(ctx[:bt], pool=True)
+                    torch.cuda.synchronize()
+                    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    f0.record()
+                    for _ in range(2):
+                        gft = enc.run_native(ctx[:bt], pool=True)["global_feat"]
+                    f1.record()
+                    torch.cuda.synchronize()
+                    tt = f0.elapsed_time(f1) / 2 * 1e-3
+                    tiers[tier] = {"segments": bt, "segments_per_sec": bt / tt, "points_per_sec": bt * N / tt,
+                                   "tensor_tflops": passes * FLOP_PER_POINT_ENCODER * bt * N / tt / 1e12,
+                                   "frac_of_tf32_peak": passes * FLOP_PER_POINT_ENCODER * bt * N / tt / 1e12 / tf32_pk,
+                                   "finite": bool(torch.isfinite(gft).all())}
+                tiers["tf32_peak_tflops"] = tf32_pk
+                tiers["tf32_peak_source"] = tf32_src
+                tiers["note"] = ("encoder + pooling; tensor_tflops counts the tensor-core passes actually issued (fp32x3: three "
+                                 "TF32 passes per k-block)")
+                extras["tiers"] = tiers
+                model.precision = args.precision
+                del gft
+                torch.cuda.empty_cache()
+
             # ---- BASELINE configs[2]: 1M segments x 2048 points over the ranks (strong scaling): every rank pushes a sample of
             #      its shard through the whole forward; inputs are generated on the device chunk by chunk
             total_seg, pts3 = 1_000_000, 2048
