@@ -100,6 +100,12 @@ class MultiScalePointNetEncoder(nn.Module):
             self._folded = (fp, ops.FoldedEncoder(tensors, self.precision, bn_eps=self.bn1.eps))
         return self._folded[1]
 
+    def invalidate(self):
+        """Drop the folded-weight cache.  The cache is keyed on (data_ptr, _version) of every parameter and buffer, which
+        catches optimizer steps, load_state_dict and .to(); an in-place edit THROUGH `.data` (p.data.copy_(ema),
+        p.data.mul_(...)) does not bump `_version` - call this (or LineRefineNet.invalidate()) after such an edit."""
+        self._folded = None
+
     # -- forward ---------------------------------------------------------------------------------
     def run_native(self, context, **outputs):
         """context (B,N,4) -> dict of requested outputs (see ops.encoder_forward)."""
@@ -193,6 +199,14 @@ class LineRefineNet(nn.Module):
         self.fast_decoder = os.environ.get("LRN_FAST_DECODER", "1") != "0"   # bf16 tier: context side on the tensor cores
         self.ctx_attention = os.environ.get("LRN_CTX_ATTN", "1") != "0"      # ... folded-query attention kernel (else K/V GEMMs + SDPA)
         self._kv_cache = None
+
+    def invalidate(self):
+        """Drop every prepared-weight cache (encoder fold, folded attention weights, point_mlp fold, K / V copies, TF32
+        copies): needed only after in-place parameter edits through `.data`, which the (data_ptr, _version) fingerprints
+        cannot see; optimizer steps, load_state_dict and .to() are detected automatically."""
+        self.context_encoder.invalidate()
+        self._kv_cache = self._attn_cache = self._pm_cache = None
+        self.__dict__.pop("_w32_cache", None)
 
     @property
     def precision(self):

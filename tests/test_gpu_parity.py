@@ -429,6 +429,24 @@ def test_refold_after_parameter_update(dev):
     assert np.abs(b.cpu().numpy() - o).max() <= 1e-3 * max(1.0, np.abs(o).max())
 
 
+def test_invalidate_after_data_edit(dev):
+    """In-place edits through `.data` do not bump `_version`: the caches keep the old weights until invalidate()."""
+    sd = synth.make_state_dict(5)
+    m = _model(sd, dev, "bf16")
+    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(2, 300, seed=8))
+    with torch.no_grad():
+        a = m(ctx, line).clone()
+        for p in m.parameters():
+            p.data.mul_(1.01)
+        m.invalidate()
+        b = m(ctx, line)
+        m2 = _model({k: (v * 1.01 if v.dtype.kind == "f" and not k.endswith(("running_mean", "running_var")) else v) for k, v in sd.items()},
+                    dev, "bf16")
+        c = m2(ctx, line)
+    assert float((a - b).abs().max()) > 0
+    assert torch.equal(b, c)
+
+
 def test_host_pipeline_matches_direct_call(dev):
     """Chunked, copy/compute-overlapped host streaming returns exactly what one direct call returns."""
     from pointnet_refine_b200.stream import HostEncoderPipeline
