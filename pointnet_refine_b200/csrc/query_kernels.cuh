@@ -150,9 +150,15 @@ self_attn32_kernel(const float* __restrict__ qk, const float* __restrict__ v, fl
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float acc = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four independent chains: one segment per block is latency-bound
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc = fmaf(q[c], ks[j * 33 + c], acc);
+      for (int c = 0; c < 32; c += 4) {
+        a0 = fmaf(q[c], ks[j * 33 + c], a0);
+        a1 = fmaf(q[c + 1], ks[j * 33 + c + 1], a1);
+        a2 = fmaf(q[c + 2], ks[j * 33 + c + 2], a2);
+        a3 = fmaf(q[c + 3], ks[j * 33 + c + 3], a3);
+      }
+      const float acc = (a0 + a1) + (a2 + a3);
       s[j] = acc;
       m = fmaxf(m, acc);
     }
