@@ -25,7 +25,8 @@
 
 namespace lrn {
 
-constexpr int kAttnThreads = 192;  // warp 0 TMA, warp 1 MMA / TMEM alloc, warps 2..5 softmax (one TMEM lane per thread)
+constexpr int kAttnThreads = 320;  // warp 0 TMA, warp 1 MMA / TMEM alloc, warps 2..9 softmax: two warps per TMEM lane quarter,
+                                   // each thread = one folded query x one half (64 points) of the step
 constexpr int kAttnStep = 128;     // points per step
 
 struct AttnSmem {
@@ -33,7 +34,8 @@ struct AttnSmem {
   static constexpr uint32_t kKp = kQ + 65536;         // 2 stages x 4 k-blocks x [64 points x 128 B]
   static constexpr uint32_t kV = kKp + 2 * 32768;     // 2 stages x 2 point-blocks x 2 dim-blocks x [64 points x 128 B]
   static constexpr uint32_t kScratch = kV + 2 * 32768;  // 4 warps x [32][33] floats (output transpose)
-  static constexpr uint32_t kBar = kScratch + 4 * 32 * 33 * 4;
+  static constexpr uint32_t kXchg = kScratch + 4 * 32 * 33 * 4;   // [2 halves][128 queries] floats: row maximum / row sum exchange
+  static constexpr uint32_t kBar = kXchg + 2 * 128 * 4;
   static constexpr uint32_t kTmemPtr = kBar + 16 * 8;
   static constexpr uint32_t kDynamic = kTmemPtr + 16 + 1024;
 };
@@ -93,7 +95,7 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::mbar_init(&kp_full[i], 1);
       ptx::mbar_init(&v_full[i], 1);
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&p_ready[i], 8);
+      ptx::mbar_init(&p_ready[i], 16);
       ptx::mbar_init(&o_done[i], 1);
     }
     ptx::fence_mbar_init();
@@ -203,10 +205,20 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax warps (both CTAs): thread = folded query
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ softmax warps (both CTAs)
+    // Two warps share a TMEM lane quarter (32 folded queries): warp `half` owns points [64 half, 64 half + 64) of every
+    // step, loads its 64 scores with two tensor-memory loads in flight and ONE wait, and works from registers.  (The first
+    // version - one warp per quarter, eight serialised load / wait round trips per step - made the softmax the limiter:
+    // 4.6k cycles per step against 2k of tensor work, 3.6 TB/s.  Now the kernel reads Kp / Mem at 5.2 TB/s, 0.79 of the
+    // measured copy bandwidth: HBM-bound for its 1 KB per point and layer.)
+    // The row maximum is exchanged through shared memory (one 64-thread named barrier per step); each warp keeps its own
+    // partial row sum, added up once per item.
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which 64 of the step's 128 points
+    const int row = q * 32 + lane;     // folded query of this thread within the CTA's 128
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t ready_leader[2] = {ptx::mapa(ptx::smem_u32(&p_ready[0]), 0), ptx::mapa(ptx::smem_u32(&p_ready[1]), 0)};
+    float* xchg = reinterpret_cast<float*>(smem + L::kXchg);
     int g0 = 0;
     for (int item = cluster_id; item < p.items; item += num_clusters) {
       const int step0 = item_step0(item), steps = item_steps(item);
@@ -215,27 +227,38 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int g = g0 + j;
         const int st = g & 1;
         const uint32_t t_s = t_lane + st * 128;
-        const int valid = min(kAttnStep, p.N - (step0 + j) * kAttnStep);
+        const int valid = min(kAttnStep, p.N - (step0 + j) * kAttnStep) - 64 * half;  // valid points of this half (may be <= 0)
         ptx::mbar_wait(&s_full[st], (g >> 1) & 1);
         ptx::tc_fence_after();
-        // pass 1: maximum of this row over the step's points
-        float m_t = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(t_s + 32 * c, r);
-          ptx::tmem_ld_wait();
-          if (valid >= 32 * c + 32) {
+        // this thread's 64 scores: two loads in flight, one wait; everything below works from registers
+        uint32_t sr[64];
+        ptx::tmem_ld_32x32b_x32(t_s + 64 * half, reinterpret_cast<uint32_t(&)[32]>(sr[0]));
+        ptx::tmem_ld_32x32b_x32(t_s + 64 * half + 32, reinterpret_cast<uint32_t(&)[32]>(sr[32]));
+        ptx::tmem_ld_wait();
+        if (valid < 64) {  // last step of a ragged segment: points past N never win the maximum and get p = 0
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m_t = fmaxf(m_t, __uint_as_float(r[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (32 * c + i < valid) m_t = fmaxf(m_t, __uint_as_float(r[i]));
-          }
+          for (int i = 0; i < 64; ++i)
+            if (i >= valid) sr[i] = 0xff800000u;
         }
+        float m_t;
+        {
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(sr[i]));
+            m1 = fmaxf(m1, __uint_as_float(sr[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(sr[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(sr[i + 3]));
+          }
+          m_t = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        }
+        xchg[half * 128 + row] = m_t;
+        ptx::named_bar_sync(1 + q, 64);
+        m_t = fmaxf(m_t, xchg[(half ^ 1) * 128 + row]);
+        ptx::named_bar_sync(1 + q, 64);   // both warps have read before the next step overwrites
         // Lazy rescale: the reference maximum only moves when the row maximum grew by more than 2^8 (p <= 256 stays
-        // exact enough in bf16 / fp32); then this row of O and its running sum are scaled down once.
+        // exact enough in bf16 / fp32); then this row of O and its running sum are scaled down once.  Both warps of a
+        // quarter see the same m_t / m_ref and take the same decision; each rescales half of the 256 output columns.
         const bool grow = m_t > m_ref + 8.f;
         if (j == 0) {
           m_ref = m_t;
@@ -244,7 +267,7 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ptx::mbar_wait(&o_done[st ^ 1], ((g - 1) >> 1) & 1);  // O_{j-1} has been accumulated
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 4 * half; c < 4 * half + 4; ++c) {
             uint32_t r[32];
             ptx::tmem_ld_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
             ptx::tmem_ld_wait();
@@ -255,67 +278,68 @@ ctx_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           l_sum *= f;
           if (grow) m_ref = m_t;
         }
-        // pass 2: P = exp2(S - m_ref) as bf16 pairs over the first 64 columns of the same buffer (writes trail reads)
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          uint32_t a[32], b[32], o[32];
-          ptx::tmem_ld_32x32b_x32(t_s + 64 * h, a);
-          ptx::tmem_ld_32x32b_x32(t_s + 64 * h + 32, b);
-          ptx::tmem_ld_wait();
-          const int c0 = 64 * h;
+        // P = exp2(S - m_ref) as bf16 pairs: packed column c of the S buffer = points 2c, 2c + 1; this warp writes packed
+        // columns [32 half, 32 half + 32).  (The other warp's scores in those columns are already in ITS registers: the
+        // second named barrier above comes after both warps' loads.)
+        {
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+          uint32_t o[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float e0 = ex2_approx(__uint_as_float(a[2 * i]) - m_ref), e1 = ex2_approx(__uint_as_float(a[2 * i + 1]) - m_ref);
-            float e2 = ex2_approx(__uint_as_float(b[2 * i]) - m_ref), e3 = ex2_approx(__uint_as_float(b[2 * i + 1]) - m_ref);
-            if (valid < kAttnStep) {
-              if (c0 + 2 * i >= valid) e0 = 0.f;
-              if (c0 + 2 * i + 1 >= valid) e1 = 0.f;
-              if (c0 + 32 + 2 * i >= valid) e2 = 0.f;
-              if (c0 + 32 + 2 * i + 1 >= valid) e3 = 0.f;
-            }
-            l_sum += (e0 + e1) + (e2 + e3);
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = ex2_approx(__uint_as_float(sr[2 * i]) - m_ref), e1 = ex2_approx(__uint_as_float(sr[2 * i + 1]) - m_ref);
+            const float e2 = ex2_approx(__uint_as_float(sr[2 * i + 2]) - m_ref), e3 = ex2_approx(__uint_as_float(sr[2 * i + 3]) - m_ref);
+            l0 += e0; l1 += e1; l2 += e2; l3 += e3;
             o[i] = ptx::pack_bf16x2(e0, e1);
-            o[16 + i] = ptx::pack_bf16x2(e2, e3);
+            o[i + 1] = ptx::pack_bf16x2(e2, e3);
           }
-          ptx::tmem_st_32x32b_x32(t_s + 32 * h, o);
+          ptx::tmem_st_32x32b_x32(t_s + 32 * half, o);
+          l_sum += (l0 + l1) + (l2 + l3);
         }
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(ready_leader[st]);
       }
-      // ---- epilogue: O / l -> global (through a per-warp transpose so that rows are written 128 B at a time)
+      // ---- epilogue: O / l -> global (through a per-warp transpose so that rows are written 128 B at a time); the two
+      //      warps of a quarter add their partial row sums and take four of the eight 32-column chunks each
       {
         const int last = g0 + steps - 1;
+        xchg[half * 128 + row] = l_sum;
+        ptx::named_bar_sync(1 + q, 64);
+        l_sum += xchg[(half ^ 1) * 128 + row];
+        ptx::named_bar_sync(1 + q, 64);
         ptx::mbar_wait(&o_done[last & 1], (last >> 1) & 1);
         ptx::tc_fence_after();
         const float inv = 1.f / l_sum;
-        float* scratch = reinterpret_cast<float*>(smem + L::kScratch) + (warp - 2) * 32 * 33;
+        float* scratch = reinterpret_cast<float*>(smem + L::kScratch) + q * 32 * 33;   // shared by the two warps of a quarter, in turn
         const int64_t out_row0 = (static_cast<int64_t>(item) * 256 + rank * 128 + q * 32);
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
-          ptx::tmem_ld_wait();
+          if ((c >> 2) == half) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tmem_o + (static_cast<uint32_t>(q * 32) << 16) + 32 * c, r);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = __uint_as_float(r[i]) * inv;
-          __syncwarp();
-          if (p.out_bf16) {  // two rows per instruction, 16 lanes x bf16 pair = 64 contiguous bytes per row
-            uint32_t* o16 = reinterpret_cast<uint32_t*>(p.out);
-            const int half = lane >> 4, l = lane & 15;
+            for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = __uint_as_float(r[i]) * inv;
+            __syncwarp();
+            if (p.out_bf16) {  // two rows per instruction, 16 lanes x bf16 pair = 64 contiguous bytes per row
+              uint32_t* o16 = reinterpret_cast<uint32_t*>(p.out);
+              const int hh = lane >> 4, l = lane & 15;
 #pragma unroll 4
-            for (int rr = 0; rr < 32; rr += 2) {
-              const float* src = scratch + (rr + half) * 33 + 2 * l;
-              o16[((out_row0 + rr + half) * 256 + 32 * c) / 2 + l] = ptx::pack_bf16x2(src[0], src[1]);
+              for (int rr = 0; rr < 32; rr += 2) {
+                const float* src = scratch + (rr + hh) * 33 + 2 * l;
+                o16[((out_row0 + rr + hh) * 256 + 32 * c) / 2 + l] = ptx::pack_bf16x2(src[0], src[1]);
+              }
+            } else {
+              float* o32 = reinterpret_cast<float*>(p.out);
+#pragma unroll 4
+              for (int rr = 0; rr < 32; ++rr) o32[(out_row0 + rr) * 256 + 32 * c + lane] = scratch[rr * 33 + lane];
             }
-          } else {
-            float* o32 = reinterpret_cast<float*>(p.out);
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) o32[(out_row0 + rr) * 256 + 32 * c + lane] = scratch[rr * 33 + lane];
+            __syncwarp();
           }
-          __syncwarp();
+          if (c == 3) ptx::named_bar_sync(1 + q, 64);   // hand the quarter's scratch from warp `half 0` to warp `half 1`
         }
-        p.lse[out_row0 + lane] = m_ref + log2f(l_sum);
+        if (half == 0) p.lse[out_row0 + lane] = m_ref + log2f(l_sum);
       }
       g0 += steps;
     }
