@@ -498,7 +498,7 @@ class LineRefineNet(nn.Module):
         tc = rows >= 256 and rows % 64 == 0   # query-side linears on the bf16 tensor-core path (fwd, dgrad, wgrad)
 
         def lin(x, w, b):
-            return linear_bf16(x, w, b).float() if tc else F.linear(x, w, b)
+            return linear_bf16(x, w, b, torch.float32) if tc else F.linear(x, w, b)
 
         pe0, pe2 = self.pos_emb.mlp[0], self.pos_emb.mlp[2]
         tgt = self.point_mlp(noisy_line.transpose(2, 1)).transpose(2, 1)

@@ -178,14 +178,14 @@ class LinearBf16Fn(torch.autograd.Function):
     split-K).  x (P, K) any float dtype, W (N, K) fp32, b (N) fp32; K % 64 == 0, N % 128 == 0.  Output bf16."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, out_dtype=torch.bfloat16):
         from . import ops
         xb = x.detach().to(torch.bfloat16).contiguous()
         wb = weight.detach().to(torch.bfloat16).contiguous()
         ctx.save_for_backward(xb, wb)
         ctx.needs = (x.requires_grad, weight.requires_grad, bias is not None and bias.requires_grad)
         ctx.x_dtype = x.dtype
-        return ops.gemm_bias_act(xb, wb, bias.detach() if bias is not None else None, out_dtype=torch.bfloat16)
+        return ops.gemm_bias_act(xb, wb, bias.detach() if bias is not None else None, out_dtype=out_dtype)
 
     @staticmethod
     def backward(ctx, dy):
@@ -200,7 +200,7 @@ class LinearBf16Fn(torch.autograd.Function):
             dw = ops.gemm_tn(dyb, xb)
         if need_b:
             db = _col_sum(dyb)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class KVGradShare:
@@ -415,8 +415,10 @@ def add_layernorm(x, y, norm: torch.nn.LayerNorm):
     return AddLayerNormFn.apply(x, y, norm.weight, norm.bias, norm.eps)
 
 
-def linear_bf16(x, weight, bias):
-    """Differentiable bf16 tensor-core linear layer over the last dimension of x (leading dims flattened)."""
+def linear_bf16(x, weight, bias, out_dtype=torch.bfloat16):
+    """Differentiable bf16 tensor-core linear layer over the last dimension of x (leading dims flattened); the result is
+    bf16, or fp32 written straight from the accumulators (out_dtype=torch.float32: no conversion pass for consumers that
+    want fp32, e.g. the residual + LayerNorm kernels)."""
     lead = x.shape[:-1]
-    y = LinearBf16Fn.apply(x.reshape(-1, x.shape[-1]), weight, bias)
+    y = LinearBf16Fn.apply(x.reshape(-1, x.shape[-1]), weight, bias, out_dtype)
     return y.view(*lead, weight.shape[0])
