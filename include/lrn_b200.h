@@ -157,8 +157,9 @@ enum lrn_stage {
   LRN_STAGE_COUNT = 7
 };
 int lrn_profile_enable(int on);
-/* Tuning aid: while `device_buffer` (>= 256 int64, zeroed by the caller) is non-null, cluster 0 of the
- * fusion kernel records clock64() stamps of its first 16 tiles there (see tools/timeline.py). */
+/* Tuning aid, only in the -DLRN_TIMELINE build (python pointnet_refine_b200/build.py --timeline; the product library
+ * contains no timing code and returns LRN_ERR_BAD_ARG here): while `device_buffer` (>= 256 int64, zeroed by the caller) is
+ * non-null, cluster 0 of the fusion / chain kernel records clock64() stamps of its first 16 tiles there (tools/timeline.py). */
 int lrn_debug_timeline(long long* device_buffer);
 int lrn_profile_read(float* ms_per_stage /*[LRN_STAGE_COUNT]*/, int64_t* launches_per_stage /*[LRN_STAGE_COUNT]*/);
 

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblrn_b200.so")
+# LRN_B200_LIB selects another build of the same ABI (tools/timeline.py: the -DLRN_TIMELINE tuning variant)
+LIB_PATH = os.environ.get("LRN_B200_LIB") or os.path.join(_HERE, "liblrn_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "lrn_b200.h")
 

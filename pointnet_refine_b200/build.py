@@ -15,16 +15,20 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+TIMELINE_LIB_PATH = os.path.join(HERE, "liblrn_b200_timeline.so")   # tuning variant with clock64() stamps (tools/timeline.py)
+
+
+def build(force: bool = False, verbose: bool = False, timeline: bool = False) -> str:
+    out = TIMELINE_LIB_PATH if timeline else LIB_PATH
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [HEADER]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs):
-        return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "lrn_abi.cu")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(s) <= os.path.getmtime(out) for s in srcs):
+        return out
+    cmd = ["nvcc", *NVCC_FLAGS, *(["-DLRN_TIMELINE"] if timeline else []), "-o", out, os.path.join(CSRC, "lrn_abi.cu")]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, timeline="--timeline" in sys.argv))

@@ -301,7 +301,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
         const uint32_t par = it & 1;
         const bool stamp = p.dbg && cluster_id == 0 && lane == 0 && it < 16;
-        if (stamp) p.dbg[it * 8 + 0] = clock64();
+        LRN_STAMP(stamp, p.dbg, it * 8 + 0);
         // Barrier bookkeeping.  The conv4 chunks are not handed back through acc_free (buf0 becomes conv5's A operand,
         // buf1 its accumulators): acc_free completes once per tile, and the buffers are reusable once the tensor pipe
         // (in order) is past conv5 and acc5_free says the last conv5 chunks have been drained.
@@ -331,12 +331,12 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
           ptx::mbar_wait(a4_ready, par);
           ptx::tc_fence_after();
           const bool stamp5 = p.dbg && cluster_id == 0 && lane == 0 && it == 1;
-          if (stamp5) p.dbg[128 + 8] = clock64();  // feat4 in TMEM
+          LRN_STAMP(stamp5, p.dbg, 128 + 8);  // feat4 in TMEM
           for (int n = 0; n < 8; ++n) {
             const int b = n & 1, j = n >> 1;
             ptx::mbar_wait(&acc5_free[b], (j & 1) ^ 1);  // chunk n - 2 (or the previous tile's chunk 6 / 7) drained
             ptx::tc_fence_after();
-            if (stamp5) p.dbg[128 + 16 + n] = clock64();  // accumulator free
+            LRN_STAMP(stamp5, p.dbg, 128 + 16 + n);  // accumulator free
             for (int kb2 = 0; kb2 < 4; ++kb2) {
               const int st = pb;
               pb = pb + 1 == W ? 0 : pb + 1;
@@ -355,10 +355,10 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
               }
               __syncwarp();
             }
-            if (stamp5) p.dbg[128 + n] = clock64();  // chunk n issued
+            LRN_STAMP(stamp5, p.dbg, 128 + n);  // chunk n issued
           }
         }
-        if (stamp) p.dbg[it * 8 + 1] = clock64();
+        LRN_STAMP(stamp, p.dbg, it * 8 + 1);
       }
     }
   } else {
@@ -434,7 +434,7 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       staging_free(1);
       ptx::mbar_wait(&acc_full[0], 0);
       ptx::tc_fence_after();
-      if (stamp) p.dbg[it * 8 + 2] = clock64();  // conv2 accumulator ready
+      LRN_STAMP(stamp, p.dbg, it * 8 + 2);  // conv2 accumulator ready
       chain_drain<2>(t_lane + 64 * sub, 64 * sub, sconst + L::kB2, sF2, rr);
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
@@ -449,12 +449,12 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         store_blk(smem + L::kF2 + kChainBlock, 128, row0);
         ptx::bulk_commit();
       }
-      if (stamp) p.dbg[it * 8 + 3] = clock64();  // conv2 drained, F2 stores issued
+      LRN_STAMP(stamp, p.dbg, it * 8 + 3);  // conv2 drained, F2 stores issued
       // ---- conv3 epilogue: buf1 -> F3 (4 blocks); this warp: columns [128 sub, 128 sub + 128)
       staging_free(1);  // F3 doubled as feat4 staging of the previous tile: f4c1(t-1), then only F2(t)
       ptx::mbar_wait(&acc_full[1], 0);
       ptx::tc_fence_after();
-      if (stamp) p.dbg[it * 8 + 4] = clock64();  // conv3 accumulator ready
+      LRN_STAMP(stamp, p.dbg, it * 8 + 4);  // conv3 accumulator ready
       chain_drain<4>(t_lane + 256 + 128 * sub, 128 * sub, sconst + L::kB3, sF3, rr);
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
@@ -469,11 +469,11 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         for (int b = 0; b < 4; ++b) store_blk(smem + L::kF3 + b * kChainBlock, 192 + 64 * b, row0);
         ptx::bulk_commit();
       }
-      if (stamp) p.dbg[it * 8 + 5] = clock64();  // conv3 drained, F3 stores issued
+      LRN_STAMP(stamp, p.dbg, it * 8 + 5);  // conv3 drained, F3 stores issued
       // ---- next tile's conv1 while conv4 chunk 0 runs (F1 / GH are free: conv2 of this tile has completed)
       const bool has_next = tile + num_clusters < p.num_tiles;
       if (has_next) embed(tile + num_clusters, x_next);
-      if (stamp) p.dbg[it * 8 + 6] = clock64();  // next tile's conv1 done
+      LRN_STAMP(stamp, p.dbg, it * 8 + 6);  // next tile's conv1 done
       // ---- conv4 epilogues: feat4 channels [256 c + 128 sub, +128) -> staging blocks -> operand row columns 448 + ...
       //      chunk 0 is staged in F2 + Z (conv3 of this tile is done with F2), chunk 1 in F3 (all of conv4 has
       //      completed once its accumulator is ready).
@@ -533,10 +533,10 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
           // but the most recent group (chunk n - 1) must have been read
           staging_free(n == 0 ? 0 : 1);
           const bool stamp5 = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it == 1;
-          if (stamp5) p.dbg[128 + 24 + n] = clock64();  // staging free
+          LRN_STAMP(stamp5, p.dbg, 128 + 24 + n);  // staging free
           ptx::mbar_wait(&acc5_full[b], j & 1);
           ptx::tc_fence_after();
-          if (stamp5) p.dbg[128 + 32 + n] = clock64();  // accumulator ready
+          LRN_STAMP(stamp5, p.dbg, 128 + 32 + n);  // accumulator ready
           chain_drain<2>(t_lane + 256 + 128 * b + 64 * sub, 64 * sub, sconst + L::kB5 + 128 * n, sF3 + 2 * b * kChainBlock, rr);
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
@@ -549,10 +549,10 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
               store_blk(smem + L::kF3 + (2 * b + bb) * kChainBlock, 960 + 128 * n + 64 * bb, row0);
             ptx::bulk_commit();
           }
-          if (stamp5) p.dbg[128 + 40 + n] = clock64();  // drained, stores issued
+          LRN_STAMP(stamp5, p.dbg, 128 + 40 + n);  // drained, stores issued
         }
       }
-      if (stamp) p.dbg[it * 8 + 7] = clock64();  // conv4 drained
+      LRN_STAMP(stamp, p.dbg, it * 8 + 7);  // conv4 drained
     }
     if (issuer) ptx::bulk_wait_all();
   }

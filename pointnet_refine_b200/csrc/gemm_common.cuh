@@ -17,6 +17,14 @@
 #pragma once
 #include "ptx.cuh"
 
+// clock64() stamps for tools/timeline.py exist only in the tuning build (-DLRN_TIMELINE, liblrn_b200_timeline.so): the
+// product library carries no timing code in its TMA / MMA / epilogue loops.
+#ifdef LRN_TIMELINE
+#define LRN_STAMP(cond, buf, idx) do { if (cond) (buf)[idx] = clock64(); } while (0)
+#else
+#define LRN_STAMP(cond, buf, idx) do { } while (0)
+#endif
+
 namespace lrn {
 
 constexpr int BM = 128;             // points per tile (= TMEM lanes)

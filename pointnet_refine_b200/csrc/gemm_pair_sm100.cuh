@@ -221,7 +221,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int work = cluster_id; work < num_tiles; work += num_clusters, ++it) {
         const int kb_total = kb_count(work);
         const bool stamp = p.dbg && cluster_id == 0 && lane == 0 && it < 16;
-        if (stamp) p.dbg[it * 8 + 0] = clock64();  // tile start
+        LRN_STAMP(stamp, p.dbg, it * 8 + 0);  // tile start
         // EPI_ACT: accumulator stage it&1, completes every second tile.  EPI_FUSION: F_t lives in region
         // it&1 and G_t in the other one; every region is written exactly once per tile, so all
         // region barriers complete once per tile (parity it&1).
@@ -260,7 +260,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           __syncwarp();
         }
-        if (stamp) p.dbg[it * 8 + 1] = clock64();  // last MMA of the tile issued
+        LRN_STAMP(stamp, p.dbg, it * 8 + 1);  // last MMA of the tile issued
       }
     }
   } else {
@@ -297,15 +297,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t* staging = smem + L::kStagingOff;
         const bool issuer = (ew & 3) == 0 && lane == 0;  // one thread per column half issues the TMA stores
         const bool stamp = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it < 16;
-        if (stamp) p.dbg[it * 8 + 2] = clock64();  // epilogue of this tile starts
+        LRN_STAMP(stamp, p.dbg, it * 8 + 2);  // epilogue of this tile starts
         if (STAGED) {
           if (issuer) ptx::bulk_wait_read_all();  // the previous tile's stores have drained the staging blocks
           ptx::named_bar_sync(2 + half, 128);
         }
-        if (stamp) p.dbg[it * 8 + 3] = clock64();  // staging free
+        LRN_STAMP(stamp, p.dbg, it * 8 + 3);  // staging free
         ptx::mbar_wait(&bar_tfull[as], (it >> 1) & 1);
         ptx::tc_fence_after();
-        if (stamp) p.dbg[it * 8 + 4] = clock64();  // accumulator ready
+        LRN_STAMP(stamp, p.dbg, it * 8 + 4);  // accumulator ready
         // software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
         uint32_t r[2][32];
         ptx::tmem_ld_32x32b_x32(t_lane + as * BN + col_lo, r[0]);
@@ -344,7 +344,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tc_fence_before();
         if (STAGED) ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
         __syncwarp();
-        if (stamp) p.dbg[it * 8 + 5] = clock64();  // accumulator drained
+        LRN_STAMP(stamp, p.dbg, it * 8 + 5);  // accumulator drained
         if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[as]), 0));
         if (STAGED) {
           ptx::named_bar_sync(2 + half, 128);
@@ -377,7 +377,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool exact = TF32 && p.exact_gate;  // fp32x3 tier: G stays in tensor memory until phase B (no 16-bit gamma)
         ptx::mbar_wait(&bar_tfull[rf ^ 1], it & 1);
         ptx::tc_fence_after();
-        if (stamp) p.dbg[it * 8 + 2] = clock64();  // G ready
+        LRN_STAMP(stamp, p.dbg, it * 8 + 2);  // G ready
 #pragma unroll
         for (int i = 0; i < (exact ? 0 : kChunks); ++i) {  // both phases hide under the next main loop: no need to pipeline the loads
           const int c0 = col_lo + 32 * i;
@@ -395,12 +395,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0 && !exact) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[rf ^ 1]), 0));  // G region drained
-        if (stamp) p.dbg[it * 8 + 3] = clock64();  // phase A done
+        LRN_STAMP(stamp, p.dbg, it * 8 + 3);  // phase A done
 
         // ---- phase B: v = relu(F_t + bf) * gamma, stores, pooling
         ptx::mbar_wait(&bar_tfull[rf], it & 1);
         ptx::tc_fence_after();
-        if (stamp) p.dbg[it * 8 + 4] = clock64();  // F ready
+        LRN_STAMP(stamp, p.dbg, it * 8 + 4);  // F ready
         {
 #pragma unroll
           for (int i = 0; i < kChunks; ++i) {
@@ -459,7 +459,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (stamp) p.dbg[it * 8 + 5] = clock64();  // phase B done
+        LRN_STAMP(stamp, p.dbg, it * 8 + 5);  // phase B done
         if (lane == 0) {
           ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[rf]), 0));  // F region drained
           if (exact) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tempty[rf ^ 1]), 0));  // ... and G with it

@@ -497,8 +497,10 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       cp.b4 = reinterpret_cast<const float*>(pk + L.b[4]);
       cp.b5 = reinterpret_cast<const float*>(pk + L.b[5]);
       cp.cat = cat;
+#ifdef LRN_TIMELINE
       static const int dbg_layer = [] { const char* e = getenv("LRN_DBG_LAYER"); return e ? atoi(e) : 0; }();
       cp.dbg = dbg_layer == 4 ? g_dbg : nullptr;
+#endif
       StageTimer timer(LRN_STAGE_CONV5, s);  // reported as stage "conv5"; the other chain stages then read 0
       const int grid = 2 * std::min(cp.num_tiles, dev.sms / 2);
       chain_pair_kernel<<<grid, kPairThreads, ChainSmem::kDynamic, s>>>(tw_chain[0], tw_chain[1], tw_chain[2], tw_chain[3], ta, cp);
@@ -531,8 +533,10 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.relu = 1;
       p.round_tf32 = tf32 ? 1 : 0;
       p.out_col0 = kCatOff[k];  // staged TMA stores go through the operand-row tensor map itself
+#ifdef LRN_TIMELINE
       static const int dbg_layer = [] { const char* e = getenv("LRN_DBG_LAYER"); return e ? atoi(e) : 0; }();
       p.dbg = (k == dbg_layer) ? g_dbg : nullptr;
+#endif
       StageTimer timer(LRN_STAGE_CONV2 + (k - 2), s);
       st = launch_gemm(precision, plan[k], EPI_ACT, ta, tw[k], p, dev.sms, s, &ta);
       if (st) return st;
@@ -561,7 +565,9 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.pool_key = keys;
       p.fused_cn = fused;
       p.fused_pm = fused_pm;
+#ifdef LRN_TIMELINE
       p.dbg = getenv("LRN_DBG_LAYER") ? nullptr : g_dbg;
+#endif
       StageTimer timer(LRN_STAGE_FUSION, s);
       st = launch_gemm(precision, plan_f, EPI_FUSION, ta, twfg, p, dev.sms, s);
       if (st) return st;
@@ -844,8 +850,13 @@ int lrn_scene_segments(const float* scene_pts, int64_t S, const float* scene_sor
 }
 
 int lrn_debug_timeline(long long* device_buffer) {
+#ifdef LRN_TIMELINE
   g_dbg = device_buffer;
   return LRN_OK;
+#else
+  (void)device_buffer;
+  return fail(LRN_ERR_BAD_ARG, "this library was built without -DLRN_TIMELINE (tools/timeline.py builds the tuning variant)");
+#endif
 }
 
 int lrn_profile_enable(int on) {

@@ -1,6 +1,10 @@
 """clock64() timeline of the fusion kernel's first tiles on cluster 0 (tuning aid)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import importlib.util
+_spec = importlib.util.spec_from_file_location("_lrn_build", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pointnet_refine_b200", "build.py"))
+_b = importlib.util.module_from_spec(_spec); _spec.loader.exec_module(_b)
+os.environ["LRN_B200_LIB"] = _b.build(timeline=True)      # the product library carries no stamps: use the tuning build
 import torch
 import pointnet_refine_b200 as prb
 from pointnet_refine_b200 import _lib
