@@ -287,6 +287,22 @@ def test_ddp_step_two_ranks():
     assert r.returncode == 0 and "ddp ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_data_parallel_step_two_ranks_one_gpu():
+    """The same check on a single-GPU box: two ranks share cuda:0 and talk over gloo (NCCL refuses two ranks on one
+    device).  Exercises DistributedDataParallel's hooks through the native autograd nodes and FlatDataParallel's flat
+    buffers / two-slice all-reduce / FlatAdam on the real kernels; gradients identical across ranks and equal between the
+    two wrappers, parameters in sync."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LRN_DDP_BACKEND="gloo", LRN_DDP_ONE_GPU="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29537", os.path.join(root, "tools", "ddp_check.py"), "8", "512"],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "ddp ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_linear_bf16_autograd(dev):
     """The differentiable tensor-core linear used for context_proj / K / V projections in train mode."""
     from pointnet_refine_b200.train_ops import linear_bf16

@@ -12,9 +12,22 @@ import pointnet_refine_b200 as prb
 from pointnet_refine_b200 import optim as lrn_optim
 
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+backend = os.environ.get("LRN_DDP_BACKEND", "nccl")
+if os.environ.get("LRN_DDP_ONE_GPU") == "1":      # single-GPU box: every rank on cuda:0, gloo as the transport (NCCL refuses
+    local = 0                                     # two ranks on one device); exercises the same hooks / flat buffers / kernels
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+if backend == "nccl":
+    dist.init_process_group("nccl", device_id=dev)
+else:
+    dist.init_process_group(backend)
+
+
+def barrier():
+    if backend == "nccl":
+        dist.barrier(device_ids=[local])
+    else:
+        dist.barrier()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 g = torch.Generator(device=dev).manual_seed(100 + rank)                    # different shard per rank
@@ -47,7 +60,7 @@ def run(kind):
         assert opt._grad is net.flat.grad, "FlatAdam must adopt FlatDataParallel's flat buffers"
     times, grads = [], None
     for it in range(5):
-        torch.cuda.synchronize(); dist.barrier(device_ids=[local]); t0 = time.perf_counter()
+        torch.cuda.synchronize(); barrier(); t0 = time.perf_counter()
         opt.zero_grad()
         out = net(ctx, line)
         loss = lrn_optim.deep_supervision_l1(out, tgt)
@@ -73,7 +86,7 @@ rel = float((g_flat - g_ddp).norm() / g_ddp.norm())
 # flip, which is the same noise the gradient parity test allows (tests/test_gpu_train.py: 2e-2)
 assert rel <= 2e-2, f"flat-buffer gradients differ from DDP's: rel-L2 {rel}"
 if rank == 0:
-    print("ddp ok: " + json.dumps({"world": world, "segments_per_rank": B, "points": N, "loss_ddp": round(loss_ddp, 5),
+    print("ddp ok: " + json.dumps({"world": world, "backend": backend, "segments_per_rank": B, "points": N, "loss_ddp": round(loss_ddp, 5),
                                    "loss_flat": round(loss_flat, 5), "grad_rel_l2_flat_vs_ddp": rel,
                                    "step_ms_ddp_adam": round(1e3 * t_ddp, 2), "step_ms_flat_dp_flat_adam": round(1e3 * t_flat, 2),
                                    "segments_per_s_flat": round(world * B / t_flat), "allreduce_calls_per_step": calls // 5}))
