@@ -1202,12 +1202,12 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
     LRN_CUDA(cudaGetLastError());
     LRN_CUDA(d2d(g->gate2_b, Sz, 1024));
     const int uo = kUOff[5];
-    bn_bwd_reduce_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, 0, U + uo, kULd, P, mean + uo,
+    bn_bwd_reduce_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, nullptr, U + uo, kULd, P, mean + uo,
                                                              rstd + uo, S1 + uo, S2 + uo);
     LRN_CUDA(cudaGetLastError());
     LRN_CUDA(d2d(g->fusion_bn_b, S1 + uo, 1024));
     LRN_CUDA(d2d(g->fusion_bn_w, S2 + uo, 1024));
-    bn_bwd_apply_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, 0, U + uo, kULd, P, 1024, mean + uo,
+    bn_bwd_apply_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, nullptr, U + uo, kULd, P, 1024, mean + uo,
                                                             rstd + uo, pr->fusion_bn_w, S1 + uo, S2 + uo, dU, 1024);
     LRN_CUDA(cudaGetLastError());
     // d(fusion conv bias) = sum_p dU is exactly zero: dU is the output of a batch-statistic BatchNorm backward, whose
@@ -1227,12 +1227,12 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
   for (int k = 5; k >= 1; --k) {
     const int i = k - 1, C = kChan[k], uo = kUOff[i], xo = kCatOff[k];
     const __nv_bfloat16* d2 = k < 5 ? dB : nullptr;
-    bn_bwd_reduce_kernel<<<stats_grid(C, P), 256, 0, s>>>(dA + xo, kCat, d2, 512, X + xo, kCat, U + uo, kULd, P, mean + uo,
+    bn_bwd_reduce_kernel<<<stats_grid(C, P), 256, 0, s>>>(dA + xo, kCat, d2, 512, scale + uo, shift + uo, U + uo, kULd, P, mean + uo,
                                                           rstd + uo, S1 + uo, S2 + uo);
     LRN_CUDA(cudaGetLastError());
     LRN_CUDA(d2d(g->bn_b[i], S1 + uo, C));
     LRN_CUDA(d2d(g->bn_w[i], S2 + uo, C));
-    bn_bwd_apply_kernel<<<stats_grid(C, P), 256, 0, s>>>(dA + xo, kCat, d2, 512, X + xo, kCat, U + uo, kULd, P, C, mean + uo,
+    bn_bwd_apply_kernel<<<stats_grid(C, P), 256, 0, s>>>(dA + xo, kCat, d2, 512, scale + uo, shift + uo, U + uo, kULd, P, C, mean + uo,
                                                          rstd + uo, pr->bn_w[i], S1 + uo, S2 + uo, dU, 1024);
     LRN_CUDA(cudaGetLastError());
     if (k == 1) break;

@@ -336,45 +336,58 @@ fusion_gate_bwd_kernel(const float* __restrict__ dfused, const float* __restrict
 }
 
 // BatchNorm backward, pass 1: S1[c] = sum_p dY, S2[c] = sum_p dY * xhat, where
-//   dY = (d1 + d2) * [X > 0]   (d2 / X optional: two gradient sources, ReLU mask from the stored activation)
+//   dY = (d1 + d2) * [scale * U + shift > 0]   (d2 optional: a second gradient source; the ReLU mask is re-derived from
+//        the pre-activation U, which this pass reads anyway, with the forward's own scale / shift - the same fmaf whose
+//        sign decided the stored activation - instead of reading the activation matrix as a fourth stream; msc = null: no ReLU)
 //   xhat = (U - mean) * rstd
-// Block = 64 columns (32 bf16 pairs) x 8 row lanes.
+// Block = 64 columns as 8 channel groups of 8 (16-byte loads) x 32 row lanes; grid = (C / 64, row slabs).
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ d1, long long ld1, const __nv_bfloat16* __restrict__ d2,
-                     long long ld2, const __nv_bfloat16* __restrict__ X, long long ldx,
+                     long long ld2, const float* __restrict__ msc, const float* __restrict__ msh,
                      const __nv_bfloat16* __restrict__ U, long long ldu, long long rows, const float* __restrict__ mean,
                      const float* __restrict__ rstd, float* __restrict__ S1, float* __restrict__ S2) {
-  const int cp = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
-  const int c = blockIdx.x * 64 + 2 * cp;
-  const float m0 = mean[c], m1 = mean[c + 1], rs0 = rstd[c], rs1 = rstd[c + 1];
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-  const long long stride = gridDim.y * 8ll;
-#pragma unroll 2
-  for (long long r = blockIdx.y * 8ll + lane_r; r < rows; r += stride) {
-    float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d1 + r * ld1 + c));
-    const float2 u = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(U + r * ldu + c));
-    if (d2) {
-      const float2 e = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d2 + r * ld2 + c));
-      d.x += e.x; d.y += e.y;
-    }
-    if (X) {
-      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(X + r * ldx + c));
-      if (!(x.x > 0.f)) d.x = 0.f;
-      if (!(x.y > 0.f)) d.y = 0.f;
-    }
-    a0 += d.x; a1 += d.y;
-    b0 = fmaf(d.x, (u.x - m0) * rs0, b0);
-    b1 = fmaf(d.y, (u.y - m1) * rs1, b1);
-  }
-  __shared__ float sh[4][8][32];
-  sh[0][lane_r][cp] = a0; sh[1][lane_r][cp] = a1; sh[2][lane_r][cp] = b0; sh[3][lane_r][cp] = b1;
-  __syncthreads();
-  if (lane_r < 4) {
-    float t = 0.f;
+  const int cg = threadIdx.x & 7, lane_r = threadIdx.x >> 3;
+  const int c = blockIdx.x * 64 + 8 * cg;
+  float m[8], rs[8], sc[8], sh[8], a[8], b[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sh[lane_r][k][cp];
-    if (lane_r < 2) atomicAdd(S1 + c + lane_r, t);
-    else atomicAdd(S2 + c + (lane_r - 2), t);
+  for (int j = 0; j < 8; ++j) {
+    m[j] = mean[c + j];
+    rs[j] = rstd[c + j];
+    sc[j] = msc ? msc[c + j] : 0.f;
+    sh[j] = msc ? msh[c + j] : 0.f;
+    a[j] = b[j] = 0.f;
+  }
+  const long long stride = gridDim.y * 32ll;
+  for (long long r = blockIdx.y * 32ll + lane_r; r < rows; r += stride) {
+    const uint4 r1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c);
+    const uint4 ru = *reinterpret_cast<const uint4*>(U + r * ldu + c);
+    uint4 r2 = make_uint4(0, 0, 0, 0);
+    if (d2) r2 = *reinterpret_cast<const uint4*>(d2 + r * ld2 + c);
+    const __nv_bfloat16 *p1 = reinterpret_cast<const __nv_bfloat16*>(&r1), *p2 = reinterpret_cast<const __nv_bfloat16*>(&r2),
+                        *pu = reinterpret_cast<const __nv_bfloat16*>(&ru);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = bf2f(p1[j]);
+      const float u = bf2f(pu[j]);
+      if (d2) d += bf2f(p2[j]);
+      if (msc && !(fmaf(u, sc[j], sh[j]) > 0.f)) d = 0.f;
+      a[j] += d;
+      b[j] = fmaf(d, (u - m[j]) * rs[j], b[j]);
+    }
+  }
+  __shared__ float shm[2][32][65];   // [S1 | S2][row lane][column of the block]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    shm[0][lane_r][8 * cg + j] = a[j];
+    shm[1][lane_r][8 * cg + j] = b[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) t += shm[which][k][col];
+    atomicAdd((which == 0 ? S1 : S2) + blockIdx.x * 64 + col, t);
   }
 }
 
@@ -383,16 +396,18 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ d1, long long ld1, const 
 // d1 may alias dU (in place): every element is read before it is written by the same thread.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16* d1, long long ld1, const __nv_bfloat16* __restrict__ d2, long long ld2,
-                    const __nv_bfloat16* __restrict__ X, long long ldx, const __nv_bfloat16* __restrict__ U,
+                    const float* __restrict__ msc, const float* __restrict__ msh, const __nv_bfloat16* __restrict__ U,
                     long long ldu, long long rows, int C, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ S1,
                     const float* __restrict__ S2, __nv_bfloat16* dU, long long ldo) {
   const int c0 = blockIdx.x * 64 + (threadIdx.x & 7) * 8;
   const float inv_n = 1.f / static_cast<float>(rows);
-  float A[8], Bc[8], Cc[8];
+  float A[8], Bc[8], Cc[8], sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
+    sc[j] = msc ? msc[c] : 0.f;
+    sh[j] = msc ? msh[c] : 0.f;
     const float gr = gamma[c] * rstd[c];
     A[j] = gr;
     Bc[j] = -gr * rstd[c] * S2[c] * inv_n;
@@ -401,18 +416,18 @@ bn_bwd_apply_kernel(const __nv_bfloat16* d1, long long ld1, const __nv_bfloat16*
   for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
     const uint4 r1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c0);
     const uint4 ru = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
-    uint4 r2 = make_uint4(0, 0, 0, 0), rx = make_uint4(0, 0, 0, 0);
+    uint4 r2 = make_uint4(0, 0, 0, 0);
     if (d2) r2 = *reinterpret_cast<const uint4*>(d2 + r * ld2 + c0);
-    if (X) rx = *reinterpret_cast<const uint4*>(X + r * ldx + c0);
     const __nv_bfloat16 *p1 = reinterpret_cast<const __nv_bfloat16*>(&r1), *p2 = reinterpret_cast<const __nv_bfloat16*>(&r2),
-                        *px = reinterpret_cast<const __nv_bfloat16*>(&rx), *pu = reinterpret_cast<const __nv_bfloat16*>(&ru);
+                        *pu = reinterpret_cast<const __nv_bfloat16*>(&ru);
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float d = bf2f(p1[j]);
+      const float u = bf2f(pu[j]);
       if (d2) d += bf2f(p2[j]);
-      if (X && !(bf2f(px[j]) > 0.f)) d = 0.f;
-      v[j] = fmaf(A[j], d, fmaf(Bc[j], bf2f(pu[j]), Cc[j]));
+      if (msc && !(fmaf(u, sc[j], sh[j]) > 0.f)) d = 0.f;   // ReLU mask from the pre-activation (see bn_bwd_reduce_kernel)
+      v[j] = fmaf(A[j], d, fmaf(Bc[j], u, Cc[j]));
     }
     *reinterpret_cast<uint4*>(dU + r * ldo + c0) =
         make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
