@@ -650,7 +650,20 @@ int lrn_gemm_tn(const void* At, int64_t lda, const void* Bt, int64_t ldb, float*
   p.out_f32 = 1;
   const int out_tiles = p.m_tiles * p.n_tiles, slots = dev.sms / 2;
   if (out_tiles < slots && p.kb_main >= 64) {  // split K over the idle CTA pairs (fp32 atomic accumulation)
-    const int want = std::min((2 * slots + out_tiles - 1) / out_tiles, p.kb_main / 16);
+    // The kernel is persistent (one CTA pair per slot walks the work items): pick the split count whose item count fills
+    // whole rounds of the `slots` pairs best - e.g. 32 output tiles: 9 splits = 288 items = 3.9 rounds of 74, where
+    // "about two items per pair" (5 splits = 160 items = 2.2 rounds) left a third of the last round empty.
+    int want = 1;
+    double best = 0.0;
+    const int max_split = std::min(p.kb_main / 16, 6 * slots / out_tiles + 1);
+    for (int sp = 2; sp <= max_split; ++sp) {
+      const int items = out_tiles * sp, rounds = (items + slots - 1) / slots;
+      const double eff = double(items) / (double(rounds) * slots);
+      if (eff > best + 0.02) {  // prefer fewer splits (fewer atomic passes over the output) unless clearly better
+        best = eff;
+        want = sp;
+      }
+    }
     if (want > 1) {
       p.kb_per_split = (p.kb_main + want - 1) / want;
       p.k_splits = (p.kb_main + p.kb_per_split - 1) / p.kb_per_split;
