@@ -944,7 +944,11 @@ int lrn_gemm_bias_act(int precision, const void* A, int64_t lda, const void* Wt,
   DeviceInfo dev;
   int st = device_info(&dev);
   if (st) return st;
-  const GemmPlan g = plan_gemm(N, EPI_ACT);
+  GemmPlan g = plan_gemm(N, EPI_ACT);
+  if (g.bn == 256 && ((M + g.m_rows - 1) / g.m_rows) * (N / 256) < dev.sms / 2) {
+    g.bn = 128;  // few tiles (the decoder's query side: a few thousand rows): 128-column tiles give the idle CTA pairs work
+    g.b_box_rows = 64;
+  }
   CUtensorMap ta, tb;
   st = make_tmap(&ta, precision, A, M, K, lda, BM);
   if (st) return st;
