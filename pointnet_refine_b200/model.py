@@ -491,7 +491,7 @@ class LineRefineNet(nn.Module):
         h = pos_hidden_train(context, self.pos_emb.mlp[0].weight, self.pos_emb.mlp[0].bias)    # (B,N,256) bf16
         posm = linear_bf16(h, self.pos_emb.mlp[2].weight, self.pos_emb.mlp[2].bias)
         share = KVGradShare()                           # the attention backward writes dK / dV of all layers in place
-        k_l = kv_proj(mem + posm, wk, bk, 6, H, share)  # six (B, H, N, 32) views of one (B, N, 6, H, 32) GEMM result
+        k_l = kv_proj(mem + posm, wk, bk, 6, H, share, zero_bias_grad=True)  # six (B, H, N, 32) views of one (B, N, 6, H, 32) GEMM result
         v_l = kv_proj(mem, wv, bv, 6, H, share)
         native_ca = noisy_line.shape[1] == 32           # 32 queries per segment: lrn_train_attention_* (else SDPA)
         rows = B * noisy_line.shape[1]
@@ -532,7 +532,7 @@ class LineRefineNet(nn.Module):
             tgt = add_layernorm(tgt, layer.dropout2(lin(att, ca.out_proj.weight, ca.out_proj.bias)), layer.norm2)
             ffn = lin(layer.dropout(F.relu(lin(tgt, layer.linear1.weight, layer.linear1.bias))), layer.linear2.weight, layer.linear2.bias)
             tgt = add_layernorm(tgt, layer.dropout3(ffn), layer.norm3)
-            current = current + head(tgt)
+            current = current + head[2](F.relu(lin(tgt, head[0].weight, head[0].bias)))   # reg_branches[i]: 256 -> 128 on the tensor cores
             outs.append(current - noisy_line)
         return torch.stack(outs)
 

@@ -225,9 +225,10 @@ class KVProjFn(torch.autograd.Function):
     like LinearBf16Fn.  x (B, N, K) bf16 or fp32, weight (L*H*hd, K) fp32, bias fp32."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, L, H, share):
+    def forward(ctx, x, weight, bias, L, H, share, zero_bias_grad=False):
         from . import ops
         B, N, K = x.shape
+        ctx.zero_bias_grad = bool(zero_bias_grad)
         xb = x.detach().to(torch.bfloat16).contiguous().view(B * N, K)
         wb = weight.detach().to(torch.bfloat16).contiguous()
         ctx.save_for_backward(xb, wb)
@@ -269,13 +270,17 @@ class KVProjFn(torch.autograd.Function):
         if need_w:
             dw = ops.gemm_tn(dyb, xb)
         if need_b:
-            db = _col_sum(dyb)
-        return dx, dw, db, None, None, None
+            # K projection: a key bias shifts every score of a query by the same amount, which softmax ignores, so its
+            # gradient sum_n dK[n] vanishes identically (rows of the score gradient sum to zero, with or without dropout);
+            # the reference produces fp32 rounding noise there, a bf16 column sum would produce more - write the exact zero
+            db = torch.zeros(wb.shape[0], dtype=torch.float32, device=xb.device) if ctx.zero_bias_grad else _col_sum(dyb)
+        return dx, dw, db, None, None, None, None
 
 
-def kv_proj(x, weight, bias, layers: int, heads: int, share: KVGradShare | None = None):
-    """(B, N, K) -> tuple of `layers` tensors (B, heads, N, hd), see KVProjFn."""
-    return KVProjFn.apply(x, weight, bias, layers, heads, share)
+def kv_proj(x, weight, bias, layers: int, heads: int, share: KVGradShare | None = None, zero_bias_grad: bool = False):
+    """(B, N, K) -> tuple of `layers` tensors (B, heads, N, hd), see KVProjFn.  zero_bias_grad: the K projection (its
+    bias gradient is identically zero)."""
+    return KVProjFn.apply(x, weight, bias, layers, heads, share, zero_bias_grad)
 
 
 class CrossAttnTrainFn(torch.autograd.Function):
