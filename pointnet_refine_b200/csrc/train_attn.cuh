@@ -73,6 +73,12 @@ __device__ __forceinline__ void frag_b_kn(uint32_t (&r)[4], uint32_t t, int k0, 
   ldsm_x4_t(r, t + ((k0 + (mi & 1) * 8 + row) * kTaPitch + n0 + (mi >> 1) * 8) * 2);
 }
 
+__device__ __forceinline__ float ta_ex2(float x) {   // 2^x, one MUFU op (exp2f adds range fix-ups the softmax does not need)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // One 32-bit hash decides TWO adjacent keys (its low / high 16 bits against p * 2^16): `idx` is the element index of the
 // even key of the pair.  Returns the keep / (1 - p) factors of (even key, odd key).
 __device__ __forceinline__ void ta_keep_pair(unsigned long long seed, unsigned long long idx, uint32_t thresh16, float inv_keep,
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(128, 3) train_attn_fwd_kernel(const TrainAttnP
       for (int hi = 0; hi < 2; ++hi) {
         bm[hi] = fmaxf(bm[hi], __shfl_xor_sync(0xffffffffu, bm[hi], 1));
         bm[hi] = fmaxf(bm[hi], __shfl_xor_sync(0xffffffffu, bm[hi], 2));
-        const float sc = exp2f(mrun[mt][hi] - bm[hi]);  // 0 on the first block
+        const float sc = ta_ex2(mrun[mt][hi] - bm[hi]);  // 0 on the first block
         lrun[mt][hi] *= sc;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(128, 3) train_attn_fwd_kernel(const TrainAttnP
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int hi = 0; hi < 2; ++hi) {
-          const float p0 = exp2f(s[mt][nt][2 * hi] - bm[hi]), p1 = exp2f(s[mt][nt][2 * hi + 1] - bm[hi]);
+          const float p0 = ta_ex2(s[mt][nt][2 * hi] - bm[hi]), p1 = ta_ex2(s[mt][nt][2 * hi + 1] - bm[hi]);
           ls[hi] += p0 + p1;
           float k0 = 1.f, k1 = 1.f;
           if (thresh) {
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(128, 3) train_attn_fwd_kernel(const TrainAttnP
 #pragma unroll
     for (int ww = 0; ww < 4; ++ww) {
       const float mw = red[(ww * 34) * 32 + qi];
-      const float f = mw == -INFINITY ? 0.f : exp2f(mw - M);
+      const float f = mw == -INFINITY ? 0.f : ta_ex2(mw - M);
       L = fmaf(red[(ww * 34 + 1) * 32 + qi], f, L);
       acc = fmaf(red[(ww * 34 + 2 + c) * 32 + qi], f, acc);
     }
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(128) train_attn_bwd_kernel(const TrainAttnPara
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const int e = 2 * hi + j;
-              const float pe = key + j < p.N ? exp2f(s[mt][nt][e] - lse_r[mt][hi]) : 0.f;
+              const float pe = key + j < p.N ? ta_ex2(s[mt][nt][e] - lse_r[mt][hi]) : 0.f;
               s[mt][nt][e] = pe * (keep[j] * dp[mt][nt][e] - del_r[mt][hi]);  // G
               dp[mt][nt][e] = pe * keep[j];                                    // Pd
             }
