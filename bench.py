@@ -358,7 +358,7 @@ def main():
                             "encoder, context_proj, folded-query cross attention (K/V never materialised) and the query side on the "
                             "sm_100a kernels"}
                 del out_full
-                if B * N >= 1024 * 1024:   # inference_whole_scene.py's setting: 1024 context points per line
+                if B >= 1024 and B * N >= 1024 * 1024:   # inference_whole_scene.py's setting: 1024 context points per line
                     ctx_ws = ctx.reshape(-1, 4)[:1024 * 1024].view(1024, 1024, 4)
                     for _ in range(2):
                         model(ctx_ws, line[:1024])
@@ -542,8 +542,8 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
     m = prb.LineRefineNet().to(dev).train()
     m.context_encoder.native_training = True
     net = m
-    if world > 1:     # where train_dist.py:147 wraps the model in DistributedDataParallel: one flat gradient buffer, two
-        net = prb.FlatDataParallel(m, overlap=os.environ.get("LRN_FDP_OVERLAP", "1") != "0")   # all-reduce slices over NCCL, the first overlapped with the encoder's backward
+    if world > 1:     # where train_dist.py:147 wraps the model in DistributedDataParallel: one flat gradient buffer,
+        net = prb.FlatDataParallel(m, overlap=os.environ.get("LRN_FDP_OVERLAP", "0") == "1")   # ONE all-reduce of the flat gradient buffer per step
     opt = lrn_optim.FlatAdam(m.parameters(), lr=1e-3)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     ctx = torch.randn(Bt, Nt, 4, device=dev, generator=g)

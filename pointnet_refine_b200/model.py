@@ -538,6 +538,9 @@ class LineRefineNet(nn.Module):
 
     def forward(self, context, noisy_line):
         _require_cuda(context, "LineRefineNet")
+        if context.dim() != 3 or noisy_line.dim() != 3 or context.shape[0] != noisy_line.shape[0] or context.shape[-1] != 4 \
+                or noisy_line.shape[-1] != 3:
+            raise ValueError(f"expected context (B,N,4) and noisy_line (B,M,3), got {tuple(context.shape)} and {tuple(noisy_line.shape)}")
         if not _use_native(self, context, noisy_line):
             from .train_ops import native_train_supported
             if (self.training and self.fast_decoder and self.precision == "bf16" and self.context_encoder.native_training

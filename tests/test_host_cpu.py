@@ -174,7 +174,7 @@ def _fdp_worker(rank, world, port, q):
         with torch.no_grad():
             for p in m.parameters():
                 p.add_(1.0)
-    net = FlatDataParallel(m)
+    net = FlatDataParallel(m, overlap=True)     # two slices: the decoder side as soon as it is complete, the encoder's at the end
     opt = torch.optim.SGD(net.parameters(), lr=0.1)
     x = torch.randn(16, 4, generator=torch.Generator().manual_seed(100 + rank))
     grads = None
