@@ -290,7 +290,7 @@ def test_ddp_step_two_ranks():
 def test_data_parallel_step_two_ranks_one_gpu():
     """The same check on a single-GPU box: two ranks share cuda:0 and talk over gloo (NCCL refuses two ranks on one
     device).  Exercises DistributedDataParallel's hooks through the native autograd nodes and FlatDataParallel's flat
-    buffers / two-slice all-reduce / FlatAdam on the real kernels; gradients identical across ranks and equal between the
+    buffers / all-reduce / FlatAdam on the real kernels; gradients identical across ranks and equal between the
     two wrappers, parameters in sync."""
     import os
     import subprocess

@@ -1,6 +1,6 @@
 """Data-parallel training step (reference train_dist.py:143-189) on the native train path: one process per GPU, NCCL.
 Runs the same step under (a) torch's DistributedDataParallel, exactly as train_dist.py:147 wraps the model, and (b)
-pointnet_refine_b200.FlatDataParallel + FlatAdam (one flat gradient buffer, two overlapped all-reduce slices, one Adam
+pointnet_refine_b200.FlatDataParallel + FlatAdam (one flat gradient buffer, one all-reduce, one Adam
 launch).  Checks for both that gradients are averaged and identical on all ranks and that parameters stay in sync,
 that (a) and (b) produce the same averaged gradients, and prints the step times.  Launch with torchrun."""
 import json, os, sys, time
