@@ -64,10 +64,10 @@ struct ChainSmem {
   // fp32 constants: w1 (256) b1 (64) wg1 (64) bg1 (64) b2 (128) b3 (256) b4 (512) b5 (1024)
   static constexpr int kW1 = 0, kB1 = 256, kWg1 = 320, kBg1 = 384, kB2 = 448, kB3 = 576, kB4 = 832, kB5 = 1344,
                        kNumConst = 2368;
-  // w_full[W] w_empty[W] act_ready[3] acc_full[2] acc_free[2] a4_ready acc5_full[2] acc5_free[2] fz_free
+  // w_full[W] w_empty[W] act_ready[3] acc_full[2] acc_free[2] a4_ready acc5_full[2] acc5_free[2] fz_free x_full[2] f1gh_free f1gh_used
   static constexpr int kW = kChainStages + 4;  // + the four F2 / Z blocks borrowed as weight stages while conv5 runs
   static constexpr int kBarOff = kConst + kNumConst * 4;
-  static constexpr int kTmemPtrOff = kBarOff + (2 * kW + 13) * 8;
+  static constexpr int kTmemPtrOff = kBarOff + (2 * kW + 17) * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
   static constexpr int kDynamic = kTotal + 1024;
 };
@@ -161,6 +161,12 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
   uint64_t* acc5_full = a4_ready + 1;  // [2]: conv5 accumulator chunk written
   uint64_t* acc5_free = acc5_full + 2; // [2]: conv5 accumulator chunk drained by both CTAs (leader's copy is used)
   uint64_t* fz_free = acc5_free + 2;   // this CTA's F2 / Z blocks may be overwritten by conv5 weights (local)
+  // The first two weight stages of a tile's conv5 (chunk 0, K = 0..255) live in the F1 / GH blocks, which are idle from
+  // the end of conv2 until the next tile's conv1: those loads are issued ~10k cycles before feat4 is complete, so conv5
+  // starts with its weights in place instead of waiting a TMA round trip for them (2k cycles per tile).
+  uint64_t* x_full = fz_free + 1;      // [2]: weights landed in F1 / GH (both CTAs' halves; leader's copy is used)
+  uint64_t* f1gh_free = x_full + 2;    // this CTA's F1 / GH: conv2 has read F1, their TMA store has been read (local)
+  uint64_t* f1gh_used = f1gh_free + 1; // conv5's MMAs on the F1 / GH weights have completed (both CTAs, by tcgen05.commit)
   // weight stage s: 0..S-1 = dedicated stages, S..S+3 = blocks F2[0], F2[1], Z[0], Z[1]
   auto stage_ptr = [&](int st) { return smem + (st < S ? L::kStages + st * kChainBlock : L::kF2 + (st - S) * kChainBlock); };
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
@@ -183,6 +189,10 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       ptx::mbar_init(&w_empty[s], 1);
     }
     ptx::mbar_init(fz_free, 1);
+    ptx::mbar_init(&x_full[0], 1);
+    ptx::mbar_init(&x_full[1], 1);
+    ptx::mbar_init(f1gh_free, 1);
+    ptx::mbar_init(f1gh_used, 1);
     for (int i = 0; i < 3; ++i) ptx::mbar_init(&act_ready[i], 2 * kPairEpiWarps);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
@@ -248,6 +258,19 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         bool fz_ok = false;
         for (int n = 0; n < 8; ++n)
           for (int kb2 = 0; kb2 < 4; ++kb2) {   // one stage = two 64-wide k-blocks of this CTA's 64 weight rows (2 x 8 KB)
+            if (n == 0 && kb2 < 2) {  // the tile's first two conv5 stages: F1 / GH, free long before feat4 is complete
+              if (kb2 == 0) ptx::mbar_wait(f1gh_free, it & 1);
+              if (ptx::elect_one()) {
+                uint8_t* dst = smem + (kb2 == 0 ? L::kF1 : L::kGH);
+                const uint32_t xl = ptx::mapa(ptx::smem_u32(&x_full[kb2]), 0);
+                if (leader) ptx::mbar_arrive_expect_tx(&x_full[kb2], 2 * kChainBlock);
+                const int nrow = static_cast<int>(rank) * 64;
+                ptx::tma_load_2d_pair(dst, &tmW5, xl, (2 * kb2) * 64, nrow);
+                ptx::tma_load_2d_pair(dst + kChainBlock / 2, &tmW5, xl, (2 * kb2 + 1) * 64, nrow);
+              }
+              __syncwarp();
+              continue;
+            }
             const int st = pb;
             pb = pb + 1 == W ? 0 : pb + 1;
             if (st >= S && !fz_ok) {  // borrowed block: the feat4 store that staged through it must have drained it
@@ -338,6 +361,24 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
             ptx::tc_fence_after();
             LRN_STAMP(stamp5, p.dbg, 128 + 16 + n);  // accumulator free
             for (int kb2 = 0; kb2 < 4; ++kb2) {
+              if (n == 0 && kb2 < 2) {  // weights of the tile's first two conv5 stages sit in F1 / GH
+                ptx::mbar_wait(&x_full[kb2], par);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                  const uint32_t wb = ptx::smem_u32(smem + (kb2 == 0 ? L::kF1 : L::kGH));
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const uint64_t db = ptx::make_smem_desc_sw128(wb + h * (kChainBlock / 2));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      tc_mma_ts_pair(tmem_base + 256, tmem_base + (2 * kb2 + h) * 32 + k * 8, db + 2 * k, kIdesc128,
+                                     (kb2 > 0 || h > 0 || k > 0) ? 1u : 0u);
+                  }
+                  if (kb2 == 1) ptx::tc_commit_pair(f1gh_used, 3);   // F1 / GH may take the next tile's conv1 output
+                }
+                __syncwarp();
+                continue;
+              }
               const int st = pb;
               pb = pb + 1 == W ? 0 : pb + 1;
               wait_stage(st, pb);
@@ -393,20 +434,25 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
       const int grow = tile * 2 * BM + static_cast<int>(rank) * BM + rr;
       return tile < p.num_tiles && grow < p.M ? __ldg(p.ctx + grow) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    auto embed = [&](int tile, const float4 x) {
+    // The work is split in two steps (conv1 -> F1, gate layer 1 -> GH + hand-over) so that, done between conv5 chunk
+    // drains, neither step is longer than the slack the double-buffered conv5 accumulators can absorb.
+    auto embed = [&](int tile, const float4 x, int part /* 0: conv1, 1: gate + hand-over, 2: both */) {
       const int row0 = tile * 2 * BM + static_cast<int>(rank) * BM;
-      staging_free(4);  // F1GH(t) was followed by f4c0(t-1) f4c1(t-1) F2(t) F3(t)
+      if (part != 1) staging_free(4);  // the F1GH store of the previous use of these blocks lies many groups back
       {
         // both warp groups do half of each: channels [32 sub, 32 sub + 32) of conv1 (4 FMA per channel) and of the gate's
         // first layer (1 FMA per channel) - conv1 on one group and the gate on the other left the conv1 warps 4x longer
         const int h = sub;
         float v[32];
+        if (part != 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 w = reinterpret_cast<const float4*>(sconst + L::kW1)[32 * h + j];
-          v[j] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, sconst[L::kB1 + 32 * h + j]))));
+          for (int j = 0; j < 32; ++j) {
+            const float4 w = reinterpret_cast<const float4*>(sconst + L::kW1)[32 * h + j];
+            v[j] = fmaf(w.x, x.x, fmaf(w.y, x.y, fmaf(w.z, x.z, fmaf(w.w, x.w, sconst[L::kB1 + 32 * h + j]))));
+          }
+          stage_row_chunk_relu(sF1, rr, 32 * h, v);
+          if (part == 0) return;
         }
-        stage_row_chunk_relu(sF1, rr, 32 * h, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           v[j] = fmaf(sconst[L::kWg1 + 32 * h + j], x.w, sconst[L::kBg1 + 32 * h + j]);
@@ -424,16 +470,18 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     };
 
     int it = 0;
-    if (cluster_id < p.num_tiles) embed(cluster_id, load_point(cluster_id));
+    if (cluster_id < p.num_tiles) embed(cluster_id, load_point(cluster_id), 2);
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
       const int row0 = tile * 2 * BM + static_cast<int>(rank) * BM;
       const float4 x_next = load_point(tile + num_clusters);
       // ---- conv2 epilogue: buf0[0:128) -> F2 (2 blocks); this warp: columns [64 sub, 64 sub + 64)
       const bool stamp = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it < 16;
-      // F2 doubled as staging in the previous tile: feat4 chunk 0 (then only f4c1), or conv5 chunk 2 (then only chunk 3)
-      staging_free(1);
+      // F2 doubled as staging in the previous tile (feat4 chunk 0) and every group up to the last one committed has been
+      // read; on the first tile the only group is F1GH of this very tile, which must be complete before F1 / GH are reused
+      staging_free(it == 0 ? 0 : 1);
       ptx::mbar_wait(&acc_full[0], 0);
       ptx::tc_fence_after();
+      if (issuer) ptx::mbar_arrive(f1gh_free);  // conv2 has read F1, the F1GH store has been read: conv5 weights may land there
       LRN_STAMP(stamp, p.dbg, it * 8 + 2);  // conv2 accumulator ready
       chain_drain<2>(t_lane + 64 * sub, 64 * sub, sconst + L::kB2, sF2, rr);
       ptx::tc_fence_before();
@@ -470,16 +518,14 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         ptx::bulk_commit();
       }
       LRN_STAMP(stamp, p.dbg, it * 8 + 5);  // conv3 drained, F3 stores issued
-      // ---- next tile's conv1 while conv4 chunk 0 runs (F1 / GH are free: conv2 of this tile has completed)
       const bool has_next = tile + num_clusters < p.num_tiles;
-      if (has_next) embed(tile + num_clusters, x_next);
-      LRN_STAMP(stamp, p.dbg, it * 8 + 6);  // next tile's conv1 done
+      LRN_STAMP(stamp, p.dbg, it * 8 + 6);
       // ---- conv4 epilogues: feat4 channels [256 c + 128 sub, +128) -> staging blocks -> operand row columns 448 + ...
       //      chunk 0 is staged in F2 + Z (conv3 of this tile is done with F2), chunk 1 in F3 (all of conv4 has
       //      completed once its accumulator is ready).
       for (int c = 0; c < 2; ++c) {
-        // c = 0 needs F2(t) drained (later groups: F3(t) [F1GH(t+1)]); c = 1 needs F3(t) ([F1GH(t+1)] f4c0(t))
-        staging_free(has_next ? 2 : 1);
+        // c = 0 needs F2(t) drained (later group: F3(t)); c = 1 needs F3(t) (later group: f4c0(t))
+        staging_free(1);
         ptx::mbar_wait(&acc_full[c], 1);
         ptx::tc_fence_after();
         uint32_t keep[64];
@@ -530,8 +576,9 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         for (int n = 0; n < 8; ++n) {
           const int b = n & 1, j = n >> 1;
           // blocks 2b, 2b + 1 of F3 were last read by the store of feat4 chunk 1 (n < 2) or of conv5 chunk n - 2: everything
-          // but the most recent group (chunk n - 1) must have been read
-          staging_free(n == 0 ? 0 : 1);
+          // but the most recent group (chunk n - 1) must have been read - and, for n = 4, 5, the F1GH group of the next
+          // tile's conv1 / gate layer 1, which is committed between chunks 3 and 4
+          staging_free(n == 0 ? 0 : ((n == 4 || n == 5) && has_next) ? 2 : 1);
           const bool stamp5 = p.dbg && cluster_id == 0 && leader && warp == 2 && lane == 0 && it == 1;
           LRN_STAMP(stamp5, p.dbg, 128 + 24 + n);  // staging free
           ptx::mbar_wait(&acc5_full[b], j & 1);
@@ -550,6 +597,13 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
             ptx::bulk_commit();
           }
           LRN_STAMP(stamp5, p.dbg, 128 + 40 + n);  // drained, stores issued
+          if (has_next && (n == 1 || n == 3)) {
+            // ---- next tile's conv1 (after chunk 1) and gate layer 1 (after chunk 3), in the shadow of conv5 (the epilogue
+            //      warps idle about half of every chunk): F1 / GH held this tile's first conv5 weights until the tensor
+            //      pipe finished the MMAs that read them
+            if (n == 1) ptx::mbar_wait(f1gh_used, it & 1);
+            embed(tile + num_clusters, x_next, n == 1 ? 0 : 1);
+          }
         }
       }
       LRN_STAMP(stamp, p.dbg, it * 8 + 7);  // conv4 drained
