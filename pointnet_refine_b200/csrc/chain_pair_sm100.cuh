@@ -16,8 +16,8 @@
 //                 (w & 3) and column half ((w - 2) >> 2).
 //
 // TMEM: two 256-column accumulator buffers.  conv2 -> buf0[0:128), conv3 -> buf1, conv4 chunk 0 -> buf0,
-// conv4 chunk 1 -> buf1, so conv4's second chunk runs while the first one is drained, and the next
-// tile's conv1 is computed while conv4's first chunk runs.
+// conv4 chunk 1 -> buf1, so conv4's second chunk runs while the first one is drained.  The next tile's conv1 and
+// gate layer 1 are computed by the epilogue warps in the shadow of conv5 (between its chunk drains).
 //
 // conv5 (512 -> 1024, src/model.py:47; 75 % of the chain's FLOPs) runs in the same kernel with its A operand in
 // TENSOR MEMORY: the conv4 epilogue writes feat4 as packed bf16 into TMEM columns [0, 256) (row = lane,
@@ -28,7 +28,9 @@
 // the single accumulator that fits beside feat4 serialise MMAs and drains (8.6k instead of 2 x 2.5k cycles per 256
 // channels).  Only the weights touch shared memory: conv5 streams 512 KB of them per CTA and tile, and while it runs
 // the four F2 / Z blocks (idle then) serve as four more 16 KB weight stages (7 in flight; one stage = two 64-wide
-// k-blocks of the CTA's 64 weight rows = 8 MMAs per barrier round trip).
+// k-blocks of the CTA's 64 weight rows = 8 MMAs per barrier round trip).  The F1 / GH blocks, idle from the end of conv2
+// until the next tile's conv1, take the tile's first two conv5 stages ~10k cycles ahead of time, so conv5 starts with
+// weights in place (a TMA round trip under load is ~2.8k cycles).
 #pragma once
 #include "gemm_pair_sm100.cuh"
 
