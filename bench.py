@@ -544,7 +544,7 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
     net = m
     if world > 1:     # where train_dist.py:147 wraps the model in DistributedDataParallel: one flat gradient buffer,
         net = prb.FlatDataParallel(m, overlap=os.environ.get("LRN_FDP_OVERLAP", "0") == "1")   # ONE all-reduce of the flat gradient buffer per step
-    opt = lrn_optim.FlatAdam(m.parameters(), lr=1e-3)
+    opt = lrn_optim.FlatAdam(m.parameters(), lr=1e-3, capturable=True)     # step count on the device: the step can be graph-captured
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     ctx = torch.randn(Bt, Nt, 4, device=dev, generator=g)
     line = torch.randn(Bt, 32, 3, device=dev, generator=g)
@@ -555,25 +555,48 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
         loss = lrn_optim.deep_supervision_l1(net(ctx, line), tgt)
         loss.backward()
         opt.step()
-        return loss
+        return loss.detach()      # no autograd graph kept alive (its AccumulateGrad nodes would pin this stream at capture time)
 
-    for _ in range(4):     # the caching allocator settles within a few steps (a training loop's steady state)
-        one()
-    barrier()
-    stats0 = torch.cuda.memory_stats(dev)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     steps = 8
-    for _ in range(steps):
-        loss = one()
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    stats1 = torch.cuda.memory_stats(dev)
-    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def timed(fn, warm):
+        for _ in range(warm):     # the caching allocator settles within a few steps (a training loop's steady state)
+            fn()
+        barrier()
+        s0 = torch.cuda.memory_stats(dev)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        clk = sampler.stop() if rank == 0 else None
+        s1 = torch.cuda.memory_stats(dev)
+        return (max_over_ranks(e0.elapsed_time(e1)) / steps, out, clk,
+                int(s1.get("num_device_alloc", 0) - s0.get("num_device_alloc", 0)))
+
+    # (1) the loop body of train.py:56-72 launched from Python, one kernel at a time (~800 launches, ~60 ms of host time)
+    eager_ms, loss, eager_clocks, eager_mallocs = timed(one, 4)
+    # (2) the same step captured once and replayed (pointnet_refine_b200.GraphedTrainStep): the inputs are copied into the
+    #     graph's static buffers inside the timed region; under FlatDataParallel the buffer broadcast and the flat-gradient
+    #     all-reduce are nodes of the graph
+    ms, clocks, mallocs, mode, graph_note = eager_ms, eager_clocks, eager_mallocs, "eager", None
+    if os.environ.get("LRN_BENCH_TRAIN_GRAPH", "1") == "1":
+        gstep = None
+        try:
+            gstep = prb.GraphedTrainStep(net, opt, ctx, line, tgt)
+            ms, out, clocks, mallocs = timed(lambda: gstep(ctx, line, tgt), 3)
+            loss, mode = out[0].clone(), "cuda_graph_replay"
+            del out
+        except Exception as e:      # report the eager figure and say why
+            graph_note = f"{type(e).__name__}: {e}"[:300]
+        finally:
+            if gstep is not None:
+                gstep.close()       # before destroy_process_group: NCCL waits for graphs that hold its collectives
+                del gstep
     allreduce_ms = None
     if world > 1:      # the gradient all-reduce alone: 9,695,954 fp32 = 38.8 MB (what DDP moves per step, train_dist.py:188)
         flat = torch.zeros(9_695_954, device=dev)
@@ -615,10 +638,10 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
     return {"workload": "1024 segments x 1024 points per GPU, LineRefineNet train step: forward + L1 deep supervision + backward + Adam "
                         "(BASELINE.json configs[3]); FlatDataParallel (flat gradient buffer, NCCL all-reduce) when n_gpus > 1",
             "ms_per_step": ms, "segments_per_sec": world * Bt / (ms * 1e-3), "n_gpus": world, "allreduce_ms": allreduce_ms,
+            "mode": mode, "eager_ms_per_step": eager_ms, "graph_note": graph_note,
             "loss": float(loss.detach()), "finite": bool(torch.isfinite(loss.detach())),
             "bound_ms": TRAIN_BOUND_MS, "frac_of_bound_sustained": TRAIN_BOUND_MS["sustained"] / ms, "peak_mem_gb": peak_gb,
-            "steps": steps, "clocks": clocks,
-            "device_mallocs_in_timed_region": int(stats1.get("num_device_alloc", 0) - stats0.get("num_device_alloc", 0))}
+            "steps": steps, "clocks": clocks, "device_mallocs_in_timed_region": mallocs}
 
 
 if __name__ == "__main__":

@@ -334,12 +334,14 @@ int lrn_ctx_attention_merge(const float* part, const float* lse, int B, int spli
  * likewise).  q, out, dout, dq: (B, 32, 256) fp32, heads concatenated; lse (B, 8, 32) fp32 is written by the forward and
  * read by the backward.  The backward writes dk / dv for every key in the same addressing (row pitches ld_dk / ld_dv),
  * complete for this call: no per-head gradient tensors, no gathers.  Dropout: counter-based hash of (seed, segment, head,
- * query, key), regenerated by the backward; pass a fresh seed per call and the same one to its backward. */
+ * query, key), regenerated by the backward; pass a fresh seed per call and the same one to its backward.  seed_state
+ * (may be NULL) is a device word added to `seed` when the kernel runs: a captured CUDA graph (GraphedTrainStep) advances
+ * that word inside the graph, so every replay draws a new mask although the launch arguments are frozen. */
 int lrn_train_attention_forward(const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N, float* out,
-                                float* lse, float p_drop, uint64_t seed, lrn_stream_t stream);
+                                float* lse, float p_drop, uint64_t seed, const uint64_t* seed_state, lrn_stream_t stream);
 int lrn_train_attention_backward(const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N,
                                  const float* out, const float* lse, const float* dout, float* dq, void* dk, int64_t ld_dk, void* dv,
-                                 int64_t ld_dv, float p_drop, uint64_t seed, lrn_stream_t stream);
+                                 int64_t ld_dv, float p_drop, uint64_t seed, const uint64_t* seed_state, lrn_stream_t stream);
 
 /* out[c] = sum over rows of the bf16 matrix A (rows, cols), row pitch ld: the bias gradient of a linear layer whose output
  * gradient is bf16 (cols % 64 == 0, ld % 8 == 0, A 16-byte aligned). */
@@ -354,6 +356,11 @@ int lrn_gather_heads(const void* src, int B, int H, int N, int layer, int L, voi
  * torch.optim.Adam semantics without amsgrad, weight decay added to the gradient); step counts from 1. */
 int lrn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, lrn_stream_t stream);
+/* The same step with the step count kept on the device (torch.optim.Adam(capturable=True) semantics): *step_state is
+ * incremented by a one-thread kernel first, the bias corrections are computed from it on the device, so the two launches
+ * can be captured in a CUDA graph and replayed (train.py:71 optimizer.step() inside GraphedTrainStep). */
+int lrn_adam_step_capturable(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int64_t* step_state, lrn_stream_t stream);
 /* Deep-supervision loss of train.py:63-69: loss[0] = (1/L) sum_l L1Loss(pred[l], target) for pred (L, n) and target (n)
  * (n = B*M*3 elements per decoder layer), and its gradient dpred (L, n) = sign(pred - target) / (L n); dpred may be NULL. */
 int lrn_l1_deep_supervision(const float* pred, const float* target, int L, int64_t n, float* loss, float* dpred,

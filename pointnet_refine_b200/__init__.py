@@ -8,8 +8,8 @@ from . import _lib, ops  # noqa: F401  (loads liblrn_b200.so; raises if missing)
 from .model import (DetrTransformerDecoderLayer, LineRefineNet, MultiScalePointNetEncoder,  # noqa: F401
                     PositionalEncoding)
 
-from .graph import GraphedLineRefineNet  # noqa: F401,E402
+from .graph import GraphedLineRefineNet, GraphedTrainStep  # noqa: F401,E402
 from .ddp import FlatDataParallel  # noqa: F401,E402  (flat-gradient data parallelism for train_dist.py-style loops)
 from . import scene  # noqa: F401,E402  (whole-scene front end: build_segments, refine_scene)
 
-__all__ = ["FlatDataParallel", "GraphedLineRefineNet", "LineRefineNet", "MultiScalePointNetEncoder", "PositionalEncoding", "DetrTransformerDecoderLayer", "ops", "scene"]
+__all__ = ["FlatDataParallel", "GraphedLineRefineNet", "GraphedTrainStep", "LineRefineNet", "MultiScalePointNetEncoder", "PositionalEncoding", "DetrTransformerDecoderLayer", "ops", "scene"]

@@ -27,7 +27,7 @@ EXPORTS = [
     "lrn_head_forward", "lrn_gemm_bias_act", "lrn_profile_enable", "lrn_profile_read", "lrn_debug_timeline", "lrn_train_workspace_bytes",
     "lrn_encoder_train_forward", "lrn_encoder_train_backward", "lrn_gemm_tn", "lrn_point_embed",
     "lrn_ctx_attention_splits", "lrn_ctx_attention", "lrn_pos_hidden", "lrn_pos_hidden_backward",
-    "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_scene_resample", "lrn_adam_step", "lrn_l1_deep_supervision", "lrn_col_sum_bf16", "lrn_gather_heads",
+    "lrn_scene_workspace_bytes", "lrn_scene_segments", "lrn_scene_resample", "lrn_adam_step", "lrn_adam_step_capturable", "lrn_l1_deep_supervision", "lrn_col_sum_bf16", "lrn_gather_heads",
     "lrn_add_layernorm", "lrn_add_layernorm_backward", "lrn_self_attention32", "lrn_head_update",
     "lrn_rows_linear", "lrn_query_pos_hidden", "lrn_add", "lrn_ctx_attention_merge", "lrn_cross_attention32", "lrn_train_attention_forward", "lrn_train_attention_backward",
 ]
@@ -101,6 +101,8 @@ def _load():
     lib.lrn_col_sum_bf16.argtypes = [vp, i64, i64, i64, vp, vp]
     lib.lrn_adam_step.restype = ci
     lib.lrn_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]
+    lib.lrn_adam_step_capturable.restype = ci
+    lib.lrn_adam_step_capturable.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
     lib.lrn_l1_deep_supervision.restype = ci
     lib.lrn_l1_deep_supervision.argtypes = [vp, vp, ci, i64, vp, vp, vp]
     lib.lrn_pos_hidden_backward.restype = ci
@@ -114,9 +116,9 @@ def _load():
     lib.lrn_add.restype = ci
     lib.lrn_add.argtypes = [vp, vp, vp, i64, ci, vp]
     lib.lrn_train_attention_forward.restype = ci
-    lib.lrn_train_attention_forward.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp, vp, C.c_float, C.c_uint64, vp]
+    lib.lrn_train_attention_forward.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp, vp, C.c_float, C.c_uint64, vp, vp]
     lib.lrn_train_attention_backward.restype = ci
-    lib.lrn_train_attention_backward.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp, vp, vp, vp, vp, i64, vp, i64, C.c_float, C.c_uint64, vp]
+    lib.lrn_train_attention_backward.argtypes = [vp, vp, i64, vp, i64, ci, ci, vp, vp, vp, vp, vp, i64, vp, i64, C.c_float, C.c_uint64, vp, vp]
     lib.lrn_cross_attention32.restype = ci
     lib.lrn_cross_attention32.argtypes = [vp, vp, vp, i64, ci, ci, vp, vp]
     lib.lrn_ctx_attention_merge.restype = ci

@@ -1067,6 +1067,16 @@ dim3 stats_grid(int C, int64_t rows) {
   return dim3(C / 64, unsigned(slabs));
 }
 
+// The same partition sized to what is resident: the blocks of these streaming kernels loop over the rows, so a grid of
+// exactly (SMs x resident blocks per SM) leaves no partial last wave (1200 blocks at 2 per SM were 4.05 waves).
+template <typename Kernel>
+dim3 stream_grid(Kernel kernel, int C, int64_t rows, int sms) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 31) / 32, int64_t(sms) * per_sm / (C / 64)));
+  return dim3(C / 64, unsigned(slabs));
+}
+
 int elem_grid(long long total) { return int(std::min<long long>((total + 255) / 256, 148 * 32)); }
 
 }  // namespace
@@ -1121,7 +1131,7 @@ int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running
     const int C = kUW[i], uo = kUOff[i];
     const float* gamma = i < 5 ? pr->bn_w[i] : pr->fusion_bn_w;
     const float* beta = i < 5 ? pr->bn_b[i] : pr->fusion_bn_b;
-    col_stats_kernel<<<stats_grid(C, P), 256, 0, s>>>(U + uo, kULd, P, sum + uo, sumsq + uo, 1);
+    col_stats_kernel<<<stream_grid(col_stats_kernel, C, P, dev.sms), 256, 0, s>>>(U + uo, kULd, P, sum + uo, sumsq + uo, 1);
     LRN_CUDA(cudaGetLastError());
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum + uo, sumsq + uo, U + uo, P, C, gamma, beta, pr->bn_eps, momentum,
                                                        running ? running->mean[i] : nullptr,
@@ -1129,7 +1139,7 @@ int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running
                                                        scale + uo, shift + uo);
     LRN_CUDA(cudaGetLastError());
     if (i == 5) break;
-    bn_relu_apply_kernel<<<stats_grid(C, P), 256, 0, s>>>(U + uo, kULd, P, C, scale + uo, shift + uo, X + kCatOff[i + 1], kCat);
+    bn_relu_apply_kernel<<<stream_grid(bn_relu_apply_kernel, C, P, dev.sms), 256, 0, s>>>(U + uo, kULd, P, C, scale + uo, shift + uo, X + kCatOff[i + 1], kCat);
     LRN_CUDA(cudaGetLastError());
     if (i < 4) {  // next layer's pre-activation: U_{k+1} = X_k W_{k+1}^T + b_{k+1}
       const int k = i + 2;
@@ -1144,7 +1154,7 @@ int lrn_encoder_train_forward(const lrn_encoder_params* pr, const lrn_bn_running
     }
   }
   if (fused_point_major) {
-    fusion_gate_fwd_pm_kernel<<<stats_grid(1024, P), 256, 0, s>>>(U + kUOff[5], kULd, Z, 1024, P, scale + kUOff[5],
+    fusion_gate_fwd_pm_kernel<<<stream_grid(fusion_gate_fwd_pm_kernel, 1024, P, dev.sms), 256, 0, s>>>(U + kUOff[5], kULd, Z, 1024, P, scale + kUOff[5],
                                                                    shift + kUOff[5], static_cast<__nv_bfloat16*>(fused));
   } else {
     dim3 grid(unsigned((P + 31) / 32), 32);
@@ -1204,27 +1214,28 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
 
   // ---- fused output: gate, ReLU, fusion BatchNorm
   {
-    if (fused_point_major) {
-      fusion_gate_bwd_pm_kernel<<<stats_grid(1024, P), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(d_fused), U + kUOff[5],
-                                                                     kULd, Z, 1024, P, scale + kUOff[5], shift + kUOff[5], dU,
-                                                                     dZ, 1024);
+    const int uo = kUOff[5];
+    if (fused_point_major) {   // dY, dZ and the column sums S1 / S2 (BatchNorm backward) and Sz (gate bias) in one pass
+      fusion_gate_bwd_pm_kernel<<<stream_grid(fusion_gate_bwd_pm_kernel, 1024, P, dev.sms), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(d_fused), U + uo, kULd, Z,
+                                                                     1024, P, scale + uo, shift + uo, mean + uo, rstd + uo, dU, dZ,
+                                                                     1024, S1 + uo, S2 + uo, Sz);
+      LRN_CUDA(cudaGetLastError());
     } else {
       dim3 grid(unsigned((P + 31) / 32), 32);
       fusion_gate_bwd_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(d_fused), d_global_feat,
-                                                  reinterpret_cast<const long long*>(argmax), U + kUOff[5], kULd, Z, 1024, P, int(N),
-                                                  scale + kUOff[5], shift + kUOff[5], dU, dZ, 1024);
+                                                  reinterpret_cast<const long long*>(argmax), U + uo, kULd, Z, 1024, P, int(N),
+                                                  scale + uo, shift + uo, dU, dZ, 1024);
+      LRN_CUDA(cudaGetLastError());
+      col_stats_kernel<<<stream_grid(col_stats_kernel, 1024, P, dev.sms), 256, 0, s>>>(dZ, 1024, P, Sz, nullptr, 0);  // d(gate layer 2 bias)
+      LRN_CUDA(cudaGetLastError());
+      bn_bwd_reduce_kernel<<<stream_grid(bn_bwd_reduce_kernel, 1024, P, dev.sms), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, nullptr, U + uo, kULd, P, mean + uo,
+                                                               rstd + uo, S1 + uo, S2 + uo);
+      LRN_CUDA(cudaGetLastError());
     }
-    LRN_CUDA(cudaGetLastError());
-    col_stats_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dZ, 1024, P, Sz, nullptr, 0);  // d(gate layer 2 bias)
-    LRN_CUDA(cudaGetLastError());
     LRN_CUDA(d2d(g->gate2_b, Sz, 1024));
-    const int uo = kUOff[5];
-    bn_bwd_reduce_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, nullptr, U + uo, kULd, P, mean + uo,
-                                                             rstd + uo, S1 + uo, S2 + uo);
-    LRN_CUDA(cudaGetLastError());
     LRN_CUDA(d2d(g->fusion_bn_b, S1 + uo, 1024));
     LRN_CUDA(d2d(g->fusion_bn_w, S2 + uo, 1024));
-    bn_bwd_apply_kernel<<<stats_grid(1024, P), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, nullptr, U + uo, kULd, P, 1024, mean + uo,
+    bn_bwd_apply_kernel<<<stream_grid(bn_bwd_apply_kernel, 1024, P, dev.sms), 256, 0, s>>>(dU, 1024, nullptr, 0, nullptr, nullptr, U + uo, kULd, P, 1024, mean + uo,
                                                             rstd + uo, pr->fusion_bn_w, S1 + uo, S2 + uo, dU, 1024);
     LRN_CUDA(cudaGetLastError());
     // d(fusion conv bias) = sum_p dU is exactly zero: dU is the output of a batch-statistic BatchNorm backward, whose
@@ -1244,12 +1255,12 @@ int lrn_encoder_train_backward(const lrn_encoder_params* pr, const float* contex
   for (int k = 5; k >= 1; --k) {
     const int i = k - 1, C = kChan[k], uo = kUOff[i], xo = kCatOff[k];
     const __nv_bfloat16* d2 = k < 5 ? dB : nullptr;
-    bn_bwd_reduce_kernel<<<stats_grid(C, P), 256, 0, s>>>(dA + xo, kCat, d2, 512, scale + uo, shift + uo, U + uo, kULd, P, mean + uo,
+    bn_bwd_reduce_kernel<<<stream_grid(bn_bwd_reduce_kernel, C, P, dev.sms), 256, 0, s>>>(dA + xo, kCat, d2, 512, scale + uo, shift + uo, U + uo, kULd, P, mean + uo,
                                                           rstd + uo, S1 + uo, S2 + uo);
     LRN_CUDA(cudaGetLastError());
     LRN_CUDA(d2d(g->bn_b[i], S1 + uo, C));
     LRN_CUDA(d2d(g->bn_w[i], S2 + uo, C));
-    bn_bwd_apply_kernel<<<stats_grid(C, P), 256, 0, s>>>(dA + xo, kCat, d2, 512, scale + uo, shift + uo, U + uo, kULd, P, C, mean + uo,
+    bn_bwd_apply_kernel<<<stream_grid(bn_bwd_apply_kernel, C, P, dev.sms), 256, 0, s>>>(dA + xo, kCat, d2, 512, scale + uo, shift + uo, U + uo, kULd, P, C, mean + uo,
                                                          rstd + uo, pr->bn_w[i], S1 + uo, S2 + uo, dU, 1024);
     LRN_CUDA(cudaGetLastError());
     if (k == 1) break;
@@ -1280,6 +1291,22 @@ int lrn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   const int grid = int(std::min<int64_t>((n + 255) / 256, int64_t(dev.sms) * 16));
   adam_step_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, float(double(lr) / bc1),
                                                                               beta1, beta2, eps, weight_decay, float(1.0 / sqrt(bc2)));
+  LRN_CUDA(cudaGetLastError());
+  return LRN_OK;
+}
+
+int lrn_adam_step_capturable(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int64_t* step_state, lrn_stream_t stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !step_state) return fail(LRN_ERR_BAD_ARG, "null pointer");
+  if (n <= 0) return fail(LRN_ERR_BAD_SHAPE, "n=%lld", (long long)n);
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = int(std::min<int64_t>((n + 255) / 256, int64_t(dev.sms) * 16));
+  adam_bump_step_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(step_state));
+  adam_step_dev_kernel<<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                            reinterpret_cast<const long long*>(step_state));
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }
@@ -1454,7 +1481,7 @@ int lrn_ctx_attention_merge(const float* part, const float* lse, int B, int spli
 }
 
 static int train_attn_args(TrainAttnParams* p, const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N,
-                           float* out, float* lse, float p_drop, uint64_t seed) {
+                           float* out, float* lse, float p_drop, uint64_t seed, const uint64_t* seed_state) {
   if (!q || !k || !v || !out || !lse) return fail(LRN_ERR_BAD_ARG, "null pointer");
   if (B <= 0 || N <= 0 || ld_k < 32 || ld_k % 8 || ld_v < 32 || ld_v % 8 || int64_t(B) * 8 >= (int64_t(1) << 31))
     return fail(LRN_ERR_BAD_SHAPE, "B=%d N=%d ld_k=%lld ld_v=%lld", B, N, (long long)ld_k, (long long)ld_v);
@@ -1472,13 +1499,14 @@ static int train_attn_args(TrainAttnParams* p, const float* q, const void* k, in
   p->lse = lse;
   p->p_drop = p_drop;
   p->seed = seed;
+  p->seed_state = reinterpret_cast<const unsigned long long*>(seed_state);
   return LRN_OK;
 }
 
 int lrn_train_attention_forward(const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N, float* out,
-                                float* lse, float p_drop, uint64_t seed, lrn_stream_t stream) {
+                                float* lse, float p_drop, uint64_t seed, const uint64_t* seed_state, lrn_stream_t stream) {
   TrainAttnParams p{};
-  int st = train_attn_args(&p, q, k, ld_k, v, ld_v, B, N, out, lse, p_drop, seed);
+  int st = train_attn_args(&p, q, k, ld_k, v, ld_v, B, N, out, lse, p_drop, seed, seed_state);
   if (st) return st;
   DeviceInfo dev;
   if ((st = device_info(&dev))) return st;
@@ -1489,9 +1517,9 @@ int lrn_train_attention_forward(const float* q, const void* k, int64_t ld_k, con
 
 int lrn_train_attention_backward(const float* q, const void* k, int64_t ld_k, const void* v, int64_t ld_v, int B, int N,
                                  const float* out, const float* lse, const float* dout, float* dq, void* dk, int64_t ld_dk, void* dv,
-                                 int64_t ld_dv, float p_drop, uint64_t seed, lrn_stream_t stream) {
+                                 int64_t ld_dv, float p_drop, uint64_t seed, const uint64_t* seed_state, lrn_stream_t stream) {
   TrainAttnParams p{};
-  int st = train_attn_args(&p, q, k, ld_k, v, ld_v, B, N, const_cast<float*>(out), const_cast<float*>(lse), p_drop, seed);
+  int st = train_attn_args(&p, q, k, ld_k, v, ld_v, B, N, const_cast<float*>(out), const_cast<float*>(lse), p_drop, seed, seed_state);
   if (st) return st;
   if (!dout || !dq || !dk || !dv) return fail(LRN_ERR_BAD_ARG, "null pointer");
   if (ld_dk < 32 || ld_dk % 2 || ld_dv < 32 || ld_dv % 2 || (reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dq)) & 15 ||
@@ -1514,9 +1542,12 @@ int lrn_col_sum_bf16(const void* A, int64_t ld, int64_t rows, int64_t cols, floa
   if (!A || !out) return fail(LRN_ERR_BAD_ARG, "null pointer");
   if (rows <= 0 || cols <= 0 || cols % 64 || ld < cols || ld % 8) return fail(LRN_ERR_BAD_SHAPE, "rows=%lld cols=%lld ld=%lld (cols %% 64 == 0, ld %% 8 == 0)", (long long)rows, (long long)cols, (long long)ld);
   if (reinterpret_cast<uintptr_t>(A) & 15) return fail(LRN_ERR_MISALIGNED, "A needs 16-byte alignment");
+  DeviceInfo dev;
+  int st = device_info(&dev);
+  if (st) return st;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   LRN_CUDA(cudaMemsetAsync(out, 0, size_t(cols) * 4, s));
-  col_stats_kernel<<<stats_grid(int(cols), rows), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(A), ld, rows, out, nullptr, 0);
+  col_stats_kernel<<<stream_grid(col_stats_kernel, int(cols), rows, dev.sms), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(A), ld, rows, out, nullptr, 0);
   LRN_CUDA(cudaGetLastError());
   return LRN_OK;
 }

@@ -33,6 +33,7 @@ struct TrainAttnParams {
   float* lse;                // (B, 8, 32): log2 of the softmax denominator (+ running maximum), for the backward
   float p_drop;              // 0 = no dropout
   unsigned long long seed;
+  const unsigned long long* seed_state;   // optional device word added to `seed` (a CUDA-graph replay draws a new mask without a new launch argument)
   // backward only
   const float* dout;         // (B, 32, 256)
   float* dq;                 // (B, 32, 256)
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(128, 3) train_attn_fwd_kernel(const TrainAttnP
   const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.N * p.ld + h * 32;
   const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.N * p.ldv + h * 32;
   const uint32_t thresh = static_cast<uint32_t>(p.p_drop * 65536.f);
+  const unsigned long long seed = p.seed + (p.seed_state ? __ldg(p.seed_state) : 0ull);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   float o[2][4][4], mrun[2][2], lrun[2][2];
 #pragma unroll
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(128, 3) train_attn_fwd_kernel(const TrainAttnP
           float k0 = 1.f, k1 = 1.f;
           if (thresh) {
             const int qi = 16 * mt + g + 8 * hi, key = key0 + 8 * nt + 2 * t;
-            ta_keep_pair(p.seed, (static_cast<unsigned long long>(blockIdx.x) * 32 + qi) * p.N + key, thresh, inv_keep, k0, k1);
+            ta_keep_pair(seed, (static_cast<unsigned long long>(blockIdx.x) * 32 + qi) * p.N + key, thresh, inv_keep, k0, k1);
           }
           s[mt][nt][2 * hi] = p0 * k0;
           s[mt][nt][2 * hi + 1] = p1 * k1;
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(128) train_attn_bwd_kernel(const TrainAttnPara
   __nv_bfloat16* dkb = p.dk + static_cast<long long>(b) * p.N * p.ldg + h * 32;
   __nv_bfloat16* dvb = p.dv + static_cast<long long>(b) * p.N * p.ldgv + h * 32;
   const uint32_t thresh = static_cast<uint32_t>(p.p_drop * 65536.f);
+  const unsigned long long seed = p.seed + (p.seed_state ? __ldg(p.seed_state) : 0ull);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const unsigned long long idx0 = static_cast<unsigned long long>(blockIdx.x) * 32;
   float dq[2][4][4];
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(128) train_attn_bwd_kernel(const TrainAttnPara
           for (int hi = 0; hi < 2; ++hi) {
             const int qi = 16 * mt + g + 8 * hi, key = key0 + 8 * nt + 2 * t;
             float keep[2] = {1.f, 1.f};
-            if (thresh) ta_keep_pair(p.seed, (idx0 + qi) * p.N + key, thresh, inv_keep, keep[0], keep[1]);
+            if (thresh) ta_keep_pair(seed, (idx0 + qi) * p.N + key, thresh, inv_keep, keep[0], keep[1]);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const int e = 2 * hi + j;

@@ -61,7 +61,7 @@ train_embed_kernel(const float4* __restrict__ ctx, long long rows, const float* 
 // Block = 64 columns as 8 channel groups of 8 (one 16-byte load per thread and row: 8 threads cover 128 contiguous bytes)
 // x 32 row lanes, two independent loads in flight per thread; grid = (C / 64, row slabs).  Requires a 16-byte aligned base
 // and a row pitch that is a multiple of 8 elements.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 col_stats_kernel(const __nv_bfloat16* __restrict__ A, long long ld, long long rows, float* __restrict__ sum,
                  float* __restrict__ sumsq, int shifted) {
   const int cg = threadIdx.x & 7, lane_r = threadIdx.x >> 3;
@@ -86,15 +86,20 @@ col_stats_kernel(const __nv_bfloat16* __restrict__ A, long long ld, long long ro
       q[j] = fmaf(f, f, q[j]);
     }
   };
+  // four independent 16-byte loads in flight per thread (4 resident blocks x 256 threads: 64 KB per SM on the wire)
   const long long stride = gridDim.y * 32ll;
   long long r = blockIdx.y * 32ll + lane_r;
-  for (; r + stride < rows; r += 2 * stride) {
+  for (; r + 3 * stride < rows; r += 4 * stride) {
     const uint4 v0 = *reinterpret_cast<const uint4*>(A + r * ld + c);
     const uint4 v1 = *reinterpret_cast<const uint4*>(A + (r + stride) * ld + c);
+    const uint4 v2 = *reinterpret_cast<const uint4*>(A + (r + 2 * stride) * ld + c);
+    const uint4 v3 = *reinterpret_cast<const uint4*>(A + (r + 3 * stride) * ld + c);
     acc(v0);
     acc(v1);
+    acc(v2);
+    acc(v3);
   }
-  if (r < rows) acc(*reinterpret_cast<const uint4*>(A + r * ld + c));
+  for (; r < rows; r += stride) acc(*reinterpret_cast<const uint4*>(A + r * ld + c));
   __shared__ float sh[2][32][65];   // [sum | sumsq][row lane][column of the block]
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -140,7 +145,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
 // X[:, c] = relu(U[:, c] * scale[c] + shift[c]).  Channel-stationary threads: a thread owns 8 channels (its
 // scale / shift stay in registers) and walks down the rows; 8 threads cover 128 contiguous bytes of a row.
 // grid = (C / 64, row slabs), block = 8 channel groups x 32 row lanes.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ U, long long ldu, long long rows, int C,
                      const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ X,
                      long long ldx) {
@@ -148,8 +153,7 @@ bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ U, long long ldu, long lo
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
-  for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
+  auto apply = [&](const uint4& raw, long long r) {
     const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(&raw);
     float v[8];
 #pragma unroll
@@ -157,7 +161,20 @@ bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ U, long long ldu, long lo
     *reinterpret_cast<uint4*>(X + r * ldx + c0) =
         make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
                    ptx::pack_bf16x2(v[6], v[7]));
+  };
+  const long long stride = gridDim.y * 32ll;
+  long long r = blockIdx.y * 32ll + (threadIdx.x >> 3);
+  for (; r + 3 * stride < rows; r += 4 * stride) {   // four loads in flight per thread
+    const uint4 v0 = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
+    const uint4 v1 = *reinterpret_cast<const uint4*>(U + (r + stride) * ldu + c0);
+    const uint4 v2 = *reinterpret_cast<const uint4*>(U + (r + 2 * stride) * ldu + c0);
+    const uint4 v3 = *reinterpret_cast<const uint4*>(U + (r + 3 * stride) * ldu + c0);
+    apply(v0, r);
+    apply(v1, r + stride);
+    apply(v2, r + 2 * stride);
+    apply(v3, r + 3 * stride);
   }
+  for (; r < rows; r += stride) apply(*reinterpret_cast<const uint4*>(U + r * ldu + c0), r);
 }
 
 __device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
@@ -236,7 +253,7 @@ pool_rows_kernel(const float* __restrict__ fused, long long rows /* B * 1024 */,
 }
 
 // Point-major variants (no layout change): fused_pm[p, c] bf16, channel-stationary threads like bn_relu_apply_kernel.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 fusion_gate_fwd_pm_kernel(const __nv_bfloat16* __restrict__ Uf, long long ldu, const __nv_bfloat16* __restrict__ Z,
                           long long ldz, long long rows, const float* __restrict__ scale, const float* __restrict__ shift,
                           __nv_bfloat16* __restrict__ fused_pm) {
@@ -258,34 +275,63 @@ fusion_gate_fwd_pm_kernel(const __nv_bfloat16* __restrict__ Uf, long long ldu, c
   }
 }
 
-__global__ void __launch_bounds__(256)
+// Besides dY / dZ it accumulates the three column sums the next steps need, from the rounded values it stores - the
+// fusion BatchNorm backward's S1 = sum dY, S2 = sum dY * xhat (xhat = (Uf - mean) * rstd) and Sz = sum dZ (the gate
+// layer 2 bias gradient) - so neither dY nor dZ is read again for a reduction pass.
+__global__ void __launch_bounds__(256, 3)
 fusion_gate_bwd_pm_kernel(const __nv_bfloat16* __restrict__ dfused_pm, const __nv_bfloat16* __restrict__ Uf, long long ldu,
                           const __nv_bfloat16* __restrict__ Z, long long ldz, long long rows,
-                          const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ dY,
-                          __nv_bfloat16* __restrict__ dZ, long long ldd) {
-  const int c0 = blockIdx.x * 64 + (threadIdx.x & 7) * 8;
-  float sc[8], sh[8];
+                          const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dY, __nv_bfloat16* __restrict__ dZ,
+                          long long ldd, float* __restrict__ S1, float* __restrict__ S2, float* __restrict__ Sz) {
+  const int cg = threadIdx.x & 7, lane_r = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  float sc[8], sh[8], m[8], s1[8], s2[8], sz[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
-  for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[c0 + j];
+    sh[j] = shift[c0 + j];
+    m[j] = mean[c0 + j];
+    s1[j] = s2[j] = sz[j] = 0.f;
+  }
+  for (long long r = blockIdx.y * 32ll + lane_r; r < rows; r += gridDim.y * 32ll) {
     const uint4 rd = *reinterpret_cast<const uint4*>(dfused_pm + r * 1024 + c0);
     const uint4 ru = *reinterpret_cast<const uint4*>(Uf + r * ldu + c0);
     const uint4 rz = *reinterpret_cast<const uint4*>(Z + r * ldz + c0);
     const __nv_bfloat16 *d = reinterpret_cast<const __nv_bfloat16*>(&rd), *u = reinterpret_cast<const __nv_bfloat16*>(&ru),
                         *z = reinterpret_cast<const __nv_bfloat16*>(&rz);
-    float a[8], b[8];
+    __align__(16) __nv_bfloat16 a[8], b[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float df = bf2f(d[j]);
-      const float y0 = fmaf(bf2f(u[j]), sc[j], sh[j]);
+      const float uj = bf2f(u[j]);
+      const float y0 = fmaf(uj, sc[j], sh[j]);
       const float g = sigmoidf_fast(bf2f(z[j]));
-      a[j] = y0 > 0.f ? df * (0.5f + 0.5f * g) : 0.f;
-      b[j] = df * fmaxf(y0, 0.f) * 0.5f * g * (1.f - g);
+      a[j] = __float2bfloat16_rn(y0 > 0.f ? df * (0.5f + 0.5f * g) : 0.f);
+      b[j] = __float2bfloat16_rn(df * fmaxf(y0, 0.f) * 0.5f * g * (1.f - g));
+      const float af = bf2f(a[j]);
+      s1[j] += af;
+      s2[j] = fmaf(af, uj - m[j], s2[j]);      // rstd is applied once per block below
+      sz[j] += bf2f(b[j]);
     }
-    *reinterpret_cast<uint4*>(dY + r * ldd + c0) = make_uint4(ptx::pack_bf16x2(a[0], a[1]), ptx::pack_bf16x2(a[2], a[3]),
-                                                              ptx::pack_bf16x2(a[4], a[5]), ptx::pack_bf16x2(a[6], a[7]));
-    *reinterpret_cast<uint4*>(dZ + r * ldd + c0) = make_uint4(ptx::pack_bf16x2(b[0], b[1]), ptx::pack_bf16x2(b[2], b[3]),
-                                                              ptx::pack_bf16x2(b[4], b[5]), ptx::pack_bf16x2(b[6], b[7]));
+    *reinterpret_cast<uint4*>(dY + r * ldd + c0) = *reinterpret_cast<const uint4*>(a);
+    *reinterpret_cast<uint4*>(dZ + r * ldd + c0) = *reinterpret_cast<const uint4*>(b);
+  }
+  __shared__ float shm[3][32][65];   // [S1 | S2 | Sz][row lane][column of the block]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    shm[0][lane_r][8 * cg + j] = s1[j];
+    shm[1][lane_r][8 * cg + j] = s2[j];
+    shm[2][lane_r][8 * cg + j] = sz[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 192) {
+    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) t += shm[which][k][col];
+    if (which == 1) t *= rstd[blockIdx.x * 64 + col];
+    atomicAdd((which == 0 ? S1 : which == 1 ? S2 : Sz) + blockIdx.x * 64 + col, t);
   }
 }
 
@@ -341,28 +387,24 @@ fusion_gate_bwd_kernel(const float* __restrict__ dfused, const float* __restrict
 //        sign decided the stored activation - instead of reading the activation matrix as a fourth stream; msc = null: no ReLU)
 //   xhat = (U - mean) * rstd
 // Block = 64 columns as 8 channel groups of 8 (16-byte loads) x 32 row lanes; grid = (C / 64, row slabs).
-__global__ void __launch_bounds__(256)
+// The thread accumulates A = sum dY and T = sum dY * (U - mean); S2 = rstd * T is formed once per block (rstd is not held
+// per thread: 3 resident blocks, and two rows = up to six 16-byte loads in flight per thread).
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ d1, long long ld1, const __nv_bfloat16* __restrict__ d2,
                      long long ld2, const float* __restrict__ msc, const float* __restrict__ msh,
                      const __nv_bfloat16* __restrict__ U, long long ldu, long long rows, const float* __restrict__ mean,
                      const float* __restrict__ rstd, float* __restrict__ S1, float* __restrict__ S2) {
   const int cg = threadIdx.x & 7, lane_r = threadIdx.x >> 3;
   const int c = blockIdx.x * 64 + 8 * cg;
-  float m[8], rs[8], sc[8], sh[8], a[8], b[8];
+  float sc[8], sh[8], m[8], a[8], t[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    m[j] = mean[c + j];
-    rs[j] = rstd[c + j];
     sc[j] = msc ? msc[c + j] : 0.f;
     sh[j] = msc ? msh[c + j] : 0.f;
-    a[j] = b[j] = 0.f;
+    m[j] = mean[c + j];
+    a[j] = t[j] = 0.f;
   }
-  const long long stride = gridDim.y * 32ll;
-  for (long long r = blockIdx.y * 32ll + lane_r; r < rows; r += stride) {
-    const uint4 r1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c);
-    const uint4 ru = *reinterpret_cast<const uint4*>(U + r * ldu + c);
-    uint4 r2 = make_uint4(0, 0, 0, 0);
-    if (d2) r2 = *reinterpret_cast<const uint4*>(d2 + r * ld2 + c);
+  auto acc = [&](const uint4& r1, const uint4& r2, const uint4& ru) {
     const __nv_bfloat16 *p1 = reinterpret_cast<const __nv_bfloat16*>(&r1), *p2 = reinterpret_cast<const __nv_bfloat16*>(&r2),
                         *pu = reinterpret_cast<const __nv_bfloat16*>(&ru);
 #pragma unroll
@@ -372,29 +414,56 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ d1, long long ld1, const 
       if (d2) d += bf2f(p2[j]);
       if (msc && !(fmaf(u, sc[j], sh[j]) > 0.f)) d = 0.f;
       a[j] += d;
-      b[j] = fmaf(d, (u - m[j]) * rs[j], b[j]);
+      t[j] = fmaf(d, u - m[j], t[j]);
     }
+  };
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const long long stride = gridDim.y * 32ll;
+  long long r = blockIdx.y * 32ll + lane_r;
+  for (; r + stride < rows; r += 2 * stride) {
+    const long long rb = r + stride;
+    const uint4 a1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c);
+    const uint4 au = *reinterpret_cast<const uint4*>(U + r * ldu + c);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(d1 + rb * ld1 + c);
+    const uint4 bu = *reinterpret_cast<const uint4*>(U + rb * ldu + c);
+    uint4 a2 = zero, b2 = zero;
+    if (d2) {
+      a2 = *reinterpret_cast<const uint4*>(d2 + r * ld2 + c);
+      b2 = *reinterpret_cast<const uint4*>(d2 + rb * ld2 + c);
+    }
+    acc(a1, a2, au);
+    acc(b1, b2, bu);
   }
-  __shared__ float shm[2][32][65];   // [S1 | S2][row lane][column of the block]
+  if (r < rows) {
+    const uint4 a1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c);
+    const uint4 au = *reinterpret_cast<const uint4*>(U + r * ldu + c);
+    const uint4 a2 = d2 ? *reinterpret_cast<const uint4*>(d2 + r * ld2 + c) : zero;
+    acc(a1, a2, au);
+  }
+  __shared__ float shm[2][32][65];   // [A | T][row lane][column of the block]
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     shm[0][lane_r][8 * cg + j] = a[j];
-    shm[1][lane_r][8 * cg + j] = b[j];
+    shm[1][lane_r][8 * cg + j] = t[j];
   }
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
-    float t = 0.f;
+  if (threadIdx.x < 64) {
+    const int col = threadIdx.x, ch = blockIdx.x * 64 + col;
+    float sa = 0.f, st = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < 32; ++k) t += shm[which][k][col];
-    atomicAdd((which == 0 ? S1 : S2) + blockIdx.x * 64 + col, t);
+    for (int k = 0; k < 32; ++k) {
+      sa += shm[0][k][col];
+      st += shm[1][k][col];
+    }
+    atomicAdd(S1 + ch, sa);
+    atomicAdd(S2 + ch, rstd[ch] * st);
   }
 }
 
 // BatchNorm backward, pass 2: dU = gamma * rstd * (dY - S1/P - xhat * S2/P) = A_c dY + B_c U + C_c with per-channel
 // coefficients kept in registers (channel-stationary threads as in bn_relu_apply_kernel).
 // d1 may alias dU (in place): every element is read before it is written by the same thread.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* d1, long long ld1, const __nv_bfloat16* __restrict__ d2, long long ld2,
                     const float* __restrict__ msc, const float* __restrict__ msh, const __nv_bfloat16* __restrict__ U,
                     long long ldu, long long rows, int C, const float* __restrict__ mean,
@@ -413,11 +482,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* d1, long long ld1, const __nv_bfloat16*
     Bc[j] = -gr * rstd[c] * S2[c] * inv_n;
     Cc[j] = -gr * S1[c] * inv_n - Bc[j] * mean[c];
   }
-  for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
-    const uint4 r1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c0);
-    const uint4 ru = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
-    uint4 r2 = make_uint4(0, 0, 0, 0);
-    if (d2) r2 = *reinterpret_cast<const uint4*>(d2 + r * ld2 + c0);
+  auto apply = [&](const uint4& r1, const uint4& r2, const uint4& ru, long long r) {
     const __nv_bfloat16 *p1 = reinterpret_cast<const __nv_bfloat16*>(&r1), *p2 = reinterpret_cast<const __nv_bfloat16*>(&r2),
                         *pu = reinterpret_cast<const __nv_bfloat16*>(&ru);
     float v[8];
@@ -432,6 +497,29 @@ bn_bwd_apply_kernel(const __nv_bfloat16* d1, long long ld1, const __nv_bfloat16*
     *reinterpret_cast<uint4*>(dU + r * ldo + c0) =
         make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
                    ptx::pack_bf16x2(v[6], v[7]));
+  };
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const long long stride = gridDim.y * 32ll;
+  long long r = blockIdx.y * 32ll + (threadIdx.x >> 3);
+  for (; r + stride < rows; r += 2 * stride) {   // two rows = up to six loads in flight per thread; both rows are read
+    const long long rb = r + stride;             // before either is written (d1 may alias dU)
+    const uint4 a1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c0);
+    const uint4 au = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(d1 + rb * ld1 + c0);
+    const uint4 bu = *reinterpret_cast<const uint4*>(U + rb * ldu + c0);
+    uint4 a2 = zero, b2 = zero;
+    if (d2) {
+      a2 = *reinterpret_cast<const uint4*>(d2 + r * ld2 + c0);
+      b2 = *reinterpret_cast<const uint4*>(d2 + rb * ld2 + c0);
+    }
+    apply(a1, a2, au, r);
+    apply(b1, b2, bu, rb);
+  }
+  if (r < rows) {
+    const uint4 a1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c0);
+    const uint4 au = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
+    const uint4 a2 = d2 ? *reinterpret_cast<const uint4*>(d2 + r * ld2 + c0) : zero;
+    apply(a1, a2, au, r);
   }
 }
 
@@ -517,6 +605,34 @@ gather_heads_kernel(const uint4* __restrict__ src, int B, int H, int N, int laye
 __global__ void __launch_bounds__(256)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                  float step_size, float b1, float b2, float eps, float wd, float inv_bc2_sqrt) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = fmaf(1.f - b1, gi - m[i], m[i]);
+    const float vi = fmaf(1.f - b2, gi * gi, b2 * v[i]);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * (mi / (sqrtf(vi) * inv_bc2_sqrt + eps));
+  }
+}
+
+// The same step with the step count in device memory (torch.optim.Adam(capturable=True)): a captured CUDA graph replays
+// it with the right bias corrections.  adam_bump_step_kernel runs first in the stream (step += 1).
+__global__ void adam_bump_step_kernel(long long* step) { *step += 1; }
+
+__global__ void __launch_bounds__(256)
+adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                     float lr, float b1, float b2, float eps, float wd, const long long* __restrict__ step) {
+  __shared__ float sh[2];
+  if (threadIdx.x == 0) {
+    const double t = static_cast<double>(*step);
+    sh[0] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(b1), t)));
+    sh[1] = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), t)));
+  }
+  __syncthreads();
+  const float step_size = sh[0], inv_bc2_sqrt = sh[1];
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     float gi = g[i];

@@ -16,7 +16,7 @@ from .ops import _stream_ptr
 
 
 class FlatAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, capturable=False):
         params = [p for p in params]
         if not params:
             raise ValueError("FlatAdam got an empty parameter list")
@@ -31,6 +31,14 @@ class FlatAdam(torch.optim.Optimizer):
         self._v = torch.zeros_like(self._flat)
         self._views = list(zip(self._fp.params, self._fp.grad_views))
         self._step = 0
+        # capturable (torch.optim.Adam's flag of the same name): the step count lives on the device and the bias
+        # corrections are computed there, so step() can be captured in a CUDA graph and replayed (graph.GraphedTrainStep)
+        self.capturable = bool(capturable)
+        self._step_dev = torch.zeros(1, dtype=torch.int64, device=self._flat.device) if capturable else None
+
+    @property
+    def steps_taken(self) -> int:
+        return int(self._step_dev.item()) if self.capturable else self._step
 
     def _attach(self, keep_foreign: bool = True):
         """Make every parameter's .grad the view of the flat gradient buffer.  A gradient some other code bound to
@@ -50,7 +58,7 @@ class FlatAdam(torch.optim.Optimizer):
     def state_dict(self):
         """Adam moments and the step count live in the flat buffers, not in `self.state`: add them to the checkpoint."""
         sd = super().state_dict()
-        sd["flat_adam"] = {"exp_avg": self._m.clone(), "exp_avg_sq": self._v.clone(), "step": self._step}
+        sd["flat_adam"] = {"exp_avg": self._m.clone(), "exp_avg_sq": self._v.clone(), "step": self.steps_taken}
         return sd
 
     def load_state_dict(self, state_dict):
@@ -63,6 +71,8 @@ class FlatAdam(torch.optim.Optimizer):
             self._m.copy_(flat["exp_avg"])
             self._v.copy_(flat["exp_avg_sq"])
             self._step = int(flat["step"])
+            if self.capturable:
+                self._step_dev.fill_(self._step)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -74,6 +84,15 @@ class FlatAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         self._step += 1
         dev = self._flat.device
+        if self.capturable:
+            with torch.cuda.device(dev):
+                _lib.check(lib.lrn_adam_step_capturable(self._flat.data_ptr(), self._grad.data_ptr(), self._m.data_ptr(),
+                                                        self._v.data_ptr(), self._flat.numel(), float(g["lr"]), float(g["betas"][0]),
+                                                        float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                                                        self._step_dev.data_ptr(), _stream_ptr(dev)), "lrn_adam_step_capturable")
+            _lib.launch_counter += 2
+            torch.autograd.graph.increment_version([p for p, _ in self._views])
+            return loss
         with torch.cuda.device(dev):
             _lib.check(lib.lrn_adam_step(self._flat.data_ptr(), self._grad.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
                                          self._flat.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),

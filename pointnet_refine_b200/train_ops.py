@@ -283,6 +283,25 @@ def kv_proj(x, weight, bias, layers: int, heads: int, share: KVGradShare | None 
     return KVProjFn.apply(x, weight, bias, layers, heads, share, zero_bias_grad)
 
 
+class DropoutSeedState:
+    """Where the train attention kernels' dropout seed comes from.  Default: a fresh 62-bit draw from torch's host
+    generator per attention call, passed as a launch argument.  Under a CUDA-graph capture launch arguments are frozen,
+    so graph.GraphedTrainStep installs a device word here instead (`word`, int64 on the GPU, advanced inside the
+    graph): every attention call of the step then passes a fixed per-call salt as `seed` and the kernels add the word."""
+    word = None      # int64 CUDA tensor of one element, or None
+    calls = 0        # attention calls since the word was installed / the step began (the per-call salt)
+
+    @classmethod
+    def next(cls, p_drop):
+        """(seed, seed_state pointer or None) for one attention call."""
+        if p_drop <= 0:
+            return 0, None
+        if cls.word is None:
+            return int(torch.randint(0, 2 ** 62, (1,)).item()), None     # host generator: follows torch.manual_seed
+        cls.calls += 1
+        return (cls.calls * 0x9E3779B97F4A7C15) & (2 ** 62 - 1), cls.word.data_ptr()
+
+
 class CrossAttnTrainFn(torch.autograd.Function):
     """Attention of the 32 polyline queries of a segment in train mode (8 heads x 32, dropout on the attention weights),
     forward and backward on lrn_train_attention_*.  Cross attention: K / V are read straight from the K / V projection's
@@ -299,20 +318,20 @@ class CrossAttnTrainFn(torch.autograd.Function):
             raise ValueError("CrossAttnTrainFn: expected q (B,32,256) and (B,8,N,32) bf16 views with heads 32 elements apart")
         out = torch.empty_like(q)
         lse = torch.empty(B, 8, 32, dtype=torch.float32, device=q.device)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0     # host generator: follows torch.manual_seed
+        seed, seed_state = DropoutSeedState.next(p_drop)
         with torch.cuda.device(q.device):
             _lib.check(lib.lrn_train_attention_forward(q.data_ptr(), k.data_ptr(), ldk, v.data_ptr(), ldv, B, N, out.data_ptr(),
-                                                       lse.data_ptr(), float(p_drop), seed, _stream_ptr(q.device)),
+                                                       lse.data_ptr(), float(p_drop), seed, seed_state, _stream_ptr(q.device)),
                        "lrn_train_attention_forward")
         _lib.launch_counter += 1
         ctx.save_for_backward(q, k, v, out, lse)
-        ctx.cfg = (float(p_drop), seed, share, int(layer))
+        ctx.cfg = (float(p_drop), seed, seed_state, share, int(layer))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         q, k, v, out, lse = ctx.saved_tensors
-        p_drop, seed, share, layer = ctx.cfg
+        p_drop, seed, seed_state, share, layer = ctx.cfg
         B, H, N, hd = k.shape
         dout = _f32c(dout)
         dq = torch.empty_like(q)
@@ -327,7 +346,7 @@ class CrossAttnTrainFn(torch.autograd.Function):
             _lib.check(lib.lrn_train_attention_backward(q.data_ptr(), k.data_ptr(), k.stride(2), v.data_ptr(), v.stride(2), B, N,
                                                         out.data_ptr(), lse.data_ptr(), dout.data_ptr(), dq.data_ptr(),
                                                         gk.data_ptr(), gk.stride(2), gv.data_ptr(), gv.stride(2), p_drop, seed,
-                                                        _stream_ptr(q.device)), "lrn_train_attention_backward")
+                                                        seed_state, _stream_ptr(q.device)), "lrn_train_attention_backward")
         _lib.launch_counter += 1
         return dq, gk, gv, None, None, None
 

@@ -519,3 +519,132 @@ def test_train_self_attention_matches_torch(dev):
     rel = lambda a, b: float((a.detach().double() - b.detach()).norm() / b.detach().norm())
     assert rel(out, ref) <= 1e-2
     assert rel(qk.grad, qd.grad) <= 2e-2 and rel(v.grad, vd.grad) <= 2e-2
+
+
+def test_train_attention_seed_state_word(dev):
+    """Graph-safe dropout: with train_ops.DropoutSeedState.word installed the kernels use seed = per-call salt + the device
+    word (lrn_train_attention_* `seed_state`), forward and backward alike, and a changed word draws a different mask."""
+    from pointnet_refine_b200 import train_ops
+    from pointnet_refine_b200.train_ops import CrossAttnTrainFn, DropoutSeedState
+    B, N, p = 2, 40, 0.25
+    g = torch.Generator(device=dev).manual_seed(3)
+    q = torch.randn(B, 32, 256, device=dev, generator=g, requires_grad=True)
+    k = torch.randn(B, N, 8, 32, device=dev, generator=g).bfloat16().requires_grad_()
+    v = torch.randn(B, N, 8, 32, device=dev, generator=g).bfloat16().requires_grad_()
+    r = torch.randn(B, 32, 256, device=dev, generator=g)
+    word = torch.tensor([123456789012345], dtype=torch.int64, device=dev)
+    outs = []
+    for w in (123456789012345, 123456789012345, 987654321):
+        word.fill_(w)
+        DropoutSeedState.word, DropoutSeedState.calls = word, 0
+        try:
+            for t in (q, k, v):
+                t.grad = None
+            out = CrossAttnTrainFn.apply(q, k.transpose(1, 2), v.transpose(1, 2), p, None, 0)
+            (out * r).sum().backward()
+        finally:
+            DropoutSeedState.word = None
+        outs.append((out.detach().clone(), q.grad.clone(), k.grad.clone()))
+    seed = ((1 * 0x9E3779B97F4A7C15) & (2 ** 62 - 1)) + 123456789012345
+    qd = q.detach().double().view(B, 32, 8, 32).transpose(1, 2).requires_grad_()
+    kd = k.detach().double().transpose(1, 2).requires_grad_()
+    vd = v.detach().double().transpose(1, 2)
+    P = torch.softmax(qd @ kd.transpose(2, 3) / 32 ** 0.5, dim=-1) * _ta_keep_mask(seed, B, N, p, dev).double()
+    ref = (P @ vd).transpose(1, 2).reshape(B, 32, 256)
+    (ref * r.double()).sum().backward()
+    rel = lambda a, b: float((a.double() - b.detach()).norm() / b.detach().norm())
+    assert rel(outs[0][0], ref) <= 1e-2, rel(outs[0][0], ref)
+    assert rel(outs[0][1], qd.grad.transpose(1, 2).reshape(B, 32, 256)) <= 2e-2
+    assert rel(outs[0][2], kd.grad.transpose(1, 2)) <= 2e-2
+    assert torch.equal(outs[0][0], outs[1][0])                       # same word -> same mask
+    assert rel(outs[2][0], ref) > 0.1                                # another word -> another mask
+
+
+def test_flat_adam_capturable_matches_host_step(dev):
+    """FlatAdam(capturable=True): the step count and bias corrections live on the device (lrn_adam_step_capturable);
+    same trajectory as the host-counted step, and the count round-trips through state_dict."""
+    from pointnet_refine_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    net_a = torch.nn.Linear(96, 64).to(dev)
+    net_b = copy.deepcopy(net_a)
+    opt_a, opt_b = FlatAdam(net_a.parameters(), lr=1e-3, capturable=True), FlatAdam(net_b.parameters(), lr=1e-3)
+    x = torch.randn(16, 96, device=dev)
+    for _ in range(7):
+        for net, opt in ((net_a, opt_a), (net_b, opt_b)):
+            opt.zero_grad()
+            net(x).square().mean().backward()
+            opt.step()
+    for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+        assert float((pa - pb).detach().abs().max()) <= 1e-6
+    assert opt_a.steps_taken == 7 and opt_a.state_dict()["flat_adam"]["step"] == 7
+    opt_c = FlatAdam(copy.deepcopy(net_a).parameters(), lr=1e-3, capturable=True)
+    opt_c.load_state_dict(opt_a.state_dict())
+    assert opt_c.steps_taken == 7
+
+
+def _no_dropout(m):
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, torch.nn.MultiheadAttention):
+            mod.dropout = 0.0
+
+
+def test_graphed_train_step_matches_eager(dev):
+    """GraphedTrainStep (zero_grad -> forward -> loss -> backward -> FlatAdam step as ONE CUDA-graph replay) against the
+    same loop run eagerly, dropout off so both are deterministic up to the order of the fp32 atomics: same losses, same
+    parameters, BatchNorm counters and Adam step count advance per replay, construction leaves the model untouched."""
+    import pointnet_refine_b200 as prb
+    from pointnet_refine_b200.optim import FlatAdam, deep_supervision_l1
+    torch.manual_seed(0)
+    m_g = prb.LineRefineNet().to(dev).train()
+    m_g.context_encoder.native_training = True
+    _no_dropout(m_g)
+    m_e = copy.deepcopy(m_g)
+    before = {k: v.clone() for k, v in m_g.state_dict().items()}
+    # lr 1e-4: two runs of the SAME loop drift apart step by step (fp32 atomics order feeding bf16 roundings), slowly enough
+    # at this rate that eight steps stay comparable
+    opt_g, opt_e = FlatAdam(m_g.parameters(), lr=1e-4, capturable=True), FlatAdam(m_e.parameters(), lr=1e-4)
+    batches = []
+    for s in range(4):
+        ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(8, 512, seed=20 + s))
+        batches.append((ctx, line, 0.1 * torch.randn(8, 32, 3, device=dev)))
+    step = prb.GraphedTrainStep(m_g, opt_g, *batches[0])
+    for k, v in m_g.state_dict().items():                       # warm-up steps were rolled back
+        assert torch.equal(v, before[k]), k
+    assert opt_g.steps_taken == 0
+    for it in range(8):
+        ctx, line, tgt = batches[it % 4]
+        loss_g, pred_g = step(ctx, line, tgt)
+        opt_e.zero_grad()
+        pred_e = m_e(ctx, line)
+        loss_e = deep_supervision_l1(pred_e, tgt)
+        loss_e.backward()
+        opt_e.step()
+        tol = 2e-2 if it < 3 else 6e-2
+        assert abs(float(loss_g) - float(loss_e.detach())) <= tol * abs(float(loss_e.detach())), (it, float(loss_g), float(loss_e.detach()))
+    assert opt_g.steps_taken == 8 and int(m_g.context_encoder.bn1.num_batches_tracked) == 8
+    assert all(p._version > 0 for p in m_g.parameters())
+    m_g.eval(); m_e.eval()
+    with torch.no_grad():
+        og, oe = m_g(*batches[0][:2]), m_e(*batches[0][:2])
+    assert torch.isfinite(og).all()
+    assert float((og - oe).abs().max()) <= 0.15 * float(oe.abs().max()), float((og - oe).abs().max())
+
+
+def test_graphed_train_step_with_dropout_trains(dev):
+    """The reference's configuration (dropout 0.1 in the attention weights and the decoder layers): replays draw new
+    masks (the seed word advances inside the graph) and the loss goes down."""
+    import pointnet_refine_b200 as prb
+    from pointnet_refine_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    m = prb.LineRefineNet().to(dev).train()
+    m.context_encoder.native_training = True
+    opt = FlatAdam(m.parameters(), lr=1e-3, capturable=True)
+    ctx, line = (torch.from_numpy(a).to(dev) for a in synth.make_inputs(8, 512, seed=5))
+    tgt = 0.1 * torch.randn(8, 32, 3, device=dev)
+    step = prb.GraphedTrainStep(m, opt, ctx, line, tgt)
+    w0 = int(step._seed)
+    losses = [float(step(ctx, line, tgt)[0]) for _ in range(12)]
+    assert int(step._seed) != w0 and step.replays == 12
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
