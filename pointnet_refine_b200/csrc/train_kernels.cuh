@@ -498,24 +498,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* d1, long long ld1, const __nv_bfloat16*
         make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
                    ptx::pack_bf16x2(v[6], v[7]));
   };
+  // one row per step: with two rows in flight the 40 per-channel coefficients no longer fit next to the loads (spills) and
+  // the kernel did not get faster (measured) - its mixed read / write stream sits at ~0.73 of the copy bandwidth either way
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  const long long stride = gridDim.y * 32ll;
-  long long r = blockIdx.y * 32ll + (threadIdx.x >> 3);
-  for (; r + stride < rows; r += 2 * stride) {   // two rows = up to six loads in flight per thread; both rows are read
-    const long long rb = r + stride;             // before either is written (d1 may alias dU)
-    const uint4 a1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c0);
-    const uint4 au = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
-    const uint4 b1 = *reinterpret_cast<const uint4*>(d1 + rb * ld1 + c0);
-    const uint4 bu = *reinterpret_cast<const uint4*>(U + rb * ldu + c0);
-    uint4 a2 = zero, b2 = zero;
-    if (d2) {
-      a2 = *reinterpret_cast<const uint4*>(d2 + r * ld2 + c0);
-      b2 = *reinterpret_cast<const uint4*>(d2 + rb * ld2 + c0);
-    }
-    apply(a1, a2, au, r);
-    apply(b1, b2, bu, rb);
-  }
-  if (r < rows) {
+  for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
     const uint4 a1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c0);
     const uint4 au = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
     const uint4 a2 = d2 ? *reinterpret_cast<const uint4*>(d2 + r * ld2 + c0) : zero;

@@ -195,7 +195,10 @@ class LinearBf16Fn(torch.autograd.Function):
         need_x, need_w, need_b = ctx.needs
         dx = dw = db = None
         if need_x:
-            dx = ops.gemm_bias_act(dyb, wb.t().contiguous(), None, out_dtype=torch.bfloat16).to(ctx.x_dtype)
+            direct = ctx.x_dtype in (torch.float32, torch.bfloat16)     # fp32 straight from the accumulators: no cast pass
+            dx = ops.gemm_bias_act(dyb, wb.t().contiguous(), None, out_dtype=ctx.x_dtype if direct else torch.bfloat16)
+            if not direct:
+                dx = dx.to(ctx.x_dtype)
         if need_w:
             dw = ops.gemm_tn(dyb, xb)
         if need_b:
