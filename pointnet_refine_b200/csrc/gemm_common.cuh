@@ -71,6 +71,7 @@ struct GemmParams {
   float* fused_cn;               // (B, 1024, N) fp32
   void* fused_pm;                // (M, 1024) operand type, rows local to this launch
   long long* dbg;                // optional: clock64() stamps of cluster 0 (tools/timeline.py), normally null
+  int a_ring;                    // -DLRN_TIMELINE build only (tools/l2_ring_probe.py): A row tiles are read modulo this count
 };
 
 // In-warp transpose-reduce: every lane holds 32 values (one per channel of the chunk, for its own

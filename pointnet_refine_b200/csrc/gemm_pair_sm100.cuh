@@ -200,8 +200,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               ptx::tma_load_2d_pair(sa + L::kA + b * 8192, &tmB, full_leader,
                                     n_blk * BN + static_cast<int>(rank) * (BN / 2) + 64 * b, kcol * BK);
           } else {
+#ifdef LRN_TIMELINE   // tools/l2_ring_probe.py: read the operand rows of tile (m_blk mod ring) - an L2-resident stand-in
+            const int a_blk = p.a_ring > 0 ? m_blk % p.a_ring : m_blk;
+#else
+            const int a_blk = m_blk;
+#endif
             if (p.a_tiled)  // one contiguous 16 KB block: (column block, row tile) of the tiled operand matrix
-              ptx::tma_load_4d_pair(sa, &tmA, full_leader, 0, 0, (p.a_col0 + kcol * BK) / BK, m_blk * 2 + static_cast<int>(rank));
+              ptx::tma_load_4d_pair(sa, &tmA, full_leader, 0, 0, (p.a_col0 + kcol * BK) / BK, a_blk * 2 + static_cast<int>(rank));
             else
               ptx::tma_load_2d_pair(sa, &tmA, full_leader, p.a_col0 + kcol * BK + a_extra, m_blk * 2 * BM + static_cast<int>(rank) * BM);
             ptx::tma_load_2d_pair(sa + L::kA, &tmB, full_leader, kcol * BK + b_extra, n_blk * BN + static_cast<int>(rank) * (BN / 2));

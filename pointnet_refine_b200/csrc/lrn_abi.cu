@@ -503,6 +503,10 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
 #endif
       StageTimer timer(LRN_STAGE_CONV5, s);  // reported as stage "conv5"; the other chain stages then read 0
       const int grid = 2 * std::min(cp.num_tiles, dev.sms / 2);
+#ifdef LRN_TIMELINE   // tools/l2_ring_probe.py: fusion kernel alone on whatever the operand buffer holds
+      const char* skip_chain = getenv("LRN_DBG_SKIP_CHAIN");
+      if (!(skip_chain && atoi(skip_chain)))
+#endif
       chain_pair_kernel<<<grid, kPairThreads, ChainSmem::kDynamic, s>>>(tw_chain[0], tw_chain[1], tw_chain[2], tw_chain[3], ta, cp);
       LRN_CUDA(cudaGetLastError());
     } else {  // layer 1 (+ gate layer 1): raw points -> operand columns
@@ -567,6 +571,7 @@ int lrn_encoder_forward(const void* packed, int precision, const float* context,
       p.fused_pm = fused_pm;
 #ifdef LRN_TIMELINE
       p.dbg = getenv("LRN_DBG_LAYER") ? nullptr : g_dbg;
+      if (const char* ring = getenv("LRN_DBG_RING")) p.a_ring = atoi(ring);
 #endif
       StageTimer timer(LRN_STAGE_FUSION, s);
       st = launch_gemm(precision, plan_f, EPI_FUSION, ta, twfg, p, dev.sms, s);
