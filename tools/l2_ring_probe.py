@@ -17,7 +17,7 @@ if "LRN_B200_LIB" not in os.environ:
     sys.path.insert(0, os.path.join(ROOT, "pointnet_refine_b200"))
     import build as lrn_build
     lib = lrn_build.build(timeline=True)
-    for ring, skip in (("0", "0"), ("0", "1"), ("74", "1"), ("37", "1"), ("0", "1")):
+    for ring, skip in (("0", "0"), ("0", "1"), ("37", "1"), ("74", "1"), ("0", "1"), ("37", "1")):
         env = dict(os.environ, LRN_B200_LIB=lib, LRN_DBG_RING=ring, LRN_DBG_SKIP_CHAIN=skip, LRN_DBG_LAYER="9")
         subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, check=True)
     sys.exit(0)
@@ -58,7 +58,7 @@ with torch.no_grad():
     th = threading.Thread(target=samp)
     th.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 40
+    reps = int(os.environ.get("LRN_PROBE_REPS", "200"))      # ~6 s of load: long enough for the power cap to settle
     e0.record()
     for _ in range(reps):
         enc.run_native(ctx, pool=True)
