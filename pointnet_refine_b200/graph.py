@@ -61,6 +61,9 @@ class GraphedTrainStep:
       word to their seed (train_ops.DropoutSeedState), advanced inside the graph; torch's own dropout kernels take their
       Philox offsets from the graph-registered generator;
     * no host synchronisation anywhere in the step (there is none: the loss stays on the device).
+    Launch arguments are frozen at capture: the optimizer's lr / betas / eps / weight decay, the dropout rates and the batch
+    shape are the ones in force when the step was built (the reference trains at a constant lr, train.py:21,40); build a
+    new GraphedTrainStep to change them.
     `net` may be the bare model or `FlatDataParallel(model)`: its buffer broadcast and the flat-gradient all-reduce are
     NCCL launches on the capture stream and become graph nodes.  Parameters, Adam moments, BatchNorm buffers and the
     step count are snapshotted before the eager warm-up steps and restored after them, so construction does not train.
