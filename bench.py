@@ -46,7 +46,11 @@ FLOP_PER_POINT_FUSION_KERNEL = 2 * (1984 + 64) * 1024   # fusion conv + gate lay
 FLOP_PER_POINT_CHAIN_KERNEL = 2 * (64 * 128 + 128 * 256 + 256 * 512 + 512 * 1024)   # conv2..conv5 = 1,392,640
 FLOP_PER_POINT_FORWARD = 8_013_952      # whole LineRefineNet.forward per context point (+ 0.399 GFLOP per segment)
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
-TRAIN_BOUND_MS = {"burst": 16.2, "sustained": 19.3}   # 26.4 TFLOP per 1024 x 1024 step / measured peaks
+# 26.4 TFLOP per 1024 x 1024 step / measured peaks (pure-FLOP bound).  "dataflow": the floor of the step as it
+# is built: every GEMM at the larger of its tensor time and its HBM time (17.4 ms,
+# profiles/r02u_train_gemm_shapes.jsonl: seven of the nine layers are HBM-bound at this batch), the BatchNorm / gate passes
+# (10.3 ms) and the attention K / V / dK / dV traffic (3.0 ms) at the measured copy bandwidth, ~3 ms of query-side work.
+TRAIN_BOUND_MS = {"burst": 16.2, "sustained": 19.3, "dataflow": 34.0}
 
 
 def load_peaks():
@@ -640,7 +644,8 @@ def train_step_bench(prb, torch, dist, dev, local_rank, rank, world, barrier, ma
             "ms_per_step": ms, "segments_per_sec": world * Bt / (ms * 1e-3), "n_gpus": world, "allreduce_ms": allreduce_ms,
             "mode": mode, "eager_ms_per_step": eager_ms, "graph_note": graph_note,
             "loss": float(loss.detach()), "finite": bool(torch.isfinite(loss.detach())),
-            "bound_ms": TRAIN_BOUND_MS, "frac_of_bound_sustained": TRAIN_BOUND_MS["sustained"] / ms, "peak_mem_gb": peak_gb,
+            "bound_ms": TRAIN_BOUND_MS, "frac_of_bound_sustained": TRAIN_BOUND_MS["sustained"] / ms,
+            "frac_of_dataflow_floor": TRAIN_BOUND_MS["dataflow"] / ms, "peak_mem_gb": peak_gb,
             "steps": steps, "clocks": clocks, "device_mallocs_in_timed_region": mallocs}
 
 
