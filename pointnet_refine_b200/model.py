@@ -480,7 +480,7 @@ class LineRefineNet(nn.Module):
         as DetrTransformerDecoderLayer; dropout draws differ from the reference's RNG stream (they would from run to
         run there, too)."""
         from .train_ops import (KVGradShare, add_layernorm, cross_attention_train, kv_proj, linear_bf16, pos_hidden_train,
-                                self_attention_train)
+                                self_attention_train, thin_linear)
         B, N, _ = context.shape
         d, H = self.d_model, 8
         wk = torch.cat([l.cross_attn.in_proj_weight[d:2 * d] for l in self.decoder_layers])
@@ -505,7 +505,7 @@ class LineRefineNet(nn.Module):
         current = noisy_line
         outs = []
         for i, (layer, head) in enumerate(zip(self.decoder_layers, self.reg_branches)):
-            qpos = lin(F.relu(pe0(current)), pe2.weight, pe2.bias)
+            qpos = lin(F.relu(thin_linear(current, pe0.weight, pe0.bias)), pe2.weight, pe2.bias)
             q = tgt + qpos
             sa = layer.self_attn
             if native_ca:     # [q | k] and v stay bf16 where the tensor-core linear produced them; attention on lrn_train_attention_*
@@ -532,7 +532,7 @@ class LineRefineNet(nn.Module):
             tgt = add_layernorm(tgt, layer.dropout2(lin(att, ca.out_proj.weight, ca.out_proj.bias)), layer.norm2)
             ffn = lin(layer.dropout(F.relu(lin(tgt, layer.linear1.weight, layer.linear1.bias))), layer.linear2.weight, layer.linear2.bias)
             tgt = add_layernorm(tgt, layer.dropout3(ffn), layer.norm3)
-            current = current + head[2](F.relu(lin(tgt, head[0].weight, head[0].bias)))   # reg_branches[i]: 256 -> 128 on the tensor cores
+            current = current + thin_linear(F.relu(lin(tgt, head[0].weight, head[0].bias)), head[2].weight, head[2].bias)   # reg_branches[i]: 256 -> 128 on the tensor cores
             outs.append(current - noisy_line)
         return torch.stack(outs)
 

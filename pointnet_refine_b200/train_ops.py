@@ -442,6 +442,42 @@ def add_layernorm(x, y, norm: torch.nn.LayerNorm):
     return AddLayerNormFn.apply(x, y, norm.weight, norm.bias, norm.eps)
 
 
+class ThinLinearFn(torch.autograd.Function):
+    """fp32 y = x W^T + b for the layers with 3 input or 3 output features on the polyline rows (pos_emb.mlp[0] on the
+    current points, reg_branches[i][2]; src/model.py:66-75,172-179).  Forward and dx are ordinary small matmuls; the weight
+    gradient dW = dy^T x reduces over ALL rows (32 k at B = 1024) into a 256 x 3 or 3 x 128 result, which a library GEMM
+    runs as one or two CTAs looping over K (80 us per launch, 12 per step): here the rows are split into 64 slabs whose
+    partial products come from one batched matmul and are summed (two launches of a few microseconds)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dx = dw = db = None
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        if ctx.needs_input_grad[0]:
+            dx = (dy2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            rows = dy2.shape[0]
+            slabs = 64 if rows % 64 == 0 and rows >= 4096 else 1
+            if slabs > 1:
+                dw = torch.bmm(dy2.view(slabs, rows // slabs, -1).transpose(1, 2), x2.view(slabs, rows // slabs, -1)).sum(0)
+            else:
+                dw = dy2.t() @ x2
+        if ctx.needs_input_grad[2]:
+            db = dy2.sum(0)
+        return dx, dw, db
+
+
+def thin_linear(x, weight, bias):
+    return ThinLinearFn.apply(x, weight, bias)
+
+
 def linear_bf16(x, weight, bias, out_dtype=torch.bfloat16):
     """Differentiable bf16 tensor-core linear layer over the last dimension of x (leading dims flattened); the result is
     bf16, or fp32 written straight from the accumulators (out_dtype=torch.float32: no conversion pass for consumers that

@@ -220,3 +220,23 @@ def test_flat_data_parallel_two_ranks_gloo():
         assert res[rank][3] == 4                    # two slices per step, two steps
     for a, b in zip(res[0][1], res[1][1]):
         assert np.array_equal(a, b)                 # parameters identical after two optimizer steps
+
+
+def test_thin_linear_split_k_weight_gradient():
+    """train_ops.thin_linear (pos_emb.mlp[0] on the polyline points, reg_branches[i][2]): same values and gradients as
+    F.linear, with the weight gradient formed as 64 slab products + a sum once there are >= 4096 rows."""
+    import torch
+    from pointnet_refine_b200.train_ops import thin_linear
+    torch.manual_seed(0)
+    for rows, fin, fout in ((4096, 3, 256), (4096, 128, 3), (96, 3, 256)):
+        x = torch.randn(rows // 32, 32, fin, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(fout, fin, dtype=torch.float64, requires_grad=True)
+        b = torch.randn(fout, dtype=torch.float64, requires_grad=True)
+        r = torch.randn(rows // 32, 32, fout, dtype=torch.float64)
+        y = thin_linear(x, w, b)
+        ref = torch.nn.functional.linear(x, w, b)
+        assert torch.equal(y, ref)
+        g = torch.autograd.grad((y * r).sum(), (x, w, b))
+        gr = torch.autograd.grad((ref * r).sum(), (x, w, b))
+        for a, c in zip(g, gr):
+            assert float((a - c).abs().max()) <= 1e-10 * max(1.0, float(c.abs().max()))
