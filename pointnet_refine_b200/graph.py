@@ -108,6 +108,14 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph, stream=self._side):
                 self._seed.add_(0x2545F4914F6CDD1D)        # every replay: a new dropout stream for the attention kernels
                 loss, pred = self._step_body()
+        except RuntimeError as e:
+            if "capturing" in str(e) or "capture" in str(e):
+                raise RuntimeError(
+                    "GraphedTrainStep: the CUDA-graph capture of the train step failed.  The usual cause is an autograd graph "
+                    "kept alive from an earlier eager step (e.g. a `loss` tensor still referenced): its AccumulateGrad nodes "
+                    "stay bound to the stream that step ran on.  Drop those references (`del loss`) or keep only "
+                    "`loss.detach()` / `loss.item()`, then build the step again.") from e
+            raise
         finally:
             train_ops.DropoutSeedState.word = None
         optimizer._step = host_step                        # the capture executed nothing
