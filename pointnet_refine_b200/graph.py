@@ -72,7 +72,8 @@ class GraphedTrainStep:
     AccumulateGrad nodes bound to the stream those steps ran on, and the capture then fails with
     cudaErrorStreamCaptureImplicit.
 
-    __call__ returns (loss, pred_stack): static tensors, overwritten by the next call."""
+    __call__ returns (loss, pred_stack): static tensors, overwritten by the next call.  A batch of another shape (the ragged
+    last batch of an epoch) runs the same step eagerly (`eager`)."""
 
     def __init__(self, net, optimizer, context, noisy_line, target, loss_fn=None, warmup: int = 2):
         from . import train_ops
@@ -141,7 +142,20 @@ class GraphedTrainStep:
         self.opt.step()
         return loss, pred
 
+    def eager(self, context, noisy_line, target):
+        """The same step launched kernel by kernel, for a batch whose shape differs from the captured one (the ragged last
+        batch of an epoch when the DataLoader does not drop it).  Shares the optimizer state, the device step count and the
+        parameters with the replays; returns (loss, pred_stack) detached."""
+        self.opt.zero_grad()
+        pred = self.net(context, noisy_line)
+        loss = self.loss_fn(pred, target)
+        loss.backward()
+        self.opt.step()
+        return loss.detach(), pred.detach()
+
     def __call__(self, context, noisy_line, target):
+        if context.shape != self.ctx.shape or noisy_line.shape != self.line.shape or target.shape != self.tgt.shape:
+            return self.eager(context, noisy_line, target)
         self.ctx.copy_(context, non_blocking=True)
         self.line.copy_(noisy_line, non_blocking=True)
         self.tgt.copy_(target, non_blocking=True)

@@ -648,3 +648,8 @@ def test_graphed_train_step_with_dropout_trains(dev):
     losses = [float(step(ctx, line, tgt)[0]) for _ in range(12)]
     assert int(step._seed) != w0 and step.replays == 12
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    # a ragged last batch goes through the same step eagerly and shares optimizer state / step count with the replays
+    loss_r, pred_r = step(ctx[:5], line[:5], tgt[:5])
+    assert pred_r.shape == (6, 5, 32, 3) and bool(torch.isfinite(loss_r)) and step.replays == 12 and opt.steps_taken == 13
+    assert np.isfinite(float(step(ctx, line, tgt)[0])) and opt.steps_taken == 14
+    step.close()
