@@ -482,6 +482,9 @@ def main():
         pass
     roofline = {"bound": "tensor", "kernel": "gemm_pair_kernel<256,EPI_FUSION> (fusion conv + gate + pooling, cta_group::2)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,
+                # the same kernel time against the burst figure (cuBLAS best of 10, not power-capped): the step's kernels are
+                # timed at whatever clock the cap leaves on this box, the sustained figure at a median 1320 MHz
+                "frac_of_burst_peak": (achieved / float(peaks["bf16_tflops"])) if args.precision != "tf32" else None,
                 "traffic": traffic.get("fusion_dram_bytes_per_launch") if args.precision == "bf16" else None,
                 "kernel_ms_per_launch": f_ms / max(f_n, 1), "kernel_share_of_step": f_ms / total_ms if total_ms else None,
                 "stage_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()},
