@@ -1066,13 +1066,8 @@ int pack_w(const float* src, int rows, int cols, void* dst, int64_t ld, bool tra
   return LRN_OK;
 }
 
-// (column blocks of 64 channels, row slabs): enough blocks to fill the chip (~8 per SM) whatever C is
-dim3 stats_grid(int C, int64_t rows) {
-  const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (148 * 8) / (C / 64) + 1));  // blocks walk 32 (or 8) rows per step
-  return dim3(C / 64, unsigned(slabs));
-}
-
-// The same partition sized to what is resident: the blocks of these streaming kernels loop over the rows, so a grid of
+// Streaming kernels over a (rows x C) bf16 matrix: grid = (column blocks of 64 channels, row slabs), blocks loop over the rows.
+// The grid is sized to what is resident: the blocks of these streaming kernels loop over the rows, so a grid of
 // exactly (SMs x resident blocks per SM) leaves no partial last wave (1200 blocks at 2 per SM were 4.05 waves).
 template <typename Kernel>
 dim3 stream_grid(Kernel kernel, int C, int64_t rows, int sms) {
