@@ -179,6 +179,16 @@ bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ U, long long ldu, long lo
 
 __device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
 
+// 16-byte shared-memory read that the compiler may not hoist out of a loop: per-channel constants that are re-read per row
+// instead of living in registers (the streaming kernels below trade eight LDS.128 per row for 16 - 24 registers, i.e. for
+// a second row of loads in flight at the same occupancy).
+__device__ __forceinline__ float4 lds_f4_pinned(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ptx::smem_u32(p)));
+  return v;
+}
+
+
 // fused[b, c, n] = relu(Uf[p, c] * scale[c] + shift[c]) * (0.5 + 0.5 * sigmoid(Z[p, c])),  p = b * N + n
 // (src/model.py:51,54-55, train mode).  32 points x 32 channels per block, transposed through shared memory so
 // both the point-major reads and the channel-major (B,1024,N) writes are coalesced.
@@ -469,14 +479,19 @@ bn_bwd_apply_kernel(const __nv_bfloat16* d1, long long ld1, const __nv_bfloat16*
                     long long ldu, long long rows, int C, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ S1,
                     const float* __restrict__ S2, __nv_bfloat16* dU, long long ldo) {
-  const int c0 = blockIdx.x * 64 + (threadIdx.x & 7) * 8;
+  __shared__ __align__(16) float smask[2][64];   // the ReLU mask's scale / shift of the block's 64 channels
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, col = threadIdx.x & 63;
+    smask[which][col] = msc ? (which ? msh : msc)[blockIdx.x * 64 + col] : 0.f;
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 7;
+  const int c0 = blockIdx.x * 64 + cg * 8;
   const float inv_n = 1.f / static_cast<float>(rows);
-  float A[8], Bc[8], Cc[8], sc[8], sh[8];
+  float A[8], Bc[8], Cc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
-    sc[j] = msc ? msc[c] : 0.f;
-    sh[j] = msc ? msh[c] : 0.f;
     const float gr = gamma[c] * rstd[c];
     A[j] = gr;
     Bc[j] = -gr * rstd[c] * S2[c] * inv_n;
@@ -487,21 +502,48 @@ bn_bwd_apply_kernel(const __nv_bfloat16* d1, long long ld1, const __nv_bfloat16*
                         *pu = reinterpret_cast<const __nv_bfloat16*>(&ru);
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float d = bf2f(p1[j]);
-      const float u = bf2f(pu[j]);
-      if (d2) d += bf2f(p2[j]);
-      if (msc && !(fmaf(u, sc[j], sh[j]) > 0.f)) d = 0.f;   // ReLU mask from the pre-activation (see bn_bwd_reduce_kernel)
-      v[j] = fmaf(A[j], d, fmaf(Bc[j], u, Cc[j]));
+    for (int hq = 0; hq < 2; ++hq) {
+      float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+      if (msc) {
+        const float4 a = lds_f4_pinned(&smask[0][8 * cg + 4 * hq]), b = lds_f4_pinned(&smask[1][8 * cg + 4 * hq]);
+        sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w;
+        sh[0] = b.x; sh[1] = b.y; sh[2] = b.z; sh[3] = b.w;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * hq + jj;
+        float d = bf2f(p1[j]);
+        const float u = bf2f(pu[j]);
+        if (d2) d += bf2f(p2[j]);
+        if (msc && !(fmaf(u, sc[jj], sh[jj]) > 0.f)) d = 0.f;   // ReLU mask from the pre-activation (see bn_bwd_reduce_kernel)
+        v[j] = fmaf(A[j], d, fmaf(Bc[j], u, Cc[j]));
+      }
     }
     *reinterpret_cast<uint4*>(dU + r * ldo + c0) =
         make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]),
                    ptx::pack_bf16x2(v[6], v[7]));
   };
-  // one row per step: with two rows in flight the 40 per-channel coefficients no longer fit next to the loads (spills) and
-  // the kernel did not get faster (measured) - its mixed read / write stream sits at ~0.73 of the copy bandwidth either way
+  // two rows = up to six 16-byte loads in flight per thread at 3 resident blocks (the mask constants come from shared
+  // memory per row, so the 24 BatchNorm coefficients + two rows of loads fit without spills); both rows are read before
+  // either is written (d1 may alias dU)
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  for (long long r = blockIdx.y * 32ll + (threadIdx.x >> 3); r < rows; r += gridDim.y * 32ll) {
+  const long long stride = gridDim.y * 32ll;
+  long long r = blockIdx.y * 32ll + (threadIdx.x >> 3);
+  for (; r + stride < rows; r += 2 * stride) {
+    const long long rb = r + stride;
+    const uint4 a1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c0);
+    const uint4 au = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(d1 + rb * ld1 + c0);
+    const uint4 bu = *reinterpret_cast<const uint4*>(U + rb * ldu + c0);
+    uint4 a2 = zero, b2 = zero;
+    if (d2) {
+      a2 = *reinterpret_cast<const uint4*>(d2 + r * ld2 + c0);
+      b2 = *reinterpret_cast<const uint4*>(d2 + rb * ld2 + c0);
+    }
+    apply(a1, a2, au, r);
+    apply(b1, b2, bu, rb);
+  }
+  if (r < rows) {
     const uint4 a1 = *reinterpret_cast<const uint4*>(d1 + r * ld1 + c0);
     const uint4 au = *reinterpret_cast<const uint4*>(U + r * ldu + c0);
     const uint4 a2 = d2 ? *reinterpret_cast<const uint4*>(d2 + r * ld2 + c0) : zero;
