@@ -30,7 +30,10 @@
 // the four F2 / Z blocks (idle then) serve as four more 16 KB weight stages (7 in flight; one stage = two 64-wide
 // k-blocks of the CTA's 64 weight rows = 8 MMAs per barrier round trip).  The F1 / GH blocks, idle from the end of conv2
 // until the next tile's conv1, take the tile's first two conv5 stages ~10k cycles ahead of time, so conv5 starts with
-// weights in place (a TMA round trip under load is ~2.8k cycles).
+// weights in place (a TMA round trip under load is ~2.8k cycles).  conv4 has the same problem at a smaller scale - eight
+// k-blocks consumed in ~0.5k cycles each through three dedicated stages - so two of its first chunk's k-blocks land in
+// the Z blocks (idle until that chunk's drain stages feat4 through them): five k-blocks are in flight before conv4 starts
+// (0.403 -> 0.385 ms per launch).
 #pragma once
 #include "gemm_pair_sm100.cuh"
 
@@ -254,8 +257,13 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
       load(next_a(), &tmW2, 0, static_cast<int>(rank) * 64, 64 * 128);                                    // conv2: N = 128
       for (int kb = 0; kb < 2; ++kb) load(next_a(), &tmW3, kb * 64, static_cast<int>(rank) * 128, 128 * 128);  // conv3: N = 256
-      for (int c = 0; c < 2; ++c)                                                                        // conv4: 2 x (N = 256)
-        for (int kb = 0; kb < 4; ++kb) load(next_a(), &tmW4, kb * 64, c * 256 + static_cast<int>(rank) * 128, 128 * 128);
+      // conv4: 2 x (N = 256), eight 16 KB k-blocks per CTA.  Three dedicated stages cannot cover a ~2.8k-cycle TMA round trip
+      // at conv4's rate (a k-block is consumed in ~0.5k cycles): the second and third k-block of the first chunk land in the
+      // two Z blocks, which are idle from the end of the previous tile's conv5 until this tile's first conv4 drain stages
+      // feat4 through them (that drain waits for the whole chunk's MMAs) - five k-blocks are in flight before conv4 starts.
+      for (int c = 0; c < 2; ++c)
+        for (int kb = 0; kb < 4; ++kb)
+          load((c == 0 && (kb == 1 || kb == 2)) ? S + 1 + kb : next_a(), &tmW4, kb * 64, c * 256 + static_cast<int>(rank) * 128, 128 * 128);
       {                                                                                                  // conv5: 8 x (N = 128)
         bool fz_ok = false;
         for (int n = 0; n < 8; ++n)
@@ -319,6 +327,19 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         }
         __syncwarp();
       };
+      // the same for an explicit stage `st` (next stage of the sequence: `nx`)
+      auto kblock_at = [&](int st, int nx, uint32_t a_off, uint32_t d_tmem, uint32_t idesc, bool first) {
+        wait_stage(st, nx);
+        if (ptx::elect_one()) {
+          const uint64_t da = ptx::make_smem_desc_sw128(ptx::smem_u32(smem + a_off));
+          const uint64_t db = ptx::make_smem_desc_sw128(ptx::smem_u32(stage_ptr(st)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::tc_mma_ss_pair<false>(d_tmem, da + 2 * k, db + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+          ptx::tc_commit_pair(&w_empty[st], 3);
+        }
+        __syncwarp();
+      };
       auto commit_acc = [&](int buf) {
         if (ptx::elect_one()) ptx::tc_commit_pair(&acc_full[buf], 3);
         __syncwarp();
@@ -344,11 +365,24 @@ chain_pair_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid_constan
         commit_acc(1);
         // conv4: F3 (K = 256) -> buf0 (channels 0..255), buf1 (channels 256..511)
         ptx::mbar_wait(&act_ready[2], par);
-        for (int c = 0; c < 2; ++c) {
-          ptx::mbar_wait(&acc_free[c], par);  // this tile's conv2 / conv3 accumulator drained
-          ptx::tc_fence_after();
-          for (int kb = 0; kb < 4; ++kb) kblock(L::kF3 + kb * kChainBlock, tmem_base + c * 256, kIdesc256, kb == 0);
-          commit_acc(c);
+        {
+          int stq[9];   // weight stages in the producer's order: k-blocks 1 and 2 of the first chunk sit in the Z blocks
+          for (int i = 0; i < 8; ++i) {
+            if (i == 1 || i == 2) {
+              stq[i] = S + 1 + i;
+            } else {
+              stq[i] = pa;
+              pa = pa + 1 == S ? 0 : pa + 1;
+            }
+          }
+          stq[8] = pa;
+          for (int c = 0; c < 2; ++c) {
+            ptx::mbar_wait(&acc_free[c], par);  // this tile's conv2 / conv3 accumulator drained
+            ptx::tc_fence_after();
+            for (int kb = 0; kb < 4; ++kb)
+              kblock_at(stq[4 * c + kb], stq[4 * c + kb + 1], L::kF3 + kb * kChainBlock, tmem_base + c * 256, kIdesc256, kb == 0);
+            commit_acc(c);
+          }
         }
         {
           // conv5: A = feat4 in TMEM columns [0, 256) (K = 512); eight 128-channel chunks alternate between two
