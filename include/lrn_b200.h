@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define LRN_ABI_VERSION 1
+/* 2: lrn_train_attention_forward / _backward take `seed_state`; lrn_adam_step_capturable added */
+#define LRN_ABI_VERSION 2
 
 typedef struct CUstream_st* lrn_stream_t; /* == cudaStream_t */
 

@@ -16,6 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "lrn_b200.h")
 
 # enums of include/lrn_b200.h
+ABI_VERSION = 2      # LRN_ABI_VERSION
 LRN_OK = 0
 PREC_BF16, PREC_TF32, PREC_FP32X3 = 0, 1, 2
 OUT_POOL, OUT_ARGMAX, OUT_FUSED, OUT_MEMORY, OUT_MEMORY_BF16 = 1, 2, 4, 8, 16
@@ -125,8 +126,9 @@ def _load():
     lib.lrn_ctx_attention_merge.argtypes = [vp, vp, ci, ci, vp, ci, vp]
     lib.lrn_debug_timeline.restype = ci
     lib.lrn_debug_timeline.argtypes = [vp]
-    if lib.lrn_abi_version() != 1:
-        raise RuntimeError("liblrn_b200.so ABI version mismatch; rebuild it")
+    if lib.lrn_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"liblrn_b200.so has ABI version {lib.lrn_abi_version()}, this package binds version {ABI_VERSION}; rebuild it "
+                           "(python pointnet_refine_b200/build.py --force)")
     return lib
 
 
